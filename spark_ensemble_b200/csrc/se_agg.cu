@@ -1,0 +1,258 @@
+// se_agg.cu — ensemble Model.predict / predictRaw aggregation kernels (sm_100a).
+//
+// Reference per-row bodies (one JVM call per row through a UDF):
+//   regression/GBMRegressor.scala:531-539        init + Σ_m a_m·P[m]
+//   regression/BaggingRegressor.scala:221-228    (Σ_m P[m]) / M
+//   classification/GBMClassifier.scala:564-589   res_j = init_j + Σ_m a_mj·P[m][j]; binary dim 1 -> (-res,res)
+//   classification/BaggingClassifier.scala:260-287   soft: Σ_m p_m ; hard: Σ_m onehot(ŷ_m) ; prob = raw/M
+//   classification/BoostingClassifier.scala:342-382  real: Σ_m (K-1)(ℓ_mk − mean_k ℓ_mk) ; discrete: ±a_m votes;
+//                                                    prob = softmax(raw/(K-1))
+//
+// All of them are one streaming pass over the stacked base-model outputs P (the only large operand:
+// 4·M·width B/row) followed by a tiny per-row epilogue.  Stage 1 (sum / vote histogram) is the
+// HBM-bound kernel; stage 2 (finalize) touches only C values per row.
+#include "se_kernels.h"
+#include "../../include/se_abi.h"
+
+namespace se {
+
+namespace {
+
+constexpr float kSparkEps = 2.220446049250313e-16f;
+constexpr int MU = 8;  // models loaded per batch: 8 independent 16 B requests per thread
+
+// out[c][i] = init_c + Σ_m a[m][c] · f(P[m][c][i]),  f = identity or log(max(·,ε))
+// P row (m,c) lives at P + (cols ? cols[m] : m*width + c) * ld.
+template <bool LOGP>
+__global__ void __launch_bounds__(kBlock) agg_sum_kernel(const float* __restrict__ P, int64_t n,
+                                                        int64_t ld, int M, int width,
+                                                        const float* __restrict__ a,
+                                                        const float* __restrict__ init,
+                                                        const int32_t* __restrict__ cols,
+                                                        float post_div, float* __restrict__ out,
+                                                        int64_t ld_out) {
+  const int64_t n4 = n >> 2;
+  for (int64_t g = (int64_t)blockIdx.x * kBlock + threadIdx.x; g < n4;
+       g += (int64_t)gridDim.x * kBlock) {
+    for (int c = 0; c < width; ++c) {
+      float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0;
+      for (int m0 = 0; m0 < M; m0 += MU) {
+        float4 v[MU];
+        float wv[MU];
+#pragma unroll
+        for (int u = 0; u < MU; ++u) {
+          const int m = m0 + u;
+          if (m < M) {
+            const int64_t rowi = cols ? (int64_t)cols[m] : (int64_t)m * width + c;
+            v[u] = ld_stream4(P + rowi * ld + 4 * g);
+            wv[u] = a ? a[(int64_t)m * width + c] : 1.0f;
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < MU; ++u) {
+          if (m0 + u < M) {
+            float4 x = v[u];
+            if (LOGP) {
+              x.x = logf(fmaxf(x.x, kSparkEps)); x.y = logf(fmaxf(x.y, kSparkEps));
+              x.z = logf(fmaxf(x.z, kSparkEps)); x.w = logf(fmaxf(x.w, kSparkEps));
+            }
+            float4& s = (u & 1) ? s1 : s0;  // two accumulator sets: shorter dependency chains
+            s.x = fmaf(wv[u], x.x, s.x); s.y = fmaf(wv[u], x.y, s.y);
+            s.z = fmaf(wv[u], x.z, s.z); s.w = fmaf(wv[u], x.w, s.w);
+          }
+        }
+      }
+      const float b = init ? init[c] : 0.f;
+      float4 r = make_float4(b + (s0.x + s1.x), b + (s0.y + s1.y), b + (s0.z + s1.z), b + (s0.w + s1.w));
+      if (post_div != 0.f) { r.x /= post_div; r.y /= post_div; r.z /= post_div; r.w /= post_div; }
+      st_stream4(out + c * ld_out + 4 * g, r);
+    }
+  }
+  // tail rows
+  const int tail = (int)(n & 3);
+  if (blockIdx.x == 0 && threadIdx.x < tail) {
+    const int64_t i = (n4 << 2) + threadIdx.x;
+    for (int c = 0; c < width; ++c) {
+      float s = 0.f;
+      for (int m = 0; m < M; ++m) {
+        const int64_t rowi = cols ? (int64_t)cols[m] : (int64_t)m * width + c;
+        float x = P[rowi * ld + i];
+        if (LOGP) x = logf(fmaxf(x, kSparkEps));
+        s = fmaf(a ? a[(int64_t)m * width + c] : 1.0f, x, s);
+      }
+      float r = (init ? init[c] : 0.f) + s;
+      if (post_div != 0.f) r /= post_div;
+      out[c * ld_out + i] = r;
+    }
+  }
+}
+
+// Vote histogram: A_c = Σ_{m: vote_m == c} a_m (a_m = 1 when a == nullptr).  One row per thread,
+// per-thread histogram in shared memory laid out [K][kBlock] (conflict-free).
+__global__ void __launch_bounds__(kBlock) agg_votes_kernel(const float* __restrict__ votes, int64_t n,
+                                                          int64_t ld, int M, int K,
+                                                          const float* __restrict__ a,
+                                                          float* __restrict__ out, int64_t ld_out) {
+  extern __shared__ float hist[];  // [K][kBlock]
+  for (int64_t i0 = (int64_t)blockIdx.x * kBlock; i0 < n; i0 += (int64_t)gridDim.x * kBlock) {
+    const int64_t i = i0 + threadIdx.x;
+    for (int c = 0; c < K; ++c) hist[c * kBlock + threadIdx.x] = 0.f;
+    if (i < n) {
+      for (int m0 = 0; m0 < M; m0 += MU) {
+        float v[MU];
+#pragma unroll
+        for (int u = 0; u < MU; ++u)
+          if (m0 + u < M) v[u] = ld_stream1(votes + (int64_t)(m0 + u) * ld + i);
+#pragma unroll
+        for (int u = 0; u < MU; ++u)
+          if (m0 + u < M) {
+            const int c = (int)v[u];
+            if (c >= 0 && c < K) hist[c * kBlock + threadIdx.x] += a ? a[m0 + u] : 1.0f;
+          }
+      }
+      for (int c = 0; c < K; ++c) out[c * ld_out + i] = hist[c * kBlock + threadIdx.x];
+    }
+  }
+}
+
+// Stage 2: per-row epilogue on tmp[C][n] (in RAW) -> raw, prob, label.
+struct FinArgs {
+  int kind, C, K, dim, loss, M;
+  float sum_a;  // Σ a_m (boosting discrete)
+  int64_t n, ld;
+  float* raw;
+  float* prob;
+  float* label;
+};
+
+__device__ __forceinline__ float fin_raw(const FinArgs& f, float t, float mean_t) {
+  switch (f.kind) {
+    case SE_AGG_BOOSTING_REAL:  // (K-1)(L_k − mean L)   BoostingClassifier.scala:355-360
+      return (float)(f.K - 1) * (t - mean_t);
+    case SE_AGG_BOOSTING_DISCRETE:  // +a on the vote, −a/(K-1) elsewhere   :371-376
+      return (t * (float)f.K - f.sum_a) / (float)(f.K - 1);
+    default: return t;
+  }
+}
+
+__global__ void __launch_bounds__(kBlock) agg_finalize_kernel(const FinArgs f) {
+  for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < f.n;
+       i += (int64_t)gridDim.x * kBlock) {
+    if (f.kind == SE_AGG_GBM_CLASSIFIER && f.dim == 1 && f.K == 2) {
+      // GBMClassifier.scala:583-584 + GBMLoss.scala:284-289,311-316 (raw(0) = −F)
+      const float res = f.raw[i];
+      const float r0 = -res;
+      float p1;
+      if (f.loss == SE_LOSS_EXPONENTIAL) p1 = 1.0f / (1.0f + expf(-2.0f * r0));
+      else p1 = 1.0f / (1.0f + expf(r0));
+      f.raw[i] = r0;
+      f.raw[f.ld + i] = res;
+      f.prob[i] = 1.0f - p1;
+      f.prob[f.ld + i] = p1;
+      f.label[i] = (res > r0) ? 1.0f : 0.0f;  // argmax, first maximum on ties
+      continue;
+    }
+    const int C = f.C;
+    float mean_t = 0.f;
+    if (f.kind == SE_AGG_BOOSTING_REAL) {
+      float s = 0.f;
+      for (int c = 0; c < C; ++c) s += f.raw[c * f.ld + i];
+      mean_t = s / (float)C;
+    }
+    // pass 1: raw, max / argmax
+    float best = -INFINITY;
+    int am = 0;
+    for (int c = 0; c < C; ++c) {
+      const float r = fin_raw(f, f.raw[c * f.ld + i], mean_t);
+      if (r > best) { best = r; am = c; }
+    }
+    f.label[i] = (float)am;
+    const bool softmax = (f.kind == SE_AGG_BOOSTING_REAL || f.kind == SE_AGG_BOOSTING_DISCRETE ||
+                          (f.kind == SE_AGG_GBM_CLASSIFIER));
+    if (softmax) {
+      // boosting: softmax(raw/(K-1)) (:342-346); GBM logloss: softmax(raw) (GBMLoss.scala:258-261)
+      const float sc = (f.kind == SE_AGG_GBM_CLASSIFIER) ? 1.0f : 1.0f / (float)(f.K - 1);
+      float s = 0.f;
+      for (int c = 0; c < C; ++c) s += expf((fin_raw(f, f.raw[c * f.ld + i], mean_t) - best) * sc);
+      const float inv = 1.0f / s;
+      for (int c = 0; c < C; ++c) {
+        const float r = fin_raw(f, f.raw[c * f.ld + i], mean_t);
+        f.prob[c * f.ld + i] = expf((r - best) * sc) * inv;
+        f.raw[c * f.ld + i] = r;
+      }
+    } else {
+      // bagging: prob = raw · (1/M)   (BaggingClassifier.scala:285-287)
+      const float invM = 1.0f / (float)f.M;
+      for (int c = 0; c < C; ++c) f.prob[c * f.ld + i] = f.raw[c * f.ld + i] * invM;
+    }
+  }
+}
+
+inline int grid_rows(int64_t items, int64_t per_cta, int ctas_per_sm, int sms) {
+  int64_t need = (items + per_cta - 1) / per_cta;
+  if (need < 1) need = 1;
+  const int64_t cap = (int64_t)ctas_per_sm * sms;
+  return (int)(need < cap ? need : cap);
+}
+
+}  // namespace
+
+cudaError_t launch_agg(const AggArgs& a, int ctas_per_sm, int sms, cudaStream_t st) {
+  const int grid4 = grid_rows(a.n >> 2, kBlock, ctas_per_sm, sms);
+  const int grid1 = grid_rows(a.n, kBlock, ctas_per_sm, sms);
+  FinArgs f{};
+  f.kind = a.kind; f.K = a.K; f.dim = a.dim; f.loss = a.loss; f.M = a.M;
+  f.n = a.n; f.ld = a.ld_out; f.raw = a.raw; f.prob = a.prob; f.label = a.label;
+  f.sum_a = 0.f;
+  switch (a.kind) {
+    case SE_AGG_GBM_REGRESSOR:
+      agg_sum_kernel<false><<<grid4, kBlock, 0, st>>>(a.P, a.n, a.ld, a.M, 1, a.weights, a.init,
+                                                       nullptr, 0.f, a.raw, a.ld_out);
+      return cudaGetLastError();
+    case SE_AGG_BAGGING_REGRESSOR:
+      agg_sum_kernel<false><<<grid4, kBlock, 0, st>>>(a.P, a.n, a.ld, a.M, 1, nullptr, nullptr,
+                                                       nullptr, (float)a.M, a.raw, a.ld_out);
+      return cudaGetLastError();
+    case SE_AGG_GBM_CLASSIFIER:
+      agg_sum_kernel<false><<<grid4, kBlock, 0, st>>>(a.P, a.n, a.ld, a.M, a.dim, a.weights, a.init,
+                                                       nullptr, 0.f, a.raw, a.ld_out);
+      f.C = (a.dim == 1 && a.K == 2) ? 2 : a.dim;
+      break;
+    case SE_AGG_BAGGING_SOFT:
+      agg_sum_kernel<false><<<grid4, kBlock, 0, st>>>(a.P, a.n, a.ld, a.M, a.K, nullptr, nullptr,
+                                                       nullptr, 0.f, a.raw, a.ld_out);
+      f.C = a.K;
+      break;
+    case SE_AGG_BOOSTING_REAL:
+      agg_sum_kernel<true><<<grid4, kBlock, 0, st>>>(a.P, a.n, a.ld, a.M, a.K, nullptr, nullptr,
+                                                      nullptr, 0.f, a.raw, a.ld_out);
+      f.C = a.K;
+      break;
+    case SE_AGG_BAGGING_HARD:
+    case SE_AGG_BOOSTING_DISCRETE: {
+      const size_t smem = (size_t)a.K * kBlock * sizeof(float);
+      if (smem > 200 * 1024) return cudaErrorInvalidValue;
+      if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(agg_votes_kernel,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+      }
+      agg_votes_kernel<<<grid1, kBlock, smem, st>>>(
+          a.P, a.n, a.ld, a.M, a.K, a.kind == SE_AGG_BOOSTING_DISCRETE ? a.weights : nullptr, a.raw,
+          a.ld_out);
+      f.C = a.K;
+      break;
+    }
+    default: return cudaErrorInvalidValue;
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  if (a.kind == SE_AGG_BOOSTING_DISCRETE) {
+    // Σ a_m is needed by the epilogue (host-side sum of the tiny weight vector)
+    f.sum_a = a.sum_weights;
+  }
+  agg_finalize_kernel<<<grid1, kBlock, 0, st>>>(f);
+  return cudaGetLastError();
+}
+
+}  // namespace se

@@ -1,0 +1,1166 @@
+// se_api.cu — host side of libse_b200.so: the extern "C" ABI declared in include/se_abi.h.
+//
+// Owns the per-GPU context (stream, device slots, reduction workspace, scalar block, NCCL
+// communicator) and turns each ABI call into kernel launches on the context stream.  No CPU
+// fallback exists: every compute entry point needs a working CUDA device.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/se_abi.h"
+#include "se_kernels.h"
+#include "se_loss.cuh"
+
+using namespace se;
+
+// ------------------------------------------------------------------------------------------------
+// NCCL is bound at run time (dlopen) so the library loads on boxes/processes without it and never
+// clashes with a copy another component (e.g. a host framework) already loaded.
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+typedef struct { char internal[128]; } nccl_uid_t;
+typedef void* nccl_comm_t;
+struct NcclApi {
+  void* handle = nullptr;
+  int (*GetUniqueId)(nccl_uid_t*) = nullptr;
+  int (*CommInitRank)(nccl_comm_t*, int, nccl_uid_t, int) = nullptr;
+  int (*CommDestroy)(nccl_comm_t) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, nccl_comm_t, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+  int (*GetVersion)(int*) = nullptr;
+  bool ok = false;
+  std::string why;
+};
+constexpr int kNcclFloat64 = 8;  // ncclDouble
+constexpr int kNcclSum = 0;
+
+NcclApi& nccl() {
+  static NcclApi api;
+  static bool tried = false;
+  if (tried) return api;
+  tried = true;
+  const char* names[] = {getenv("SE_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+  for (const char* nm : names) {
+    if (!nm || !*nm) continue;
+    api.handle = dlopen(nm, RTLD_NOW | RTLD_LOCAL);
+    if (api.handle) break;
+  }
+  if (!api.handle) {
+    api.why = std::string("dlopen(libnccl.so.2) failed: ") + (dlerror() ? dlerror() : "?");
+    return api;
+  }
+#define SE_SYM(field, name)                                                     \
+  api.field = reinterpret_cast<decltype(api.field)>(dlsym(api.handle, name));   \
+  if (!api.field) { api.why = std::string("missing symbol ") + name; return api; }
+  SE_SYM(GetUniqueId, "ncclGetUniqueId")
+  SE_SYM(CommInitRank, "ncclCommInitRank")
+  SE_SYM(CommDestroy, "ncclCommDestroy")
+  SE_SYM(AllReduce, "ncclAllReduce")
+  SE_SYM(GetErrorString, "ncclGetErrorString")
+  SE_SYM(GetVersion, "ncclGetVersion")
+#undef SE_SYM
+  api.ok = true;
+  return api;
+}
+
+thread_local std::string g_last_error;
+
+constexpr int kScal = 128;          // doubles in the device/host scalar blocks
+constexpr int kScalRound = 64;      // offset of the async squared-round results
+constexpr int kScalHost = 96;       // offset used by se_comm_allreduce_host
+constexpr int kSmallBytes = 1 << 20;  // small device scratch: weights, init, tree arrays, factors
+
+struct SlotBuf {
+  float* d = nullptr;
+  int64_t rows = 0, cols = 0, ld = 0;
+  size_t bytes = 0;
+};
+
+}  // namespace
+
+struct se_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  bool timing = false;
+  double last_ms = 0.0;
+  int sms = 148;
+  int ctas_per_sm = 4;
+  int64_t launches = 0;
+  SlotBuf slot[SE_NUM_SLOTS];
+  double* d_scal = nullptr;
+  double* h_scal = nullptr;  // pinned
+  double* d_partials = nullptr;
+  unsigned int* d_counter = nullptr;
+  unsigned char* d_small = nullptr;
+  unsigned char* h_small = nullptr;  // pinned staging for d_small
+  float* h_stage = nullptr;          // pinned staging for f64 uploads / scaled downloads
+  size_t h_stage_bytes = 0;
+  struct {
+    bool on = false;
+    int64_t n = 0, nv = 0;
+    int dim = 1, loss = 0;
+    double param = 0.0;
+    bool has_w = false;
+    double wsum = 0.0;
+    bool wsum_valid = false;
+    double n_global = 0.0, nv_global = 0.0;
+    bool counts_valid = false;
+  } gbm;
+  struct {
+    bool on = false;
+    int64_t n = 0;
+    int K = 2;
+    bool real = false;
+  } boost;
+  struct {
+    bool on = false;
+    int kind = 0, M = 0, K = 0, dim = 1, loss = 0, width = 1, C = 1;
+    int64_t n = 0;
+  } agg;
+  nccl_comm_t comm = nullptr;
+  int nranks = 1, rank = 0;
+  std::string err;
+};
+
+namespace {
+
+int fail(se_ctx* ctx, int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  if (ctx) ctx->err = buf;
+  return code;
+}
+
+#define SE_CUDA(ctx, call)                                                                    \
+  do {                                                                                        \
+    cudaError_t e__ = (call);                                                                 \
+    if (e__ != cudaSuccess)                                                                   \
+      return fail(ctx, SE_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #call,              \
+                  cudaGetErrorString(e__));                                                   \
+  } while (0)
+
+#define SE_LAUNCH(ctx, call)                                                                  \
+  do {                                                                                        \
+    cudaError_t e__ = (call);                                                                 \
+    (ctx)->launches++;                                                                        \
+    if (e__ != cudaSuccess)                                                                   \
+      return fail(ctx, SE_ERR_CUDA, "%s:%d launch %s -> %s", __FILE__, __LINE__, #call,       \
+                  cudaGetErrorString(e__));                                                   \
+  } while (0)
+
+#define SE_TRY(expr)                \
+  do {                              \
+    int rc__ = (expr);              \
+    if (rc__ != SE_OK) return rc__; \
+  } while (0)
+
+#define SE_REQUIRE(ctx, cond, code, ...) \
+  do {                                   \
+    if (!(cond)) return fail(ctx, code, __VA_ARGS__); \
+  } while (0)
+
+int begin(se_ctx* ctx) {
+  if (!ctx) return fail(nullptr, SE_ERR_ARG, "null context");
+  SE_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (ctx->timing) SE_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+  return SE_OK;
+}
+
+int end(se_ctx* ctx) {
+  if (ctx->timing) SE_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+  return SE_OK;
+}
+
+RedWs red_ws(se_ctx* ctx, int out_offset = 0) {
+  RedWs ws;
+  ws.partials = ctx->d_partials;
+  ws.counter = ctx->d_counter;
+  ws.out = ctx->d_scal + out_offset;
+  return ws;
+}
+
+// all-reduce d_scal[off..off+count) in-stream (no-op without communicator)
+int allreduce_dev(se_ctx* ctx, int off, int count) {
+  if (!ctx->comm || ctx->nranks <= 1) return SE_OK;
+  NcclApi& api = nccl();
+  int rc = api.AllReduce(ctx->d_scal + off, ctx->d_scal + off, (size_t)count, kNcclFloat64, kNcclSum,
+                         ctx->comm, ctx->stream);
+  if (rc != 0) return fail(ctx, SE_ERR_NCCL, "ncclAllReduce: %s", api.GetErrorString(rc));
+  return SE_OK;
+}
+
+// (all-reduce and) bring d_scal[off..off+count) to the host; synchronises the stream
+int fetch_scalars(se_ctx* ctx, int off, int count, double* out) {
+  SE_TRY(allreduce_dev(ctx, off, count));
+  SE_CUDA(ctx, cudaMemcpyAsync(ctx->h_scal + off, ctx->d_scal + off, sizeof(double) * count,
+                               cudaMemcpyDeviceToHost, ctx->stream));
+  SE_TRY(end(ctx));
+  SE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  for (int i = 0; i < count; ++i) out[i] = ctx->h_scal[off + i];
+  return SE_OK;
+}
+
+int slot_alloc2d(se_ctx* ctx, int slot, int64_t rows, int64_t cols) {
+  SE_REQUIRE(ctx, slot >= 0 && slot < SE_NUM_SLOTS, SE_ERR_ARG, "bad slot %d", slot);
+  SE_REQUIRE(ctx, rows >= 1 && cols >= 0, SE_ERR_ARG, "bad slot shape %lld x %lld", (long long)rows,
+             (long long)cols);
+  SlotBuf& s = ctx->slot[slot];
+  const int64_t ld = (rows > 1) ? ((cols + 31) / 32) * 32 : cols;
+  const size_t bytes = sizeof(float) * (size_t)(rows * ld + 32);
+  if (s.d && s.bytes >= bytes) {
+    s.rows = rows; s.cols = cols; s.ld = ld;
+    return SE_OK;
+  }
+  if (s.d) SE_CUDA(ctx, cudaFree(s.d));
+  s = SlotBuf();
+  SE_CUDA(ctx, cudaMalloc(&s.d, bytes));
+  s.rows = rows; s.cols = cols; s.ld = ld; s.bytes = bytes;
+  return SE_OK;
+}
+
+int need_slot(se_ctx* ctx, int slot, int64_t rows, int64_t cols, const char* what) {
+  const SlotBuf& s = ctx->slot[slot];
+  if (!s.d || s.rows != rows || s.cols != cols)
+    return fail(ctx, SE_ERR_STATE, "%s: slot %d must hold [%lld][%lld] (has [%lld][%lld])", what,
+                slot, (long long)rows, (long long)cols, (long long)s.rows, (long long)s.cols);
+  return SE_OK;
+}
+
+int ensure_stage(se_ctx* ctx, size_t bytes) {
+  if (ctx->h_stage_bytes >= bytes) return SE_OK;
+  if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+  ctx->h_stage = nullptr;
+  ctx->h_stage_bytes = 0;
+  SE_CUDA(ctx, cudaMallocHost(&ctx->h_stage, bytes));
+  ctx->h_stage_bytes = bytes;
+  return SE_OK;
+}
+
+// logical flat [rows][cols] range -> per-row physical segments
+template <class Fn>
+int for_segments(se_ctx* ctx, const SlotBuf& s, int64_t count, int64_t offset, Fn fn) {
+  SE_REQUIRE(ctx, s.d, SE_ERR_STATE, "slot not allocated");
+  SE_REQUIRE(ctx, offset >= 0 && count >= 0 && offset + count <= s.rows * s.cols, SE_ERR_ARG,
+             "range [%lld,+%lld) outside slot of %lld elements", (long long)offset,
+             (long long)count, (long long)(s.rows * s.cols));
+  int64_t done = 0;
+  while (done < count) {
+    const int64_t pos = offset + done;
+    const int64_t r = (s.cols > 0) ? pos / s.cols : 0, c = (s.cols > 0) ? pos % s.cols : 0;
+    int64_t len = s.cols - c;
+    if (len > count - done) len = count - done;
+    SE_TRY(fn(s.d + r * s.ld + c, done, len));
+    done += len;
+  }
+  return SE_OK;
+}
+
+int ensure_counts(se_ctx* ctx) {
+  if (ctx->gbm.counts_valid) return SE_OK;
+  double v[2] = {(double)ctx->gbm.n, (double)ctx->gbm.nv};
+  SE_TRY(se_comm_allreduce_host(ctx, v, 2));
+  ctx->gbm.n_global = v[0];
+  ctx->gbm.nv_global = v[1];
+  ctx->gbm.counts_valid = true;
+  return SE_OK;
+}
+
+int ensure_wsum(se_ctx* ctx) {
+  if (ctx->gbm.wsum_valid) return SE_OK;
+  SE_TRY(ensure_counts(ctx));
+  if (!ctx->gbm.has_w) {
+    ctx->gbm.wsum = ctx->gbm.n_global;
+  } else {
+    SE_TRY(need_slot(ctx, SE_SLOT_W, 1, ctx->gbm.n, "instance weights"));
+    SE_LAUNCH(ctx, launch_sum(ctx->slot[SE_SLOT_W].d, ctx->gbm.n, red_ws(ctx), ctx->ctas_per_sm,
+                              ctx->sms, ctx->stream));
+    double s = 0.0;
+    SE_TRY(fetch_scalars(ctx, 0, 1, &s));
+    ctx->gbm.wsum = s;
+  }
+  ctx->gbm.wsum_valid = true;
+  return SE_OK;
+}
+
+GbmArgs gbm_args(se_ctx* ctx, bool validation) {
+  GbmArgs a;
+  const auto& g = ctx->gbm;
+  a.y = ctx->slot[validation ? SE_SLOT_VY : SE_SLOT_Y].d;
+  a.F = ctx->slot[validation ? SE_SLOT_VF : SE_SLOT_F].d;
+  a.h = ctx->slot[validation ? SE_SLOT_VH : SE_SLOT_H].d;
+  a.w = (!validation && g.has_w) ? ctx->slot[SE_SLOT_W].d : nullptr;
+  a.r = validation ? nullptr : ctx->slot[SE_SLOT_R].d;
+  a.wout = validation ? nullptr : ctx->slot[SE_SLOT_WOUT].d;
+  a.n = validation ? g.nv : g.n;
+  a.ld = ctx->slot[validation ? SE_SLOT_VF : SE_SLOT_F].ld;
+  a.dim = g.dim;
+  a.param = (float)g.param;
+  a.ws = red_ws(ctx);
+  return a;
+}
+
+// ---- Brent, commons-math3 3.6.1 BrentOptimizer semantics (call site GBMRegressor.scala:311,413-421).
+// Golden-section fallback, parabolic interpolation when the fit lies inside the bracket and is
+// shrinking, never evaluates closer than tol1 = rel*|x| + abs to a previous abscissa, stops when
+// |x - mid| <= 2*tol1 - (hi-lo)/2; returns the best point evaluated.
+bool within_one_ulp(double a, double b) {
+  return a == b || (!isnan(a) && !isnan(b) && nextafter(a, b) == b);
+}
+
+int brent_impl(se_fn1 f, void* user, double lo, double hi, double start, double rel, double abs_tol,
+               int max_eval, double* x_out, double* f_out, int* n_eval) {
+  static const double kGolden = 0.5 * (3.0 - sqrt(5.0));
+  double left = lo < hi ? lo : hi, right = lo < hi ? hi : lo;
+  double x = start, w = start, v = start;       // best, second best, previous second best
+  double step = 0.0, prev_step = 0.0;           // "d" and "e" of the classic formulation
+  int evals = 0;
+  double fx = f(x, user);
+  ++evals;
+  double fw = fx, fv = fx;
+  double bx = x, bf = fx;                       // best-of-all-evaluations bookkeeping
+  double last_x = x, last_f = fx;
+  bool have_two = false;
+  double before_x = 0.0, before_f = 0.0;
+  int status = SE_OK;
+  auto consider = [&](double cx, double cf) {
+    if (!(bf <= cf)) { bx = cx; bf = cf; }
+  };
+  for (;;) {
+    const double mid = 0.5 * (left + right);
+    const double tol1 = rel * fabs(x) + abs_tol, tol2 = 2.0 * tol1;
+    if (fabs(x - mid) <= tol2 - 0.5 * (right - left)) {
+      if (have_two && before_f <= last_f) consider(before_x, before_f);
+      else consider(last_x, last_f);
+      break;
+    }
+    bool use_golden = true;
+    double u;
+    if (fabs(prev_step) > tol1) {
+      double r = (x - w) * (fx - fv);
+      double q = (x - v) * (fx - fw);
+      double p = (x - v) * q - (x - w) * r;
+      q = 2.0 * (q - r);
+      if (q > 0.0) p = -p; else q = -q;
+      r = prev_step;
+      prev_step = step;
+      if (p > q * (left - x) && p < q * (right - x) && fabs(p) < fabs(0.5 * q * r)) {
+        step = p / q;
+        u = x + step;
+        if (u - left < tol2 || right - u < tol2) step = (x <= mid) ? tol1 : -tol1;
+        use_golden = false;
+      }
+    }
+    if (use_golden) {
+      prev_step = (x < mid) ? right - x : left - x;
+      step = kGolden * prev_step;
+    }
+    u = (fabs(step) < tol1) ? (step >= 0.0 ? x + tol1 : x - tol1) : x + step;
+    if (evals >= max_eval) { status = SE_ERR_OPT; break; }
+    const double fu = f(u, user);
+    ++evals;
+    before_x = last_x; before_f = last_f; have_two = true;
+    last_x = u; last_f = fu;
+    if (before_f <= last_f) consider(before_x, before_f);
+    else consider(last_x, last_f);
+    if (fu <= fx) {
+      if (u < x) right = x; else left = x;
+      v = w; fv = fw;
+      w = x; fw = fx;
+      x = u; fx = fu;
+    } else {
+      if (u < x) left = u; else right = u;
+      if (fu <= fw || within_one_ulp(w, x)) {
+        v = w; fv = fw;
+        w = u; fw = fu;
+      } else if (fu <= fv || within_one_ulp(v, x) || within_one_ulp(v, w)) {
+        v = u; fv = fu;
+      }
+    }
+  }
+  if (x_out) *x_out = bx;
+  if (f_out) *f_out = bf;
+  if (n_eval) *n_eval = evals;
+  return status;
+}
+
+}  // namespace
+
+// ================================================================================================
+extern "C" {
+
+int se_abi_version(void) { return SE_ABI_VERSION; }
+
+const char* se_last_error(const se_ctx* ctx) {
+  if (ctx && !ctx->err.empty()) return ctx->err.c_str();
+  return g_last_error.c_str();
+}
+
+int se_device_count(int* out) {
+  if (!out) return fail(nullptr, SE_ERR_ARG, "null out");
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) {
+    *out = 0;
+    return fail(nullptr, SE_ERR_CUDA, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+  }
+  *out = n;
+  return SE_OK;
+}
+
+int se_ctx_create(int device, se_ctx** out) {
+  if (!out) return fail(nullptr, SE_ERR_ARG, "null out");
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n <= 0)
+    return fail(nullptr, SE_ERR_CUDA, "no CUDA device available (%s): the hot path has no CPU fallback",
+                e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+  if (device < 0 || device >= n) return fail(nullptr, SE_ERR_ARG, "device %d out of range [0,%d)", device, n);
+  se_ctx* ctx = new se_ctx();
+  ctx->device = device;
+#define SE_CREATE_CUDA(call)                                                            \
+  do {                                                                                  \
+    cudaError_t e__ = (call);                                                           \
+    if (e__ != cudaSuccess) {                                                           \
+      int rc__ = fail(nullptr, SE_ERR_CUDA, "%s -> %s", #call, cudaGetErrorString(e__)); \
+      delete ctx;                                                                       \
+      return rc__;                                                                      \
+    }                                                                                   \
+  } while (0)
+  SE_CREATE_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  SE_CREATE_CUDA(cudaGetDeviceProperties(&prop, device));
+  ctx->sms = prop.multiProcessorCount;
+  if (const char* s = getenv("SE_CTAS_PER_SM")) {
+    const int v = atoi(s);
+    if (v >= 1 && v <= 16) ctx->ctas_per_sm = v;
+  }
+  SE_CREATE_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  SE_CREATE_CUDA(cudaEventCreate(&ctx->ev0));
+  SE_CREATE_CUDA(cudaEventCreate(&ctx->ev1));
+  SE_CREATE_CUDA(cudaMalloc(&ctx->d_scal, sizeof(double) * kScal));
+  SE_CREATE_CUDA(cudaMemset(ctx->d_scal, 0, sizeof(double) * kScal));
+  SE_CREATE_CUDA(cudaMallocHost(&ctx->h_scal, sizeof(double) * kScal));
+  SE_CREATE_CUDA(cudaMalloc(&ctx->d_partials, sizeof(double) * (size_t)kMaxGridPartials * kMaxRed));
+  SE_CREATE_CUDA(cudaMalloc(&ctx->d_counter, sizeof(unsigned int)));
+  SE_CREATE_CUDA(cudaMemset(ctx->d_counter, 0, sizeof(unsigned int)));
+  SE_CREATE_CUDA(cudaMalloc(&ctx->d_small, kSmallBytes));
+  SE_CREATE_CUDA(cudaMallocHost(&ctx->h_small, kSmallBytes));
+  SE_CREATE_CUDA(cudaDeviceSynchronize());
+#undef SE_CREATE_CUDA
+  *out = ctx;
+  return SE_OK;
+}
+
+int se_ctx_destroy(se_ctx* ctx) {
+  if (!ctx) return SE_OK;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  if (ctx->comm && nccl().ok) nccl().CommDestroy(ctx->comm);
+  for (auto& s : ctx->slot)
+    if (s.d) cudaFree(s.d);
+  if (ctx->d_scal) cudaFree(ctx->d_scal);
+  if (ctx->h_scal) cudaFreeHost(ctx->h_scal);
+  if (ctx->d_partials) cudaFree(ctx->d_partials);
+  if (ctx->d_counter) cudaFree(ctx->d_counter);
+  if (ctx->d_small) cudaFree(ctx->d_small);
+  if (ctx->h_small) cudaFreeHost(ctx->h_small);
+  if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+  if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+  if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return SE_OK;
+}
+
+int se_ctx_sync(se_ctx* ctx) {
+  if (!ctx) return fail(nullptr, SE_ERR_ARG, "null context");
+  SE_CUDA(ctx, cudaSetDevice(ctx->device));
+  SE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return SE_OK;
+}
+
+int se_ctx_device(const se_ctx* ctx, int* device) {
+  if (!ctx || !device) return fail(nullptr, SE_ERR_ARG, "null argument");
+  *device = ctx->device;
+  return SE_OK;
+}
+
+int se_ctx_launch_count(const se_ctx* ctx, int64_t* out) {
+  if (!ctx || !out) return fail(nullptr, SE_ERR_ARG, "null argument");
+  *out = ctx->launches;
+  return SE_OK;
+}
+
+int se_ctx_set_timing(se_ctx* ctx, int on) {
+  if (!ctx) return fail(nullptr, SE_ERR_ARG, "null context");
+  ctx->timing = on != 0;
+  return SE_OK;
+}
+
+int se_ctx_last_ms(se_ctx* ctx, double* out) {
+  if (!ctx || !out) return fail(nullptr, SE_ERR_ARG, "null argument");
+  SE_REQUIRE(ctx, ctx->timing, SE_ERR_STATE, "timing is off (se_ctx_set_timing)");
+  SE_CUDA(ctx, cudaSetDevice(ctx->device));
+  SE_CUDA(ctx, cudaEventSynchronize(ctx->ev1));
+  float ms = 0.f;
+  SE_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+  *out = (double)ms;
+  return SE_OK;
+}
+
+// ---- communicator ------------------------------------------------------------------------------
+int se_comm_unique_id(void* out, int bytes) {
+  if (!out || bytes < SE_COMM_ID_BYTES) return fail(nullptr, SE_ERR_ARG, "id buffer must hold %d bytes", SE_COMM_ID_BYTES);
+  NcclApi& api = nccl();
+  if (!api.ok) return fail(nullptr, SE_ERR_NCCL, "NCCL unavailable: %s", api.why.c_str());
+  nccl_uid_t id;
+  int rc = api.GetUniqueId(&id);
+  if (rc != 0) return fail(nullptr, SE_ERR_NCCL, "ncclGetUniqueId: %s", api.GetErrorString(rc));
+  memcpy(out, &id, sizeof(id));
+  return SE_OK;
+}
+
+int se_comm_init(se_ctx* ctx, int nranks, int rank, const void* id, int bytes) {
+  if (!ctx) return fail(nullptr, SE_ERR_ARG, "null context");
+  SE_REQUIRE(ctx, nranks >= 1 && rank >= 0 && rank < nranks, SE_ERR_ARG, "bad rank %d of %d", rank, nranks);
+  SE_REQUIRE(ctx, !ctx->comm, SE_ERR_STATE, "communicator already attached");
+  ctx->nranks = nranks;
+  ctx->rank = rank;
+  ctx->gbm.counts_valid = ctx->gbm.wsum_valid = false;
+  if (nranks == 1) return SE_OK;
+  SE_REQUIRE(ctx, id && bytes >= SE_COMM_ID_BYTES, SE_ERR_ARG, "unique id of %d bytes required", SE_COMM_ID_BYTES);
+  NcclApi& api = nccl();
+  if (!api.ok) return fail(ctx, SE_ERR_NCCL, "NCCL unavailable: %s", api.why.c_str());
+  SE_CUDA(ctx, cudaSetDevice(ctx->device));
+  nccl_uid_t uid;
+  memcpy(&uid, id, sizeof(uid));
+  int rc = api.CommInitRank(&ctx->comm, nranks, uid, rank);
+  if (rc != 0) {
+    ctx->comm = nullptr;
+    return fail(ctx, SE_ERR_NCCL, "ncclCommInitRank: %s", api.GetErrorString(rc));
+  }
+  return SE_OK;
+}
+
+int se_comm_destroy(se_ctx* ctx) {
+  if (!ctx) return fail(nullptr, SE_ERR_ARG, "null context");
+  if (ctx->comm) {
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    nccl().CommDestroy(ctx->comm);
+    ctx->comm = nullptr;
+  }
+  ctx->nranks = 1;
+  ctx->rank = 0;
+  ctx->gbm.counts_valid = ctx->gbm.wsum_valid = false;
+  return SE_OK;
+}
+
+int se_comm_info(const se_ctx* ctx, int* nranks, int* rank) {
+  if (!ctx) return fail(nullptr, SE_ERR_ARG, "null context");
+  if (nranks) *nranks = ctx->nranks;
+  if (rank) *rank = ctx->rank;
+  return SE_OK;
+}
+
+int se_comm_allreduce_host(se_ctx* ctx, double* values, int count) {
+  if (!ctx || !values) return fail(nullptr, SE_ERR_ARG, "null argument");
+  SE_REQUIRE(ctx, count >= 0 && count <= kScal - kScalHost, SE_ERR_ARG, "count %d too large", count);
+  if (!ctx->comm || ctx->nranks <= 1 || count == 0) return SE_OK;
+  SE_CUDA(ctx, cudaSetDevice(ctx->device));
+  for (int i = 0; i < count; ++i) ctx->h_scal[kScalHost + i] = values[i];
+  SE_CUDA(ctx, cudaMemcpyAsync(ctx->d_scal + kScalHost, ctx->h_scal + kScalHost, sizeof(double) * count,
+                               cudaMemcpyHostToDevice, ctx->stream));
+  SE_TRY(allreduce_dev(ctx, kScalHost, count));
+  SE_CUDA(ctx, cudaMemcpyAsync(ctx->h_scal + kScalHost, ctx->d_scal + kScalHost, sizeof(double) * count,
+                               cudaMemcpyDeviceToHost, ctx->stream));
+  SE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  for (int i = 0; i < count; ++i) values[i] = ctx->h_scal[kScalHost + i];
+  return SE_OK;
+}
+
+// ---- slots -------------------------------------------------------------------------------------
+int se_slot_alloc(se_ctx* ctx, int slot, int64_t count) {
+  if (!ctx) return fail(nullptr, SE_ERR_ARG, "null context");
+  SE_CUDA(ctx, cudaSetDevice(ctx->device));
+  return slot_alloc2d(ctx, slot, 1, count);
+}
+
+int se_slot_alloc2d(se_ctx* ctx, int slot, int64_t rows, int64_t cols) {
+  if (!ctx) return fail(nullptr, SE_ERR_ARG, "null context");
+  SE_CUDA(ctx, cudaSetDevice(ctx->device));
+  return slot_alloc2d(ctx, slot, rows, cols);
+}
+
+int se_slot_free(se_ctx* ctx, int slot) {
+  if (!ctx) return fail(nullptr, SE_ERR_ARG, "null context");
+  SE_REQUIRE(ctx, slot >= 0 && slot < SE_NUM_SLOTS, SE_ERR_ARG, "bad slot %d", slot);
+  SE_CUDA(ctx, cudaSetDevice(ctx->device));
+  SE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (ctx->slot[slot].d) SE_CUDA(ctx, cudaFree(ctx->slot[slot].d));
+  ctx->slot[slot] = SlotBuf();
+  return SE_OK;
+}
+
+int se_slot_info(const se_ctx* ctx, int slot, void** device_ptr, int64_t* count) {
+  if (!ctx) return fail(nullptr, SE_ERR_ARG, "null context");
+  if (slot < 0 || slot >= SE_NUM_SLOTS) return fail(nullptr, SE_ERR_ARG, "bad slot %d", slot);
+  if (device_ptr) *device_ptr = ctx->slot[slot].d;
+  if (count) *count = ctx->slot[slot].rows * ctx->slot[slot].cols;
+  return SE_OK;
+}
+
+int se_slot_layout(const se_ctx* ctx, int slot, int64_t* rows, int64_t* cols, int64_t* ld) {
+  if (!ctx) return fail(nullptr, SE_ERR_ARG, "null context");
+  if (slot < 0 || slot >= SE_NUM_SLOTS) return fail(nullptr, SE_ERR_ARG, "bad slot %d", slot);
+  if (rows) *rows = ctx->slot[slot].rows;
+  if (cols) *cols = ctx->slot[slot].cols;
+  if (ld) *ld = ctx->slot[slot].ld;
+  return SE_OK;
+}
+
+int se_upload(se_ctx* ctx, int slot, const float* host, int64_t count, int64_t offset) {
+  if (!ctx || !host) return fail(ctx, SE_ERR_ARG, "null argument");
+  SE_REQUIRE(ctx, slot >= 0 && slot < SE_NUM_SLOTS, SE_ERR_ARG, "bad slot %d", slot);
+  SE_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (slot == SE_SLOT_W) ctx->gbm.wsum_valid = false;
+  SE_TRY(for_segments(ctx, ctx->slot[slot], count, offset, [&](float* d, int64_t done, int64_t len) {
+    SE_CUDA(ctx, cudaMemcpyAsync(d, host + done, sizeof(float) * len, cudaMemcpyHostToDevice, ctx->stream));
+    return SE_OK;
+  }));
+  // host buffers are borrowed for the duration of the call only
+  SE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return SE_OK;
+}
+
+int se_upload_f64(se_ctx* ctx, int slot, const double* host, int64_t count, int64_t offset) {
+  if (!ctx || !host) return fail(ctx, SE_ERR_ARG, "null argument");
+  SE_REQUIRE(ctx, slot >= 0 && slot < SE_NUM_SLOTS, SE_ERR_ARG, "bad slot %d", slot);
+  SE_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (slot == SE_SLOT_W) ctx->gbm.wsum_valid = false;
+  // narrow on the host (halves PCIe bytes) through pinned staging, in chunks
+  const int64_t chunk = 1 << 22;
+  SE_TRY(ensure_stage(ctx, sizeof(float) * (size_t)chunk));
+  SE_TRY(for_segments(ctx, ctx->slot[slot], count, offset, [&](float* d, int64_t done, int64_t len) {
+    for (int64_t c0 = 0; c0 < len; c0 += chunk) {
+      const int64_t m = (len - c0 < chunk) ? len - c0 : chunk;
+      for (int64_t i = 0; i < m; ++i) ctx->h_stage[i] = (float)host[done + c0 + i];
+      SE_CUDA(ctx, cudaMemcpyAsync(d + c0, ctx->h_stage, sizeof(float) * m, cudaMemcpyHostToDevice, ctx->stream));
+      SE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return SE_OK;
+  }));
+  return SE_OK;
+}
+
+int se_download(se_ctx* ctx, int slot, float* host, int64_t count, int64_t offset) {
+  if (!ctx || !host) return fail(ctx, SE_ERR_ARG, "null argument");
+  SE_REQUIRE(ctx, slot >= 0 && slot < SE_NUM_SLOTS, SE_ERR_ARG, "bad slot %d", slot);
+  SE_CUDA(ctx, cudaSetDevice(ctx->device));
+  SE_TRY(for_segments(ctx, ctx->slot[slot], count, offset, [&](float* d, int64_t done, int64_t len) {
+    SE_CUDA(ctx, cudaMemcpyAsync(host + done, d, sizeof(float) * len, cudaMemcpyDeviceToHost, ctx->stream));
+    return SE_OK;
+  }));
+  SE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return SE_OK;
+}
+
+int se_download_scaled(se_ctx* ctx, int slot, double scale, float* host, int64_t count, int64_t offset) {
+  if (!ctx || !host) return fail(ctx, SE_ERR_ARG, "null argument");
+  SE_TRY(se_download(ctx, slot, host, count, offset));
+  const float s = (float)scale;
+  for (int64_t i = 0; i < count; ++i) host[i] *= s;
+  return SE_OK;
+}
+
+int se_fill(se_ctx* ctx, int slot, float value, int64_t count, int64_t offset) {
+  if (!ctx) return fail(nullptr, SE_ERR_ARG, "null context");
+  SE_REQUIRE(ctx, slot >= 0 && slot < SE_NUM_SLOTS, SE_ERR_ARG, "bad slot %d", slot);
+  SE_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (slot == SE_SLOT_W) ctx->gbm.wsum_valid = false;
+  return for_segments(ctx, ctx->slot[slot], count, offset, [&](float* d, int64_t, int64_t len) {
+    SE_LAUNCH(ctx, launch_fill(d, value, len, ctx->sms, ctx->stream));
+    return SE_OK;
+  });
+}
+
+int se_copy_slot(se_ctx* ctx, int dst_slot, int src_slot) {
+  if (!ctx) return fail(nullptr, SE_ERR_ARG, "null context");
+  SE_REQUIRE(ctx, dst_slot >= 0 && dst_slot < SE_NUM_SLOTS && src_slot >= 0 && src_slot < SE_NUM_SLOTS,
+             SE_ERR_ARG, "bad slot");
+  const SlotBuf &d = ctx->slot[dst_slot], &s = ctx->slot[src_slot];
+  SE_REQUIRE(ctx, d.d && s.d && d.rows == s.rows && d.cols == s.cols, SE_ERR_STATE, "slot shapes differ");
+  SE_CUDA(ctx, cudaSetDevice(ctx->device));
+  SE_CUDA(ctx, cudaMemcpyAsync(d.d, s.d, sizeof(float) * (size_t)(s.rows * s.ld), cudaMemcpyDeviceToDevice, ctx->stream));
+  return SE_OK;
+}
+
+int se_fill_synthetic(se_ctx* ctx, int slot, int kind, uint64_t seed, double a, double b, int64_t count,
+                      int64_t offset) {
+  if (!ctx) return fail(nullptr, SE_ERR_ARG, "null context");
+  SE_REQUIRE(ctx, slot >= 0 && slot < SE_NUM_SLOTS, SE_ERR_ARG, "bad slot %d", slot);
+  SE_REQUIRE(ctx, kind >= 0 && kind <= 3, SE_ERR_ARG, "bad synthetic kind %d", kind);
+  SE_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (slot == SE_SLOT_W) ctx->gbm.wsum_valid = false;
+  return for_segments(ctx, ctx->slot[slot], count, offset, [&](float* d, int64_t done, int64_t len) {
+    SE_LAUNCH(ctx, launch_fill_synthetic(d, kind, seed, a, b, len, offset + done, ctx->sms, ctx->stream));
+    return SE_OK;
+  });
+}
+
+int se_slot_sum(se_ctx* ctx, int slot, int64_t count, double* out) {
+  if (!ctx || !out) return fail(ctx, SE_ERR_ARG, "null argument");
+  SE_REQUIRE(ctx, slot >= 0 && slot < SE_NUM_SLOTS, SE_ERR_ARG, "bad slot %d", slot);
+  const SlotBuf& s = ctx->slot[slot];
+  SE_REQUIRE(ctx, s.d && s.rows == 1 && count <= s.cols, SE_ERR_STATE, "slot %d is not a [n] vector of >= %lld", slot, (long long)count);
+  SE_TRY(begin(ctx));
+  SE_LAUNCH(ctx, launch_sum(s.d, count, red_ws(ctx), ctx->ctas_per_sm, ctx->sms, ctx->stream));
+  return fetch_scalars(ctx, 0, 1, out);
+}
+
+// ---- GBM ---------------------------------------------------------------------------------------
+int se_gbm_configure(se_ctx* ctx, int64_t n_train, int64_t n_valid, int dim, int loss, double param,
+                     int has_weights) {
+  if (!ctx) return fail(nullptr, SE_ERR_ARG, "null context");
+  SE_REQUIRE(ctx, n_train >= 0 && n_valid >= 0, SE_ERR_ARG, "negative row count");
+  SE_REQUIRE(ctx, loss >= SE_LOSS_SQUARED && loss <= SE_LOSS_LOGLOSS, SE_ERR_ARG, "unknown loss %d", loss);
+  SE_REQUIRE(ctx, dim >= 1 && dim <= kMaxDim, SE_ERR_ARG, "dim %d outside [1,%d]", dim, kMaxDim);
+  SE_REQUIRE(ctx, (loss == SE_LOSS_LOGLOSS) || dim == 1, SE_ERR_ARG, "scalar losses have dim 1 (got %d)", dim);
+  SE_CUDA(ctx, cudaSetDevice(ctx->device));
+  auto& g = ctx->gbm;
+  g.on = true; g.n = n_train; g.nv = n_valid; g.dim = dim; g.loss = loss; g.param = param;
+  g.has_w = has_weights != 0;
+  g.wsum_valid = false; g.counts_valid = false;
+  SE_TRY(slot_alloc2d(ctx, SE_SLOT_Y, 1, n_train));
+  SE_TRY(slot_alloc2d(ctx, SE_SLOT_F, dim, n_train));
+  SE_TRY(slot_alloc2d(ctx, SE_SLOT_H, dim, n_train));
+  SE_TRY(slot_alloc2d(ctx, SE_SLOT_R, dim, n_train));
+  if (g.has_w) SE_TRY(slot_alloc2d(ctx, SE_SLOT_W, 1, n_train));
+  if (n_valid > 0) {
+    SE_TRY(slot_alloc2d(ctx, SE_SLOT_VY, 1, n_valid));
+    SE_TRY(slot_alloc2d(ctx, SE_SLOT_VF, dim, n_valid));
+    SE_TRY(slot_alloc2d(ctx, SE_SLOT_VH, dim, n_valid));
+  }
+  return SE_OK;
+}
+
+int se_gbm_set_loss_param(se_ctx* ctx, double param) {
+  if (!ctx) return fail(nullptr, SE_ERR_ARG, "null context");
+  SE_REQUIRE(ctx, ctx->gbm.on, SE_ERR_STATE, "se_gbm_configure first");
+  ctx->gbm.param = param;
+  return SE_OK;
+}
+
+static int newton_finish(se_ctx* ctx, double* sum_hess) {
+  // S_j (all-reduced) -> WOUT_j *= 1/S_j   (GBMRegressor.scala:373,379; GBMClassifier.scala:344-355,364)
+  const int dim = ctx->gbm.dim;
+  double s[1 + kMaxDim];
+  SE_TRY(fetch_scalars(ctx, 0, 1 + dim, s));
+  float* fact = reinterpret_cast<float*>(ctx->h_small);
+  for (int j = 0; j < dim; ++j) {
+    fact[j] = (float)(1.0 / s[1 + j]);
+    if (sum_hess) sum_hess[j] = s[1 + j];
+  }
+  SE_CUDA(ctx, cudaMemcpyAsync(ctx->d_small, fact, sizeof(float) * dim, cudaMemcpyHostToDevice, ctx->stream));
+  const SlotBuf& wo = ctx->slot[SE_SLOT_WOUT];
+  SE_LAUNCH(ctx, launch_scale_rows(wo.d, ctx->gbm.n, wo.ld, dim, reinterpret_cast<const float*>(ctx->d_small),
+                                   ctx->sms, ctx->stream));
+  ctx->h_scal[0] = s[0];
+  return SE_OK;
+}
+
+int se_gbm_pseudo_residuals(se_ctx* ctx, int newton, double* sum_hess) {
+  if (!ctx) return fail(nullptr, SE_ERR_ARG, "null context");
+  SE_REQUIRE(ctx, ctx->gbm.on, SE_ERR_STATE, "se_gbm_configure first");
+  SE_REQUIRE(ctx, !newton || loss_has_hessian(ctx->gbm.loss), SE_ERR_ARG, "loss %d has no hessian (updates=newton)", ctx->gbm.loss);
+  SE_TRY(begin(ctx));
+  if (newton) SE_TRY(slot_alloc2d(ctx, SE_SLOT_WOUT, ctx->gbm.dim, ctx->gbm.n));
+  GbmArgs a = gbm_args(ctx, false);
+  SE_LAUNCH(ctx, launch_gbm(ctx->gbm.loss, newton ? GBM_RESID_NEWTON : GBM_RESID, a, ctx->ctas_per_sm,
+                            ctx->sms, ctx->stream));
+  if (newton) SE_TRY(newton_finish(ctx, sum_hess));
+  return end(ctx);
+}
+
+int se_gbm_linesearch_eval(se_ctx* ctx, const double* alpha, double* loss, double* grad) {
+  if (!ctx || !alpha || !loss) return fail(ctx, SE_ERR_ARG, "null argument");
+  SE_REQUIRE(ctx, ctx->gbm.on, SE_ERR_STATE, "se_gbm_configure first");
+  SE_TRY(ensure_wsum(ctx));
+  SE_TRY(begin(ctx));
+  const int dim = ctx->gbm.dim;
+  GbmArgs a = gbm_args(ctx, false);
+  for (int j = 0; j < dim; ++j) a.coef[j] = (float)alpha[j];
+  SE_LAUNCH(ctx, launch_gbm(ctx->gbm.loss, GBM_EVAL, a, ctx->ctas_per_sm, ctx->sms, ctx->stream));
+  double s[1 + kMaxDim];
+  SE_TRY(fetch_scalars(ctx, 0, 1 + dim, s));
+  // lossSum is accumulated `dim` times per row in the reference (GBMLoss.scala:60-64)
+  *loss = (double)dim * s[0] / ctx->gbm.wsum;
+  if (grad)
+    for (int j = 0; j < dim; ++j) grad[j] = s[1 + j] / ctx->gbm.wsum;
+  return SE_OK;
+}
+
+int se_gbm_linesearch_stats(se_ctx* ctx, double* stats4) {
+  if (!ctx || !stats4) return fail(ctx, SE_ERR_ARG, "null argument");
+  SE_REQUIRE(ctx, ctx->gbm.on && ctx->gbm.loss == SE_LOSS_SQUARED, SE_ERR_STATE, "squared loss only");
+  SE_TRY(ensure_wsum(ctx));
+  SE_TRY(begin(ctx));
+  GbmArgs a = gbm_args(ctx, false);
+  SE_LAUNCH(ctx, launch_gbm(SE_LOSS_SQUARED, GBM_SQ_STATS, a, ctx->ctas_per_sm, ctx->sms, ctx->stream));
+  SE_TRY(fetch_scalars(ctx, 0, 3, stats4));
+  stats4[3] = ctx->gbm.wsum;
+  return SE_OK;
+}
+
+int se_gbm_update(se_ctx* ctx, const double* step, int flags, double* loss_sum, double* sum_hess) {
+  if (!ctx || !step) return fail(ctx, SE_ERR_ARG, "null argument");
+  SE_REQUIRE(ctx, ctx->gbm.on, SE_ERR_STATE, "se_gbm_configure first");
+  const bool newton = (flags & SE_UPD_NEWTON) != 0;
+  SE_REQUIRE(ctx, !newton || loss_has_hessian(ctx->gbm.loss), SE_ERR_ARG, "loss %d has no hessian", ctx->gbm.loss);
+  SE_TRY(begin(ctx));
+  if (newton) SE_TRY(slot_alloc2d(ctx, SE_SLOT_WOUT, ctx->gbm.dim, ctx->gbm.n));
+  GbmArgs a = gbm_args(ctx, false);
+  for (int j = 0; j < ctx->gbm.dim; ++j) a.coef[j] = (float)step[j];
+  const int mode = newton ? GBM_UPDATE_NEWTON : ((flags & SE_UPD_RESIDUAL) ? GBM_UPDATE_RESID : GBM_UPDATE);
+  SE_LAUNCH(ctx, launch_gbm(ctx->gbm.loss, mode, a, ctx->ctas_per_sm, ctx->sms, ctx->stream));
+  if (newton) {
+    SE_TRY(newton_finish(ctx, sum_hess));
+    if (loss_sum) *loss_sum = ctx->h_scal[0];
+    return end(ctx);
+  }
+  if ((flags & SE_UPD_LOSS) && loss_sum) return fetch_scalars(ctx, 0, 1, loss_sum);
+  return end(ctx);
+}
+
+int se_gbm_mean_loss(se_ctx* ctx, int which, double* out) {
+  if (!ctx || !out) return fail(ctx, SE_ERR_ARG, "null argument");
+  SE_REQUIRE(ctx, ctx->gbm.on, SE_ERR_STATE, "se_gbm_configure first");
+  SE_REQUIRE(ctx, which == 0 || (which == 1 && ctx->gbm.nv > 0), SE_ERR_ARG, "no validation shard");
+  SE_TRY(ensure_counts(ctx));
+  SE_TRY(begin(ctx));
+  GbmArgs a = gbm_args(ctx, which == 1);
+  SE_LAUNCH(ctx, launch_gbm(ctx->gbm.loss, GBM_MEAN_LOSS, a, ctx->ctas_per_sm, ctx->sms, ctx->stream));
+  double s = 0.0;
+  SE_TRY(fetch_scalars(ctx, 0, 1, &s));
+  *out = s / (which == 1 ? ctx->gbm.nv_global : ctx->gbm.n_global);
+  return SE_OK;
+}
+
+int se_gbm_update_validation(se_ctx* ctx, const double* step, double* mean_loss) {
+  if (!ctx || !step) return fail(ctx, SE_ERR_ARG, "null argument");
+  SE_REQUIRE(ctx, ctx->gbm.on && ctx->gbm.nv > 0, SE_ERR_STATE, "no validation shard configured");
+  SE_TRY(ensure_counts(ctx));
+  SE_TRY(begin(ctx));
+  GbmArgs a = gbm_args(ctx, true);
+  for (int j = 0; j < ctx->gbm.dim; ++j) a.coef[j] = (float)step[j];
+  SE_LAUNCH(ctx, launch_gbm(ctx->gbm.loss, GBM_UPDATE, a, ctx->ctas_per_sm, ctx->sms, ctx->stream));
+  double s = 0.0;
+  SE_TRY(fetch_scalars(ctx, 0, 1, &s));
+  if (mean_loss) *mean_loss = s / ctx->gbm.nv_global;
+  return SE_OK;
+}
+
+namespace {
+struct EvalClosure {
+  se_ctx* ctx;
+  int rc;
+};
+double eval_cb(double x, void* user) {
+  EvalClosure* c = static_cast<EvalClosure*>(user);
+  double l = NAN;
+  if (c->rc == SE_OK) c->rc = se_gbm_linesearch_eval(c->ctx, &x, &l, nullptr);
+  return l;
+}
+struct Parabola {
+  double s0, s1, s2, ws;
+};
+double parabola_cb(double x, void* user) {
+  const Parabola* p = static_cast<const Parabola*>(user);
+  // Σ (y-F-αh)²/2 / Σw
+  return (p->s0 - 2.0 * x * p->s1 + x * x * p->s2) / (2.0 * p->ws);
+}
+}  // namespace
+
+int se_gbm_linesearch_brent(se_ctx* ctx, double lo, double hi, double start, double rel, double abs_tol,
+                            int max_eval, double* alpha, double* loss, int* n_eval) {
+  if (!ctx || !alpha) return fail(ctx, SE_ERR_ARG, "null argument");
+  SE_REQUIRE(ctx, ctx->gbm.on && ctx->gbm.dim == 1, SE_ERR_STATE, "Brent line search needs dim == 1");
+  if (ctx->gbm.loss == SE_LOSS_SQUARED) {
+    double st[4];
+    SE_TRY(se_gbm_linesearch_stats(ctx, st));
+    Parabola p{st[0], st[1], st[2], st[3]};
+    int rc = brent_impl(parabola_cb, &p, lo, hi, start, rel, abs_tol, max_eval, alpha, loss, n_eval);
+    if (rc != SE_OK) return fail(ctx, rc, "Brent exceeded MaxEval(%d)", max_eval);
+    return SE_OK;
+  }
+  EvalClosure c{ctx, SE_OK};
+  int rc = brent_impl(eval_cb, &c, lo, hi, start, rel, abs_tol, max_eval, alpha, loss, n_eval);
+  if (c.rc != SE_OK) return c.rc;
+  if (rc != SE_OK) return fail(ctx, rc, "Brent exceeded MaxEval(%d)", max_eval);
+  return SE_OK;
+}
+
+int se_gbm_round_squared_async(se_ctx* ctx, double learning_rate) {
+  if (!ctx) return fail(nullptr, SE_ERR_ARG, "null context");
+  SE_REQUIRE(ctx, ctx->gbm.on && ctx->gbm.loss == SE_LOSS_SQUARED, SE_ERR_STATE, "squared loss only");
+  SE_TRY(begin(ctx));
+  GbmArgs a = gbm_args(ctx, false);
+  a.ws = red_ws(ctx, kScalRound);  // stats -> d_scal[64..66]
+  SE_LAUNCH(ctx, launch_gbm(SE_LOSS_SQUARED, GBM_SQ_STATS, a, ctx->ctas_per_sm, ctx->sms, ctx->stream));
+  SE_TRY(allreduce_dev(ctx, kScalRound, 3));
+  GbmArgs u = gbm_args(ctx, false);
+  u.dev_stats = ctx->d_scal + kScalRound;
+  u.lr = (float)learning_rate;
+  u.ws = red_ws(ctx, kScalRound + 8);  // Σloss -> d_scal[72]
+  SE_LAUNCH(ctx, launch_gbm(SE_LOSS_SQUARED, GBM_UPDATE_RESID, u, ctx->ctas_per_sm, ctx->sms, ctx->stream));
+  SE_TRY(allreduce_dev(ctx, kScalRound + 8, 1));
+  return end(ctx);
+}
+
+int se_gbm_round_result(se_ctx* ctx, double* alpha, double* loss_sum) {
+  if (!ctx) return fail(nullptr, SE_ERR_ARG, "null context");
+  SE_CUDA(ctx, cudaSetDevice(ctx->device));
+  SE_CUDA(ctx, cudaMemcpyAsync(ctx->h_scal + kScalRound, ctx->d_scal + kScalRound, sizeof(double) * 16,
+                               cudaMemcpyDeviceToHost, ctx->stream));
+  SE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  const double s1 = ctx->h_scal[kScalRound + 1], s2 = ctx->h_scal[kScalRound + 2];
+  double al = (s2 > 0.0) ? s1 / s2 : 1.0;
+  al = fmin(fmax(al, 0.0), 100.0);
+  if (alpha) *alpha = al;
+  if (loss_sum) *loss_sum = ctx->h_scal[kScalRound + 8];
+  return SE_OK;
+}
+
+int se_brent_minimize(se_fn1 f, void* user, double lo, double hi, double start, double rel, double abs_tol,
+                      int max_eval, double* x_out, double* f_out, int* n_eval) {
+  if (!f) return fail(nullptr, SE_ERR_ARG, "null objective");
+  // commons-math3 BrentOptimizer constructor checks
+  if (rel < 2.0 * 2.220446049250313e-16) return fail(nullptr, SE_ERR_ARG, "relative threshold %g too small", rel);
+  if (abs_tol <= 0.0) return fail(nullptr, SE_ERR_ARG, "absolute threshold must be > 0");
+  int rc = brent_impl(f, user, lo, hi, start, rel, abs_tol, max_eval, x_out, f_out, n_eval);
+  if (rc != SE_OK) return fail(nullptr, rc, "Brent exceeded MaxEval(%d)", max_eval);
+  return SE_OK;
+}
+
+// ---- Boosting ----------------------------------------------------------------------------------
+int se_boost_configure(se_ctx* ctx, int64_t n, int num_classes, int real) {
+  if (!ctx) return fail(nullptr, SE_ERR_ARG, "null context");
+  SE_REQUIRE(ctx, n >= 0 && num_classes >= 2, SE_ERR_ARG, "need n >= 0 and numClasses >= 2");
+  SE_CUDA(ctx, cudaSetDevice(ctx->device));
+  ctx->boost.on = true; ctx->boost.n = n; ctx->boost.K = num_classes; ctx->boost.real = real != 0;
+  SE_TRY(slot_alloc2d(ctx, SE_SLOT_Y, 1, n));
+  SE_TRY(slot_alloc2d(ctx, SE_SLOT_BW, 1, n));
+  if (real) SE_TRY(slot_alloc2d(ctx, SE_SLOT_PROBA, num_classes, n));
+  else SE_TRY(slot_alloc2d(ctx, SE_SLOT_PRED, 1, n));
+  return SE_OK;
+}
+
+static BoostArgs boost_args(se_ctx* ctx, double sum_w) {
+  BoostArgs a;
+  a.y = ctx->slot[SE_SLOT_Y].d;
+  a.w = ctx->slot[SE_SLOT_BW].d;
+  a.proba = ctx->slot[SE_SLOT_PROBA].d;
+  a.pred = ctx->slot[SE_SLOT_PRED].d;
+  a.n = ctx->boost.n;
+  a.ld = ctx->slot[SE_SLOT_PROBA].ld;
+  a.K = ctx->boost.K;
+  a.inv_sum_w = (float)(1.0 / sum_w);
+  a.ws = red_ws(ctx);
+  return a;
+}
+
+int se_boost_real_update(se_ctx* ctx, double sum_w, double* est_err, double* new_sum) {
+  if (!ctx) return fail(nullptr, SE_ERR_ARG, "null context");
+  SE_REQUIRE(ctx, ctx->boost.on && ctx->boost.real, SE_ERR_STATE, "se_boost_configure(real=1) first");
+  SE_TRY(begin(ctx));
+  BoostArgs a = boost_args(ctx, sum_w);
+  SE_LAUNCH(ctx, launch_boost_real(a, ctx->ctas_per_sm, ctx->sms, ctx->stream));
+  double s[2];
+  SE_TRY(fetch_scalars(ctx, 0, 2, s));
+  if (est_err) *est_err = s[0];
+  if (new_sum) *new_sum = s[1];
+  return SE_OK;
+}
+
+int se_boost_discrete_error(se_ctx* ctx, double sum_w, double* est_err) {
+  if (!ctx || !est_err) return fail(ctx, SE_ERR_ARG, "null argument");
+  SE_REQUIRE(ctx, ctx->boost.on && !ctx->boost.real, SE_ERR_STATE, "se_boost_configure(real=0) first");
+  SE_TRY(begin(ctx));
+  BoostArgs a = boost_args(ctx, sum_w);
+  SE_LAUNCH(ctx, launch_boost_discrete_error(a, ctx->ctas_per_sm, ctx->sms, ctx->stream));
+  return fetch_scalars(ctx, 0, 1, est_err);
+}
+
+int se_boost_discrete_update(se_ctx* ctx, double sum_w, double beta, double* new_sum) {
+  if (!ctx) return fail(nullptr, SE_ERR_ARG, "null context");
+  SE_REQUIRE(ctx, ctx->boost.on && !ctx->boost.real, SE_ERR_STATE, "se_boost_configure(real=0) first");
+  SE_TRY(begin(ctx));
+  BoostArgs a = boost_args(ctx, sum_w);
+  a.inv_beta = (float)(1.0 / beta);
+  SE_LAUNCH(ctx, launch_boost_discrete_update(a, ctx->ctas_per_sm, ctx->sms, ctx->stream));
+  double s = 0.0;
+  SE_TRY(fetch_scalars(ctx, 0, 1, &s));
+  if (new_sum) *new_sum = s;
+  return SE_OK;
+}
+
+// ---- Aggregation -------------------------------------------------------------------------------
+int se_agg_configure(se_ctx* ctx, int kind, int num_models, int num_classes, int dim, int loss, int64_t n) {
+  if (!ctx) return fail(nullptr, SE_ERR_ARG, "null context");
+  SE_REQUIRE(ctx, kind >= SE_AGG_GBM_REGRESSOR && kind <= SE_AGG_BOOSTING_DISCRETE, SE_ERR_ARG, "bad kind %d", kind);
+  SE_REQUIRE(ctx, num_models >= 0 && n >= 0, SE_ERR_ARG, "bad sizes");
+  SE_CUDA(ctx, cudaSetDevice(ctx->device));
+  auto& g = ctx->agg;
+  g.on = true; g.kind = kind; g.M = num_models; g.K = num_classes; g.dim = dim; g.loss = loss; g.n = n;
+  switch (kind) {
+    case SE_AGG_GBM_REGRESSOR:
+    case SE_AGG_BAGGING_REGRESSOR: g.width = 1; g.C = 1; break;
+    case SE_AGG_GBM_CLASSIFIER:
+      SE_REQUIRE(ctx, dim >= 1 && num_classes >= 2, SE_ERR_ARG, "bad dim/numClasses");
+      g.width = dim; g.C = (dim == 1 && num_classes == 2) ? 2 : dim; break;
+    case SE_AGG_BAGGING_SOFT:
+    case SE_AGG_BOOSTING_REAL:
+      SE_REQUIRE(ctx, num_classes >= 2, SE_ERR_ARG, "numClasses >= 2");
+      g.width = num_classes; g.C = num_classes; break;
+    default:
+      SE_REQUIRE(ctx, num_classes >= 2, SE_ERR_ARG, "numClasses >= 2");
+      g.width = 1; g.C = num_classes; break;
+  }
+  const int64_t prow = (int64_t)(num_models > 0 ? num_models : 1) * g.width;
+  // P is allocated with rows >= 2 semantics (padded stride) so every model row is 128 B aligned
+  SE_TRY(slot_alloc2d(ctx, SE_SLOT_P, prow, n));
+  SE_TRY(slot_alloc2d(ctx, SE_SLOT_RAW, g.C, n));
+  if (kind >= SE_AGG_GBM_CLASSIFIER) {
+    SE_TRY(slot_alloc2d(ctx, SE_SLOT_PROB, g.C, n));
+    SE_TRY(slot_alloc2d(ctx, SE_SLOT_LABEL, 1, n));
+  }
+  return SE_OK;
+}
+
+int se_agg_run(se_ctx* ctx, const double* weights, const double* init) {
+  if (!ctx) return fail(nullptr, SE_ERR_ARG, "null context");
+  SE_REQUIRE(ctx, ctx->agg.on, SE_ERR_STATE, "se_agg_configure first");
+  const auto& g = ctx->agg;
+  SE_TRY(begin(ctx));
+  AggArgs a;
+  a.kind = g.kind; a.M = g.M; a.K = g.K; a.dim = g.dim; a.loss = g.loss; a.n = g.n;
+  a.P = ctx->slot[SE_SLOT_P].d; a.ld = ctx->slot[SE_SLOT_P].rows > 1 ? ctx->slot[SE_SLOT_P].ld : ctx->slot[SE_SLOT_P].cols;
+  a.raw = ctx->slot[SE_SLOT_RAW].d;
+  a.ld_out = ctx->slot[SE_SLOT_RAW].rows > 1 ? ctx->slot[SE_SLOT_RAW].ld : ctx->slot[SE_SLOT_RAW].cols;
+  a.prob = ctx->slot[SE_SLOT_PROB].d;
+  a.label = ctx->slot[SE_SLOT_LABEL].d;
+  // small operands: narrowed to fp32 and staged through pinned memory into d_small
+  float* hs = reinterpret_cast<float*>(ctx->h_small);
+  size_t used = 0;
+  const bool uses_w = (g.kind == SE_AGG_GBM_REGRESSOR || g.kind == SE_AGG_GBM_CLASSIFIER || g.kind == SE_AGG_BOOSTING_DISCRETE);
+  const int nw = g.M * ((g.kind == SE_AGG_GBM_CLASSIFIER) ? g.dim : 1);
+  SE_REQUIRE(ctx, (size_t)(nw + kMaxDim) * sizeof(float) * 2 <= (size_t)kSmallBytes, SE_ERR_ARG, "too many models");
+  // the previous run may still be reading d_small/h_small
+  SE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (uses_w) {
+    SE_REQUIRE(ctx, weights || g.M == 0, SE_ERR_ARG, "weights required for this aggregation kind");
+    double sw = 0.0;
+    for (int i = 0; i < nw; ++i) { hs[i] = (float)weights[i]; sw += weights[i]; }
+    a.weights = reinterpret_cast<const float*>(ctx->d_small);
+    a.sum_weights = (float)sw;
+    used = (size_t)nw;
+  }
+  if ((g.kind == SE_AGG_GBM_REGRESSOR || g.kind == SE_AGG_GBM_CLASSIFIER) && init) {
+    const size_t off = (used + 31) / 32 * 32;
+    for (int j = 0; j < g.dim; ++j) hs[off + j] = (float)init[j];
+    a.init = reinterpret_cast<const float*>(ctx->d_small) + off;
+    used = off + g.dim;
+  }
+  if (used) SE_CUDA(ctx, cudaMemcpyAsync(ctx->d_small, hs, used * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  SE_LAUNCH(ctx, launch_agg(a, 8, ctx->sms, ctx->stream));
+  if (g.kind >= SE_AGG_GBM_CLASSIFIER) ctx->launches++;  // finalize kernel
+  return end(ctx);
+}
+
+// ---- on-device base models ---------------------------------------------------------------------
+int se_tree_predict(se_ctx* ctx, int which, int n_nodes, const int32_t* feature, const float* threshold,
+                    const int32_t* left, const int32_t* right, const float* value,
+                    const int32_t* subspace, int n_subspace, int out_slot, int out_row) {
+  if (!ctx || !feature || !threshold || !left || !right || !value) return fail(ctx, SE_ERR_ARG, "null argument");
+  SE_REQUIRE(ctx, n_nodes >= 1 && (size_t)n_nodes * 20 <= (size_t)kSmallBytes && n_nodes * 20 <= 200 * 1024,
+             SE_ERR_ARG, "tree of %d nodes not supported", n_nodes);
+  SE_REQUIRE(ctx, out_slot >= 0 && out_slot < SE_NUM_SLOTS, SE_ERR_ARG, "bad out slot");
+  const SlotBuf& X = ctx->slot[which ? SE_SLOT_VX : SE_SLOT_X];
+  const SlotBuf& O = ctx->slot[out_slot];
+  SE_REQUIRE(ctx, X.d, SE_ERR_STATE, "feature matrix slot not allocated");
+  SE_REQUIRE(ctx, O.d && out_row >= 0 && out_row < O.rows && O.cols == X.cols, SE_ERR_STATE, "output slot shape mismatch");
+  SE_TRY(begin(ctx));
+  SE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  int32_t* hf = reinterpret_cast<int32_t*>(ctx->h_small);
+  float* ht = reinterpret_cast<float*>(hf + n_nodes);
+  int32_t* hl = reinterpret_cast<int32_t*>(ht + n_nodes);
+  int32_t* hr = hl + n_nodes;
+  float* hv = reinterpret_cast<float*>(hr + n_nodes);
+  for (int i = 0; i < n_nodes; ++i) {
+    int32_t f = feature[i];
+    if (f >= 0) {
+      if (subspace) {
+        SE_REQUIRE(ctx, f < n_subspace, SE_ERR_ARG, "node %d: feature %d outside subspace of %d", i, f, n_subspace);
+        f = subspace[f];
+      }
+      SE_REQUIRE(ctx, f >= 0 && f < X.rows, SE_ERR_ARG, "node %d: column %d outside X with %lld columns", i, f, (long long)X.rows);
+      SE_REQUIRE(ctx, left[i] >= 0 && left[i] < n_nodes && right[i] >= 0 && right[i] < n_nodes, SE_ERR_ARG, "node %d: bad child", i);
+    }
+    hf[i] = f; ht[i] = threshold[i]; hl[i] = left[i]; hr[i] = right[i]; hv[i] = value[i];
+  }
+  SE_CUDA(ctx, cudaMemcpyAsync(ctx->d_small, ctx->h_small, (size_t)n_nodes * 20, cudaMemcpyHostToDevice, ctx->stream));
+  TreeArgs t;
+  t.X = X.d; t.n = X.cols; t.ld = X.rows > 1 ? X.ld : X.cols; t.n_nodes = n_nodes;
+  t.feature = reinterpret_cast<const int32_t*>(ctx->d_small);
+  t.threshold = reinterpret_cast<const float*>(t.feature + n_nodes);
+  t.left = reinterpret_cast<const int32_t*>(t.threshold + n_nodes);
+  t.right = t.left + n_nodes;
+  t.value = reinterpret_cast<const float*>(t.right + n_nodes);
+  t.out = O.d + (int64_t)out_row * (O.rows > 1 ? O.ld : O.cols);
+  SE_LAUNCH(ctx, launch_tree_predict(t, ctx->sms, ctx->stream));
+  return end(ctx);
+}
+
+int se_linear_predict(se_ctx* ctx, int which, int n_coef, const float* coef, float intercept,
+                      const int32_t* subspace, int out_slot, int out_row) {
+  if (!ctx || (!coef && n_coef > 0)) return fail(ctx, SE_ERR_ARG, "null argument");
+  SE_REQUIRE(ctx, n_coef >= 0 && (size_t)n_coef * 8 <= (size_t)kSmallBytes, SE_ERR_ARG, "bad coefficient count");
+  SE_REQUIRE(ctx, out_slot >= 0 && out_slot < SE_NUM_SLOTS, SE_ERR_ARG, "bad out slot");
+  const SlotBuf& X = ctx->slot[which ? SE_SLOT_VX : SE_SLOT_X];
+  const SlotBuf& O = ctx->slot[out_slot];
+  SE_REQUIRE(ctx, X.d, SE_ERR_STATE, "feature matrix slot not allocated");
+  SE_REQUIRE(ctx, O.d && out_row >= 0 && out_row < O.rows && O.cols == X.cols, SE_ERR_STATE, "output slot shape mismatch");
+  SE_TRY(begin(ctx));
+  SE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  float* hc = reinterpret_cast<float*>(ctx->h_small);
+  int32_t* hcol = reinterpret_cast<int32_t*>(hc + n_coef);
+  for (int j = 0; j < n_coef; ++j) {
+    hc[j] = coef[j];
+    const int32_t col = subspace ? subspace[j] : j;
+    SE_REQUIRE(ctx, col >= 0 && col < X.rows, SE_ERR_ARG, "column %d outside X", col);
+    hcol[j] = col;
+  }
+  if (n_coef > 0)
+    SE_CUDA(ctx, cudaMemcpyAsync(ctx->d_small, ctx->h_small, (size_t)n_coef * 8, cudaMemcpyHostToDevice, ctx->stream));
+  const float* dc = reinterpret_cast<const float*>(ctx->d_small);
+  const int32_t* dcol = reinterpret_cast<const int32_t*>(dc + n_coef);
+  SE_LAUNCH(ctx, launch_linear_predict(X.d, X.cols, X.rows > 1 ? X.ld : X.cols, n_coef, dc, dcol, intercept,
+                                       O.d + (int64_t)out_row * (O.rows > 1 ? O.ld : O.cols), ctx->sms, ctx->stream));
+  return end(ctx);
+}
+
+}  // extern "C"

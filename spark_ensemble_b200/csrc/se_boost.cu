@@ -1,0 +1,185 @@
+// se_boost.cu — BoostingClassifier sample-weight update kernels (sm_100a).
+//
+// Reference: classification/BoostingClassifier.scala:168-187 (normalise), :198-230 (SAMME.R: error,
+// weight update), :231-260 (SAMME), :269 (Σw').  The reference makes two (real) or three (discrete)
+// passes over zipped RDDs per round; here SAMME.R is ONE pass (P[K][n] read once: 4K+8 B read, 4 B
+// written per row) that also produces both scalars, and SAMME is the two passes its data dependence
+// (β needs the error first) requires.  Weights are updated in place.
+#include "se_kernels.h"
+
+namespace se {
+
+namespace {
+
+constexpr float kSparkEps = 2.220446049250313e-16f;  // Spark ml.impl.Utils.EPSILON (2^-52)
+constexpr int KU = 8;                                // classes loaded per batch (8 x 16 B in flight)
+
+inline int grid_for(int64_t items, int64_t per_cta, int ctas_per_sm, int sms) {
+  int64_t need = (items + per_cta - 1) / per_cta;
+  if (need < 1) need = 1;
+  int64_t cap = (int64_t)ctas_per_sm * sms;
+  if (cap > kMaxGridPartials) cap = kMaxGridPartials;
+  return (int)(need < cap ? need : cap);
+}
+
+// Σ_k code_k log max(p_k, ε) with code_y = 1, code_{k≠y} = -1/(K-1)  (BoostingClassifier.scala:218-224)
+//   = (1 + 1/(K-1))·log p_y − (1/(K-1))·Σ_k log p_k
+struct RowState {
+  float best, sum_log, log_y;
+  int am;
+};
+
+__device__ __forceinline__ void row_step(RowState& s, float p, int k, int yi) {
+  if (p > s.best) {  // Vector.argmax: first maximum
+    s.best = p;
+    s.am = k;
+  }
+  const float lp = logf(fmaxf(p, kSparkEps));
+  s.sum_log += lp;
+  if (k == yi) s.log_y = lp;
+}
+
+__global__ void __launch_bounds__(kBlock) boost_real_kernel(const BoostArgs a) {
+  const int K = a.K;
+  const float inv_km1 = 1.0f / (float)(K - 1);
+  const float scale = -((float)(K - 1) / (float)K);
+  double acc[2] = {0.0, 0.0};
+  const int64_t n4 = a.n >> 2;
+  for (int64_t g = (int64_t)blockIdx.x * kBlock + threadIdx.x; g < n4;
+       g += (int64_t)gridDim.x * kBlock) {
+    const float4 vy = ld_stream4(a.y + 4 * g);
+    const float4 vw = ld_rw4(a.w + 4 * g);
+    RowState st[4];
+    int yi[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      st[e].best = -INFINITY; st[e].sum_log = 0.f; st[e].log_y = 0.f; st[e].am = 0;
+      yi[e] = (int)f4at(vy, e);
+    }
+    for (int k0 = 0; k0 < K; k0 += KU) {
+      float4 vp[KU];
+#pragma unroll
+      for (int u = 0; u < KU; ++u)
+        if (k0 + u < K) vp[u] = ld_stream4(a.proba + (int64_t)(k0 + u) * a.ld + 4 * g);
+#pragma unroll
+      for (int u = 0; u < KU; ++u)
+        if (k0 + u < K) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) row_step(st[e], f4at(vp[u], e), k0 + u, yi[e]);
+        }
+    }
+    float4 out;
+    float err4 = 0.f, sum4 = 0.f;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float wn = f4at(vw, e) * a.inv_sum_w;  // :186
+      err4 += (st[e].am != yi[e]) ? wn : 0.f;       // :202-209
+      const float loss = (1.0f + inv_km1) * st[e].log_y - inv_km1 * st[e].sum_log;
+      const float wo = wn * expf(scale * loss);     // :226
+      f4at(out, e) = wo;
+      sum4 += wo;
+    }
+    st_stream4(a.w + 4 * g, out);
+    acc[0] += (double)err4;
+    acc[1] += (double)sum4;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (a.n & 3)) {
+    const int64_t i = (n4 << 2) + threadIdx.x;
+    RowState st{-INFINITY, 0.f, 0.f, 0};
+    const int yi = (int)a.y[i];
+    for (int k = 0; k < K; ++k) row_step(st, a.proba[(int64_t)k * a.ld + i], k, yi);
+    const float wn = a.w[i] * a.inv_sum_w;
+    const float loss = (1.0f + inv_km1) * st.log_y - inv_km1 * st.sum_log;
+    const float wo = wn * expf(scale * loss);
+    a.w[i] = wo;
+    acc[0] += (st.am != yi) ? (double)wn : 0.0;
+    acc[1] += (double)wo;
+  }
+  block_reduce_publish<2>(acc, a.ws);
+}
+
+// SAMME: est_err = Σ wₙ·1[pred ≠ y]  (:232-242)
+__global__ void __launch_bounds__(kBlock) boost_discrete_error_kernel(const BoostArgs a) {
+  double acc[1] = {0.0};
+  const int64_t n4 = a.n >> 2;
+  for (int64_t g = (int64_t)blockIdx.x * kBlock + threadIdx.x; g < n4;
+       g += (int64_t)gridDim.x * kBlock) {
+    const float4 vy = ld_stream4(a.y + 4 * g), vp = ld_stream4(a.pred + 4 * g),
+                 vw = ld_stream4(a.w + 4 * g);
+    float e4 = 0.f;
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+      e4 += (f4at(vy, e) != f4at(vp, e)) ? f4at(vw, e) * a.inv_sum_w : 0.f;
+    acc[0] += (double)e4;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (a.n & 3)) {
+    const int64_t i = (n4 << 2) + threadIdx.x;
+    if (a.y[i] != a.pred[i]) acc[0] += (double)(a.w[i] * a.inv_sum_w);
+  }
+  block_reduce_publish<1>(acc, a.ws);
+}
+
+// SAMME: w' = wₙ·(1/β)^err  (:254-258), Σw' (:269)
+__global__ void __launch_bounds__(kBlock) boost_discrete_update_kernel(const BoostArgs a) {
+  double acc[1] = {0.0};
+  const int64_t n4 = a.n >> 2;
+  for (int64_t g = (int64_t)blockIdx.x * kBlock + threadIdx.x; g < n4;
+       g += (int64_t)gridDim.x * kBlock) {
+    const float4 vy = ld_stream4(a.y + 4 * g), vp = ld_stream4(a.pred + 4 * g);
+    const float4 vw = ld_rw4(a.w + 4 * g);
+    float4 out;
+    float s4 = 0.f;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float wn = f4at(vw, e) * a.inv_sum_w;
+      // pow(1/β, 0) == 1 even for 1/β == Inf; wn·Inf for a mis-classified row is the reference's result too
+      const float wo = (f4at(vy, e) != f4at(vp, e)) ? wn * a.inv_beta : wn;
+      f4at(out, e) = wo;
+      s4 += wo;
+    }
+    st_stream4(a.w + 4 * g, out);
+    acc[0] += (double)s4;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (a.n & 3)) {
+    const int64_t i = (n4 << 2) + threadIdx.x;
+    const float wn = a.w[i] * a.inv_sum_w;
+    const float wo = (a.y[i] != a.pred[i]) ? wn * a.inv_beta : wn;
+    a.w[i] = wo;
+    acc[0] += (double)wo;
+  }
+  block_reduce_publish<1>(acc, a.ws);
+}
+
+__global__ void __launch_bounds__(kBlock) sum_kernel(const float* x, int64_t n, const RedWs ws) {
+  double acc[1] = {0.0};
+  const int64_t n4 = n >> 2;
+  for (int64_t g = (int64_t)blockIdx.x * kBlock + threadIdx.x; g < n4;
+       g += (int64_t)gridDim.x * kBlock) {
+    const float4 v = ld_stream4(x + 4 * g);
+    acc[0] += (double)v.x + (double)v.y + (double)v.z + (double)v.w;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) acc[0] += (double)x[(n4 << 2) + threadIdx.x];
+  block_reduce_publish<1>(acc, ws);
+}
+
+}  // namespace
+
+cudaError_t launch_boost_real(const BoostArgs& a, int ctas_per_sm, int sms, cudaStream_t s) {
+  boost_real_kernel<<<grid_for(a.n >> 2, kBlock, ctas_per_sm, sms), kBlock, 0, s>>>(a);
+  return cudaGetLastError();
+}
+cudaError_t launch_boost_discrete_error(const BoostArgs& a, int ctas_per_sm, int sms, cudaStream_t s) {
+  boost_discrete_error_kernel<<<grid_for(a.n >> 2, kBlock, ctas_per_sm, sms), kBlock, 0, s>>>(a);
+  return cudaGetLastError();
+}
+cudaError_t launch_boost_discrete_update(const BoostArgs& a, int ctas_per_sm, int sms, cudaStream_t s) {
+  boost_discrete_update_kernel<<<grid_for(a.n >> 2, kBlock, ctas_per_sm, sms), kBlock, 0, s>>>(a);
+  return cudaGetLastError();
+}
+cudaError_t launch_sum(const float* x, int64_t n, const RedWs& ws, int ctas_per_sm, int sms,
+                       cudaStream_t s) {
+  sum_kernel<<<grid_for(n >> 2, kBlock, ctas_per_sm, sms), kBlock, 0, s>>>(x, n, ws);
+  return cudaGetLastError();
+}
+
+}  // namespace se

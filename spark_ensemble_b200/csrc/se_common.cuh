@@ -1,0 +1,132 @@
+// se_common.cuh — shared device helpers for the sm_100a streaming kernels.
+//
+// Every kernel on this path is elementwise + reduction and HBM-bound (no tensor cores): the
+// helpers here are the 128-bit streaming loads/stores (read-once data bypasses L1 allocation),
+// the per-thread -> warp-shuffle -> shared-memory fp64 block reduction, and the deterministic
+// cross-block "last block reduces" epilogue that leaves the global sums in a device scalar block
+// (consumed in-stream by NCCL or by the next kernel, no host round-trip required).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace se {
+
+constexpr int kBlock = 256;          // threads per CTA for the streaming kernels
+constexpr int kMaxGridPartials = 4096;  // upper bound on gridDim.x of reducing kernels
+constexpr int kMaxRed = 40;          // max number of fp64 sums one kernel reduces (dim <= 32 -> dim+3)
+
+// ---- 128-bit streaming global accesses ------------------------------------------------------
+__device__ __forceinline__ float4 ld_stream4(const float* p) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p));
+  return v;
+}
+__device__ __forceinline__ float ld_stream1(const float* p) {
+  float v;
+  asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+// read-write arrays (F is read then overwritten by the same thread): plain coherent load, no L1 allocation
+__device__ __forceinline__ float4 ld_rw4(const float* p) {
+  float4 v;
+  asm volatile("ld.global.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p));
+  return v;
+}
+__device__ __forceinline__ float ld_rw1(const float* p) {
+  float v;
+  asm volatile("ld.global.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void st_stream4(float* p, const float4& v) {
+  asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y),
+               "f"(v.z), "f"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ void st_stream1(float* p, float v) {
+  asm volatile("st.global.L1::no_allocate.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+
+__device__ __forceinline__ float& f4at(float4& v, int i) { return (&v.x)[i]; }
+__device__ __forceinline__ const float& f4at(const float4& v, int i) { return (&v.x)[i]; }
+
+// ---- fp64 reductions ------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+  return v;
+}
+
+// Reduction workspace owned by the context: partials[kMaxGridPartials][nred], a self-resetting
+// ticket counter, and the output scalar block.
+struct RedWs {
+  double* partials;
+  unsigned int* counter;
+  double* out;  // [nred] global (per-GPU) sums
+};
+
+// Block-reduce NRED per-thread fp64 accumulators, publish the block partial, and let the last CTA
+// to arrive reduce all partials in a fixed order (deterministic for a fixed launch configuration).
+template <int NRED>
+__device__ __forceinline__ void block_reduce_publish(double (&acc)[NRED], const RedWs& ws) {
+  __shared__ double sm[NRED][kBlock / 32];
+  __shared__ bool is_last;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < NRED; ++k) {
+    const double v = warp_sum(acc[k]);
+    if (lane == 0) sm[k][warp] = v;
+  }
+  __syncthreads();
+  if (warp == 0) {
+#pragma unroll
+    for (int k = 0; k < NRED; ++k) {
+      double v = (lane < kBlock / 32) ? sm[k][lane] : 0.0;
+      v = warp_sum(v);
+      if (lane == 0) ws.partials[(size_t)blockIdx.x * NRED + k] = v;
+    }
+  }
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned int ticket = atomicInc(ws.counter, gridDim.x - 1);  // wraps to 0: self-resetting
+    is_last = (ticket == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  // fixed-order accumulation over blocks: thread t takes blocks t, t+kBlock, ...
+#pragma unroll
+  for (int k = 0; k < NRED; ++k) {
+    double v = 0.0;
+    for (unsigned int b = threadIdx.x; b < gridDim.x; b += kBlock)
+      v += __ldcg(&ws.partials[(size_t)b * NRED + k]);
+    v = warp_sum(v);
+    if (lane == 0) sm[k][warp] = v;
+  }
+  __syncthreads();
+  if (warp == 0) {
+#pragma unroll
+    for (int k = 0; k < NRED; ++k) {
+      double v = (lane < kBlock / 32) ? sm[k][lane] : 0.0;
+      v = warp_sum(v);
+      if (lane == 0) ws.out[k] = v;
+    }
+  }
+}
+
+// ---- counter-based synthetic generator (bench / tests): identical integer stream on host -----
+__host__ __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+__host__ __device__ __forceinline__ float u01_from_bits(uint64_t bits) {
+  return (float)(uint32_t)(bits >> 40) * (1.0f / 16777216.0f);  // 24 random bits -> [0,1)
+}
+
+}  // namespace se

@@ -1,0 +1,419 @@
+// se_gbm.cu — GBM inner-loop kernels (sm_100a): pseudo-residuals, line-search evaluation,
+// fused prediction update + next-round residual + loss, validation loss.
+//
+// Reference (fp64, Spark RDD closures): regression/GBMRegressor.scala:368-385 (residuals),
+// :398-425 + boosting/GBMLoss.scala:50-74 (line search objective), :434-442 (F update),
+// :444-456 (validation); classification/GBMClassifier.scala:337-375, :413-431, :437-449, :451-470.
+//
+// Design: every kernel is one streaming pass over column-major fp32 rows.  A CTA owns contiguous
+// tiles of kBlock*U float4 groups; each thread issues all of its 128-bit loads for a tile before
+// computing (U x 3 independent 16 B requests in flight per thread), evaluates the loss in fp32,
+// accumulates sums in fp64, and the grid finishes with the deterministic last-CTA reduction from
+// se_common.cuh.  HBM-bound: K1 (update+residual+loss) moves 20 B/row, K2 (eval) 12 B/row.
+#include "se_kernels.h"
+#include "se_loss.cuh"
+
+namespace se {
+
+namespace {
+
+constexpr int U_SCALAR = 4;  // float4 groups per thread per tile
+
+template <int MODE>
+struct ModeTraits {
+  static constexpr bool kReadH = (MODE == GBM_EVAL || MODE == GBM_UPDATE ||
+                                  MODE == GBM_UPDATE_RESID || MODE == GBM_UPDATE_NEWTON);
+  static constexpr bool kWriteF = (MODE == GBM_UPDATE || MODE == GBM_UPDATE_RESID ||
+                                   MODE == GBM_UPDATE_NEWTON);
+  static constexpr bool kNewton = (MODE == GBM_RESID_NEWTON || MODE == GBM_UPDATE_NEWTON);
+  static constexpr bool kWriteR = (MODE == GBM_RESID || MODE == GBM_UPDATE_RESID || kNewton);
+  static constexpr bool kSumLoss = (MODE == GBM_EVAL || kWriteF || MODE == GBM_MEAN_LOSS);
+  static constexpr bool kReduce = kSumLoss || kNewton;
+};
+
+__device__ __forceinline__ float device_step(const GbmArgs& a) {
+  // squared loss closed form: alpha* = clip(Σh(y-F)/Σh², 0, 100) (Brent's interval, GBMRegressor.scala:412)
+  const double s1 = a.dev_stats[1], s2 = a.dev_stats[2];
+  double al = (s2 > 0.0) ? s1 / s2 : 1.0;
+  al = fmin(fmax(al, 0.0), 100.0);
+  return a.lr * (float)al;
+}
+
+// ------------------------------------------------------------------ scalar losses, dim == 1
+template <int LOSS, int MODE>
+__global__ void __launch_bounds__(kBlock) gbm_scalar_kernel(const GbmArgs a) {
+  using T = ModeTraits<MODE>;
+  constexpr int U = U_SCALAR;
+  float coef = a.coef[0];
+  if (T::kWriteF && a.dev_stats != nullptr) coef = device_step(a);
+  const float param = a.param;
+  const bool has_w = (a.w != nullptr);
+  double acc[2] = {0.0, 0.0};
+
+  const int64_t n4 = a.n >> 2;
+  constexpr int64_t tile = (int64_t)kBlock * U;
+  const int64_t ntiles = (n4 + tile - 1) / tile;
+
+  auto row = [&](float y, float F, float h, float w, float& Fo, float& ro, float& wo, float& l_acc,
+                 float& x_acc) {
+    const float p = T::kReadH ? fmaf(coef, h, F) : F;
+    const LGH o = eval_loss<LOSS>(y, p, param);
+    if (T::kWriteF) Fo = p;
+    if (T::kSumLoss) l_acc += o.l;
+    if (MODE == GBM_EVAL) x_acc = fmaf(h, o.g, x_acc);
+    if (T::kNewton) {
+      const float hc = fmaxf(o.h, 1e-2f);   // GBMRegressor.scala:371
+      ro = -o.g / hc;                       // :377
+      wo = 0.5f * hc * w;                   // :379 (× 1/S applied by launch_scale_rows)
+      x_acc += hc;
+    } else if (T::kWriteR) {
+      ro = -o.g;                            // :383
+    }
+  };
+
+  for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    const int64_t base = t * tile + threadIdx.x;
+    float4 vy[U], vF[U], vh[U], vw[U];
+    bool ok[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t g = base + (int64_t)u * kBlock;
+      ok[u] = g < n4;
+      if (ok[u]) {
+        vy[u] = ld_stream4(a.y + 4 * g);
+        vF[u] = T::kWriteF ? ld_rw4(a.F + 4 * g) : ld_stream4(a.F + 4 * g);
+        if (T::kReadH) vh[u] = ld_stream4(a.h + 4 * g);
+        if (T::kNewton && has_w) vw[u] = ld_stream4(a.w + 4 * g);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (!ok[u]) continue;
+      const int64_t g = base + (int64_t)u * kBlock;
+      float4 oF, oR, oW;
+      float l_acc = 0.f, x_acc = 0.f;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float w = (T::kNewton && has_w) ? f4at(vw[u], e) : 1.0f;
+        row(f4at(vy[u], e), f4at(vF[u], e), T::kReadH ? f4at(vh[u], e) : 0.f, w, f4at(oF, e),
+            f4at(oR, e), f4at(oW, e), l_acc, x_acc);
+      }
+      if (T::kWriteF) st_stream4(a.F + 4 * g, oF);
+      if (T::kWriteR) st_stream4(a.r + 4 * g, oR);
+      if (T::kNewton) st_stream4(a.wout + 4 * g, oW);
+      if (T::kSumLoss) acc[0] += (double)l_acc;
+      if (MODE == GBM_EVAL || T::kNewton) acc[1] += (double)x_acc;
+    }
+  }
+  // scalar tail (n % 4 rows)
+  if (blockIdx.x == 0 && threadIdx.x < (a.n & 3)) {
+    const int64_t i = (n4 << 2) + threadIdx.x;
+    const float w = (T::kNewton && has_w) ? a.w[i] : 1.0f;
+    float Fo = 0.f, ro = 0.f, wo = 0.f, l_acc = 0.f, x_acc = 0.f;
+    row(a.y[i], a.F[i], T::kReadH ? a.h[i] : 0.f, w, Fo, ro, wo, l_acc, x_acc);
+    if (T::kWriteF) a.F[i] = Fo;
+    if (T::kWriteR) a.r[i] = ro;
+    if (T::kNewton) a.wout[i] = wo;
+    if (T::kSumLoss) acc[0] += (double)l_acc;
+    if (MODE == GBM_EVAL || T::kNewton) acc[1] += (double)x_acc;
+  }
+  if (T::kReduce) block_reduce_publish<2>(acc, a.ws);
+}
+
+// squared loss: the three sufficient statistics of the line-search parabola, one pass (12 B/row)
+__global__ void __launch_bounds__(kBlock) gbm_sq_stats_kernel(const GbmArgs a) {
+  constexpr int U = U_SCALAR;
+  double acc[3] = {0.0, 0.0, 0.0};
+  const int64_t n4 = a.n >> 2;
+  constexpr int64_t tile = (int64_t)kBlock * U;
+  const int64_t ntiles = (n4 + tile - 1) / tile;
+  for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    const int64_t base = t * tile + threadIdx.x;
+    float4 vy[U], vF[U], vh[U];
+    bool ok[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t g = base + (int64_t)u * kBlock;
+      ok[u] = g < n4;
+      if (ok[u]) {
+        vy[u] = ld_stream4(a.y + 4 * g);
+        vF[u] = ld_stream4(a.F + 4 * g);
+        vh[u] = ld_stream4(a.h + 4 * g);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (!ok[u]) continue;
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float d = f4at(vy[u], e) - f4at(vF[u], e), h = f4at(vh[u], e);
+        s0 = fmaf(d, d, s0);
+        s1 = fmaf(h, d, s1);
+        s2 = fmaf(h, h, s2);
+      }
+      acc[0] += (double)s0;
+      acc[1] += (double)s1;
+      acc[2] += (double)s2;
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (a.n & 3)) {
+    const int64_t i = (n4 << 2) + threadIdx.x;
+    const float d = a.y[i] - a.F[i], h = a.h[i];
+    acc[0] += (double)(d * d);
+    acc[1] += (double)(h * d);
+    acc[2] += (double)(h * h);
+  }
+  block_reduce_publish<3>(acc, a.ws);
+}
+
+// ------------------------------------------------------------------ LogLoss(K), dim == K
+// boosting/GBMLoss.scala:196-263.  The reference's log Σ exp(p_k) has no max shift (overflows above
+// ~709 in fp64); here the shifted form is used — identical wherever the reference is finite.
+// Layout [K][ld]; a thread owns VEC consecutive rows and keeps all K classes in registers.
+template <int KMAX, int MODE, int VEC>
+__global__ void __launch_bounds__(kBlock) gbm_logloss_kernel(const GbmArgs a) {
+  using T = ModeTraits<MODE>;
+  const int K = a.dim;
+  const int64_t ld = a.ld;
+  const bool has_w = (a.w != nullptr);
+  constexpr int NRED = KMAX + 1;
+  double acc[NRED];
+#pragma unroll
+  for (int k = 0; k < NRED; ++k) acc[k] = 0.0;
+
+  const int64_t ngroups = (a.n + VEC - 1) / VEC;
+  for (int64_t g = (int64_t)blockIdx.x * kBlock + threadIdx.x; g < ngroups;
+       g += (int64_t)gridDim.x * kBlock) {
+    const int64_t i0 = g * VEC;
+    const bool full = (i0 + VEC <= a.n);
+    float p[KMAX][VEC], hh[KMAX][VEC], yv[VEC], wv[VEC];
+    // ---- loads
+    if (VEC == 4 && full) {
+      const float4 t = ld_stream4(a.y + i0);
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) yv[e] = f4at(t, e);
+      if (T::kNewton && has_w) {
+        const float4 tw = ld_stream4(a.w + i0);
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) wv[e] = f4at(tw, e);
+      }
+#pragma unroll
+      for (int k = 0; k < KMAX; ++k) {
+        if (k < K) {
+          const float4 tf = T::kWriteF ? ld_rw4(a.F + k * ld + i0) : ld_stream4(a.F + k * ld + i0);
+#pragma unroll
+          for (int e = 0; e < VEC; ++e) p[k][e] = f4at(tf, e);
+          if (T::kReadH) {
+            const float4 th = ld_stream4(a.h + k * ld + i0);
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) hh[k][e] = f4at(th, e);
+          }
+        }
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) {
+        const bool in = (i0 + e < a.n);
+        yv[e] = in ? a.y[i0 + e] : 0.f;
+        if (T::kNewton && has_w) wv[e] = in ? a.w[i0 + e] : 0.f;
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k) {
+          if (k < K) {
+            p[k][e] = in ? a.F[k * ld + i0 + e] : 0.f;
+            if (T::kReadH) hh[k][e] = in ? a.h[k * ld + i0 + e] : 0.f;
+          }
+        }
+      }
+    }
+    if (!(T::kNewton && has_w)) {
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) wv[e] = 1.0f;
+    }
+    // ---- per-row math
+    float outR[KMAX][VEC], outW[KMAX][VEC];
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) {
+      const bool in = (i0 + e < a.n);
+      const int yi = (int)yv[e];
+      float m = -INFINITY;
+#pragma unroll
+      for (int k = 0; k < KMAX; ++k) {
+        if (k < K) {
+          if (T::kReadH) p[k][e] = fmaf(a.coef[k], hh[k][e], p[k][e]);  // GBMLoss.scala:56-59
+          m = fmaxf(m, p[k][e]);
+        }
+      }
+      float s = 0.f, py = 0.f;
+      float ex[KMAX];
+#pragma unroll
+      for (int k = 0; k < KMAX; ++k) {
+        if (k < K) {
+          ex[k] = expf(p[k][e] - m);
+          s += ex[k];
+          if (k == yi) py = p[k][e];
+        }
+      }
+      const float lse = m + logf(s);
+      const float inv_s = 1.0f / s;
+      if (T::kSumLoss && in) acc[0] += (double)(lse - py);  // -Σ y_k (p_k - lse)  :206-221
+#pragma unroll
+      for (int k = 0; k < KMAX; ++k) {
+        if (k < K) {
+          const float sm = ex[k] * inv_s;                    // exp(p_k - lse)
+          const float gk = sm - ((k == yi) ? 1.0f : 0.0f);   // :223-238
+          if (MODE == GBM_EVAL && in) acc[1 + k] += (double)(hh[k][e] * gk);  // :66-72
+          if (T::kNewton) {
+            const float hc = fmaxf(sm * (1.0f - sm), 1e-2f);  // :240-256, GBMClassifier.scala:342
+            outR[k][e] = -gk / hc;                            // :362
+            outW[k][e] = 0.5f * hc * wv[e];                   // :364 (× 1/S_k later)
+            if (in) acc[1 + k] += (double)hc;
+          } else if (T::kWriteR) {
+            outR[k][e] = -gk;                                 // :371
+          }
+        }
+      }
+    }
+    // ---- stores
+    if (VEC == 4 && full) {
+#pragma unroll
+      for (int k = 0; k < KMAX; ++k) {
+        if (k < K) {
+          if (T::kWriteF) st_stream4(a.F + k * ld + i0, make_float4(p[k][0], p[k][1], p[k][2], p[k][3]));
+          if (T::kWriteR)
+            st_stream4(a.r + k * ld + i0, make_float4(outR[k][0], outR[k][1], outR[k][2], outR[k][3]));
+          if (T::kNewton)
+            st_stream4(a.wout + k * ld + i0, make_float4(outW[k][0], outW[k][1], outW[k][2], outW[k][3]));
+        }
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) {
+        if (i0 + e < a.n) {
+#pragma unroll
+          for (int k = 0; k < KMAX; ++k) {
+            if (k < K) {
+              if (T::kWriteF) a.F[k * ld + i0 + e] = p[k][e];
+              if (T::kWriteR) a.r[k * ld + i0 + e] = outR[k][e];
+              if (T::kNewton) a.wout[k * ld + i0 + e] = outW[k][e];
+            }
+          }
+        }
+      }
+    }
+  }
+  if (T::kReduce) block_reduce_publish<NRED>(acc, a.ws);
+}
+
+__global__ void __launch_bounds__(kBlock) scale_rows_kernel(float* a, int64_t n, int64_t ld, int dim,
+                                                            const float* factors) {
+  for (int j = 0; j < dim; ++j) {
+    const float f = factors[j];
+    float* row = a + j * ld;
+    const int64_t n4 = n >> 2;
+    for (int64_t g = (int64_t)blockIdx.x * kBlock + threadIdx.x; g < n4;
+         g += (int64_t)gridDim.x * kBlock) {
+      float4 v = ld_rw4(row + 4 * g);
+      v.x *= f; v.y *= f; v.z *= f; v.w *= f;
+      st_stream4(row + 4 * g, v);
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (n & 3)) row[(n4 << 2) + threadIdx.x] *= f;
+  }
+}
+
+__global__ void sq_alpha_kernel(const double* stats, double* out) {
+  const double s1 = stats[1], s2 = stats[2];
+  double al = (s2 > 0.0) ? s1 / s2 : 1.0;
+  out[0] = fmin(fmax(al, 0.0), 100.0);
+}
+
+inline int grid_for(int64_t work_items, int64_t per_cta, int ctas_per_sm, int sms) {
+  int64_t need = (work_items + per_cta - 1) / per_cta;
+  if (need < 1) need = 1;
+  int64_t cap = (int64_t)ctas_per_sm * sms;
+  if (cap > kMaxGridPartials) cap = kMaxGridPartials;
+  return (int)(need < cap ? need : cap);
+}
+
+template <int LOSS>
+cudaError_t launch_scalar_loss(int mode, const GbmArgs& a, int grid, cudaStream_t st) {
+  switch (mode) {
+#define SE_CASE(M) \
+  case M: gbm_scalar_kernel<LOSS, M><<<grid, kBlock, 0, st>>>(a); break;
+    SE_CASE(GBM_RESID)
+    SE_CASE(GBM_RESID_NEWTON)
+    SE_CASE(GBM_EVAL)
+    SE_CASE(GBM_UPDATE)
+    SE_CASE(GBM_UPDATE_RESID)
+    SE_CASE(GBM_UPDATE_NEWTON)
+    SE_CASE(GBM_MEAN_LOSS)
+#undef SE_CASE
+    default: return cudaErrorInvalidValue;
+  }
+  return cudaGetLastError();
+}
+
+template <int KMAX, int VEC>
+cudaError_t launch_logloss_k(int mode, const GbmArgs& a, int grid, cudaStream_t st) {
+  switch (mode) {
+#define SE_CASE(M) \
+  case M: gbm_logloss_kernel<KMAX, M, VEC><<<grid, kBlock, 0, st>>>(a); break;
+    SE_CASE(GBM_RESID)
+    SE_CASE(GBM_RESID_NEWTON)
+    SE_CASE(GBM_EVAL)
+    SE_CASE(GBM_UPDATE)
+    SE_CASE(GBM_UPDATE_RESID)
+    SE_CASE(GBM_UPDATE_NEWTON)
+    SE_CASE(GBM_MEAN_LOSS)
+#undef SE_CASE
+    default: return cudaErrorInvalidValue;
+  }
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+cudaError_t launch_gbm(int loss, int mode, const GbmArgs& a, int ctas_per_sm, int sms,
+                       cudaStream_t st) {
+  if (mode == GBM_SQ_STATS) {
+    if (loss != SE_LOSS_SQUARED) return cudaErrorInvalidValue;
+    const int grid = grid_for(a.n >> 2, (int64_t)kBlock * U_SCALAR, ctas_per_sm, sms);
+    gbm_sq_stats_kernel<<<grid, kBlock, 0, st>>>(a);
+    return cudaGetLastError();
+  }
+  if (loss != SE_LOSS_LOGLOSS) {
+    const int grid = grid_for(a.n >> 2, (int64_t)kBlock * U_SCALAR, ctas_per_sm, sms);
+    switch (loss) {
+      case SE_LOSS_SQUARED: return launch_scalar_loss<SE_LOSS_SQUARED>(mode, a, grid, st);
+      case SE_LOSS_ABSOLUTE: return launch_scalar_loss<SE_LOSS_ABSOLUTE>(mode, a, grid, st);
+      case SE_LOSS_HUBER: return launch_scalar_loss<SE_LOSS_HUBER>(mode, a, grid, st);
+      case SE_LOSS_QUANTILE: return launch_scalar_loss<SE_LOSS_QUANTILE>(mode, a, grid, st);
+      case SE_LOSS_LOGCOSH: return launch_scalar_loss<SE_LOSS_LOGCOSH>(mode, a, grid, st);
+      case SE_LOSS_SCALED_LOGCOSH: return launch_scalar_loss<SE_LOSS_SCALED_LOGCOSH>(mode, a, grid, st);
+      case SE_LOSS_BERNOULLI: return launch_scalar_loss<SE_LOSS_BERNOULLI>(mode, a, grid, st);
+      case SE_LOSS_EXPONENTIAL: return launch_scalar_loss<SE_LOSS_EXPONENTIAL>(mode, a, grid, st);
+      default: return cudaErrorInvalidValue;
+    }
+  }
+  const int K = a.dim;
+  if (K < 1 || K > kMaxDim) return cudaErrorInvalidValue;
+  if (K <= 2) return launch_logloss_k<2, 4>(mode, a, grid_for((a.n + 3) / 4, kBlock, ctas_per_sm, sms), st);
+  if (K <= 4) return launch_logloss_k<4, 4>(mode, a, grid_for((a.n + 3) / 4, kBlock, ctas_per_sm, sms), st);
+  if (K <= 8) return launch_logloss_k<8, 4>(mode, a, grid_for((a.n + 3) / 4, kBlock, ctas_per_sm, sms), st);
+  if (K <= 16) return launch_logloss_k<16, 1>(mode, a, grid_for(a.n, kBlock, ctas_per_sm, sms), st);
+  return launch_logloss_k<32, 1>(mode, a, grid_for(a.n, kBlock, ctas_per_sm, sms), st);
+}
+
+cudaError_t launch_scale_rows(float* a, int64_t n, int64_t ld, int dim, const float* factors,
+                              int sms, cudaStream_t st) {
+  const int grid = grid_for(n >> 2, kBlock, 8, sms);
+  scale_rows_kernel<<<grid, kBlock, 0, st>>>(a, n, ld, dim, factors);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_sq_alpha(const double* stats, double* out_alpha, cudaStream_t st) {
+  sq_alpha_kernel<<<1, 1, 0, st>>>(stats, out_alpha);
+  return cudaGetLastError();
+}
+
+}  // namespace se

@@ -1,0 +1,111 @@
+// se_kernels.h — host-callable launchers of the sm_100a kernels (internal to libse_b200.so).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "se_common.cuh"
+
+namespace se {
+
+constexpr int kMaxDim = 32;  // logloss classes handled in registers
+
+// ---- GBM (se_gbm.cu) -------------------------------------------------------------------------
+enum GbmMode {
+  GBM_RESID = 0,         // R = -g(y,F)
+  GBM_RESID_NEWTON = 1,  // R = -g/hc, WOUT = 1/2 hc w (unnormalised), Σhc
+  GBM_EVAL = 2,          // p = F + a h : Σloss, Σ h g      (GBMLossAggregator.add)
+  GBM_UPDATE = 3,        // F += s h : Σloss(F')
+  GBM_UPDATE_RESID = 4,  // + R = -g(y,F')
+  GBM_UPDATE_NEWTON = 5, // + R = -g/hc, WOUT = 1/2 hc w, Σhc
+  GBM_MEAN_LOSS = 6,     // Σloss(y,F)
+  GBM_SQ_STATS = 7       // squared: Σ(y-F)², Σh(y-F), Σh²
+};
+
+struct GbmArgs {
+  const float* y = nullptr;
+  const float* w = nullptr;  // nullable: unit weights
+  float* F = nullptr;
+  const float* h = nullptr;
+  float* r = nullptr;
+  float* wout = nullptr;
+  int64_t n = 0;
+  int64_t ld = 0;  // row stride of the [dim][n] arrays
+  int dim = 1;
+  float param = 0.f;
+  float coef[kMaxDim] = {0};  // alpha (eval) or step (update), per dim
+  // squared-loss device-resident step: step = lr * clip(stats[1]/stats[2], 0, 100) when non-null
+  const double* dev_stats = nullptr;
+  float lr = 1.f;
+  RedWs ws{};
+};
+
+// reduction outputs (ws.out): scalar losses: [0]=Σloss [1]=Σ h·g or Σhc ; SQ_STATS: [0..2]
+// logloss: [0]=Σloss, [1..K]=Σ h_j g_j  or Σhc_j
+cudaError_t launch_gbm(int loss, int mode, const GbmArgs& a, int ctas_per_sm, int sms,
+                       cudaStream_t stream);
+// WOUT[j][i] *= 0.5/S_j was folded: scale rows of a [dim][n] array by per-row factors
+cudaError_t launch_scale_rows(float* a, int64_t n, int64_t ld, int dim, const float* factors,
+                              int sms, cudaStream_t stream);
+// squared-loss round result: out[0] = alpha*, computed on device from stats (for se_gbm_round_result)
+cudaError_t launch_sq_alpha(const double* stats, double* out_alpha, cudaStream_t stream);
+
+// ---- Boosting (se_boost.cu) ------------------------------------------------------------------
+struct BoostArgs {
+  const float* y = nullptr;
+  float* w = nullptr;         // updated in place
+  const float* proba = nullptr;  // [K][n]
+  const float* pred = nullptr;   // [n]
+  int64_t n = 0, ld = 0;
+  int K = 2;
+  float inv_sum_w = 1.f;
+  float inv_beta = 1.f;
+  RedWs ws{};
+};
+cudaError_t launch_boost_real(const BoostArgs& a, int ctas_per_sm, int sms, cudaStream_t s);   // out: [0]=err [1]=Σw'
+cudaError_t launch_boost_discrete_error(const BoostArgs& a, int ctas_per_sm, int sms, cudaStream_t s);  // out[0]
+cudaError_t launch_boost_discrete_update(const BoostArgs& a, int ctas_per_sm, int sms, cudaStream_t s); // out[0]=Σw'
+cudaError_t launch_sum(const float* x, int64_t n, const RedWs& ws, int ctas_per_sm, int sms,
+                       cudaStream_t s);  // out[0]
+
+// ---- Aggregation (se_agg.cu) -----------------------------------------------------------------
+struct AggArgs {
+  int kind = 0;
+  const float* P = nullptr;  // [M][width][n] with row stride ld
+  float* raw = nullptr;      // [C][n]
+  float* prob = nullptr;     // [C][n] (classifiers)
+  float* label = nullptr;    // [n]    (classifiers)
+  const float* weights = nullptr;  // device [M] or [M][dim]
+  const float* init = nullptr;     // device [dim]
+  int M = 0, K = 0, dim = 1, loss = 0;
+  int64_t n = 0, ld = 0, ld_out = 0;
+  float sum_weights = 0.f;  // Σ a_m (boosting discrete epilogue)
+};
+cudaError_t launch_agg(const AggArgs& a, int ctas_per_sm, int sms, cudaStream_t s);
+
+// ---- base-model evaluators over column-major X (se_models.cu) --------------------------------
+struct TreeArgs {
+  const float* X = nullptr;  // [d][n], stride ld
+  int64_t n = 0, ld = 0;
+  int n_nodes = 0;
+  const int32_t* feature = nullptr;  // device arrays [n_nodes]; feature already mapped through subspace
+  const float* threshold = nullptr;
+  const int32_t* left = nullptr;
+  const int32_t* right = nullptr;
+  const float* value = nullptr;
+  float* out = nullptr;
+};
+cudaError_t launch_tree_predict(const TreeArgs& a, int sms, cudaStream_t s);
+cudaError_t launch_linear_predict(const float* X, int64_t n, int64_t ld, int n_coef,
+                                  const float* coef, const int32_t* cols, float intercept,
+                                  float* out, int sms, cudaStream_t s);
+
+// ---- utilities (se_util.cu) ------------------------------------------------------------------
+cudaError_t launch_fill(float* p, float v, int64_t n, int sms, cudaStream_t s);
+cudaError_t launch_fill_synthetic(float* p, int kind, uint64_t seed, double a, double b, int64_t n,
+                                  int64_t index_offset, int sms, cudaStream_t s);
+cudaError_t launch_f64_to_f32(const double* src, float* dst, int64_t n, int sms, cudaStream_t s);
+cudaError_t launch_scale_copy(const float* src, float* dst, float scale, int64_t n, int sms,
+                              cudaStream_t s);
+
+}  // namespace se

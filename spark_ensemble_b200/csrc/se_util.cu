@@ -1,0 +1,76 @@
+// se_util.cu — fills, conversions and the counter-based synthetic generator (bench / tests).
+#include "se_kernels.h"
+
+namespace se {
+
+namespace {
+
+__global__ void __launch_bounds__(kBlock) fill_kernel(float* p, float v, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += (int64_t)gridDim.x * kBlock)
+    p[i] = v;
+}
+
+// kind 0 uniform[a,b), 1 normal(mean a, sd b) (Box-Muller), 2 integer uniform in [a,b), 3 bernoulli(a)
+__global__ void __launch_bounds__(kBlock) synth_kernel(float* p, int kind, uint64_t seed, float a, float b,
+                                                      int64_t n, int64_t index_offset) {
+  for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += (int64_t)gridDim.x * kBlock) {
+    const uint64_t idx = (uint64_t)(i + index_offset);
+    const uint64_t h1 = splitmix64(seed * 0x9E3779B97F4A7C15ull + 2 * idx);
+    const float u1 = u01_from_bits(h1);
+    float v;
+    if (kind == 0) {
+      v = a + (b - a) * u1;
+    } else if (kind == 1) {
+      const uint64_t h2 = splitmix64(seed * 0x9E3779B97F4A7C15ull + 2 * idx + 1);
+      const float u2 = u01_from_bits(h2);
+      const float r = sqrtf(-2.0f * logf(fmaxf(u1, 5.9604645e-8f)));
+      v = a + b * r * cospif(2.0f * u2);
+    } else if (kind == 2) {
+      v = floorf(a + (b - a) * u1);
+      if (v >= b) v = b - 1.0f;
+    } else {
+      v = (u1 < a) ? 1.0f : 0.0f;
+    }
+    p[i] = v;
+  }
+}
+
+__global__ void __launch_bounds__(kBlock) f64_to_f32_kernel(const double* s, float* d, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += (int64_t)gridDim.x * kBlock)
+    d[i] = (float)s[i];
+}
+
+__global__ void __launch_bounds__(kBlock) scale_copy_kernel(const float* s, float* d, float scale, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += (int64_t)gridDim.x * kBlock)
+    d[i] = s[i] * scale;
+}
+
+inline int grid1(int64_t n, int sms) {
+  int64_t need = (n + kBlock - 1) / kBlock;
+  if (need < 1) need = 1;
+  const int64_t cap = (int64_t)sms * 8;
+  return (int)(need < cap ? need : cap);
+}
+
+}  // namespace
+
+cudaError_t launch_fill(float* p, float v, int64_t n, int sms, cudaStream_t s) {
+  fill_kernel<<<grid1(n, sms), kBlock, 0, s>>>(p, v, n);
+  return cudaGetLastError();
+}
+cudaError_t launch_fill_synthetic(float* p, int kind, uint64_t seed, double a, double b, int64_t n,
+                                  int64_t index_offset, int sms, cudaStream_t s) {
+  synth_kernel<<<grid1(n, sms), kBlock, 0, s>>>(p, kind, seed, (float)a, (float)b, n, index_offset);
+  return cudaGetLastError();
+}
+cudaError_t launch_f64_to_f32(const double* src, float* dst, int64_t n, int sms, cudaStream_t s) {
+  f64_to_f32_kernel<<<grid1(n, sms), kBlock, 0, s>>>(src, dst, n);
+  return cudaGetLastError();
+}
+cudaError_t launch_scale_copy(const float* src, float* dst, float scale, int64_t n, int sms,
+                              cudaStream_t s) {
+  scale_copy_kernel<<<grid1(n, sms), kBlock, 0, s>>>(src, dst, scale, n);
+  return cudaGetLastError();
+}
+
+}  // namespace se

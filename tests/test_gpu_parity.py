@@ -1,0 +1,401 @@
+"""GPU parity tests: every kernel of the hot path, called through the C ABI, against the CPU oracle on
+the same seeded fp32-representable inputs.  Tolerance: 1e-5 relative (north_star) on predictions and
+per-iteration loss / reduction scalars; written next to each assertion.  Integer outputs are exact."""
+import numpy as np
+import pytest
+
+from oracle import np_oracle as NP
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-5  # north_star: fp32 predictions and per-iteration loss within 1e-5 relative
+PARAM = {"huber": 0.9, "quantile": 0.9, "scaledlogcosh": 0.9}
+SCALAR = ["squared", "absolute", "huber", "quantile", "logcosh", "scaledlogcosh", "bernoulli",
+          "exponential"]
+HESS = ["squared", "logcosh", "scaledlogcosh", "bernoulli", "exponential"]
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from spark_ensemble_b200.context import Context
+    c = Context(0)
+    yield c
+    c.close()
+
+
+def f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def labels(name, rng, n, K=5):
+    if name in ("bernoulli", "exponential"):
+        return f32(rng.random(n) < 0.4)
+    if name == "logloss":
+        return f32(rng.integers(0, K, n))
+    return f32(rng.standard_normal(n))
+
+
+def close(a, b, rtol=RTOL, scale=None):
+    """|a-b| <= rtol * max(|b|, scale) elementwise; scale defaults to the rms magnitude of b."""
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    if scale is None:
+        scale = float(np.sqrt(np.mean(b * b))) if b.size else 1.0
+    tol = rtol * np.maximum(np.abs(b), scale)
+    bad = np.abs(a - b) > tol
+    assert not bad.any(), (f"{bad.sum()} / {b.size} mismatches; worst rel "
+                           f"{np.max(np.abs(a - b) / np.maximum(np.abs(b), scale)):.3e}")
+
+
+def setup_gbm(ctx, rng, name, n, weighted=False, K=5, nv=0):
+    from spark_ensemble_b200 import _native as N
+    dim = K if name == "logloss" else 1
+    par = PARAM.get(name, 0.0)
+    y = labels(name, rng, n, K)
+    F = f32(rng.standard_normal((dim, n)) * 0.7)
+    h = f32(rng.standard_normal((dim, n)))
+    w = f32(rng.random(n) + 0.5) if weighted else None
+    ctx.gbm_configure(n, nv, dim, name, par, weighted)
+    ctx.upload(N.SLOT_Y, y)
+    ctx.upload(N.SLOT_F, F)
+    ctx.upload(N.SLOT_H, h)
+    if weighted:
+        ctx.upload(N.SLOT_W, w)
+    return dim, par, y, F, h, w
+
+
+@pytest.mark.parametrize("name", SCALAR + ["logloss"])
+@pytest.mark.parametrize("n,weighted", [(1, False), (3, True), (1023, False), (40961, True)])
+def test_linesearch_eval(ctx, oracle, rng, name, n, weighted):
+    dim, par, y, F, h, w = setup_gbm(ctx, rng, name, n, weighted)
+    for alpha in (np.ones(dim), rng.random(dim) * 3.0, np.zeros(dim)):
+        lg, gg = ctx.gbm_linesearch_eval(alpha)
+        lo, go = oracle.linesearch_eval(O.LOSS_IDS[name], par, y, w, F, h, alpha)
+        assert lg == pytest.approx(lo, rel=RTOL, abs=1e-7)
+        scale = float(np.mean(np.abs(h))) * 1e-1  # gradient sums cancel: scale by typical |h·g|/n
+        close(gg, go, rtol=RTOL, scale=max(scale, float(np.max(np.abs(go)))))
+
+
+@pytest.mark.parametrize("name", SCALAR + ["logloss"])
+@pytest.mark.parametrize("K", [2, 3, 7, 13, 26, 32])
+def test_pseudo_residuals_gradient(ctx, oracle, rng, name, K):
+    from spark_ensemble_b200 import _native as N
+    if name != "logloss" and K != 2:
+        pytest.skip("K only varies for logloss")
+    n = 5003
+    dim, par, y, F, h, w = setup_gbm(ctx, rng, name, n, False, K=K)
+    ctx.gbm_pseudo_residuals(newton=False)
+    r = ctx.download(N.SLOT_R).reshape(dim, n)
+    ro, _, _ = oracle.pseudo_residuals(O.LOSS_IDS[name], par, dim, y, None, F, False)
+    close(r, ro, rtol=RTOL, scale=1.0)
+
+
+@pytest.mark.parametrize("name", HESS + ["logloss"])
+@pytest.mark.parametrize("weighted", [False, True])
+def test_pseudo_residuals_newton(ctx, oracle, rng, name, weighted):
+    from spark_ensemble_b200 import _native as N
+    n, K = 4099, 6
+    dim, par, y, F, h, w = setup_gbm(ctx, rng, name, n, weighted, K=K)
+    S = ctx.gbm_pseudo_residuals(newton=True)
+    r = ctx.download(N.SLOT_R).reshape(dim, n)
+    wo = ctx.download(N.SLOT_WOUT).reshape(dim, n)
+    ro, woo, So = oracle.pseudo_residuals(O.LOSS_IDS[name], par, dim, y, w, F, True)
+    close(S, So, rtol=RTOL)
+    close(r, ro, rtol=RTOL, scale=1.0)
+    close(wo, woo, rtol=RTOL)
+
+
+def test_newton_rejected_without_hessian(ctx, rng):
+    setup_gbm(ctx, rng, "absolute", 64)
+    with pytest.raises(ValueError):
+        ctx.gbm_pseudo_residuals(newton=True)
+
+
+@pytest.mark.parametrize("name", SCALAR + ["logloss"])
+@pytest.mark.parametrize("mode", ["plain", "residual", "newton"])
+def test_update_fused(ctx, oracle, rng, name, mode):
+    """K1: F' = F + step·h fused with next-round residual and Σloss(F')."""
+    from spark_ensemble_b200 import _native as N
+    if mode == "newton" and name not in HESS + ["logloss"]:
+        pytest.skip("no hessian")
+    n, K = 30011, 4
+    dim, par, y, F, h, w = setup_gbm(ctx, rng, name, n, mode == "newton", K=K)
+    step = rng.random(dim) * 0.8 + 0.1
+    ls, S = ctx.gbm_update(step, residual=(mode == "residual"), newton=(mode == "newton"), loss=True)
+    Fg = ctx.download(N.SLOT_F).reshape(dim, n)
+    Fo = F.astype(np.float64).copy()
+    oracle.update(Fo, h, step)
+    close(Fg, Fo, rtol=RTOL)  # predictions within 1e-5 relative
+    lid = O.LOSS_IDS[name]
+    assert ls / n == pytest.approx(oracle.mean_loss(lid, par, dim, y, Fo), rel=RTOL, abs=1e-7)
+    if mode != "plain":
+        ro, woo, So = oracle.pseudo_residuals(lid, par, dim, y, w, Fo, mode == "newton")
+        close(ctx.download(N.SLOT_R).reshape(dim, n), ro, rtol=RTOL, scale=1.0)
+        if mode == "newton":
+            close(S, So, rtol=RTOL)
+            close(ctx.download(N.SLOT_WOUT).reshape(dim, n), woo, rtol=RTOL)
+
+
+def test_mean_loss_and_validation(ctx, oracle, rng):
+    from spark_ensemble_b200 import _native as N
+    n, nv = 7001, 1999
+    for name in ("squared", "bernoulli", "logloss"):
+        dim, par, y, F, h, w = setup_gbm(ctx, rng, name, n, False, K=3, nv=nv)
+        vy = labels(name, rng, nv, 3)
+        vF = f32(rng.standard_normal((dim, nv)))
+        vh = f32(rng.standard_normal((dim, nv)))
+        ctx.upload(N.SLOT_VY, vy); ctx.upload(N.SLOT_VF, vF); ctx.upload(N.SLOT_VH, vh)
+        lid = O.LOSS_IDS[name]
+        assert ctx.gbm_mean_loss(False) == pytest.approx(oracle.mean_loss(lid, par, dim, y, F), rel=RTOL)
+        assert ctx.gbm_mean_loss(True) == pytest.approx(oracle.mean_loss(lid, par, dim, vy, vF), rel=RTOL)
+        step = rng.random(dim)
+        lv = ctx.gbm_update_validation(step)
+        vFo = vF.astype(np.float64).copy()
+        oracle.update(vFo, vh, step)
+        assert lv == pytest.approx(oracle.mean_loss(lid, par, dim, vy, vFo), rel=RTOL)
+        close(ctx.download(N.SLOT_VF).reshape(dim, nv), vFo)
+
+
+def test_squared_stats_brent_and_async_round(ctx, oracle, rng):
+    from spark_ensemble_b200 import _native as N
+    n = 100003
+    dim, par, y, F, h, w = setup_gbm(ctx, rng, "squared", n, True)
+    h = f32((y - F[0]) * 0.6 + 0.2 * rng.standard_normal(n)).reshape(1, n)
+    ctx.upload(N.SLOT_H, h)
+    s = ctx.gbm_linesearch_stats()
+    d = (y.astype(np.float64) - F[0]); hh = h[0].astype(np.float64)
+    close(s, [np.sum(d * d), np.sum(hh * d), np.sum(hh * hh), np.sum(w.astype(np.float64))], rtol=RTOL)
+    # native Brent over the one-pass parabola == oracle Brent over full-pass evaluations
+    a, l, ne = ctx.gbm_linesearch_brent()
+    f = lambda x: oracle.linesearch_eval(O.SQUARED, 0.0, y, w, F, h, [x])[0]
+    ao, neo, st = oracle.brent(f)
+    assert st == 0
+    assert a == pytest.approx(ao, rel=1e-5, abs=2e-6)  # optimiser tolerance tol=1e-6
+    assert l == pytest.approx(f(ao), rel=RTOL)
+    # device-resident round: closed-form alpha, no host round trip
+    ctx.gbm_configure(n, 0, 1, "squared", 0.0, False)
+    ctx.upload(N.SLOT_Y, y); ctx.upload(N.SLOT_F, F); ctx.upload(N.SLOT_H, h)
+    ctx.gbm_round_squared_async(0.5)
+    alpha, loss_sum = ctx.gbm_round_result()
+    star = float(np.clip(np.sum(hh * d) / np.sum(hh * hh), 0, 100))
+    assert alpha == pytest.approx(star, rel=RTOL)
+    Fo = F.astype(np.float64).copy()
+    oracle.update(Fo, h, [0.5 * star])
+    close(ctx.download(N.SLOT_F), Fo[0])
+    assert loss_sum / n == pytest.approx(oracle.mean_loss(O.SQUARED, 0.0, 1, y, Fo), rel=RTOL)
+    ro, _, _ = oracle.pseudo_residuals(O.SQUARED, 0.0, 1, y, None, Fo, False)
+    close(ctx.download(N.SLOT_R), ro[0], scale=1.0)
+
+
+@pytest.mark.parametrize("name", ["bernoulli", "absolute", "logcosh"])
+def test_native_brent_line_search(ctx, oracle, rng, name):
+    from spark_ensemble_b200 import _native as N
+    n = 20011
+    dim, par, y, F, h, w = setup_gbm(ctx, rng, name, n)
+    lid = O.LOSS_IDS[name]
+    r, _, _ = oracle.pseudo_residuals(lid, par, 1, y, None, F, False)
+    h = f32(r * 0.8 + 0.1 * rng.standard_normal((1, n)))
+    ctx.upload(N.SLOT_H, h)
+    a, l, ne = ctx.gbm_linesearch_brent()
+    f = lambda x: oracle.linesearch_eval(lid, par, y, None, F, h, [x])[0]
+    ao, neo, st = oracle.brent(f)
+    assert st == 0 and 3 <= ne <= 100
+    # the minimiser is defined to optimiser tolerance; the objective value is the parity quantity
+    assert l == pytest.approx(f(ao), rel=RTOL)
+    assert f(a) <= f(ao) * (1 + 1e-5)
+
+
+def test_multi_round_drift(ctx, oracle, rng):
+    """200 fused rounds of fp32 state against the fp64 oracle: predictions and per-iteration loss stay
+    within 1e-5 relative (SURVEY.md §7 'hard parts')."""
+    from spark_ensemble_b200 import _native as N
+    n = 20000
+    for name in ("squared", "bernoulli"):
+        dim, par, y, F, h, w = setup_gbm(ctx, rng, name, n)
+        lid = O.LOSS_IDS[name]
+        Fo = F.astype(np.float64).copy()
+        worst = 0.0
+        for t in range(200):
+            ro, _, _ = oracle.pseudo_residuals(lid, par, 1, y, None, Fo, False)
+            ht = f32(ro * 0.5 + 0.05 * rng.standard_normal((1, n)))
+            ctx.upload(N.SLOT_H, ht)
+            step = 0.1
+            ls, _ = ctx.gbm_update([step], residual=True, loss=True)
+            oracle.update(Fo, ht, [step])
+            lo = oracle.mean_loss(lid, par, 1, y, Fo)
+            worst = max(worst, abs(ls / n - lo) / lo)
+        assert worst < RTOL, worst
+        close(ctx.download(N.SLOT_F), Fo[0])
+
+
+# ------------------------------------------------------------------ BoostingClassifier
+@pytest.mark.parametrize("K", [2, 3, 26])
+@pytest.mark.parametrize("n", [2, 4097, 50001])
+def test_samme_r_update(ctx, oracle, rng, K, n):
+    from spark_ensemble_b200 import _native as N
+    y = f32(rng.integers(0, K, n))
+    Z = rng.standard_normal((K, n))
+    Z[y.astype(int), np.arange(n)] += 2.0
+    P = f32(NP.softmax_cols(Z))
+    P[0, : min(n, 5)] = 0.0  # exercises max(p, EPSILON)
+    w = f32(rng.random(n) + 0.1)
+    ctx.boost_configure(n, K, True)
+    ctx.upload(N.SLOT_Y, y); ctx.upload(N.SLOT_BW, w); ctx.upload(N.SLOT_PROBA, P)
+    sw = ctx.slot_sum(N.SLOT_BW)
+    assert sw == pytest.approx(oracle.sum(w), rel=1e-12)  # fp64 accumulation of fp32 values
+    e, s = ctx.boost_real_update(sw)
+    out, eo, so = oracle.samme_r_update(K, y, w, sw, P)
+    assert e == pytest.approx(eo, rel=RTOL, abs=1e-9)
+    assert s == pytest.approx(so, rel=RTOL)
+    close(ctx.download(N.SLOT_BW), out, rtol=RTOL, scale=float(np.min(out)))
+
+
+def test_samme_discrete(ctx, oracle, rng):
+    from spark_ensemble_b200 import _native as N
+    n, K = 33333, 7
+    y = f32(rng.integers(0, K, n))
+    pred = f32(np.where(rng.random(n) < 0.7, y, rng.integers(0, K, n)))
+    w = f32(rng.random(n))
+    ctx.boost_configure(n, K, False)
+    ctx.upload(N.SLOT_Y, y); ctx.upload(N.SLOT_BW, w); ctx.upload(N.SLOT_PRED, pred)
+    sw = ctx.slot_sum(N.SLOT_BW)
+    e = ctx.boost_discrete_error(sw)
+    eo = oracle.samme_error(y, w, sw, pred)
+    assert e == pytest.approx(eo, rel=RTOL)
+    beta = eo / ((1 - eo) * (K - 1))
+    s = ctx.boost_discrete_update(sw, beta)
+    out, so = oracle.samme_update(y, w, sw, pred, beta)
+    assert s == pytest.approx(so, rel=RTOL)
+    close(ctx.download(N.SLOT_BW), out, rtol=RTOL, scale=1e-12)
+
+
+# ------------------------------------------------------------------ aggregation
+@pytest.mark.parametrize("M,n", [(1, 5), (10, 4099), (512, 2051)])
+def test_agg_regressors(ctx, oracle, rng, M, n):
+    from spark_ensemble_b200 import _native as N
+    P = f32(rng.standard_normal((M, n)) + 3.0)
+    a = rng.random(M)
+    ctx.agg_configure(N.AGG_GBM_REGRESSOR, M, 0, 1, 0, n)
+    ctx.upload(N.SLOT_P, P)
+    ctx.agg_run(a, [0.25])
+    close(ctx.download(N.SLOT_RAW), oracle.agg_weighted_sum(P, a.astype(np.float32).astype(np.float64), 0.25))
+    ctx.agg_configure(N.AGG_BAGGING_REGRESSOR, M, 0, 1, 0, n)
+    ctx.upload(N.SLOT_P, P)
+    ctx.agg_run()
+    close(ctx.download(N.SLOT_RAW), oracle.agg_mean(P))
+
+
+@pytest.mark.parametrize("loss,dim,K", [("bernoulli", 1, 2), ("exponential", 1, 2), ("logloss", 2, 2),
+                                        ("logloss", 5, 5), ("logloss", 26, 26)])
+def test_agg_gbm_classifier(ctx, oracle, rng, loss, dim, K):
+    from spark_ensemble_b200 import _native as N
+    M, n = 9, 3001
+    P = f32(rng.standard_normal((M, dim, n)))
+    a = f32(rng.random((M, dim))).astype(np.float64)
+    init = f32(rng.standard_normal(dim)).astype(np.float64)
+    ctx.agg_configure(N.AGG_GBM_CLASSIFIER, M, K, dim, loss, n)
+    ctx.upload(N.SLOT_P, P)
+    ctx.agg_run(a, init)
+    raw = oracle.agg_gbm_classifier_raw(P, a, init, K)
+    close(ctx.download(N.SLOT_RAW), raw, scale=1.0)
+    close(ctx.download(N.SLOT_PROB), oracle.gbm_raw2prob(O.LOSS_IDS[loss], raw), scale=1e-3)
+    lab = ctx.download(N.SLOT_LABEL)
+    srt = np.sort(raw, axis=0)
+    clear = (srt[-1] - srt[-2]) > 1e-4  # argmax is only defined up to fp32 ties
+    np.testing.assert_array_equal(lab[clear], oracle.argmax(raw)[clear])
+
+
+@pytest.mark.parametrize("K", [2, 26])
+def test_agg_bagging_classifier(ctx, oracle, rng, K):
+    from spark_ensemble_b200 import _native as N
+    M, n = 11, 2999
+    Pk = f32(rng.random((M, K, n)))
+    ctx.agg_configure(N.AGG_BAGGING_SOFT, M, K, 1, 0, n)
+    ctx.upload(N.SLOT_P, Pk)
+    ctx.agg_run()
+    raw, prob = oracle.agg_bagging_soft(Pk)
+    close(ctx.download(N.SLOT_RAW), raw)
+    close(ctx.download(N.SLOT_PROB), prob)
+    votes = f32(rng.integers(0, K, (M, n)))
+    ctx.agg_configure(N.AGG_BAGGING_HARD, M, K, 1, 0, n)
+    ctx.upload(N.SLOT_P, votes)
+    ctx.agg_run()
+    raw, prob = oracle.agg_bagging_hard(votes, K)
+    np.testing.assert_array_equal(ctx.download(N.SLOT_RAW), raw)  # vote counts: exact
+    close(ctx.download(N.SLOT_PROB), prob)
+    np.testing.assert_array_equal(ctx.download(N.SLOT_LABEL), oracle.argmax(raw))
+
+
+@pytest.mark.parametrize("K", [2, 5, 26])
+def test_agg_boosting_classifier_and_zero_sum(ctx, oracle, rng, K):
+    """Parity + the reference's invariant (BoostingClassifierSuite.scala:126-154): rawPrediction rows
+    sum to 0 (here to fp32 rounding of the row's magnitude)."""
+    from spark_ensemble_b200 import _native as N
+    M, n = 7, 2500
+    P = f32(NP.softmax_cols(rng.standard_normal((M * K, n)).reshape(M, K, n).reshape(M * K, n)).reshape(M, K, n))
+    P = f32(P / P.sum(axis=1, keepdims=True))
+    ctx.agg_configure(N.AGG_BOOSTING_REAL, M, K, 1, 0, n)
+    ctx.upload(N.SLOT_P, P)
+    ctx.agg_run()
+    raw, prob = oracle.agg_boosting_real(P)
+    g = ctx.download(N.SLOT_RAW)
+    close(g, raw, scale=float(np.abs(raw).max()))
+    assert np.max(np.abs(g.sum(axis=0))) <= 1e-5 * np.abs(g).sum(axis=0).max()
+    close(ctx.download(N.SLOT_PROB), prob, scale=1e-3)
+    votes = f32(rng.integers(0, K, (M, n)))
+    a = f32(rng.random(M) + 0.1).astype(np.float64)
+    ctx.agg_configure(N.AGG_BOOSTING_DISCRETE, M, K, 1, 0, n)
+    ctx.upload(N.SLOT_P, votes)
+    ctx.agg_run(a)
+    raw, prob = oracle.agg_boosting_discrete(votes, a, K)
+    g = ctx.download(N.SLOT_RAW)
+    close(g, raw, scale=float(np.abs(raw).max()))
+    assert np.max(np.abs(g.sum(axis=0))) <= 1e-5 * np.abs(g).sum(axis=0).max()
+    close(ctx.download(N.SLOT_PROB), prob, scale=1e-3)
+
+
+# ------------------------------------------------------------------ on-device base models
+def test_tree_and_linear_predict(ctx, rng):
+    from sklearn.tree import DecisionTreeRegressor
+    from spark_ensemble_b200 import _native as N
+    n, d = 10007, 12
+    X = f32(rng.standard_normal((n, d)))
+    yv = X[:, 0] * 2 + np.sin(X[:, 3]) + 0.1 * rng.standard_normal(n)
+    sub = np.array([0, 2, 3, 5, 7, 11], dtype=np.int32)
+    t = DecisionTreeRegressor(max_depth=6, random_state=0).fit(X[:, sub], yv)
+    tr = t.tree_
+    tree = {"feature": np.where(tr.children_left < 0, -1, tr.feature), "threshold": tr.threshold,
+            "left": np.maximum(tr.children_left, 0), "right": np.maximum(tr.children_right, 0),
+            "value": tr.value.reshape(-1)}
+    ctx.alloc(N.SLOT_X, d, n)
+    ctx.upload(N.SLOT_X, np.ascontiguousarray(X.T))
+    ctx.alloc(N.SLOT_H, 1, n)
+    ctx.tree_predict(tree, N.SLOT_H, 0, subspace=sub)
+    # sklearn thresholds are fp64 midpoints; the fp32 rounding of a threshold can only flip rows whose
+    # feature equals it to ~1 ulp — none with continuous random data
+    np.testing.assert_allclose(ctx.download(N.SLOT_H), t.predict(X[:, sub]).astype(np.float32), rtol=1e-6)
+    coef = f32(rng.standard_normal(len(sub)))
+    ctx.linear_predict(coef, 0.5, N.SLOT_H, 0, subspace=sub)
+    ref = 0.5 + X[:, sub].astype(np.float64) @ coef.astype(np.float64)
+    close(ctx.download(N.SLOT_H), ref, scale=1.0)
+
+
+def test_synthetic_fill_statistics(ctx):
+    from spark_ensemble_b200 import _native as N
+    n = 1 << 20
+    ctx.alloc(N.SLOT_Y, n)
+    ctx.fill_synthetic(N.SLOT_Y, "normal", 7, 1.0, 2.0)
+    v = ctx.download(N.SLOT_Y).astype(np.float64)
+    assert abs(v.mean() - 1.0) < 0.01 and abs(v.std() - 2.0) < 0.01
+    ctx.fill_synthetic(N.SLOT_Y, "randint", 8, 0, 26)
+    v = ctx.download(N.SLOT_Y)
+    assert v.min() == 0 and v.max() == 25 and np.all(v == np.floor(v))
+    ctx.fill_synthetic(N.SLOT_Y, "bernoulli", 9, 0.3, 0)
+    assert abs(ctx.download(N.SLOT_Y).mean() - 0.3) < 0.01
+    # chunked fills are index-addressed: same stream regardless of how the range is split
+    ctx.fill_synthetic(N.SLOT_Y, "uniform", 10, 0, 1)
+    whole = ctx.download(N.SLOT_Y).copy()
+    ctx.fill_synthetic(N.SLOT_Y, "uniform", 10, 0, 1, count=1000, offset=0)
+    ctx.fill_synthetic(N.SLOT_Y, "uniform", 10, 0, 1, count=n - 1000, offset=1000)
+    np.testing.assert_array_equal(ctx.download(N.SLOT_Y), whole)
