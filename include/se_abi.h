@@ -98,6 +98,24 @@ SE_API int se_ctx_launch_count(const se_ctx* ctx, int64_t* out);
 SE_API int se_ctx_last_ms(se_ctx* ctx, double* out);
 /* enable/disable per-call CUDA-event timing (default off: no extra events on the stream) */
 SE_API int se_ctx_set_timing(se_ctx* ctx, int on);
+/* stopwatch on the context stream (CUDA events): start enqueues an event; stop enqueues a second
+ * one, waits for it and returns the device milliseconds in between */
+SE_API int se_ctx_timer_start(se_ctx* ctx);
+SE_API int se_ctx_timer_stop(se_ctx* ctx, double* ms);
+/* per-kernel-family device time (CUDA events bracketing each launch while kernel timing is on):
+ * families are enum se_kernel_family; total_ms / launches accumulate until reset */
+enum se_kernel_family {
+  SE_KF_SQ_STATS = 0, SE_KF_EVAL = 1, SE_KF_UPDATE = 2, SE_KF_RESID = 3, SE_KF_MEAN_LOSS = 4,
+  SE_KF_BOOST_REAL = 5, SE_KF_BOOST_ERR = 6, SE_KF_BOOST_UPD = 7, SE_KF_AGG = 8, SE_KF_TREE = 9,
+  SE_KF_LINEAR = 10, SE_KF_OTHER = 11, SE_KF_COUNT = 12
+};
+SE_API int se_ctx_kernel_timing(se_ctx* ctx, int on);
+SE_API int se_ctx_kernel_time(se_ctx* ctx, int family, double* total_ms, int64_t* launches);
+SE_API int se_ctx_kernel_time_reset(se_ctx* ctx);
+/* pinned (page-locked) host memory for the buffers handed to se_upload/se_download (JNI: wrap in a
+ * direct ByteBuffer); pageable memory works too but is staged by the driver */
+SE_API int se_host_alloc(int64_t bytes, void** out);
+SE_API int se_host_free(void* ptr);
 
 /* ---- row-shard communicator: replaces Spark treeAggregate/treeReduce ---------- */
 #define SE_COMM_ID_BYTES 128

@@ -29,6 +29,10 @@ UPD_RESIDUAL, UPD_NEWTON, UPD_LOSS = 1, 2, 4
 (AGG_GBM_REGRESSOR, AGG_BAGGING_REGRESSOR, AGG_GBM_CLASSIFIER, AGG_BAGGING_SOFT, AGG_BAGGING_HARD,
  AGG_BOOSTING_REAL, AGG_BOOSTING_DISCRETE) = range(7)
 
+# enum se_kernel_family
+KERNEL_FAMILIES = ["sq_stats", "eval", "update", "resid", "mean_loss", "boost_real", "boost_err",
+                   "boost_upd", "agg", "tree", "linear", "other"]
+
 FN1 = C.CFUNCTYPE(C.c_double, C.c_double, C.c_void_p)
 
 _i32, _i64, _u64, _d, _f = C.c_int, C.c_int64, C.c_uint64, C.c_double, C.c_float
@@ -47,6 +51,13 @@ PROTOTYPES = {
     "se_ctx_launch_count": [_vp, C.POINTER(_i64)],
     "se_ctx_last_ms": [_vp, _dp],
     "se_ctx_set_timing": [_vp, _i32],
+    "se_ctx_timer_start": [_vp],
+    "se_ctx_timer_stop": [_vp, _dp],
+    "se_ctx_kernel_timing": [_vp, _i32],
+    "se_ctx_kernel_time": [_vp, _i32, _dp, C.POINTER(_i64)],
+    "se_ctx_kernel_time_reset": [_vp],
+    "se_host_alloc": [_i64, C.POINTER(_vp)],
+    "se_host_free": [_vp],
     "se_comm_unique_id": [_vp, _i32],
     "se_comm_init": [_vp, _i32, _i32, _vp, _i32],
     "se_comm_destroy": [_vp],

@@ -57,6 +57,29 @@ class Context:
         self._ck(self._lib.se_ctx_last_ms(self._h, C.byref(v)))
         return v.value
 
+    def timer_start(self):
+        self._ck(self._lib.se_ctx_timer_start(self._h))
+
+    def timer_stop(self) -> float:
+        v = C.c_double()
+        self._ck(self._lib.se_ctx_timer_stop(self._h, C.byref(v)))
+        return v.value
+
+    def kernel_timing(self, on: bool):
+        self._ck(self._lib.se_ctx_kernel_timing(self._h, int(on)))
+
+    def kernel_times(self) -> dict:
+        out = {}
+        for i, name in enumerate(N.KERNEL_FAMILIES):
+            ms, cnt = C.c_double(), C.c_int64()
+            self._ck(self._lib.se_ctx_kernel_time(self._h, i, C.byref(ms), C.byref(cnt)))
+            if cnt.value:
+                out[name] = {"ms": ms.value, "launches": cnt.value}
+        return out
+
+    def kernel_times_reset(self):
+        self._ck(self._lib.se_ctx_kernel_time_reset(self._h))
+
     # ---- communicator
     @staticmethod
     def comm_unique_id() -> bytes:

@@ -142,12 +142,16 @@ __global__ void __launch_bounds__(kBlock) agg_finalize_kernel(const FinArgs f) {
       // GBMClassifier.scala:583-584 + GBMLoss.scala:284-289,311-316 (raw(0) = −F)
       const float res = f.raw[i];
       const float r0 = -res;
-      float p1;
-      if (f.loss == SE_LOSS_EXPONENTIAL) p1 = 1.0f / (1.0f + expf(-2.0f * r0));
-      else p1 = 1.0f / (1.0f + expf(r0));
+      // p1 = 1/(1+e^x), p0 = 1 - p1 with x = raw(0) (bernoulli) or -2 raw(0) (exponential); both
+      // formed from t = e^-|x| so the small one keeps full relative precision
+      const float x = (f.loss == SE_LOSS_EXPONENTIAL) ? -2.0f * r0 : r0;
+      const float t = expf(-fabsf(x));
+      const float inv = 1.0f / (1.0f + t);
+      const float p1 = (x >= 0.f) ? t * inv : inv;
+      const float p0 = (x >= 0.f) ? inv : t * inv;
       f.raw[i] = r0;
       f.raw[f.ld + i] = res;
-      f.prob[i] = 1.0f - p1;
+      f.prob[i] = p0;
       f.prob[f.ld + i] = p1;
       f.label[i] = (res > r0) ? 1.0f : 0.0f;  // argmax, first maximum on ties
       continue;

@@ -129,6 +129,15 @@ struct se_ctx {
   nccl_comm_t comm = nullptr;
   int nranks = 1, rank = 0;
   std::string err;
+  // stopwatch + per-kernel-family timing
+  cudaEvent_t tm0 = nullptr, tm1 = nullptr;
+  bool ktiming = false;
+  static constexpr int kRing = 128;
+  cudaEvent_t kev[kRing][2] = {};
+  int kfam[kRing] = {};
+  int kpending = 0;
+  double kms[SE_KF_COUNT] = {};
+  int64_t kcount[SE_KF_COUNT] = {};
 };
 
 namespace {
@@ -159,6 +168,43 @@ int fail(se_ctx* ctx, int code, const char* fmt, ...) {
     if (e__ != cudaSuccess)                                                                   \
       return fail(ctx, SE_ERR_CUDA, "%s:%d launch %s -> %s", __FILE__, __LINE__, #call,       \
                   cudaGetErrorString(e__));                                                   \
+  } while (0)
+
+int drain_kernel_events(se_ctx* ctx) {
+  if (ctx->kpending == 0) return SE_OK;
+  SE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  for (int i = 0; i < ctx->kpending; ++i) {
+    float ms = 0.f;
+    SE_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->kev[i][0], ctx->kev[i][1]));
+    ctx->kms[ctx->kfam[i]] += (double)ms;
+    ctx->kcount[ctx->kfam[i]] += 1;
+  }
+  ctx->kpending = 0;
+  return SE_OK;
+}
+
+// launch bracketed by CUDA events on the context stream when kernel timing is on
+#define SE_LAUNCH_T(ctx, family, call)                                                        \
+  do {                                                                                        \
+    int slot__ = -1;                                                                          \
+    if ((ctx)->ktiming) {                                                                     \
+      if ((ctx)->kpending == se_ctx::kRing) {                                                 \
+        int rc__ = drain_kernel_events(ctx);                                                  \
+        if (rc__ != SE_OK) return rc__;                                                       \
+      }                                                                                       \
+      slot__ = (ctx)->kpending;                                                               \
+      if (!(ctx)->kev[slot__][0]) {                                                           \
+        SE_CUDA(ctx, cudaEventCreate(&(ctx)->kev[slot__][0]));                                \
+        SE_CUDA(ctx, cudaEventCreate(&(ctx)->kev[slot__][1]));                                \
+      }                                                                                       \
+      SE_CUDA(ctx, cudaEventRecord((ctx)->kev[slot__][0], (ctx)->stream));                    \
+    }                                                                                         \
+    SE_LAUNCH(ctx, call);                                                                     \
+    if (slot__ >= 0) {                                                                        \
+      SE_CUDA(ctx, cudaEventRecord((ctx)->kev[slot__][1], (ctx)->stream));                    \
+      (ctx)->kfam[slot__] = (family);                                                         \
+      (ctx)->kpending = slot__ + 1;                                                           \
+    }                                                                                         \
   } while (0)
 
 #define SE_TRY(expr)                \
@@ -479,6 +525,9 @@ int se_ctx_destroy(se_ctx* ctx) {
   if (ctx->d_small) cudaFree(ctx->d_small);
   if (ctx->h_small) cudaFreeHost(ctx->h_small);
   if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+  if (ctx->tm0) cudaEventDestroy(ctx->tm0);
+  if (ctx->tm1) cudaEventDestroy(ctx->tm1);
+  for (auto& pr : ctx->kev) { if (pr[0]) cudaEventDestroy(pr[0]); if (pr[1]) cudaEventDestroy(pr[1]); }
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -519,6 +568,70 @@ int se_ctx_last_ms(se_ctx* ctx, double* out) {
   float ms = 0.f;
   SE_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
   *out = (double)ms;
+  return SE_OK;
+}
+
+int se_ctx_timer_start(se_ctx* ctx) {
+  if (!ctx) return fail(nullptr, SE_ERR_ARG, "null context");
+  SE_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (!ctx->tm0) {
+    SE_CUDA(ctx, cudaEventCreate(&ctx->tm0));
+    SE_CUDA(ctx, cudaEventCreate(&ctx->tm1));
+  }
+  SE_CUDA(ctx, cudaEventRecord(ctx->tm0, ctx->stream));
+  return SE_OK;
+}
+
+int se_ctx_timer_stop(se_ctx* ctx, double* ms) {
+  if (!ctx || !ms) return fail(ctx, SE_ERR_ARG, "null argument");
+  SE_REQUIRE(ctx, ctx->tm0, SE_ERR_STATE, "se_ctx_timer_start first");
+  SE_CUDA(ctx, cudaSetDevice(ctx->device));
+  SE_CUDA(ctx, cudaEventRecord(ctx->tm1, ctx->stream));
+  SE_CUDA(ctx, cudaEventSynchronize(ctx->tm1));
+  float f = 0.f;
+  SE_CUDA(ctx, cudaEventElapsedTime(&f, ctx->tm0, ctx->tm1));
+  *ms = (double)f;
+  return SE_OK;
+}
+
+int se_ctx_kernel_timing(se_ctx* ctx, int on) {
+  if (!ctx) return fail(nullptr, SE_ERR_ARG, "null context");
+  SE_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (!on) SE_TRY(drain_kernel_events(ctx));
+  ctx->ktiming = on != 0;
+  return SE_OK;
+}
+
+int se_ctx_kernel_time(se_ctx* ctx, int family, double* total_ms, int64_t* launches) {
+  if (!ctx) return fail(nullptr, SE_ERR_ARG, "null context");
+  SE_REQUIRE(ctx, family >= 0 && family < SE_KF_COUNT, SE_ERR_ARG, "bad kernel family %d", family);
+  SE_CUDA(ctx, cudaSetDevice(ctx->device));
+  SE_TRY(drain_kernel_events(ctx));
+  if (total_ms) *total_ms = ctx->kms[family];
+  if (launches) *launches = ctx->kcount[family];
+  return SE_OK;
+}
+
+int se_ctx_kernel_time_reset(se_ctx* ctx) {
+  if (!ctx) return fail(nullptr, SE_ERR_ARG, "null context");
+  SE_CUDA(ctx, cudaSetDevice(ctx->device));
+  SE_TRY(drain_kernel_events(ctx));
+  for (int i = 0; i < SE_KF_COUNT; ++i) { ctx->kms[i] = 0.0; ctx->kcount[i] = 0; }
+  return SE_OK;
+}
+
+int se_host_alloc(int64_t bytes, void** out) {
+  if (!out || bytes < 0) return fail(nullptr, SE_ERR_ARG, "bad argument");
+  *out = nullptr;
+  cudaError_t e = cudaMallocHost(out, (size_t)(bytes > 0 ? bytes : 1));
+  if (e != cudaSuccess) return fail(nullptr, SE_ERR_CUDA, "cudaMallocHost(%lld): %s", (long long)bytes, cudaGetErrorString(e));
+  return SE_OK;
+}
+
+int se_host_free(void* ptr) {
+  if (!ptr) return SE_OK;
+  cudaError_t e = cudaFreeHost(ptr);
+  if (e != cudaSuccess) return fail(nullptr, SE_ERR_CUDA, "cudaFreeHost: %s", cudaGetErrorString(e));
   return SE_OK;
 }
 
@@ -790,7 +903,7 @@ int se_gbm_pseudo_residuals(se_ctx* ctx, int newton, double* sum_hess) {
   SE_TRY(begin(ctx));
   if (newton) SE_TRY(slot_alloc2d(ctx, SE_SLOT_WOUT, ctx->gbm.dim, ctx->gbm.n));
   GbmArgs a = gbm_args(ctx, false);
-  SE_LAUNCH(ctx, launch_gbm(ctx->gbm.loss, newton ? GBM_RESID_NEWTON : GBM_RESID, a, ctx->ctas_per_sm,
+  SE_LAUNCH_T(ctx, SE_KF_RESID, launch_gbm(ctx->gbm.loss, newton ? GBM_RESID_NEWTON : GBM_RESID, a, ctx->ctas_per_sm,
                             ctx->sms, ctx->stream));
   if (newton) SE_TRY(newton_finish(ctx, sum_hess));
   return end(ctx);
@@ -804,7 +917,7 @@ int se_gbm_linesearch_eval(se_ctx* ctx, const double* alpha, double* loss, doubl
   const int dim = ctx->gbm.dim;
   GbmArgs a = gbm_args(ctx, false);
   for (int j = 0; j < dim; ++j) a.coef[j] = (float)alpha[j];
-  SE_LAUNCH(ctx, launch_gbm(ctx->gbm.loss, GBM_EVAL, a, ctx->ctas_per_sm, ctx->sms, ctx->stream));
+  SE_LAUNCH_T(ctx, SE_KF_EVAL, launch_gbm(ctx->gbm.loss, GBM_EVAL, a, ctx->ctas_per_sm, ctx->sms, ctx->stream));
   double s[1 + kMaxDim];
   SE_TRY(fetch_scalars(ctx, 0, 1 + dim, s));
   // lossSum is accumulated `dim` times per row in the reference (GBMLoss.scala:60-64)
@@ -820,7 +933,7 @@ int se_gbm_linesearch_stats(se_ctx* ctx, double* stats4) {
   SE_TRY(ensure_wsum(ctx));
   SE_TRY(begin(ctx));
   GbmArgs a = gbm_args(ctx, false);
-  SE_LAUNCH(ctx, launch_gbm(SE_LOSS_SQUARED, GBM_SQ_STATS, a, ctx->ctas_per_sm, ctx->sms, ctx->stream));
+  SE_LAUNCH_T(ctx, SE_KF_SQ_STATS, launch_gbm(SE_LOSS_SQUARED, GBM_SQ_STATS, a, ctx->ctas_per_sm, ctx->sms, ctx->stream));
   SE_TRY(fetch_scalars(ctx, 0, 3, stats4));
   stats4[3] = ctx->gbm.wsum;
   return SE_OK;
@@ -836,7 +949,7 @@ int se_gbm_update(se_ctx* ctx, const double* step, int flags, double* loss_sum, 
   GbmArgs a = gbm_args(ctx, false);
   for (int j = 0; j < ctx->gbm.dim; ++j) a.coef[j] = (float)step[j];
   const int mode = newton ? GBM_UPDATE_NEWTON : ((flags & SE_UPD_RESIDUAL) ? GBM_UPDATE_RESID : GBM_UPDATE);
-  SE_LAUNCH(ctx, launch_gbm(ctx->gbm.loss, mode, a, ctx->ctas_per_sm, ctx->sms, ctx->stream));
+  SE_LAUNCH_T(ctx, SE_KF_UPDATE, launch_gbm(ctx->gbm.loss, mode, a, ctx->ctas_per_sm, ctx->sms, ctx->stream));
   if (newton) {
     SE_TRY(newton_finish(ctx, sum_hess));
     if (loss_sum) *loss_sum = ctx->h_scal[0];
@@ -853,7 +966,7 @@ int se_gbm_mean_loss(se_ctx* ctx, int which, double* out) {
   SE_TRY(ensure_counts(ctx));
   SE_TRY(begin(ctx));
   GbmArgs a = gbm_args(ctx, which == 1);
-  SE_LAUNCH(ctx, launch_gbm(ctx->gbm.loss, GBM_MEAN_LOSS, a, ctx->ctas_per_sm, ctx->sms, ctx->stream));
+  SE_LAUNCH_T(ctx, SE_KF_MEAN_LOSS, launch_gbm(ctx->gbm.loss, GBM_MEAN_LOSS, a, ctx->ctas_per_sm, ctx->sms, ctx->stream));
   double s = 0.0;
   SE_TRY(fetch_scalars(ctx, 0, 1, &s));
   *out = s / (which == 1 ? ctx->gbm.nv_global : ctx->gbm.n_global);
@@ -867,7 +980,7 @@ int se_gbm_update_validation(se_ctx* ctx, const double* step, double* mean_loss)
   SE_TRY(begin(ctx));
   GbmArgs a = gbm_args(ctx, true);
   for (int j = 0; j < ctx->gbm.dim; ++j) a.coef[j] = (float)step[j];
-  SE_LAUNCH(ctx, launch_gbm(ctx->gbm.loss, GBM_UPDATE, a, ctx->ctas_per_sm, ctx->sms, ctx->stream));
+  SE_LAUNCH_T(ctx, SE_KF_UPDATE, launch_gbm(ctx->gbm.loss, GBM_UPDATE, a, ctx->ctas_per_sm, ctx->sms, ctx->stream));
   double s = 0.0;
   SE_TRY(fetch_scalars(ctx, 0, 1, &s));
   if (mean_loss) *mean_loss = s / ctx->gbm.nv_global;
@@ -920,13 +1033,13 @@ int se_gbm_round_squared_async(se_ctx* ctx, double learning_rate) {
   SE_TRY(begin(ctx));
   GbmArgs a = gbm_args(ctx, false);
   a.ws = red_ws(ctx, kScalRound);  // stats -> d_scal[64..66]
-  SE_LAUNCH(ctx, launch_gbm(SE_LOSS_SQUARED, GBM_SQ_STATS, a, ctx->ctas_per_sm, ctx->sms, ctx->stream));
+  SE_LAUNCH_T(ctx, SE_KF_SQ_STATS, launch_gbm(SE_LOSS_SQUARED, GBM_SQ_STATS, a, ctx->ctas_per_sm, ctx->sms, ctx->stream));
   SE_TRY(allreduce_dev(ctx, kScalRound, 3));
   GbmArgs u = gbm_args(ctx, false);
   u.dev_stats = ctx->d_scal + kScalRound;
   u.lr = (float)learning_rate;
   u.ws = red_ws(ctx, kScalRound + 8);  // Σloss -> d_scal[72]
-  SE_LAUNCH(ctx, launch_gbm(SE_LOSS_SQUARED, GBM_UPDATE_RESID, u, ctx->ctas_per_sm, ctx->sms, ctx->stream));
+  SE_LAUNCH_T(ctx, SE_KF_UPDATE, launch_gbm(SE_LOSS_SQUARED, GBM_UPDATE_RESID, u, ctx->ctas_per_sm, ctx->sms, ctx->stream));
   SE_TRY(allreduce_dev(ctx, kScalRound + 8, 1));
   return end(ctx);
 }
@@ -988,7 +1101,7 @@ int se_boost_real_update(se_ctx* ctx, double sum_w, double* est_err, double* new
   SE_REQUIRE(ctx, ctx->boost.on && ctx->boost.real, SE_ERR_STATE, "se_boost_configure(real=1) first");
   SE_TRY(begin(ctx));
   BoostArgs a = boost_args(ctx, sum_w);
-  SE_LAUNCH(ctx, launch_boost_real(a, ctx->ctas_per_sm, ctx->sms, ctx->stream));
+  SE_LAUNCH_T(ctx, SE_KF_BOOST_REAL, launch_boost_real(a, ctx->ctas_per_sm, ctx->sms, ctx->stream));
   double s[2];
   SE_TRY(fetch_scalars(ctx, 0, 2, s));
   if (est_err) *est_err = s[0];
@@ -1001,7 +1114,7 @@ int se_boost_discrete_error(se_ctx* ctx, double sum_w, double* est_err) {
   SE_REQUIRE(ctx, ctx->boost.on && !ctx->boost.real, SE_ERR_STATE, "se_boost_configure(real=0) first");
   SE_TRY(begin(ctx));
   BoostArgs a = boost_args(ctx, sum_w);
-  SE_LAUNCH(ctx, launch_boost_discrete_error(a, ctx->ctas_per_sm, ctx->sms, ctx->stream));
+  SE_LAUNCH_T(ctx, SE_KF_BOOST_ERR, launch_boost_discrete_error(a, ctx->ctas_per_sm, ctx->sms, ctx->stream));
   return fetch_scalars(ctx, 0, 1, est_err);
 }
 
@@ -1011,7 +1124,7 @@ int se_boost_discrete_update(se_ctx* ctx, double sum_w, double beta, double* new
   SE_TRY(begin(ctx));
   BoostArgs a = boost_args(ctx, sum_w);
   a.inv_beta = (float)(1.0 / beta);
-  SE_LAUNCH(ctx, launch_boost_discrete_update(a, ctx->ctas_per_sm, ctx->sms, ctx->stream));
+  SE_LAUNCH_T(ctx, SE_KF_BOOST_UPD, launch_boost_discrete_update(a, ctx->ctas_per_sm, ctx->sms, ctx->stream));
   double s = 0.0;
   SE_TRY(fetch_scalars(ctx, 0, 1, &s));
   if (new_sum) *new_sum = s;
@@ -1086,7 +1199,7 @@ int se_agg_run(se_ctx* ctx, const double* weights, const double* init) {
     used = off + g.dim;
   }
   if (used) SE_CUDA(ctx, cudaMemcpyAsync(ctx->d_small, hs, used * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
-  SE_LAUNCH(ctx, launch_agg(a, 8, ctx->sms, ctx->stream));
+  SE_LAUNCH_T(ctx, SE_KF_AGG, launch_agg(a, 8, ctx->sms, ctx->stream));
   if (g.kind >= SE_AGG_GBM_CLASSIFIER) ctx->launches++;  // finalize kernel
   return end(ctx);
 }
@@ -1131,7 +1244,7 @@ int se_tree_predict(se_ctx* ctx, int which, int n_nodes, const int32_t* feature,
   t.right = t.left + n_nodes;
   t.value = reinterpret_cast<const float*>(t.right + n_nodes);
   t.out = O.d + (int64_t)out_row * (O.rows > 1 ? O.ld : O.cols);
-  SE_LAUNCH(ctx, launch_tree_predict(t, ctx->sms, ctx->stream));
+  SE_LAUNCH_T(ctx, SE_KF_TREE, launch_tree_predict(t, ctx->sms, ctx->stream));
   return end(ctx);
 }
 
@@ -1158,7 +1271,7 @@ int se_linear_predict(se_ctx* ctx, int which, int n_coef, const float* coef, flo
     SE_CUDA(ctx, cudaMemcpyAsync(ctx->d_small, ctx->h_small, (size_t)n_coef * 8, cudaMemcpyHostToDevice, ctx->stream));
   const float* dc = reinterpret_cast<const float*>(ctx->d_small);
   const int32_t* dcol = reinterpret_cast<const int32_t*>(dc + n_coef);
-  SE_LAUNCH(ctx, launch_linear_predict(X.d, X.cols, X.rows > 1 ? X.ld : X.cols, n_coef, dc, dcol, intercept,
+  SE_LAUNCH_T(ctx, SE_KF_LINEAR, launch_linear_predict(X.d, X.cols, X.rows > 1 ? X.ld : X.cols, n_coef, dc, dcol, intercept,
                                        O.d + (int64_t)out_row * (O.rows > 1 ? O.ld : O.cols), ctx->sms, ctx->stream));
   return end(ctx);
 }

@@ -70,9 +70,10 @@ __device__ __forceinline__ LGH eval_loss(float y, float p, float param) {
     const float t = expf(-fabsf(z));           // in (0,1]
     const float inv = 1.0f / (1.0f + t);
     const float sig_neg = (z >= 0.f) ? t * inv : inv;  // sigma(-z) = 1/(1+e^z)
+    const float sig_pos = (z >= 0.f) ? inv : t * inv;  // sigma(z): formed directly, no 1-x cancellation
     o.l = fmaxf(-z, 0.f) + log1pf(t);
     o.g = -2.0f * ye * sig_neg;
-    o.h = 4.0f * ye * ye * sig_neg * (1.0f - sig_neg);  // 4 e^z y^2 / (1+e^z)^2
+    o.h = 4.0f * ye * ye * sig_neg * sig_pos;  // 4 e^z y^2 / (1+e^z)^2
   } else if constexpr (LOSS == SE_LOSS_EXPONENTIAL) {  // :265-291
     const float ye = 2.0f * y - 1.0f;
     const float e = expf(-ye * p);
