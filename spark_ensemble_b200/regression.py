@@ -1,0 +1,275 @@
+"""Host-side mirror of the reference's regression ensembles for the hot path:
+GBMRegressor / GBMRegressionModel (regression/GBMRegressor.scala) and BaggingRegressionModel.predict
+(regression/BaggingRegressor.scala:221-228) — same class names, UID prefixes, Params and defaults; the
+per-row RDD closures of train()/predict() are replaced by calls into libse_b200 (sm_100a kernels).
+
+On a JVM host the same substitution is made in Scala (scala/ + jni/se_jni.cpp).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import _native as N
+from .context import Context
+from .ensemble import (DataFrame, exact_quantile, fit_dummy_regressor, java_string_hash, subspace)
+from .gbm_engine import GBMEngine
+from .params import (Param, Params, ParamValidators, boosting_params, gbm_params, random_uid,
+                     shared_predictor_params, subbag_params)
+
+_REG_LOSSES = ("squared", "absolute", "huber", "quantile")  # GBMRegressor.scala:119-120
+_REG_INIT = ("constant", "zero", "base")                     # :121-123
+
+
+def _extract_instances(est: Params, dataset: DataFrame):
+    """Predictor.extractInstances: label cast to double, weight = weightCol if set and non-empty else 1."""
+    X = np.asarray(dataset[est("featuresCol")])
+    y = np.asarray(dataset[est("labelCol")], dtype=np.float64)
+    wc = est("weightCol") if est.isDefined("weightCol") else ""
+    w = np.asarray(dataset[wc], dtype=np.float64) if wc else None
+    return X, y, w
+
+
+def _split_validation(est: Params, dataset: DataFrame):
+    vc = est("validationIndicatorCol") if est.isDefined("validationIndicatorCol") else ""
+    if vc:
+        mask = np.asarray(dataset[vc], dtype=bool)
+        return dataset.filter(~mask), dataset.filter(mask)
+    return dataset, None
+
+
+class GBMRegressor(Params):
+    """regression/GBMRegressor.scala:164-476.  UID prefix "GBMRegressor2" (sic, :229)."""
+
+    def __init__(self, uid: str | None = None, device: int = 0):
+        super().__init__(uid or random_uid("GBMRegressor2"))
+        self.device = device
+
+    def copy(self, extra=None):
+        c = super().copy(extra)
+        if c.isDefined("baseLearner"):
+            c.set("baseLearner", c("baseLearner").copy(extra))  # :230-234
+        return c
+
+    def fit(self, dataset: DataFrame) -> "GBMRegressionModel":
+        return self._train(dataset)
+
+    # -- GBMRegressor.train :237-476
+    def _train(self, dataset: DataFrame) -> "GBMRegressionModel":
+        train_df, valid_df = _split_validation(self, dataset)
+        with_validation = valid_df is not None
+        X, y, w = _extract_instances(self, train_df)
+        Xv, yv, _ = _extract_instances(self, valid_df) if with_validation else (None, None, None)
+        n, nv = y.shape[0], (yv.shape[0] if with_validation else 0)
+        num_features = X.shape[1]
+        loss = self("loss").lower()
+        updates = self("updates").lower()
+        learner = self("baseLearner")
+        if self("subsampleRatio") != 1.0 or self("replacement"):
+            # RDD.sample is Spark-RNG-defined: row sub-sampling stays on the Spark side
+            raise NotImplementedError("row sub-sampling (subsampleRatio < 1 or replacement) needs Spark's RDD.sample")
+        num_learners = self("numBaseLearners")
+        seed = self("seed")
+        subspaces = [subspace(self("subspaceRatio"), num_features, seed + i) for i in range(num_learners)]  # :282-284
+
+        # init model :287-303
+        init_strategy = self("initStrategy").lower()
+        if init_strategy == "base":
+            init = learner.fit(X, y, w)
+        elif init_strategy == "zero":
+            init = fit_dummy_regressor("constant", y, constant=0.0)
+        else:
+            strat = {"squared": "mean", "absolute": "median", "huber": "median", "quantile": "quantile"}[loss]
+            init = fit_dummy_regressor(strat, y, quantile=self("alpha"))
+
+        # huber delta / quantile parameter :305-308
+        param = exact_quantile(y, self("alpha")) if loss == "huber" else self("alpha")
+        newton = updates == "newton" and loss == "squared"  # HasScalarHessian among selectable losses :369
+
+        ctx = Context(self.device)
+        try:
+            eng = GBMEngine(ctx, n, nv, 1, loss, param, has_weights=w is not None)
+            const_init = hasattr(init, "prediction")  # Dummy model: broadcast the constant on device
+            F0 = init.prediction if const_init else init.predict(X)
+            vF0 = (init.prediction if const_init else init.predict(Xv)) if with_validation else None
+            eng.load(y, w, F0, yv, vF0)
+            on_device_models = bool(self("residentFeatures"))
+            if on_device_models:
+                eng.load_features(X, Xv)
+            best = ctx.gbm_mean_loss(validation=True) if with_validation else 0.0  # :330-335
+
+            models, weights = [], []
+            history = []
+            eng.residuals(newton)  # residuals of F0; later rounds get them fused with the update
+            i = v = 0
+            while i < num_learners and v < self("numRounds"):  # :340
+                if loss == "huber":  # :342-353 (approxQuantile restated as the exact quantile)
+                    F = ctx.download(N.SLOT_F).astype(np.float64)
+                    param = exact_quantile(np.abs(y - F), self("alpha"))
+                    ctx.gbm_set_loss_param(param)
+                    eng.residuals(False)
+                sub = subspaces[i]
+                r, wout = eng.fetch_residuals(newton)
+                fit_w = wout[0] if newton else w
+                model = learner.fit(X[:, sub], r[0], fit_w)  # third party :387-396
+                eng.set_direction_from_model(0, model, sub, X)
+                if self("optimizedWeights"):  # :398-425
+                    alpha, _, _ = eng.line_search_brent(self("tol"), self("maxIter"))
+                else:
+                    alpha = 1.0
+                weight = self("learningRate") * alpha  # :427
+                loss_sum, _ = eng.update(weight, residual=(not newton and loss != "huber"), newton=newton)
+                models.append(model)
+                weights.append(weight)
+                history.append({"alpha": alpha, "trainLoss": loss_sum / n if n else float("nan")})
+                if with_validation:  # :444-465
+                    eng.set_direction_from_model(0, model, sub, Xv, validation=True)
+                    err = eng.update_validation(weight)
+                    history[-1]["validationLoss"] = err
+                    if best - err < self("validationTol") * max(err, 0.01):
+                        v += 1
+                    elif err < best:
+                        best = err
+                        v = 0
+                i += 1
+            keep = i - v  # :474
+            model = GBMRegressionModel(weights[:keep], subspaces[:keep], models[:keep], init,
+                                       device=self.device)
+            self._copyValues(model)
+            model.parent = self
+            model.trainingHistory = history
+            return model
+        finally:
+            ctx.close()
+
+
+_p, _d = shared_predictor_params()
+_ps, _ds = subbag_params()
+_pb, _db = boosting_params()
+_pg, _dg = gbm_params()
+_preg = [
+    Param("loss", "loss function, (case-insensitive). Supported options:" + ",".join(_REG_LOSSES),
+          lambda v: v.lower() in _REG_LOSSES, str),
+    Param("alpha", "The alpha-quantile of the loss function. Only for huber and quantile loss.", convert=float),
+    Param("initStrategy", "strategy for the init predictions (constant, zero, base)",
+          lambda v: v in _REG_INIT, str),
+    # the one new expert Param: keep the column-major feature matrix in HBM and evaluate
+    # fitted trees / linear models on device instead of model.predict on the host
+    Param("residentFeatures", "evaluate base models on device over the HBM-resident feature matrix", convert=bool),
+]
+_GBM_REG_DEFAULTS = {**_d, **_ds, **_db, **_dg, "loss": "squared", "alpha": 0.9, "initStrategy": "constant", "residentFeatures": False,
+                     "seed": java_string_hash("org.apache.spark.ml.regression.GBMRegressor")}
+GBMRegressor._declare(_p + _ps + _pb + _pg + _preg, _GBM_REG_DEFAULTS)
+
+
+def _stack_model_outputs(models, subspaces, X, extra=None) -> np.ndarray:
+    rows = [] if extra is None else [extra]
+    for m, s in zip(models, subspaces):
+        rows.append(m.predict(X[:, s]))
+    if not rows:
+        return np.zeros((0, X.shape[0]), dtype=np.float32)
+    return np.ascontiguousarray(np.stack(rows), dtype=np.float32)
+
+
+class GBMRegressionModel(Params):
+    """regression/GBMRegressor.scala:512-556; predict :531-539 = init + Σ_i w_i·m_i(x[S_i])."""
+
+    def __init__(self, weights, subspaces, models, init, uid: str | None = None, device: int = 0):
+        super().__init__(uid or random_uid("GBMRegressionModel"))
+        self.weights = np.asarray(weights, dtype=np.float64)
+        self.subspaces = list(subspaces)
+        self.models = list(models)
+        self.init = init
+        self.numModels = len(self.models)
+        self.device = device
+        self.parent = None
+
+    def _aggregate(self, X) -> np.ndarray:
+        n = X.shape[0]
+        const_init = hasattr(self.init, "prediction")
+        P = _stack_model_outputs(self.models, self.subspaces, X,
+                                 None if const_init else self.init.predict(X))
+        a = self.weights if const_init else np.concatenate([[1.0], self.weights])
+        with Context(self.device) as ctx:
+            ctx.agg_configure(N.AGG_GBM_REGRESSOR, P.shape[0], 0, 1, 0, n)
+            if P.shape[0]:
+                ctx.upload(N.SLOT_P, P)
+            ctx.agg_run(a, [self.init.prediction if const_init else 0.0])
+            return ctx.download(N.SLOT_RAW).astype(np.float64)
+
+    def transform(self, dataset: DataFrame) -> DataFrame:
+        X = np.asarray(dataset[self("featuresCol")])
+        return dataset.withColumn(self("predictionCol"), self._aggregate(X))
+
+    def predict(self, features) -> float:
+        return float(self._aggregate(np.asarray(features).reshape(1, -1))[0])
+
+
+GBMRegressionModel._declare(_p + _ps + _pb + _pg + _preg, _GBM_REG_DEFAULTS)
+
+
+# ---- Bagging (train is out of the hot path: embarrassingly parallel base-learner fits) ---------------
+class BaggingRegressor(Params):
+    """regression/BaggingRegressor.scala:77-172.  Only the model's predict is on the hot path; train
+    here is the minimal host loop (one base learner per bootstrap bag)."""
+
+    def __init__(self, uid: str | None = None, device: int = 0):
+        super().__init__(uid or random_uid("BaggingRegressor"))
+        self.device = device
+
+    def fit(self, dataset: DataFrame) -> "BaggingRegressionModel":
+        X, y, w = _extract_instances(self, dataset)
+        n, d = X.shape
+        seed = self("seed")
+        M = self("numBaseLearners")
+        subs = [subspace(self("subspaceRatio"), d, seed + i) for i in range(M)]
+        models = []
+        rng = np.random.default_rng(seed & 0xFFFFFFFF)  # same sample for every bag: reference quirk 3
+        if self("replacement"):
+            counts = rng.poisson(self("subsampleRatio"), n).astype(np.float64)
+        else:
+            counts = (rng.random(n) < self("subsampleRatio")).astype(np.float64)
+        bw = counts if w is None else counts * w
+        keep = bw > 0
+        for i in range(M):
+            models.append(self("baseLearner").fit(X[keep][:, subs[i]], y[keep], bw[keep]))
+        m = BaggingRegressionModel(subs, models, device=self.device)
+        self._copyValues(m)
+        m.parent = self
+        return m
+
+
+_pbag = [Param("numBaseLearners", "number of base learners", ParamValidators.gtEq(1), int),
+         Param("baseLearner", "base learner"),
+         Param("parallelism", "the number of threads to use when running parallel algorithms (>= 1)",
+               ParamValidators.gtEq(1), int)]
+_BAG_REG_DEFAULTS = {**_d, **_ds, "numBaseLearners": 10, "parallelism": 1,
+                     "seed": java_string_hash("org.apache.spark.ml.regression.BaggingRegressor")}
+BaggingRegressor._declare(_p + _ps + _pbag, _BAG_REG_DEFAULTS)
+
+
+class BaggingRegressionModel(Params):
+    """regression/BaggingRegressor.scala:208-235; predict :221-228 = (Σ_i m_i(x[S_i])) / numModels."""
+
+    def __init__(self, subspaces, models, uid: str | None = None, device: int = 0):
+        super().__init__(uid or random_uid("BaggingRegressionModel"))
+        self.subspaces, self.models = list(subspaces), list(models)
+        self.numModels = len(self.models)
+        self.device = device
+        self.parent = None
+
+    def _aggregate(self, X) -> np.ndarray:
+        P = _stack_model_outputs(self.models, self.subspaces, X)
+        with Context(self.device) as ctx:
+            ctx.agg_configure(N.AGG_BAGGING_REGRESSOR, P.shape[0], 0, 1, 0, X.shape[0])
+            ctx.upload(N.SLOT_P, P)
+            ctx.agg_run()
+            return ctx.download(N.SLOT_RAW).astype(np.float64)
+
+    def transform(self, dataset: DataFrame) -> DataFrame:
+        return dataset.withColumn(self("predictionCol"), self._aggregate(np.asarray(dataset[self("featuresCol")])))
+
+    def predict(self, features) -> float:
+        return float(self._aggregate(np.asarray(features).reshape(1, -1))[0])
+
+
+BaggingRegressionModel._declare(_p + _ps + _pbag, _BAG_REG_DEFAULTS)

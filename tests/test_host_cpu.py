@@ -1,0 +1,181 @@
+"""CPU tests of the host-side mirror logic (no GPU, no kernels): Params surface, sub-bagging,
+row partitioner, and the world_size-2 gloo check of the sharded-reduction algebra."""
+import os
+
+import numpy as np
+import pytest
+
+
+def test_uid_prefixes_and_defaults_match_reference():
+    """UID prefixes and Param defaults are part of the drop-in surface."""
+    from spark_ensemble_b200.classification import (BaggingClassifier, BoostingClassifier, GBMClassifier)
+    from spark_ensemble_b200.regression import BaggingRegressor, GBMRegressor
+    g = GBMRegressor()
+    assert g.uid.startswith("GBMRegressor2_") and len(g.uid) == len("GBMRegressor2_") + 12  # sic, :229
+    d = g.extractParamMap()
+    assert (d["numBaseLearners"], d["learningRate"], d["optimizedWeights"], d["updates"]) == (10, 1.0, True, "gradient")
+    assert (d["tol"], d["maxIter"], d["numRounds"], d["validationTol"], d["replacement"]) == (1e-6, 100, 1, 0.01, False)
+    assert (d["loss"], d["alpha"], d["initStrategy"]) == ("squared", 0.9, "constant")
+    assert (d["subsampleRatio"], d["subspaceRatio"], d["checkpointInterval"], d["aggregationDepth"]) == (1.0, 1.0, 10, 2)
+    c = GBMClassifier()
+    assert c.uid.startswith("GBMClassifier_")
+    assert (c.getLoss(), c.getInitStrategy(), c.getParallelism()) == ("logloss", "prior", 1)
+    b = BoostingClassifier()
+    assert b.uid.startswith("BoostingClassifier_") and b.getAlgorithm() == "discrete"
+    assert BaggingRegressor().uid.startswith("BaggingRegressor_")
+    bc = BaggingClassifier()
+    assert bc.uid.startswith("BaggingClassifier_") and bc.getVotingStrategy() == "hard" and bc.getReplacement() is True
+
+
+def test_param_validators_raise_like_spark():
+    from spark_ensemble_b200.regression import GBMRegressor
+    g = GBMRegressor()
+    for name, bad in [("learningRate", 0.0), ("numBaseLearners", 0), ("loss", "poisson"), ("updates", "adam"),
+                      ("subspaceRatio", 1.5), ("numRounds", 0), ("validationTol", -1.0), ("initStrategy", "mean")]:
+        with pytest.raises(ValueError):
+            g.set(name, bad)
+    assert g.setLoss("Huber").getLoss() == "Huber" and g.setUpdates("Newton")("updates") == "Newton"
+    g2 = g.copy({"learningRate": 0.3})
+    assert g2.getLearningRate() == 0.3 and g.getLearningRate() == 1.0 and g2.uid == g.uid
+    assert "learningRate" in g.explainParams()
+
+
+def test_java_string_hash_and_default_seed():
+    from spark_ensemble_b200.ensemble import java_string_hash
+    assert java_string_hash("hello") == 99162322
+    assert java_string_hash("") == 0
+    assert java_string_hash("org.apache.spark.ml.regression.GBMRegressor") == 1243996765
+
+
+def test_subspace_properties():
+    """test/ensemble/HasSubBagSuite.scala:60-105: E|subspace| = ratio*d +- 0.1*d, sorted, ratio 1 => identity."""
+    from spark_ensemble_b200.ensemble import XORShiftRandom, subspace
+    d = 200
+    for ratio in (0.1, 0.5, 0.9):
+        sizes = [len(subspace(ratio, d, seed)) for seed in range(40)]
+        assert abs(np.mean(sizes) / d - ratio) < 0.1
+        s = subspace(ratio, d, 7)
+        assert list(s) == sorted(set(s)) and s.dtype == np.int32
+    np.testing.assert_array_equal(subspace(1.0, 17, 123), np.arange(17))
+    assert len(subspace(0.0, 17, 123)) == 0
+    # determinism + hashSeed bit spread (XORShiftRandomSuite "hashSeed has random bits throughout")
+    assert list(subspace(0.5, 50, 42)) == list(subspace(0.5, 50, 42))
+    assert list(subspace(0.5, 50, 42)) != list(subspace(0.5, 50, 43))
+    for seed in range(10):
+        r = XORShiftRandom(seed)
+        assert bin(r.seed).count("1") > 20
+        u = [r.next_double() for _ in range(1000)]
+        assert 0.0 <= min(u) and max(u) < 1.0 and abs(np.mean(u) - 0.5) < 0.05
+
+
+def test_row_partition_covers_rows_aligned():
+    from spark_ensemble_b200.ensemble import row_partition
+    for n in (0, 1, 5, 8192, 100_000_003):
+        for g in (1, 2, 3, 8):
+            spans = [row_partition(n, g, r) for r in range(g)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            for (a0, a1), (b0, b1) in zip(spans, spans[1:]):
+                assert a1 == b0 and a0 <= a1
+            assert all(s0 % 4 == 0 for s0, s1 in spans if s1 > s0)  # 128-bit alignment of non-empty shards
+    with pytest.raises(ValueError):
+        row_partition(10, 2, 2)
+
+
+def test_dummy_init_models():
+    """DummyRegressorSuite.scala:78-108 / DummyClassifier.train :90-123."""
+    from spark_ensemble_b200.ensemble import exact_quantile, fit_dummy_classifier, fit_dummy_regressor
+    y = np.array([3.0, 1.0, 2.0, 10.0])
+    assert fit_dummy_regressor("mean", y).prediction == 4.0
+    assert fit_dummy_regressor("median", y).prediction == 2.0
+    assert fit_dummy_regressor("quantile", y, quantile=0.9).prediction == 10.0
+    assert fit_dummy_regressor("constant", y, constant=0.0).prediction == 0.0
+    assert exact_quantile(np.arange(1, 101), 0.9) == 90.0
+    labels = np.array([0, 0, 1, 2, 2, 2], dtype=float)
+    m = fit_dummy_classifier("prior", labels, 3)
+    np.testing.assert_allclose(m.probability, [2 / 6, 1 / 6, 3 / 6])
+    np.testing.assert_allclose(m.rawPrediction, np.log([2 / 6, 1 / 6, 3 / 6]))
+    u = fit_dummy_classifier("uniform", labels, 3)
+    np.testing.assert_allclose(u.rawPrediction, 0.0)
+    assert u.predictRaw(np.zeros((4, 2))).shape == (4, 3)
+
+
+def test_row_subsampling_is_rejected_loudly():
+    from spark_ensemble_b200 import DataFrame
+    from spark_ensemble_b200.learners import DecisionTreeRegressor
+    from spark_ensemble_b200.regression import GBMRegressor
+    df = DataFrame(features=np.zeros((8, 2), dtype=np.float32), label=np.zeros(8))
+    with pytest.raises(NotImplementedError):
+        GBMRegressor().setBaseLearner(DecisionTreeRegressor()).setSubsampleRatio(0.5).fit(df)
+
+
+def test_tree_arrays_threshold_rounding():
+    """fp32 thresholds are rounded DOWN so `x <= thr32` equals sklearn's `x <= thr64` for fp32 x."""
+    from spark_ensemble_b200.learners import DecisionTreeRegressor
+    rng = np.random.default_rng(3)
+    X = rng.standard_normal((2000, 5)).astype(np.float32)
+    y = X[:, 0] + X[:, 1] ** 2
+    m = DecisionTreeRegressor(maxDepth=7).fit(X, y)
+    t = m.tree_arrays()
+    node = np.zeros(len(X), dtype=np.int64)
+    for _ in range(10):
+        f = t["feature"][node]
+        live = f >= 0
+        x = X[np.arange(len(X)), np.maximum(f, 0)]
+        nxt = np.where(x <= t["threshold"][node], t["left"][node], t["right"][node])
+        node = np.where(live, nxt, node)
+    np.testing.assert_allclose(t["value"][node], m.predict(X), rtol=1e-6)
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    from oracle import oracle as O
+    from spark_ensemble_b200.ensemble import row_partition
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    orc = O.Oracle()
+    rng = np.random.default_rng(5)  # every rank regenerates the same global dataset
+    n, K = 10_007, 3
+    res = {}
+    for name, dim in (("bernoulli", 1), ("logloss", K), ("squared", 1)):
+        y = (rng.integers(0, K, n) if name == "logloss" else (rng.random(n) < 0.5)).astype(np.float64)
+        if name == "squared":
+            y = rng.standard_normal(n)
+        w = rng.random(n) + 0.5
+        F = rng.standard_normal((dim, n))
+        h = rng.standard_normal((dim, n))
+        alpha = rng.random(dim) + 0.5
+        s0, s1 = row_partition(n, world, rank)
+        lid = O.LOSS_IDS[name]
+        # per-shard partial sums exactly as a GPU shard produces them: (lossSum, weightSum, gradSum[dim])
+        l, g = orc.linesearch_eval(lid, 0.0, y[s0:s1], w[s0:s1], np.ascontiguousarray(F[:, s0:s1]),
+                                   np.ascontiguousarray(h[:, s0:s1]), alpha)
+        ws = float(np.sum(w[s0:s1]))
+        part = torch.tensor([l * ws, ws] + list(g * ws), dtype=torch.float64)
+        dist.all_reduce(part)  # the ONE collective of a boosting round
+        tot = part.numpy()
+        full_l, full_g = orc.linesearch_eval(lid, 0.0, y, w, F, h, alpha)
+        res[name] = (abs(tot[0] / tot[1] - full_l) / abs(full_l),
+                     float(np.max(np.abs(tot[2:] / tot[1] - full_g) / (np.abs(full_g) + 1e-12))))
+    dist.barrier()
+    dist.destroy_process_group()
+    q.put((rank, res))
+
+
+def test_sharded_reduction_world2_gloo():
+    """Rows shard contiguously; the only exchange is a sum-allreduce of dim+2 doubles: the combined result
+    equals the unsharded aggregator (what se_comm_* does over NCCL on GPUs)."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for _, res in out:
+        for name, (el, eg) in res.items():
+            assert el < 1e-12 and eg < 1e-9, (name, el, eg)
