@@ -108,35 +108,66 @@ def _pinned_array(n: int):
 
 
 # ------------------------------------------------------------------ CPU arm (oracle port)
-def cpu_reference_round(orc, y, F, h, lr=0.5, tol=1e-6, max_iter=100):
+def cpu_reference_round(orc, y, F, h, r_buf, lr=0.5, tol=1e-6, max_iter=100):
     """One reference round on the CPU: Brent with a full pass per evaluation (GBMLoss.scala:50-74 via
     RDDLossFunction), F update, next pseudo-residuals, mean loss."""
     from oracle import oracle as O
     f = lambda a: orc.linesearch_eval(O.SQUARED, 0.0, y, None, F, h, [a])[0]
     alpha, n_eval, _ = orc.brent(f, 0.0, 100.0, 1.0, tol, tol, max_iter)
     orc.update(F, h, [lr * alpha])
-    orc.pseudo_residuals(O.SQUARED, 0.0, 1, y, None, F, False)
+    orc.pseudo_residuals(O.SQUARED, 0.0, 1, y, None, F, False, out_r=r_buf, want_weights=False)
     orc.mean_loss(O.SQUARED, 0.0, 1, y, F)
     return alpha, n_eval
 
 
+def _usable_cpus() -> int:
+    """CPUs this process may actually use: affinity mask capped by the cgroup CPU quota (a container can
+    see 128 cores and be allowed 16; oversubscribed OpenMP spin-waits are then catastrophically slow)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if quota != "max":
+            n = max(1, min(n, int(float(quota) / float(period) + 0.5)))
+    except Exception:
+        pass
+    return n
+
+
 def run_cpu_arm(sample_rows: int, steps: int, warmup: int) -> dict:
+    from oracle import oracle as O
     from oracle.oracle import Oracle
     orc = Oracle(omp=True)
     rng = np.random.default_rng(1)
     y = rng.standard_normal(sample_rows)
     F = np.zeros((1, sample_rows))
     h = (0.5 * y + 0.5 * rng.standard_normal(sample_rows)).reshape(1, -1)
+    r_buf = np.zeros((1, sample_rows))
+    # "all the host threads it can use": pick the fastest thread count among powers of two up to the
+    # usable CPUs, measured on one line-search evaluation (memory-bound: more threads is not always faster)
+    cap = _usable_cpus()
+    cands = sorted({c for c in (1, 2, 4, 8, 16, 32, 64, 128, 256, cap) if c <= cap})
+    best_t, best_dt = cands[0], float("inf")
+    for t in cands:
+        orc.lib.orc_set_num_threads(t)
+        orc.linesearch_eval(O.SQUARED, 0.0, y, None, F, h, [1.0])
+        dt = float("inf")
+        for _ in range(3):
+            t0 = time.perf_counter()
+            orc.linesearch_eval(O.SQUARED, 0.0, y, None, F, h, [1.0])
+            dt = min(dt, time.perf_counter() - t0)
+        if dt < best_dt:
+            best_t, best_dt = t, dt
+    orc.lib.orc_set_num_threads(best_t)
     evals = []
     for _ in range(warmup):
-        cpu_reference_round(orc, y, F, h)
+        cpu_reference_round(orc, y, F, h, r_buf)
     t0 = time.perf_counter()
     for _ in range(steps):
-        _, ne = cpu_reference_round(orc, y, F, h)
+        _, ne = cpu_reference_round(orc, y, F, h, r_buf)
         evals.append(ne)
     dt = time.perf_counter() - t0
-    return {"value": sample_rows * steps / dt, "ms_per_step": 1e3 * dt / steps, "cores": orc.num_threads(),
-            "brent_evals_per_round": float(np.mean(evals)), "sample_rows": sample_rows}
+    return {"value": sample_rows * steps / dt, "ms_per_step": 1e3 * dt / steps, "cores": best_t,
+            "usable_cpus": cap, "brent_evals_per_round": float(np.mean(evals)), "sample_rows": sample_rows}
 
 
 # ------------------------------------------------------------------ main
@@ -171,7 +202,8 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload, "note": "reference is Scala/Spark (no JVM in this image): oracle port timed"},
             "cpu_baseline": {"value": res["value"], "unit": "rows/s", "cores": res["cores"], "kind": "port",
-                             "sample": sample, "brent_evals_per_round": res["brent_evals_per_round"]},
+                             "sample": sample, "brent_evals_per_round": res["brent_evals_per_round"],
+                             "usable_cpus": res["usable_cpus"]},
             "e2e": {"value": res["value"], "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         }))
         return 0
@@ -222,12 +254,14 @@ def main():
         loss_sum, _ = ctx.gbm_update([lr * alpha], residual=True, newton=False, loss=True)
         return alpha, loss_sum
 
-    for _ in range(args.warmup):
-        step()
-    barrier()
+    # clocks are sampled from the first warm-up step to the end of the e2e loop: the device-resident timed
+    # region alone lasts only ~K x 0.6 ms, shorter than one nvidia-smi sampling period
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    for _ in range(args.warmup):
+        step()
+    barrier()
     ctx.kernel_timing(True)
     ctx.kernel_times_reset()
     launches0 = ctx.launch_count
@@ -243,7 +277,6 @@ def main():
     launches = ctx.launch_count - launches0
     ktimes = ctx.kernel_times()
     ctx.kernel_timing(False)
-    clocks = sampler.stop() if rank == 0 else None
     ms = max(ms_dev, ms_wall)  # device events and host clock bracket the same region; host syncs are inside
     if dist is not None:
         import torch
@@ -264,6 +297,7 @@ def main():
         eng.boost_round(h_host, lr, tol, max_iter, r_host)
     ctx.sync()
     e2e_ms = 1e3 * (time.perf_counter() - t0)
+    clocks = sampler.stop() if rank == 0 else None
     if dist is not None:
         import torch
         t = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
@@ -323,7 +357,7 @@ def main():
     if world == 1:
         cpu_steps = 3
         c = run_cpu_arm(args.cpu_rows, cpu_steps, 1)
-        cpu = {"value": c["value"], "unit": "rows/s", "cores": c["cores"], "kind": "port",
+        cpu = {"value": c["value"], "unit": "rows/s", "cores": c["cores"], "usable_cpus": c["usable_cpus"], "kind": "port",
                "sample": f"{cpu_steps} reference rounds on {args.cpu_rows} rows (fp64 OpenMP restatement; "
                          f"{c['brent_evals_per_round']:.1f} full-pass Brent evaluations per round)"}
 

@@ -120,11 +120,14 @@ class Oracle:
                                      C.cast(C.byref(out_l), _dp), _p(g))
         return out_l.value, g
 
-    def pseudo_residuals(self, loss, param, dim, y, w, F, newton):
+    def pseudo_residuals(self, loss, param, dim, y, w, F, newton, out_r=None, want_weights=True):
+        """Returns (r[dim][n], wout[dim][n] or None, sum_hess[dim]).  `out_r` reuses a caller buffer and
+        want_weights=False skips the (gradient-mode) copy of the instance weights — both only matter for
+        the timed CPU baseline, which must not be dominated by page-faulting fresh arrays."""
         y, w, F = _f64(y), _f64(w), _f64(F)
         n = y.shape[0]
-        r = np.zeros((dim, n))
-        wout = np.zeros((dim, n))
+        r = np.zeros((dim, n)) if out_r is None else out_r
+        wout = np.zeros((dim, n)) if (want_weights or newton) else None
         sh = np.zeros(dim)
         self.lib.orc_pseudo_residuals(loss, param, dim, n, _p(y), _p(w), _p(F), int(newton),
                                       _p(r), _p(wout), _p(sh))

@@ -42,7 +42,10 @@ def main():
     X, y = read_libsvm(f"{REF}/cpusmall/cpusmall.svm", 12)
     np.savez_compressed(f"{HERE}/cpusmall.npz", X=X, y=y)
     X, y = read_libsvm(f"{REF}/letter/letter.svm", 16)
-    np.savez_compressed(f"{HERE}/letter.npz", X=X.astype(np.int8), y=(y - 1).astype(np.int8))  # labels 1..26 -> 0..25
+    # letter.svm is the [-1,1]-scaled variant: x = code/7.5 - 1 with integer codes 0..15; store the codes
+    codes = np.rint((X.astype(np.float64) + 1.0) * 7.5).astype(np.int8)
+    assert np.max(np.abs((codes / 7.5 - 1.0) - X)) < 1e-5
+    np.savez_compressed(f"{HERE}/letter.npz", X=codes, y=(y - 1).astype(np.int8))  # labels 1..26 -> 0..25
     X, y = read_libsvm(f"{REF}/adult/adult.svm", 123)
     X, y = X[:8000], y[:8000]
     np.savez_compressed(f"{HERE}/adult8k.npz", X=np.packbits(X.astype(bool), axis=1), y=((y + 1) / 2).astype(np.int8))

@@ -24,7 +24,7 @@ def _cpusmall():
 
 def _letter(n=6000):
     d = np.load(os.path.join(GOLD, "letter.npz"))
-    return d["X"][:n].astype(np.float32), d["y"][:n].astype(np.float64)
+    return (d["X"][:n].astype(np.float64) / 7.5 - 1.0).astype(np.float32), d["y"][:n].astype(np.float64)
 
 
 def _adult():
