@@ -399,3 +399,20 @@ def test_synthetic_fill_statistics(ctx):
     ctx.fill_synthetic(N.SLOT_Y, "uniform", 10, 0, 1, count=1000, offset=0)
     ctx.fill_synthetic(N.SLOT_Y, "uniform", 10, 0, 1, count=n - 1000, offset=1000)
     np.testing.assert_array_equal(ctx.download(N.SLOT_Y), whole)
+
+
+def test_multi_gpu_sharded_parity():
+    """Row-sharded run over NCCL (one rank per GPU, torchrun): skipped on single-GPU boxes."""
+    import os
+    import subprocess
+    import sys
+    from spark_ensemble_b200 import _native as N
+    g = N.device_count()
+    if g < 2:
+        pytest.skip("needs >= 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    world = 2
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+                          "--master-addr", "127.0.0.1", "--master-port", "29533",
+                          os.path.join(root, "tests", "mgpu_check.py")], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "MGPU_PARITY_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
