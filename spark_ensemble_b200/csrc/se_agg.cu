@@ -12,6 +12,7 @@
 // 4·M·width B/row) followed by a tiny per-row epilogue.  Stage 1 (sum / vote histogram) is the
 // HBM-bound kernel; stage 2 (finalize) touches only C values per row.
 #include "se_kernels.h"
+#include "se_loss.cuh"
 #include "../../include/se_abi.h"
 
 namespace se {
@@ -53,8 +54,8 @@ __global__ void __launch_bounds__(kBlock) agg_sum_kernel(const float* __restrict
           if (m0 + u < M) {
             float4 x = v[u];
             if (LOGP) {
-              x.x = logf(fmaxf(x.x, kSparkEps)); x.y = logf(fmaxf(x.y, kSparkEps));
-              x.z = logf(fmaxf(x.z, kSparkEps)); x.w = logf(fmaxf(x.w, kSparkEps));
+              x.x = log_fast(fmaxf(x.x, kSparkEps)); x.y = log_fast(fmaxf(x.y, kSparkEps));
+              x.z = log_fast(fmaxf(x.z, kSparkEps)); x.w = log_fast(fmaxf(x.w, kSparkEps));
             }
             float4& s = (u & 1) ? s1 : s0;  // two accumulator sets: shorter dependency chains
             s.x = fmaf(wv[u], x.x, s.x); s.y = fmaf(wv[u], x.y, s.y);
@@ -77,7 +78,7 @@ __global__ void __launch_bounds__(kBlock) agg_sum_kernel(const float* __restrict
       for (int m = 0; m < M; ++m) {
         const int64_t rowi = cols ? (int64_t)cols[m] : (int64_t)m * width + c;
         float x = P[rowi * ld + i];
-        if (LOGP) x = logf(fmaxf(x, kSparkEps));
+        if (LOGP) x = log_fast(fmaxf(x, kSparkEps));
         s = fmaf(a ? a[(int64_t)m * width + c] : 1.0f, x, s);
       }
       float r = (init ? init[c] : 0.f) + s;
@@ -145,8 +146,8 @@ __global__ void __launch_bounds__(kBlock) agg_finalize_kernel(const FinArgs f) {
       // p1 = 1/(1+e^x), p0 = 1 - p1 with x = raw(0) (bernoulli) or -2 raw(0) (exponential); both
       // formed from t = e^-|x| so the small one keeps full relative precision
       const float x = (f.loss == SE_LOSS_EXPONENTIAL) ? -2.0f * r0 : r0;
-      const float t = expf(-fabsf(x));
-      const float inv = 1.0f / (1.0f + t);
+      const float t = exp_neg_fast(-fabsf(x));
+      const float inv = rcp_approx(1.0f + t);
       const float p1 = (x >= 0.f) ? t * inv : inv;
       const float p0 = (x >= 0.f) ? inv : t * inv;
       f.raw[i] = r0;
@@ -177,11 +178,11 @@ __global__ void __launch_bounds__(kBlock) agg_finalize_kernel(const FinArgs f) {
       // boosting: softmax(raw/(K-1)) (:342-346); GBM logloss: softmax(raw) (GBMLoss.scala:258-261)
       const float sc = (f.kind == SE_AGG_GBM_CLASSIFIER) ? 1.0f : 1.0f / (float)(f.K - 1);
       float s = 0.f;
-      for (int c = 0; c < C; ++c) s += expf((fin_raw(f, f.raw[c * f.ld + i], mean_t) - best) * sc);
-      const float inv = 1.0f / s;
+      for (int c = 0; c < C; ++c) s += exp_neg_fast((fin_raw(f, f.raw[c * f.ld + i], mean_t) - best) * sc);
+      const float inv = rcp_approx(s);
       for (int c = 0; c < C; ++c) {
         const float r = fin_raw(f, f.raw[c * f.ld + i], mean_t);
-        f.prob[c * f.ld + i] = expf((r - best) * sc) * inv;
+        f.prob[c * f.ld + i] = exp_neg_fast((r - best) * sc) * inv;
         f.raw[c * f.ld + i] = r;
       }
     } else {

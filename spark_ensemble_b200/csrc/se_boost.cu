@@ -6,6 +6,7 @@
 // written per row) that also produces both scalars, and SAMME is the two passes its data dependence
 // (β needs the error first) requires.  Weights are updated in place.
 #include "se_kernels.h"
+#include "se_loss.cuh"
 
 namespace se {
 
@@ -34,7 +35,7 @@ __device__ __forceinline__ void row_step(RowState& s, float p, int k, int yi) {
     s.best = p;
     s.am = k;
   }
-  const float lp = logf(fmaxf(p, kSparkEps));
+  const float lp = log_fast(fmaxf(p, kSparkEps));
   s.sum_log += lp;
   if (k == yi) s.log_y = lp;
 }
@@ -75,7 +76,7 @@ __global__ void __launch_bounds__(kBlock) boost_real_kernel(const BoostArgs a) {
       const float wn = f4at(vw, e) * a.inv_sum_w;  // :186
       err4 += (st[e].am != yi[e]) ? wn : 0.f;       // :202-209
       const float loss = (1.0f + inv_km1) * st[e].log_y - inv_km1 * st[e].sum_log;
-      const float wo = wn * expf(scale * loss);     // :226
+      const float wo = wn * exp_fast(scale * loss);  // :226
       f4at(out, e) = wo;
       sum4 += wo;
     }
@@ -90,7 +91,7 @@ __global__ void __launch_bounds__(kBlock) boost_real_kernel(const BoostArgs a) {
     for (int k = 0; k < K; ++k) row_step(st, a.proba[(int64_t)k * a.ld + i], k, yi);
     const float wn = a.w[i] * a.inv_sum_w;
     const float loss = (1.0f + inv_km1) * st.log_y - inv_km1 * st.sum_log;
-    const float wo = wn * expf(scale * loss);
+    const float wo = wn * exp_fast(scale * loss);
     a.w[i] = wo;
     acc[0] += (st.am != yi) ? (double)wn : 0.0;
     acc[1] += (double)wo;
@@ -102,15 +103,29 @@ __global__ void __launch_bounds__(kBlock) boost_real_kernel(const BoostArgs a) {
 __global__ void __launch_bounds__(kBlock) boost_discrete_error_kernel(const BoostArgs a) {
   double acc[1] = {0.0};
   const int64_t n4 = a.n >> 2;
-  for (int64_t g = (int64_t)blockIdx.x * kBlock + threadIdx.x; g < n4;
-       g += (int64_t)gridDim.x * kBlock) {
-    const float4 vy = ld_stream4(a.y + 4 * g), vp = ld_stream4(a.pred + 4 * g),
-                 vw = ld_stream4(a.w + 4 * g);
-    float e4 = 0.f;
+  constexpr int U = 4;  // 12 independent 16 B loads per thread in flight
+  const int64_t stride = (int64_t)gridDim.x * kBlock;
+  for (int64_t g0 = (int64_t)blockIdx.x * kBlock + threadIdx.x; g0 < n4; g0 += stride * U) {
+    float4 vy[U], vp[U], vw[U];
 #pragma unroll
-    for (int e = 0; e < 4; ++e)
-      e4 += (f4at(vy, e) != f4at(vp, e)) ? f4at(vw, e) * a.inv_sum_w : 0.f;
-    acc[0] += (double)e4;
+    for (int u = 0; u < U; ++u) {
+      const int64_t g = g0 + u * stride;
+      if (g < n4) {
+        vy[u] = ld_stream4(a.y + 4 * g);
+        vp[u] = ld_stream4(a.pred + 4 * g);
+        vw[u] = ld_stream4(a.w + 4 * g);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (g0 + u * stride < n4) {
+        float e4 = 0.f;
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          e4 += (f4at(vy[u], e) != f4at(vp[u], e)) ? f4at(vw[u], e) * a.inv_sum_w : 0.f;
+        acc[0] += (double)e4;
+      }
+    }
   }
   if (blockIdx.x == 0 && threadIdx.x < (a.n & 3)) {
     const int64_t i = (n4 << 2) + threadIdx.x;
