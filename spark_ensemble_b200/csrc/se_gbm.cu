@@ -10,6 +10,8 @@
 // computing (U x 3 independent 16 B requests in flight per thread), evaluates the loss in fp32,
 // accumulates sums in fp64, and the grid finishes with the deterministic last-CTA reduction from
 // se_common.cuh.  HBM-bound: K1 (update+residual+loss) moves 20 B/row, K2 (eval) 12 B/row.
+#include <stdlib.h>
+
 #include "se_kernels.h"
 #include "se_loss.cuh"
 
@@ -416,6 +418,13 @@ cudaError_t launch_gbm(int loss, int mode, const GbmArgs& a, int ctas_per_sm, in
   }
   const int K = a.dim;
   if (K < 1 || K > kMaxDim) return cudaErrorInvalidValue;
+  // K classes per row in registers up to `staged_min_k - 1`; wider K goes through shared-memory staging
+  static const int staged_min_k = [] {
+    const char* e = getenv("SE_LOGLOSS_STAGED_MIN_K");
+    const int v = e ? atoi(e) : 5;
+    return v < 2 ? 2 : v;
+  }();
+  if (K >= staged_min_k) return launch_gbm_logloss_staged(mode, a, sms, st);
   if (K <= 2) return launch_logloss_k<2, 4>(mode, a, grid_for((a.n + 3) / 4, kBlock, ctas_per_sm, sms), st);
   if (K <= 4) return launch_logloss_k<4, 4>(mode, a, grid_for((a.n + 3) / 4, kBlock, ctas_per_sm, sms), st);
   if (K <= 8) return launch_logloss_k<8, 4>(mode, a, grid_for((a.n + 3) / 4, kBlock, ctas_per_sm, sms), st);

@@ -37,6 +37,7 @@ struct GbmArgs {
   // squared-loss device-resident step: step = lr * clip(stats[1]/stats[2], 0, 100) when non-null
   const double* dev_stats = nullptr;
   float lr = 1.f;
+  int stages = 2;  // staged logloss kernel: shared-memory stages (1 or 2)
   RedWs ws{};
 };
 
@@ -44,6 +45,8 @@ struct GbmArgs {
 // logloss: [0]=Σloss, [1..K]=Σ h_j g_j  or Σhc_j
 cudaError_t launch_gbm(int loss, int mode, const GbmArgs& a, int ctas_per_sm, int sms,
                        cudaStream_t stream);
+// LogLoss(K) through shared-memory staging (TMA bulk copies, double buffered): wide K (se_gbm_staged.cu)
+cudaError_t launch_gbm_logloss_staged(int mode, const GbmArgs& a, int sms, cudaStream_t stream);
 // WOUT[j][i] *= 0.5/S_j was folded: scale rows of a [dim][n] array by per-row factors
 cudaError_t launch_scale_rows(float* a, int64_t n, int64_t ld, int dim, const float* factors,
                               int sms, cudaStream_t stream);

@@ -416,3 +416,40 @@ def test_multi_gpu_sharded_parity():
                           "--master-addr", "127.0.0.1", "--master-port", "29533",
                           os.path.join(root, "tests", "mgpu_check.py")], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and "MGPU_PARITY_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
+
+
+@pytest.mark.parametrize("K", [9, 26, 32])
+@pytest.mark.parametrize("n", [1, 127, 128, 129, 40961])
+def test_logloss_wide_k_staged_kernels(ctx, oracle, rng, K, n):
+    """LogLoss with K > 8 runs through the TMA/shared-memory staged kernels (se_gbm_staged.cu): every mode,
+    tile tails included."""
+    from spark_ensemble_b200 import _native as N
+    dim, par, y, F, h, w = setup_gbm(ctx, rng, "logloss", n, True, K=K)
+    lid = O.LOGLOSS
+    alpha = rng.random(K) * 2.0
+    lg, gg = ctx.gbm_linesearch_eval(alpha)
+    lo, go = oracle.linesearch_eval(lid, 0.0, y, w, F, h, alpha)
+    assert lg == pytest.approx(lo, rel=RTOL)
+    close(gg, go, rtol=RTOL, scale=float(np.max(np.abs(go))))
+    assert ctx.gbm_mean_loss(False) == pytest.approx(oracle.mean_loss(lid, 0.0, K, y, F), rel=RTOL)
+    S = ctx.gbm_pseudo_residuals(newton=True)
+    ro, woo, So = oracle.pseudo_residuals(lid, 0.0, K, y, w, F, True)
+    close(S, So, rtol=RTOL)
+    close(ctx.download(N.SLOT_R).reshape(K, n), ro, rtol=RTOL, scale=1.0)
+    close(ctx.download(N.SLOT_WOUT).reshape(K, n), woo, rtol=RTOL)
+    ctx.gbm_pseudo_residuals(newton=False)
+    rg, _, _ = oracle.pseudo_residuals(lid, 0.0, K, y, None, F, False)
+    close(ctx.download(N.SLOT_R).reshape(K, n), rg, rtol=RTOL, scale=1.0)
+    step = rng.random(K) * 0.5
+    for mode in ("residual", "newton", "plain"):
+        ls, S = ctx.gbm_update(step, residual=(mode == "residual"), newton=(mode == "newton"), loss=True)
+        Fo = F.astype(np.float64).copy() if mode == "residual" else Fo
+        oracle.update(Fo, h, step)
+        close(ctx.download(N.SLOT_F).reshape(K, n), Fo, rtol=RTOL, scale=1.0)
+        assert ls / n == pytest.approx(oracle.mean_loss(lid, 0.0, K, y, Fo), rel=RTOL, abs=1e-7)
+        if mode != "plain":
+            ro, woo, So = oracle.pseudo_residuals(lid, 0.0, K, y, w, Fo, mode == "newton")
+            close(ctx.download(N.SLOT_R).reshape(K, n), ro, rtol=RTOL, scale=1.0)
+            if mode == "newton":
+                close(S, So, rtol=RTOL)
+                close(ctx.download(N.SLOT_WOUT).reshape(K, n), woo, rtol=RTOL)
