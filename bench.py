@@ -38,6 +38,19 @@ BYTES_K1 = 20  # y,F,h read + F',r written, fp32
 BYTES_K2 = 12  # y,F,h read
 
 
+def _ncu_traffic(rows: int):
+    """DRAM bytes per K1 launch from the committed `ncu --set full` capture (profiles/), if it was taken at
+    this row count."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        d = json.load(open(p))
+        if int(d["rows"]) == int(rows):
+            return float(d["k1_dram_bytes_per_launch"])
+    except Exception:
+        pass
+    return None
+
+
 def _peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -335,6 +348,26 @@ def main():
                                     "rows_per_s_per_gpu": n / (kt["ms"] / kt["launches"] * 1e-3),
                                     "note": "on-device base-model predict over column-major X; reported separately"}
 
+        # e2e with the base model evaluated on device: only the tree (bytes) goes host->device per round
+        for _ in range(2):
+            ctx.tree_predict(tree, N.SLOT_H, 0)
+            a_, _, _ = ctx.gbm_linesearch_brent(0.0, 100.0, 1.0, tol, tol, max_iter)
+            ctx.gbm_update([lr * a_], residual=True, loss=True)
+            ctx.download(N.SLOT_R, out=r_host)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            ctx.tree_predict(tree, N.SLOT_H, 0)
+            a_, _, _ = ctx.gbm_linesearch_brent(0.0, 100.0, 1.0, tol, tol, max_iter)
+            ctx.gbm_update([lr * a_], residual=True, loss=True)
+            ctx.download(N.SLOT_R, out=r_host)
+        ctx.sync()
+        dt_ms = 1e3 * (time.perf_counter() - t0)
+        extras["e2e_device_tree"] = {"rows_per_s_per_gpu": n * e2e_steps / (dt_ms * 1e-3), "ms_per_step": dt_ms / e2e_steps,
+                                     "h2d_bytes_per_step": 20 * nn, "d2h_bytes_per_step": 4 * n + 32,
+                                     "note": "direction = depth-6 tree evaluated on device over the resident feature matrix; "
+                                             "pseudo-residuals still go device->host for the (host) base-learner fit"}
+
     if rank != 0:
         ctx.close()
         if dist is not None:
@@ -376,7 +409,7 @@ def main():
         "gpu_launches": int(launches),
         "roofline": {"kernel": "gbm_scalar_kernel<squared, UPDATE_RESID> (K1: F update + residual + loss)",
                      "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": peak_src, "bytes_per_row": BYTES_K1, "ms_per_launch": k1_ms,
+                     "traffic": _ncu_traffic(n), "peak_source": peak_src, "bytes_per_row": BYTES_K1, "ms_per_launch": k1_ms,
                      "launches_timed": k1["launches"]},
         "cpu_baseline": cpu,
         "extras": extras,

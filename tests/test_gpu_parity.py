@@ -453,3 +453,58 @@ def test_logloss_wide_k_staged_kernels(ctx, oracle, rng, K, n):
             if mode == "newton":
                 close(S, So, rtol=RTOL)
                 close(ctx.download(N.SLOT_WOUT).reshape(K, n), woo, rtol=RTOL)
+
+
+def test_abi_utilities(ctx, rng):
+    """Slots, uploads (fp32/fp64, logical offsets over padded rows), scaled download, copy, fill, timers,
+    launch counter, error paths: every remaining exported entry point is exercised."""
+    from spark_ensemble_b200 import _native as N
+    n, rows = 1003, 3
+    ctx.alloc(N.SLOT_P, rows, n)
+    r, c, ld = ctx.layout(N.SLOT_P)
+    assert (r, c) == (rows, n) and ld % 32 == 0 and ld >= n  # padded, 128-byte aligned rows
+    a = f32(rng.standard_normal((rows, n)))
+    ctx.upload(N.SLOT_P, a)
+    np.testing.assert_array_equal(ctx.download(N.SLOT_P), a)
+    # logical offsets crossing a row boundary
+    patch = f32(rng.standard_normal(50))
+    ctx.upload(N.SLOT_P, patch, offset=n - 20)
+    a.reshape(-1)[n - 20:n + 30] = patch
+    np.testing.assert_array_equal(ctx.download(N.SLOT_P), a)
+    np.testing.assert_array_equal(ctx.download(N.SLOT_P, count=100, offset=2 * n - 50), a.reshape(-1)[2 * n - 50:2 * n + 50])
+    # fp64 upload narrows on the host
+    d = rng.standard_normal(n)
+    ctx.alloc(N.SLOT_Y, n)
+    ctx.upload(N.SLOT_Y, d)
+    np.testing.assert_array_equal(ctx.download(N.SLOT_Y), d.astype(np.float32))
+    np.testing.assert_allclose(ctx.download(N.SLOT_Y, scale=0.25), d.astype(np.float32) * np.float32(0.25), rtol=1e-7)
+    ctx.alloc(N.SLOT_W, n)
+    ctx.copy_slot(N.SLOT_W, N.SLOT_Y)
+    np.testing.assert_array_equal(ctx.download(N.SLOT_W), d.astype(np.float32))
+    ctx.fill(N.SLOT_W, 2.5, 10, 5)
+    w = ctx.download(N.SLOT_W)
+    assert np.all(w[5:15] == 2.5) and w[4] == np.float32(d[4]) and w[15] == np.float32(d[15])
+    assert ctx.slot_sum(N.SLOT_W) == pytest.approx(float(np.sum(w.astype(np.float64))), rel=1e-12)
+    # timers and counters
+    before = ctx.launch_count
+    ctx.timer_start()
+    ctx.fill(N.SLOT_W, 1.0)
+    ms = ctx.timer_stop()
+    assert ms >= 0.0 and ctx.launch_count == before + 1
+    ctx.kernel_timing(True); ctx.kernel_times_reset()
+    ctx.slot_sum(N.SLOT_W)
+    ctx.kernel_timing(False)
+    assert ctx.comm_info() == (1, 0)
+    np.testing.assert_array_equal(ctx.allreduce_host([1.0, 2.0]), [1.0, 2.0])  # no communicator: identity
+    # error paths: bad slot, range outside slot, state errors -> exceptions, never a crash
+    with pytest.raises(ValueError):
+        ctx.alloc(99, 4)
+    with pytest.raises(ValueError):
+        ctx.upload(N.SLOT_W, np.zeros(n + 1, dtype=np.float32))
+    ctx.free(N.SLOT_VY)
+    with pytest.raises(N.NativeError):
+        ctx.download(N.SLOT_VY, count=1)
+    with pytest.raises(ValueError):
+        ctx.gbm_configure(10, 0, 3, "squared")  # scalar losses have dim 1
+    with pytest.raises(ValueError):
+        ctx.gbm_configure(10, 0, 64, "logloss")  # dim > 32
