@@ -202,6 +202,18 @@ SE_API int se_boost_real_update(se_ctx* ctx, double sum_w, double* est_err, doub
 SE_API int se_boost_discrete_error(se_ctx* ctx, double sum_w, double* est_err);
 SE_API int se_boost_discrete_update(se_ctx* ctx, double sum_w, double beta, double* new_sum);
 
+/* ---- BoostingRegressor (AdaBoost.R2) weight update: regression/BoostingRegressor.scala:205-263 (§8f-2) */
+enum se_r2_loss { SE_R2_EXPONENTIAL = 0, SE_R2_LINEAR = 1, SE_R2_SQUARED = 2 }; /* :97-106 */
+/* allocates Y, BW and PRED[n] */
+SE_API int se_boostreg_configure(se_ctx* ctx, int64_t n);
+/* maxError = max_i |y_i − pred_i| (:231-234), max-all-reduced across shards */
+SE_API int se_boostreg_max_error(se_ctx* ctx, double* max_error);
+/* estimatorError = Σ wₙ·loss(|y−pred| / maxError) (loss(|y−pred|) when maxError == 0), wₙ = BW/sum_w (:236-249) */
+SE_API int se_boostreg_error(se_ctx* ctx, double sum_w, int loss_type, double max_error, double* est_err);
+/* BW ← wₙ·β^(1−loss) (:256-260); new_sum = Σ BW (:263) */
+SE_API int se_boostreg_update(se_ctx* ctx, double sum_w, int loss_type, double max_error, double beta,
+                              double* new_sum);
+
 /* ---- ensemble Model.predict / predictRaw aggregation ------------------------ */
 enum se_agg_kind {
   SE_AGG_GBM_REGRESSOR = 0,      /* regression/GBMRegressor.scala:531-539   init + Σ a_m P[m]     */
@@ -210,7 +222,9 @@ enum se_agg_kind {
   SE_AGG_BAGGING_SOFT = 3,       /* classification/BaggingClassifier.scala:260-287 soft vote      */
   SE_AGG_BAGGING_HARD = 4,       /* ... hard vote: P holds predicted labels [M][n]                */
   SE_AGG_BOOSTING_REAL = 5,      /* classification/BoostingClassifier.scala:348-364               */
-  SE_AGG_BOOSTING_DISCRETE = 6   /* classification/BoostingClassifier.scala:366-382               */
+  SE_AGG_BOOSTING_DISCRETE = 6,  /* classification/BoostingClassifier.scala:366-382               */
+  SE_AGG_BOOSTING_REG_MEDIAN = 7, /* regression/BoostingRegressor.scala:333-337 + ensemble/Utils.scala:26-40 (weighted median) */
+  SE_AGG_BOOSTING_REG_MEAN = 8    /* regression/BoostingRegressor.scala:339-342  dot(p, w) / Σw    */
 };
 /* allocates P ([M][n] or [M][width][n]), RAW, PROB and LABEL for classifiers.
  * width: GBM classifier = dim; soft/real = num_classes; others 1. */

@@ -87,6 +87,13 @@ class Oracle:
         L.orc_agg_boosting_discrete.restype = None
         L.orc_agg_boosting_discrete.argtypes = [i32, i32, i64, _dp, _dp, _dp, _dp]
         L.orc_argmax.restype = None; L.orc_argmax.argtypes = [i32, i64, _dp, _dp]
+        L.orc_r2_max_error.restype = d; L.orc_r2_max_error.argtypes = [i64, _dp, _dp]
+        L.orc_r2_estimator_error.restype = d
+        L.orc_r2_estimator_error.argtypes = [i32, i64, _dp, _dp, _dp, d, d]
+        L.orc_r2_update.restype = None
+        L.orc_r2_update.argtypes = [i32, i64, _dp, _dp, _dp, d, d, d, _dp, _dp]
+        L.orc_agg_weighted_median.restype = None; L.orc_agg_weighted_median.argtypes = [i32, i64, _dp, _dp, _dp]
+        L.orc_agg_weighted_mean.restype = None; L.orc_agg_weighted_mean.argtypes = [i32, i64, _dp, _dp, _dp]
         L.orc_num_threads.restype = i32
         L.orc_set_num_threads.argtypes = [i32]
 
@@ -179,6 +186,40 @@ class Oracle:
         self.lib.orc_samme_update(n, _p(y), _p(w), sum_w, _p(pred), beta, _p(out),
                                   C.cast(C.byref(s), _dp))
         return out, s.value
+
+    # ---- BoostingRegressor (AdaBoost.R2)
+    R2_LOSS = {"exponential": 0, "linear": 1, "squared": 2}
+
+    def r2_max_error(self, y, pred):
+        y, pred = _f64(y), _f64(pred)
+        return self.lib.orc_r2_max_error(y.shape[0], _p(y), _p(pred))
+
+    def r2_estimator_error(self, loss_type, y, pred, w, sum_w, max_error):
+        y, pred, w = _f64(y), _f64(pred), _f64(w)
+        return self.lib.orc_r2_estimator_error(self.R2_LOSS[loss_type], y.shape[0], _p(y), _p(pred), _p(w),
+                                               sum_w, max_error)
+
+    def r2_update(self, loss_type, y, pred, w, sum_w, max_error, beta):
+        y, pred, w = _f64(y), _f64(pred), _f64(w)
+        out = np.zeros(y.shape[0])
+        s = C.c_double()
+        self.lib.orc_r2_update(self.R2_LOSS[loss_type], y.shape[0], _p(y), _p(pred), _p(w), sum_w, max_error,
+                               beta, _p(out), C.cast(C.byref(s), _dp))
+        return out, s.value
+
+    def agg_weighted_median(self, P, a):
+        P, a = _f64(P), _f64(a)
+        M, n = P.shape
+        out = np.zeros(n)
+        self.lib.orc_agg_weighted_median(M, n, _p(P), _p(a), _p(out))
+        return out
+
+    def agg_weighted_mean(self, P, a):
+        P, a = _f64(P), _f64(a)
+        M, n = P.shape
+        out = np.zeros(n)
+        self.lib.orc_agg_weighted_mean(M, n, _p(P), _p(a), _p(out))
+        return out
 
     # ---- aggregation
     def agg_weighted_sum(self, P, a, init):

@@ -640,6 +640,88 @@ void orc_agg_boosting_discrete(int M, int K, int64_t n, const double* votes, con
   }
 }
 
+/* ------------------------------------------------------------------ BoostingRegressor (AdaBoost.R2) */
+
+static inline double r2_loss(int loss_type, double e) {
+  /* regression/BoostingRegressor.scala:97-106 */
+  if (loss_type == 0) return 1.0 - exp(-e);
+  if (loss_type == 1) return e;
+  return pow(e, 2.0);
+}
+
+double orc_r2_max_error(int64_t n, const double* y, const double* pred) {
+  double m = -INFINITY;
+  for (int64_t i = 0; i < n; ++i) {
+    const double e = fabs(y[i] - pred[i]); /* :169 */
+    if (e > m) m = e;                      /* treeReduce(_ max _) :234 */
+  }
+  return m;
+}
+
+double orc_r2_estimator_error(int loss_type, int64_t n, const double* y, const double* pred,
+                              const double* w, double sum_w, double max_error) {
+  double acc = 0.0;
+#ifdef _OPENMP
+#pragma omp parallel for reduction(+ : acc) schedule(static)
+#endif
+  for (int64_t i = 0; i < n; ++i) {
+    const double e = fabs(y[i] - pred[i]);
+    const double l = (max_error == 0.0) ? r2_loss(loss_type, e) : r2_loss(loss_type, e / max_error); /* :236-242 */
+    acc += (w[i] / sum_w) * l;                                                                          /* :244-249 */
+  }
+  return acc;
+}
+
+void orc_r2_update(int loss_type, int64_t n, const double* y, const double* pred, const double* w,
+                   double sum_w, double max_error, double beta, double* w_out, double* new_sum) {
+  double ns = 0.0;
+#ifdef _OPENMP
+#pragma omp parallel for reduction(+ : ns) schedule(static)
+#endif
+  for (int64_t i = 0; i < n; ++i) {
+    const double e = fabs(y[i] - pred[i]);
+    const double l = (max_error == 0.0) ? r2_loss(loss_type, e) : r2_loss(loss_type, e / max_error);
+    const double wo = (w[i] / sum_w) * pow(beta, 1.0 - l); /* :256-260 */
+    w_out[i] = wo;
+    ns += wo;
+  }
+  *new_sum = ns;
+}
+
+void orc_agg_weighted_median(int M, int64_t n, const double* P, const double* a, double* out) {
+  /* ensemble/Utils.scala:26-40: stable sort by value, cumulative weights, first index with cusum >= half */
+  int* idx = (int*)malloc(sizeof(int) * (size_t)M);
+  for (int64_t i = 0; i < n; ++i) {
+    for (int m = 0; m < M; ++m) idx[m] = m;
+    for (int m = 1; m < M; ++m) { /* stable insertion sort */
+      const int v = idx[m];
+      int j = m - 1;
+      while (j >= 0 && P[(int64_t)idx[j] * n + i] > P[(int64_t)v * n + i]) { idx[j + 1] = idx[j]; --j; }
+      idx[j + 1] = v;
+    }
+    double total = 0.0;
+    for (int m = 0; m < M; ++m) total += a[idx[m]];
+    double cum = 0.0;
+    int pick = M - 1;
+    for (int m = 0; m < M; ++m) {
+      cum += a[idx[m]];
+      if (cum >= 0.5 * total) { pick = m; break; }
+    }
+    out[i] = P[(int64_t)idx[pick] * n + i];
+  }
+  free(idx);
+}
+
+void orc_agg_weighted_mean(int M, int64_t n, const double* P, const double* a, double* out) {
+  double sw = 0.0;
+  for (int m = 0; m < M; ++m) sw += a[m];
+  for (int64_t i = 0; i < n; ++i) {
+    double dot = 0.0;
+    for (int m = 0; m < M; ++m) dot += P[(int64_t)m * n + i] * a[m];
+    out[i] = dot / sw; /* BLAS.dot(...) / sumWeights :340-342 */
+  }
+}
+
 void orc_argmax(int C, int64_t n, const double* raw, double* pred) {
 #ifdef _OPENMP
 #pragma omp parallel for schedule(static)

@@ -108,6 +108,19 @@ void orc_agg_bagging_hard(int M, int K, int64_t n, const double* votes, double* 
 void orc_agg_boosting_real(int M, int K, int64_t n, const double* P, double* raw, double* prob);
 void orc_agg_boosting_discrete(int M, int K, int64_t n, const double* votes, const double* a,
                                double* raw, double* prob);
+/* ---- BoostingRegressor (AdaBoost.R2) regression/BoostingRegressor.scala:97-106,169-171,225-263 ----
+ * loss_type: 0 exponential (1 - exp(-e)), 1 linear (e), 2 squared (e^2). */
+double orc_r2_max_error(int64_t n, const double* y, const double* pred);                  /* :231-234 */
+/* losses_i = loss(err_i / maxError) (loss(err_i) when maxError == 0) ; returns Σ (w_i/sum_w)·loss_i :236-249 */
+double orc_r2_estimator_error(int loss_type, int64_t n, const double* y, const double* pred,
+                              const double* w, double sum_w, double max_error);
+/* w'_i = (w_i/sum_w)·beta^(1 - loss_i) :256-260 ; *new_sum = Σ w' :263 */
+void orc_r2_update(int loss_type, int64_t n, const double* y, const double* pred, const double* w,
+                   double sum_w, double max_error, double beta, double* w_out, double* new_sum);
+/* BoostingRegressionModel.predict :333-347 + ensemble/Utils.scala:26-40. P[M][n], a[M]. */
+void orc_agg_weighted_median(int M, int64_t n, const double* P, const double* a, double* out);
+void orc_agg_weighted_mean(int M, int64_t n, const double* P, const double* a, double* out);
+
 /* Spark ClassificationModel.raw2prediction = argmax (first maximum). raw[C][n] -> pred[n] */
 void orc_argmax(int C, int64_t n, const double* raw, double* pred);
 

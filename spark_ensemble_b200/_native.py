@@ -27,7 +27,8 @@ NUM_SLOTS = 18
 UPD_RESIDUAL, UPD_NEWTON, UPD_LOSS = 1, 2, 4
 # enum se_agg_kind
 (AGG_GBM_REGRESSOR, AGG_BAGGING_REGRESSOR, AGG_GBM_CLASSIFIER, AGG_BAGGING_SOFT, AGG_BAGGING_HARD,
- AGG_BOOSTING_REAL, AGG_BOOSTING_DISCRETE) = range(7)
+ AGG_BOOSTING_REAL, AGG_BOOSTING_DISCRETE, AGG_BOOSTING_REG_MEDIAN, AGG_BOOSTING_REG_MEAN) = range(9)
+R2_LOSS = {"exponential": 0, "linear": 1, "squared": 2}
 
 # enum se_kernel_family
 KERNEL_FAMILIES = ["sq_stats", "eval", "update", "resid", "mean_loss", "boost_real", "boost_err",
@@ -92,6 +93,10 @@ PROTOTYPES = {
     "se_boost_real_update": [_vp, _d, _dp, _dp],
     "se_boost_discrete_error": [_vp, _d, _dp],
     "se_boost_discrete_update": [_vp, _d, _d, _dp],
+    "se_boostreg_configure": [_vp, _i64],
+    "se_boostreg_max_error": [_vp, _dp],
+    "se_boostreg_error": [_vp, _d, _i32, _d, _dp],
+    "se_boostreg_update": [_vp, _d, _i32, _d, _d, _dp],
     "se_agg_configure": [_vp, _i32, _i32, _i32, _i32, _i32, _i64],
     "se_agg_run": [_vp, _dp, _dp],
     "se_tree_predict": [_vp, _i32, _i32, _ip, _fp, _ip, _ip, _fp, _ip, _i32, _i32, _i32],

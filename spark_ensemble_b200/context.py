@@ -252,6 +252,26 @@ class Context:
         self._ck(self._lib.se_boost_discrete_update(self._h, float(sum_w), float(beta), C.byref(s)))
         return s.value
 
+    # ---- BoostingRegressor (AdaBoost.R2)
+    def boostreg_configure(self, n: int):
+        self._ck(self._lib.se_boostreg_configure(self._h, n))
+
+    def boostreg_max_error(self) -> float:
+        v = C.c_double()
+        self._ck(self._lib.se_boostreg_max_error(self._h, C.byref(v)))
+        return v.value
+
+    def boostreg_error(self, sum_w: float, loss_type: str, max_error: float) -> float:
+        v = C.c_double()
+        self._ck(self._lib.se_boostreg_error(self._h, float(sum_w), N.R2_LOSS[loss_type], float(max_error), C.byref(v)))
+        return v.value
+
+    def boostreg_update(self, sum_w: float, loss_type: str, max_error: float, beta: float) -> float:
+        v = C.c_double()
+        self._ck(self._lib.se_boostreg_update(self._h, float(sum_w), N.R2_LOSS[loss_type], float(max_error),
+                                              float(beta), C.byref(v)))
+        return v.value
+
     # ---- aggregation
     def agg_configure(self, kind: int, num_models: int, num_classes: int, dim: int, loss, n: int):
         lid = N.LOSS[loss] if isinstance(loss, str) else int(loss)

@@ -116,6 +116,39 @@ __global__ void __launch_bounds__(kBlock) agg_votes_kernel(const float* __restri
   }
 }
 
+// Weighted median over M model outputs per row (ensemble/Utils.scala:26-40 via
+// regression/BoostingRegressor.scala:333-337): the smallest value v whose cumulative weight
+// W(v) = Σ_{p_i <= v} a_i reaches half of Σ a.  The tile [M][kWmRows] is staged in shared memory (coalesced
+// column loads); each thread scans its own row: O(M²) compares, exact tie semantics, no sort.
+constexpr int kWmRows = 128;
+__global__ void __launch_bounds__(kWmRows) agg_wmedian_kernel(const float* __restrict__ P, int64_t n, int64_t ld,
+                                                            int M, const double* __restrict__ a,
+                                                            float* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char wm_raw[];
+  double* s_a = reinterpret_cast<double*>(wm_raw);
+  float* s_p = reinterpret_cast<float*>(s_a + M);
+  double total = 0.0;
+  for (int m = threadIdx.x; m < M; m += kWmRows) s_a[m] = a[m];
+  __syncthreads();
+  for (int m = 0; m < M; ++m) total += s_a[m];
+  const double half = 0.5 * total;
+  for (int64_t r0 = (int64_t)blockIdx.x * kWmRows; r0 < n; r0 += (int64_t)gridDim.x * kWmRows) {
+    const int64_t row = r0 + threadIdx.x;
+    const bool in = row < n;
+    for (int m = 0; m < M; ++m) s_p[m * kWmRows + threadIdx.x] = in ? ld_stream1(P + (int64_t)m * ld + row) : 0.f;
+    // own column only: no synchronisation needed between fill and scan
+    float best = INFINITY;
+    for (int j = 0; j < M; ++j) {
+      const float v = s_p[j * kWmRows + threadIdx.x];
+      if (v >= best) continue;  // cannot improve the minimum
+      double W = 0.0;
+      for (int i = 0; i < M; ++i) W += (s_p[i * kWmRows + threadIdx.x] <= v) ? s_a[i] : 0.0;
+      if (W >= half) best = v;
+    }
+    if (in) out[row] = best;
+  }
+}
+
 // Stage 2: per-row epilogue on tmp[C][n] (in RAW) -> raw, prob, label.
 struct FinArgs {
   int kind, C, K, dim, loss, M;
@@ -218,6 +251,21 @@ cudaError_t launch_agg(const AggArgs& a, int ctas_per_sm, int sms, cudaStream_t 
       agg_sum_kernel<false><<<grid4, kBlock, 0, st>>>(a.P, a.n, a.ld, a.M, 1, nullptr, nullptr,
                                                        nullptr, (float)a.M, a.raw, a.ld_out);
       return cudaGetLastError();
+    case SE_AGG_BOOSTING_REG_MEAN:  // dot(predictions, weights) / Σ weights  (BoostingRegressor.scala:339-342)
+      agg_sum_kernel<false><<<grid4, kBlock, 0, st>>>(a.P, a.n, a.ld, a.M, 1, a.weights, nullptr,
+                                                       nullptr, a.sum_weights, a.raw, a.ld_out);
+      return cudaGetLastError();
+    case SE_AGG_BOOSTING_REG_MEDIAN: {
+      const size_t smem = (size_t)a.M * sizeof(double) + (size_t)a.M * kWmRows * sizeof(float);
+      if (smem > 200 * 1024) return cudaErrorInvalidValue;
+      if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(agg_wmedian_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+      }
+      const int grid = grid_rows(a.n, kWmRows, 8, sms);
+      agg_wmedian_kernel<<<grid, kWmRows, smem, st>>>(a.P, a.n, a.ld, a.M, a.weights64, a.raw);
+      return cudaGetLastError();
+    }
     case SE_AGG_GBM_CLASSIFIER:
       agg_sum_kernel<false><<<grid4, kBlock, 0, st>>>(a.P, a.n, a.ld, a.M, a.dim, a.weights, a.init,
                                                        nullptr, 0.f, a.raw, a.ld_out);

@@ -41,6 +41,7 @@ struct NcclApi {
 };
 constexpr int kNcclFloat64 = 8;  // ncclDouble
 constexpr int kNcclSum = 0;
+constexpr int kNcclMax = 2;
 
 NcclApi& nccl() {
   static NcclApi api;
@@ -126,6 +127,10 @@ struct se_ctx {
     int kind = 0, M = 0, K = 0, dim = 1, loss = 0, width = 1, C = 1;
     int64_t n = 0;
   } agg;
+  struct {
+    bool on = false;
+    int64_t n = 0;
+  } boostreg;
   nccl_comm_t comm = nullptr;
   int nranks = 1, rank = 0;
   std::string err;
@@ -239,18 +244,18 @@ RedWs red_ws(se_ctx* ctx, int out_offset = 0) {
 }
 
 // all-reduce d_scal[off..off+count) in-stream (no-op without communicator)
-int allreduce_dev(se_ctx* ctx, int off, int count) {
+int allreduce_dev(se_ctx* ctx, int off, int count, int op = kNcclSum) {
   if (!ctx->comm || ctx->nranks <= 1) return SE_OK;
   NcclApi& api = nccl();
-  int rc = api.AllReduce(ctx->d_scal + off, ctx->d_scal + off, (size_t)count, kNcclFloat64, kNcclSum,
+  int rc = api.AllReduce(ctx->d_scal + off, ctx->d_scal + off, (size_t)count, kNcclFloat64, op,
                          ctx->comm, ctx->stream);
   if (rc != 0) return fail(ctx, SE_ERR_NCCL, "ncclAllReduce: %s", api.GetErrorString(rc));
   return SE_OK;
 }
 
 // (all-reduce and) bring d_scal[off..off+count) to the host; synchronises the stream
-int fetch_scalars(se_ctx* ctx, int off, int count, double* out) {
-  SE_TRY(allreduce_dev(ctx, off, count));
+int fetch_scalars(se_ctx* ctx, int off, int count, double* out, int op = kNcclSum) {
+  SE_TRY(allreduce_dev(ctx, off, count, op));
   SE_CUDA(ctx, cudaMemcpyAsync(ctx->h_scal + off, ctx->d_scal + off, sizeof(double) * count,
                                cudaMemcpyDeviceToHost, ctx->stream));
   SE_TRY(end(ctx));
@@ -1131,17 +1136,80 @@ int se_boost_discrete_update(se_ctx* ctx, double sum_w, double beta, double* new
   return SE_OK;
 }
 
+// ---- BoostingRegressor (AdaBoost.R2) -----------------------------------------------------------
+int se_boostreg_configure(se_ctx* ctx, int64_t n) {
+  if (!ctx) return fail(nullptr, SE_ERR_ARG, "null context");
+  SE_REQUIRE(ctx, n >= 0, SE_ERR_ARG, "negative row count");
+  SE_CUDA(ctx, cudaSetDevice(ctx->device));
+  ctx->boostreg.on = true;
+  ctx->boostreg.n = n;
+  SE_TRY(slot_alloc2d(ctx, SE_SLOT_Y, 1, n));
+  SE_TRY(slot_alloc2d(ctx, SE_SLOT_BW, 1, n));
+  SE_TRY(slot_alloc2d(ctx, SE_SLOT_PRED, 1, n));
+  return SE_OK;
+}
+
+static BoostRegArgs boostreg_args(se_ctx* ctx, double sum_w, int loss_type, double max_error) {
+  BoostRegArgs a;
+  a.y = ctx->slot[SE_SLOT_Y].d;
+  a.pred = ctx->slot[SE_SLOT_PRED].d;
+  a.w = ctx->slot[SE_SLOT_BW].d;
+  a.n = ctx->boostreg.n;
+  a.loss_type = loss_type;
+  a.inv_sum_w = (float)(1.0 / sum_w);
+  a.inv_max_err = (max_error == 0.0) ? 1.0f : (float)(1.0 / max_error);
+  a.ws = red_ws(ctx);
+  return a;
+}
+
+int se_boostreg_max_error(se_ctx* ctx, double* max_error) {
+  if (!ctx || !max_error) return fail(ctx, SE_ERR_ARG, "null argument");
+  SE_REQUIRE(ctx, ctx->boostreg.on, SE_ERR_STATE, "se_boostreg_configure first");
+  SE_TRY(begin(ctx));
+  BoostRegArgs a = boostreg_args(ctx, 1.0, 0, 0.0);
+  SE_LAUNCH_T(ctx, SE_KF_OTHER, launch_boostreg_max(a, ctx->ctas_per_sm, ctx->sms, ctx->stream));
+  return fetch_scalars(ctx, 0, 1, max_error, kNcclMax);
+}
+
+int se_boostreg_error(se_ctx* ctx, double sum_w, int loss_type, double max_error, double* est_err) {
+  if (!ctx || !est_err) return fail(ctx, SE_ERR_ARG, "null argument");
+  SE_REQUIRE(ctx, ctx->boostreg.on, SE_ERR_STATE, "se_boostreg_configure first");
+  SE_REQUIRE(ctx, loss_type >= SE_R2_EXPONENTIAL && loss_type <= SE_R2_SQUARED, SE_ERR_ARG, "bad loss type %d", loss_type);
+  SE_TRY(begin(ctx));
+  BoostRegArgs a = boostreg_args(ctx, sum_w, loss_type, max_error);
+  SE_LAUNCH_T(ctx, SE_KF_BOOST_ERR, launch_boostreg_error(a, ctx->ctas_per_sm, ctx->sms, ctx->stream));
+  return fetch_scalars(ctx, 0, 1, est_err);
+}
+
+int se_boostreg_update(se_ctx* ctx, double sum_w, int loss_type, double max_error, double beta, double* new_sum) {
+  if (!ctx) return fail(nullptr, SE_ERR_ARG, "null context");
+  SE_REQUIRE(ctx, ctx->boostreg.on, SE_ERR_STATE, "se_boostreg_configure first");
+  SE_REQUIRE(ctx, loss_type >= SE_R2_EXPONENTIAL && loss_type <= SE_R2_SQUARED, SE_ERR_ARG, "bad loss type %d", loss_type);
+  SE_TRY(begin(ctx));
+  BoostRegArgs a = boostreg_args(ctx, sum_w, loss_type, max_error);
+  a.log2_beta = (float)log2(beta);
+  SE_LAUNCH_T(ctx, SE_KF_BOOST_UPD, launch_boostreg_update(a, ctx->ctas_per_sm, ctx->sms, ctx->stream));
+  double s = 0.0;
+  SE_TRY(fetch_scalars(ctx, 0, 1, &s));
+  if (new_sum) *new_sum = s;
+  return SE_OK;
+}
+
 // ---- Aggregation -------------------------------------------------------------------------------
 int se_agg_configure(se_ctx* ctx, int kind, int num_models, int num_classes, int dim, int loss, int64_t n) {
   if (!ctx) return fail(nullptr, SE_ERR_ARG, "null context");
-  SE_REQUIRE(ctx, kind >= SE_AGG_GBM_REGRESSOR && kind <= SE_AGG_BOOSTING_DISCRETE, SE_ERR_ARG, "bad kind %d", kind);
+  SE_REQUIRE(ctx, kind >= SE_AGG_GBM_REGRESSOR && kind <= SE_AGG_BOOSTING_REG_MEAN, SE_ERR_ARG, "bad kind %d", kind);
   SE_REQUIRE(ctx, num_models >= 0 && n >= 0, SE_ERR_ARG, "bad sizes");
   SE_CUDA(ctx, cudaSetDevice(ctx->device));
   auto& g = ctx->agg;
   g.on = true; g.kind = kind; g.M = num_models; g.K = num_classes; g.dim = dim; g.loss = loss; g.n = n;
   switch (kind) {
     case SE_AGG_GBM_REGRESSOR:
-    case SE_AGG_BAGGING_REGRESSOR: g.width = 1; g.C = 1; break;
+    case SE_AGG_BAGGING_REGRESSOR:
+    case SE_AGG_BOOSTING_REG_MEAN: g.width = 1; g.C = 1; break;
+    case SE_AGG_BOOSTING_REG_MEDIAN:
+      SE_REQUIRE(ctx, num_models >= 1 && num_models <= 256, SE_ERR_ARG, "weighted median supports 1..256 models (got %d)", num_models);
+      g.width = 1; g.C = 1; break;
     case SE_AGG_GBM_CLASSIFIER:
       SE_REQUIRE(ctx, dim >= 1 && num_classes >= 2, SE_ERR_ARG, "bad dim/numClasses");
       g.width = dim; g.C = (dim == 1 && num_classes == 2) ? 2 : dim; break;
@@ -1157,7 +1225,7 @@ int se_agg_configure(se_ctx* ctx, int kind, int num_models, int num_classes, int
   // P is allocated with rows >= 2 semantics (padded stride) so every model row is 128 B aligned
   SE_TRY(slot_alloc2d(ctx, SE_SLOT_P, prow, n));
   SE_TRY(slot_alloc2d(ctx, SE_SLOT_RAW, g.C, n));
-  if (kind >= SE_AGG_GBM_CLASSIFIER) {
+  if (kind >= SE_AGG_GBM_CLASSIFIER && kind <= SE_AGG_BOOSTING_DISCRETE) {
     SE_TRY(slot_alloc2d(ctx, SE_SLOT_PROB, g.C, n));
     SE_TRY(slot_alloc2d(ctx, SE_SLOT_LABEL, 1, n));
   }
@@ -1179,7 +1247,8 @@ int se_agg_run(se_ctx* ctx, const double* weights, const double* init) {
   // small operands: narrowed to fp32 and staged through pinned memory into d_small
   float* hs = reinterpret_cast<float*>(ctx->h_small);
   size_t used = 0;
-  const bool uses_w = (g.kind == SE_AGG_GBM_REGRESSOR || g.kind == SE_AGG_GBM_CLASSIFIER || g.kind == SE_AGG_BOOSTING_DISCRETE);
+  const bool uses_w = (g.kind == SE_AGG_GBM_REGRESSOR || g.kind == SE_AGG_GBM_CLASSIFIER || g.kind == SE_AGG_BOOSTING_DISCRETE ||
+                       g.kind == SE_AGG_BOOSTING_REG_MEAN || g.kind == SE_AGG_BOOSTING_REG_MEDIAN);
   const int nw = g.M * ((g.kind == SE_AGG_GBM_CLASSIFIER) ? g.dim : 1);
   SE_REQUIRE(ctx, (size_t)(nw + kMaxDim) * sizeof(float) * 2 <= (size_t)kSmallBytes, SE_ERR_ARG, "too many models");
   // the previous run may still be reading d_small/h_small
@@ -1198,9 +1267,17 @@ int se_agg_run(se_ctx* ctx, const double* weights, const double* init) {
     a.init = reinterpret_cast<const float*>(ctx->d_small) + off;
     used = off + g.dim;
   }
+  if (g.kind == SE_AGG_BOOSTING_REG_MEDIAN) {
+    // cumulative weights are compared in fp64 like the reference: ship the weights as doubles too
+    const size_t off = (used + 63) / 64 * 64;  // floats; keeps the doubles 8-byte aligned
+    double* hd = reinterpret_cast<double*>(hs + off);
+    for (int i = 0; i < g.M; ++i) hd[i] = weights[i];
+    a.weights64 = reinterpret_cast<const double*>(reinterpret_cast<const float*>(ctx->d_small) + off);
+    used = off + 2 * (size_t)g.M;
+  }
   if (used) SE_CUDA(ctx, cudaMemcpyAsync(ctx->d_small, hs, used * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
   SE_LAUNCH_T(ctx, SE_KF_AGG, launch_agg(a, 8, ctx->sms, ctx->stream));
-  if (g.kind >= SE_AGG_GBM_CLASSIFIER) ctx->launches++;  // finalize kernel
+  if (g.kind >= SE_AGG_GBM_CLASSIFIER && g.kind <= SE_AGG_BOOSTING_DISCRETE) ctx->launches++;  // finalize kernel
   return end(ctx);
 }
 

@@ -177,7 +177,76 @@ __global__ void __launch_bounds__(kBlock) sum_kernel(const float* x, int64_t n, 
   block_reduce_publish<1>(acc, ws);
 }
 
+// ---- AdaBoost.R2 -----------------------------------------------------------------------------------
+// loss(e) for e = |y - pred| / maxError in [0,1] (regression/BoostingRegressor.scala:97-106)
+__device__ __forceinline__ float r2_loss(int loss_type, float e) {
+  if (loss_type == 1) return e;
+  if (loss_type == 2) return e * e;
+  // 1 - exp(-e): series below 0.25 (no cancellation), SFU form above
+  const float ser = e * fmaf(e, fmaf(e, fmaf(e, fmaf(e, fmaf(e, -1.0f / 720.0f, 1.0f / 120.0f), -1.0f / 24.0f),
+                                              1.0f / 6.0f), -0.5f), 1.0f);
+  return (e < 0.25f) ? ser : 1.0f - exp_neg_fast(-e);
+}
+
+__global__ void __launch_bounds__(kBlock) boostreg_max_kernel(const BoostRegArgs a) {
+  float m = -INFINITY;
+  const int64_t n4 = a.n >> 2;
+  for (int64_t g = (int64_t)blockIdx.x * kBlock + threadIdx.x; g < n4; g += (int64_t)gridDim.x * kBlock) {
+    const float4 vy = ld_stream4(a.y + 4 * g), vp = ld_stream4(a.pred + 4 * g);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) m = fmaxf(m, fabsf(f4at(vy, e) - f4at(vp, e)));  // :169,231-234
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (a.n & 3)) {
+    const int64_t i = (n4 << 2) + threadIdx.x;
+    m = fmaxf(m, fabsf(a.y[i] - a.pred[i]));
+  }
+  block_max_publish((double)m, a.ws.partials, a.ws.counter, a.ws.out);
+}
+
+template <bool UPDATE>
+__global__ void __launch_bounds__(kBlock) boostreg_pass_kernel(const BoostRegArgs a) {
+  double acc[1] = {0.0};
+  const int64_t n4 = a.n >> 2;
+  auto one = [&](float y, float p, float w, float& wo) -> float {
+    const float l = r2_loss(a.loss_type, fabsf(y - p) * a.inv_max_err);  // :236-242
+    const float wn = w * a.inv_sum_w;
+    if (!UPDATE) return wn * l;                                            // :244-249
+    wo = wn * ex2_approx((1.0f - l) * a.log2_beta);                        // wₙ·β^(1-loss) :256-260
+    return wo;
+  };
+  for (int64_t g = (int64_t)blockIdx.x * kBlock + threadIdx.x; g < n4; g += (int64_t)gridDim.x * kBlock) {
+    const float4 vy = ld_stream4(a.y + 4 * g), vp = ld_stream4(a.pred + 4 * g);
+    const float4 vw = UPDATE ? ld_rw4(a.w + 4 * g) : ld_stream4(a.w + 4 * g);
+    float4 out;
+    float s4 = 0.f;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) s4 += one(f4at(vy, e), f4at(vp, e), f4at(vw, e), f4at(out, e));
+    if (UPDATE) st_stream4(a.w + 4 * g, out);
+    acc[0] += (double)s4;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (a.n & 3)) {
+    const int64_t i = (n4 << 2) + threadIdx.x;
+    float wo = 0.f;
+    acc[0] += (double)one(a.y[i], a.pred[i], a.w[i], wo);
+    if (UPDATE) a.w[i] = wo;
+  }
+  block_reduce_publish<1>(acc, a.ws);
+}
+
 }  // namespace
+
+cudaError_t launch_boostreg_max(const BoostRegArgs& a, int ctas_per_sm, int sms, cudaStream_t s) {
+  boostreg_max_kernel<<<grid_for(a.n >> 2, kBlock, ctas_per_sm, sms), kBlock, 0, s>>>(a);
+  return cudaGetLastError();
+}
+cudaError_t launch_boostreg_error(const BoostRegArgs& a, int ctas_per_sm, int sms, cudaStream_t s) {
+  boostreg_pass_kernel<false><<<grid_for(a.n >> 2, kBlock, ctas_per_sm, sms), kBlock, 0, s>>>(a);
+  return cudaGetLastError();
+}
+cudaError_t launch_boostreg_update(const BoostRegArgs& a, int ctas_per_sm, int sms, cudaStream_t s) {
+  boostreg_pass_kernel<true><<<grid_for(a.n >> 2, kBlock, ctas_per_sm, sms), kBlock, 0, s>>>(a);
+  return cudaGetLastError();
+}
 
 cudaError_t launch_boost_real(const BoostArgs& a, int ctas_per_sm, int sms, cudaStream_t s) {
   boost_real_kernel<<<grid_for(a.n >> 2, kBlock, ctas_per_sm, sms), kBlock, 0, s>>>(a);

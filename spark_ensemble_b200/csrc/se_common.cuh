@@ -60,6 +60,43 @@ __device__ __forceinline__ double warp_sum(double v) {
   for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
   return v;
 }
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) v = fmax(v, __shfl_down_sync(0xffffffffu, v, off));
+  return v;
+}
+// max-reduction twin of block_reduce_publish (one value): AdaBoost.R2's maxError
+__device__ __forceinline__ void block_max_publish(double v, double* partials, unsigned int* counter,
+                                                  double* out) {
+  __shared__ double smx[kBlock / 32];
+  __shared__ bool last;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  v = warp_max(v);
+  if (lane == 0) smx[warp] = v;
+  __syncthreads();
+  if (warp == 0) {
+    double m = (lane < kBlock / 32) ? smx[lane] : -INFINITY;
+    m = warp_max(m);
+    if (lane == 0) partials[blockIdx.x] = m;
+  }
+  if (threadIdx.x == 0) {
+    __threadfence();
+    last = (atomicInc(counter, gridDim.x - 1) == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  double m = -INFINITY;
+  for (unsigned int b = threadIdx.x; b < gridDim.x; b += kBlock) m = fmax(m, __ldcg(&partials[b]));
+  m = warp_max(m);
+  if (lane == 0) smx[warp] = m;
+  __syncthreads();
+  if (warp == 0) {
+    double t = (lane < kBlock / 32) ? smx[lane] : -INFINITY;
+    t = warp_max(t);
+    if (lane == 0) out[0] = t;
+  }
+}
 
 // Reduction workspace owned by the context: partials[kMaxGridPartials][nred], a self-resetting
 // ticket counter, and the output scalar block.

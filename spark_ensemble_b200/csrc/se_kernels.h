@@ -70,6 +70,21 @@ cudaError_t launch_boost_discrete_error(const BoostArgs& a, int ctas_per_sm, int
 cudaError_t launch_boost_discrete_update(const BoostArgs& a, int ctas_per_sm, int sms, cudaStream_t s); // out[0]=Σw'
 cudaError_t launch_sum(const float* x, int64_t n, const RedWs& ws, int ctas_per_sm, int sms,
                        cudaStream_t s);  // out[0]
+// AdaBoost.R2 (regression/BoostingRegressor.scala:225-263). loss_type 0 exponential, 1 linear, 2 squared.
+struct BoostRegArgs {
+  const float* y = nullptr;
+  const float* pred = nullptr;
+  float* w = nullptr;  // updated in place by the update kernel
+  int64_t n = 0;
+  int loss_type = 0;
+  float inv_sum_w = 1.f;
+  float inv_max_err = 1.f;  // 1/maxError, or 1 when maxError == 0 (:236-242)
+  float log2_beta = 0.f;
+  RedWs ws{};
+};
+cudaError_t launch_boostreg_max(const BoostRegArgs& a, int ctas_per_sm, int sms, cudaStream_t s);     // out[0] = max|y-pred|
+cudaError_t launch_boostreg_error(const BoostRegArgs& a, int ctas_per_sm, int sms, cudaStream_t s);   // out[0] = Σ wₙ·loss
+cudaError_t launch_boostreg_update(const BoostRegArgs& a, int ctas_per_sm, int sms, cudaStream_t s);  // out[0] = Σ w'
 
 // ---- Aggregation (se_agg.cu) -----------------------------------------------------------------
 struct AggArgs {
@@ -82,7 +97,8 @@ struct AggArgs {
   const float* init = nullptr;     // device [dim]
   int M = 0, K = 0, dim = 1, loss = 0;
   int64_t n = 0, ld = 0, ld_out = 0;
-  float sum_weights = 0.f;  // Σ a_m (boosting discrete epilogue)
+  float sum_weights = 0.f;  // Σ a_m (boosting discrete epilogue, boosting-regressor mean)
+  const double* weights64 = nullptr;  // device [M] fp64 (weighted median cumulative sums)
 };
 cudaError_t launch_agg(const AggArgs& a, int ctas_per_sm, int sms, cudaStream_t s);
 

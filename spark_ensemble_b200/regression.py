@@ -273,3 +273,94 @@ class BaggingRegressionModel(Params):
 
 
 BaggingRegressionModel._declare(_p + _ps + _pbag, _BAG_REG_DEFAULTS)
+
+
+# ---- BoostingRegressor (AdaBoost.R2, Drucker 1997): SURVEY.md §8f-2 -----------------------------------
+class BoostingRegressor(Params):
+    """regression/BoostingRegressor.scala:138-282.  Per round: maxError, estimatorError = Σ wₙ·loss, weight
+    update wₙ·β^(1-loss), Σw' — three streaming passes on the device instead of four RDD jobs."""
+
+    def __init__(self, uid: str | None = None, device: int = 0):
+        super().__init__(uid or random_uid("BoostingRegressor"))
+        self.device = device
+
+    def fit(self, dataset: DataFrame) -> "BoostingRegressionModel":
+        X, y, w = _extract_instances(self, dataset)
+        n = y.shape[0]
+        loss_type = self("lossType").lower()
+        learner = self("baseLearner")
+        models, est_weights, history = [], [], []
+        ctx = Context(self.device)
+        try:
+            ctx.boostreg_configure(n)
+            ctx.upload(N.SLOT_Y, y)
+            ctx.upload(N.SLOT_BW, np.ones(n) if w is None else w)  # :205
+            sum_w = ctx.slot_sum(N.SLOT_BW)                          # :212
+            i, best, done = 0, 0, False
+            while i < self("numBaseLearners") and not done and sum_w > 0:  # :218
+                wn = ctx.download(N.SLOT_BW, scale=1.0 / sum_w)     # :222-225
+                model = learner.fit(X, y, wn)                        # third party :231-233
+                ctx.upload(N.SLOT_PRED, model.predict(X))
+                max_error = ctx.boostreg_max_error()                 # :235-238
+                if max_error == 0:                                   # :240-243
+                    best, done = i, True
+                est_err = ctx.boostreg_error(sum_w, loss_type, max_error)  # :248-254
+                if est_err >= 0.5:                                   # :256
+                    best, done = i - 1, True
+                beta = est_err / (1 - est_err)
+                est_weight = 1.0 if beta == 0.0 else float(np.log(1.0 / beta))
+                sum_w = ctx.boostreg_update(sum_w, loss_type, max_error, beta) if beta > 0 else 0.0  # :261-268
+                est_weights.append(est_weight)
+                models.append(model)
+                history.append({"maxError": max_error, "estimatorError": est_err, "sumWeights": sum_w})
+                best = i
+                i += 1
+            best += 1
+            m = BoostingRegressionModel(est_weights[:best], models[:best], device=self.device)
+            self._copyValues(m)
+            m.parent = self
+            m.trainingHistory = history
+            return m
+        finally:
+            ctx.close()
+
+
+_pbr = [Param("lossType", "loss function, exponential by default (case-insensitive). Supported: exponential,squared,linear",
+              lambda v: v.lower() in ("exponential", "squared", "linear"), str),
+        Param("votingStrategy", "voting strategy, (case-insensitive). Supported options: median,mean",
+              lambda v: v.lower() in ("median", "mean"), str),
+        Param("seed", "random seed", convert=int)]
+_BOOST_REG_DEFAULTS = {**_d, **_db, "lossType": "exponential", "votingStrategy": "median",
+                       "seed": java_string_hash("org.apache.spark.ml.regression.BoostingRegressor")}
+BoostingRegressor._declare(_p + _pb + _pbr, _BOOST_REG_DEFAULTS)
+
+
+class BoostingRegressionModel(Params):
+    """regression/BoostingRegressor.scala:318-360: weighted median (ensemble/Utils.scala:26-40) or weighted
+    mean of the members' predictions."""
+
+    def __init__(self, weights, models, uid: str | None = None, device: int = 0):
+        super().__init__(uid or random_uid("BoostingRegressionModel"))
+        self.weights = np.asarray(weights, dtype=np.float64)
+        self.models = list(models)
+        self.numModels = len(self.models)
+        self.device = device
+        self.parent = None
+
+    def _aggregate(self, X) -> np.ndarray:
+        P = np.ascontiguousarray(np.stack([m.predict(X) for m in self.models]), dtype=np.float32)
+        kind = N.AGG_BOOSTING_REG_MEDIAN if self("votingStrategy").lower() == "median" else N.AGG_BOOSTING_REG_MEAN
+        with Context(self.device) as ctx:
+            ctx.agg_configure(kind, P.shape[0], 0, 1, 0, X.shape[0])
+            ctx.upload(N.SLOT_P, P)
+            ctx.agg_run(self.weights)
+            return ctx.download(N.SLOT_RAW).astype(np.float64)
+
+    def transform(self, dataset: DataFrame) -> DataFrame:
+        return dataset.withColumn(self("predictionCol"), self._aggregate(np.asarray(dataset[self("featuresCol")])))
+
+    def predict(self, features) -> float:
+        return float(self._aggregate(np.asarray(features).reshape(1, -1))[0])
+
+
+BoostingRegressionModel._declare(_p + _pb + _pbr, _BOOST_REG_DEFAULTS)

@@ -248,3 +248,37 @@ def test_bagging_models_aggregate_members():
             P = np.stack([mm.predictProbability(Xl[:, s]) for mm, s in zip(mc.models, mc.subspaces)])
             np.testing.assert_allclose(out["rawPrediction"], P.sum(axis=0), rtol=RTOL, atol=1e-6)
         assert np.mean(out["prediction"] == yl) > 0.4
+
+
+@pytest.mark.parametrize("loss_type,voting", [("exponential", "median"), ("linear", "mean"), ("squared", "median")])
+def test_boosting_regressor_adaboost_r2(oracle, loss_type, voting):
+    """BoostingRegressorSuite.scala:51-132: beats a single tree; weight recursion replayed through the oracle."""
+    from spark_ensemble_b200 import DataFrame
+    from spark_ensemble_b200.learners import DecisionTreeRegressor
+    from spark_ensemble_b200.regression import BoostingRegressor
+    X, y = _cpusmall()
+    br = (BoostingRegressor().setBaseLearner(DecisionTreeRegressor(maxDepth=5)).setNumBaseLearners(8)
+          .setLossType(loss_type).setVotingStrategy(voting))
+    assert br.uid.startswith("BoostingRegressor_")
+    model = br.fit(DataFrame(features=X, label=y))
+    assert model.uid.startswith("BoostingRegressionModel_") and 1 <= model.numModels <= 8
+    w = np.ones(len(y))
+    sw = float(len(y))
+    for t, m in enumerate(model.models):
+        pred = m.predict(X).astype(np.float32).astype(np.float64)
+        mx = oracle.r2_max_error(y.astype(np.float32).astype(np.float64), pred)
+        e = oracle.r2_estimator_error(loss_type, y, pred, w, sw, mx)
+        h = model.trainingHistory[t]
+        assert h["maxError"] == pytest.approx(mx, rel=1e-6)
+        assert h["estimatorError"] == pytest.approx(e, rel=1e-4)
+        beta = e / (1 - e)
+        assert model.weights[t] == pytest.approx(np.log(1 / beta), rel=1e-3)
+        w, sw = oracle.r2_update(loss_type, y, pred, w, sw, mx, beta)
+        assert h["sumWeights"] == pytest.approx(sw, rel=1e-4)
+    pred = model.transform(DataFrame(features=X))["prediction"]
+    P = np.stack([m.predict(X).astype(np.float32) for m in model.models])
+    ref = (oracle.agg_weighted_median(P, model.weights) if voting == "median"
+           else oracle.agg_weighted_mean(P, model.weights))
+    np.testing.assert_allclose(pred, ref, rtol=1e-5, atol=1e-5 * np.abs(ref).mean())
+    rmse = lambda p: float(np.sqrt(np.mean((p - y) ** 2)))
+    assert rmse(pred) < rmse(DecisionTreeRegressor(maxDepth=5).fit(X, y).predict(X)) * 1.05

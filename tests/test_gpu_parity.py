@@ -508,3 +508,46 @@ def test_abi_utilities(ctx, rng):
         ctx.gbm_configure(10, 0, 3, "squared")  # scalar losses have dim 1
     with pytest.raises(ValueError):
         ctx.gbm_configure(10, 0, 64, "logloss")  # dim > 32
+
+
+@pytest.mark.parametrize("loss_type", ["exponential", "linear", "squared"])
+@pytest.mark.parametrize("n", [3, 4097, 60001])
+def test_adaboost_r2_kernels(ctx, oracle, rng, loss_type, n):
+    """BoostingRegressor (AdaBoost.R2) weight recursion, SURVEY.md §8f-2."""
+    from spark_ensemble_b200 import _native as N
+    y = f32(rng.standard_normal(n))
+    pred = f32(y + 0.4 * rng.standard_normal(n))
+    w = f32(rng.random(n) + 0.1)
+    ctx.boostreg_configure(n)
+    ctx.upload(N.SLOT_Y, y); ctx.upload(N.SLOT_PRED, pred); ctx.upload(N.SLOT_BW, w)
+    sw = ctx.slot_sum(N.SLOT_BW)
+    mx = ctx.boostreg_max_error()
+    assert mx == pytest.approx(oracle.r2_max_error(y, pred), rel=1e-6)  # fp32 subtraction rounds once
+    e = ctx.boostreg_error(sw, loss_type, mx)
+    eo = oracle.r2_estimator_error(loss_type, y, pred, w, sw, mx)
+    assert e == pytest.approx(eo, rel=RTOL)
+    beta = eo / (1 - eo)
+    s = ctx.boostreg_update(sw, loss_type, mx, beta)
+    out, so = oracle.r2_update(loss_type, y, pred, w, sw, mx, beta)
+    assert s == pytest.approx(so, rel=RTOL)
+    close(ctx.download(N.SLOT_BW), out, rtol=RTOL, scale=float(np.min(out)))
+    # maxError == 0 branch: losses are loss(err) (all zero) and every weight is multiplied by beta
+    ctx.upload(N.SLOT_PRED, y); ctx.upload(N.SLOT_BW, w)
+    assert ctx.boostreg_max_error() == 0.0
+    assert ctx.boostreg_error(sw, loss_type, 0.0) == 0.0
+
+
+@pytest.mark.parametrize("M,n", [(1, 5), (10, 4099), (64, 1001), (200, 300)])
+def test_agg_boosting_regressor(ctx, oracle, rng, M, n):
+    from spark_ensemble_b200 import _native as N
+    P = f32(rng.standard_normal((M, n)))
+    P[:, : n // 3] = np.round(P[:, : n // 3], 1)  # ties between members
+    a = rng.random(M) + 0.05
+    ctx.agg_configure(N.AGG_BOOSTING_REG_MEDIAN, M, 0, 1, 0, n)
+    ctx.upload(N.SLOT_P, P)
+    ctx.agg_run(a)
+    np.testing.assert_array_equal(ctx.download(N.SLOT_RAW), oracle.agg_weighted_median(P, a).astype(np.float32))
+    ctx.agg_configure(N.AGG_BOOSTING_REG_MEAN, M, 0, 1, 0, n)
+    ctx.upload(N.SLOT_P, P)
+    ctx.agg_run(a)
+    close(ctx.download(N.SLOT_RAW), oracle.agg_weighted_mean(P, a.astype(np.float32).astype(np.float64)), scale=0.1)

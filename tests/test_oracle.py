@@ -248,3 +248,34 @@ def test_openmp_build_agrees(rng):
     b, gb = o2.linesearch_eval(O.LOGCOSH, 0.0, y, None, F, h, [0.7])
     assert a == pytest.approx(b, rel=1e-12) and ga[0] == pytest.approx(gb[0], rel=1e-11)
     assert o2.num_threads() >= 1
+
+
+def test_weighted_median_properties(oracle, rng):
+    """test/ensemble/UtilsSuite.scala:29-67: weighted median == median under uniform weights; 0/1 weights
+    select among the kept values; scaling the weights changes nothing."""
+    M, n = 9, 200
+    P = rng.standard_normal((M, n))
+    np.testing.assert_array_equal(oracle.agg_weighted_median(P, np.ones(M)), np.sort(P, axis=0)[(M - 1) // 2])
+    keep = np.array([1, 0, 1, 1, 0, 0, 1, 1, 0], dtype=float)
+    med = oracle.agg_weighted_median(P, keep)
+    sub = np.sort(P[keep > 0], axis=0)
+    np.testing.assert_array_equal(med, sub[(int(keep.sum()) - 1) // 2])
+    a = rng.random(M) + 0.1
+    np.testing.assert_array_equal(oracle.agg_weighted_median(P, a), oracle.agg_weighted_median(P, 7.5 * a))
+    np.testing.assert_allclose(oracle.agg_weighted_mean(P, a), (a[:, None] * P).sum(0) / a.sum(), rtol=1e-13)
+
+
+def test_adaboost_r2_oracle(oracle, rng):
+    n = 1000
+    y = rng.standard_normal(n); pred = y + 0.3 * rng.standard_normal(n); w = rng.random(n) + 0.1
+    sw = w.sum()
+    mx = oracle.r2_max_error(y, pred)
+    assert mx == np.max(np.abs(y - pred))
+    for lt, f in (("linear", lambda e: e), ("squared", lambda e: e ** 2), ("exponential", lambda e: 1 - np.exp(-e))):
+        e = oracle.r2_estimator_error(lt, y, pred, w, sw, mx)
+        L = f(np.abs(y - pred) / mx)
+        assert e == pytest.approx(np.sum(w / sw * L), rel=1e-12)
+        beta = e / (1 - e)
+        out, s = oracle.r2_update(lt, y, pred, w, sw, mx, beta)
+        np.testing.assert_allclose(out, w / sw * beta ** (1 - L), rtol=1e-12)
+        assert s == pytest.approx(out.sum(), rel=1e-12)
