@@ -81,7 +81,8 @@ enum se_slot {
   SE_SLOT_LABEL = 15, /* [n]        prediction column of classifiers (argmax raw)              */
   SE_SLOT_X = 16,     /* [d][n]     feature matrix, column-major (on-device base-model predict) */
   SE_SLOT_VX = 17,    /* [d][nv]    validation feature matrix                                   */
-  SE_NUM_SLOTS = 18
+  SE_SLOT_BAG = 18,   /* [n]        bag multiplicities of RDD.sample (0/1 without, Poisson counts with replacement) */
+  SE_NUM_SLOTS = 19
 };
 
 /* ---- library / context ---------------------------------------------------------------------- */
@@ -145,6 +146,11 @@ SE_API int se_copy_slot(se_ctx* ctx, int dst_slot, int src_slot);
  * 2 integer uniform in [a,b) stored as float, 3 bernoulli(p=a) 0/1 */
 SE_API int se_fill_synthetic(se_ctx* ctx, int slot, int kind, uint64_t seed, double a, double b,
                       int64_t count, int64_t offset);
+/* Exact q-quantile (the ceil(q·N)-th smallest of the GLOBAL N values, i.e. what Spark's approxQuantile
+ * returns as relativeError -> 0) by 4 radix-select passes over the fp32 keys; histograms are all-reduced.
+ * which = 0: values of `slot`; which = 1: |Y − F| on the train shard (huber δ, regression/GBMRegressor.scala:
+ * 342-353).  Used for DummyRegressor median/quantile inits (:119-125) and huber's δ (:305-308). SURVEY §8f-3 */
+SE_API int se_quantile(se_ctx* ctx, int which, int slot, int64_t count, double q, double* out);
 /* Σ slot[0..count) in fp64, all-reduced (BoostingClassifier.scala:175,269 sumWeights) */
 SE_API int se_slot_sum(se_ctx* ctx, int slot, int64_t count, double* out);
 
@@ -154,6 +160,12 @@ SE_API int se_slot_sum(se_ctx* ctx, int slot, int64_t count, double* out);
 SE_API int se_gbm_configure(se_ctx* ctx, int64_t n_train, int64_t n_valid, int dim, int loss,
                      double param, int has_weights);
 SE_API int se_gbm_set_loss_param(se_ctx* ctx, double param); /* huber: delta re-estimated each round (:342-353) */
+/* Row sub-sampling (regression/GBMRegressor.scala:357-359, classification/GBMClassifier.scala:329-331):
+ * on != 0 allocates SE_SLOT_BAG[n]; the host uploads the multiplicity of every train row in the bag (the
+ * sample itself is Spark's RDD.sample — same seed every round, reference quirk 3).  While enabled, the
+ * line-search sums (eval / stats: lossSum, weightSum, gradSum) and newton's Σ max(H,1e-2) run over the bag;
+ * the F update, the fused residuals and the train loss stay on the full train set (reference quirk 4). */
+SE_API int se_gbm_set_bag(se_ctx* ctx, int on);
 /* pseudo-residuals from the current F (GBMRegressor.scala:368-385, GBMClassifier.scala:337-375).
  * newton=0: R=-g (base-learner weight stays the instance weight W).  newton=1 (loss has a hessian):
  * h=max(H,1e-2), S=Σh (all-reduced), R=-g/h, WOUT=1/2·h/S·w; sum_hess[dim] receives S. */

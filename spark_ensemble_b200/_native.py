@@ -21,8 +21,8 @@ LOSS = {"squared": 0, "absolute": 1, "huber": 2, "quantile": 3, "logcosh": 4, "s
         "bernoulli": 6, "exponential": 7, "logloss": 8}
 # enum se_slot
 (SLOT_Y, SLOT_W, SLOT_F, SLOT_H, SLOT_R, SLOT_WOUT, SLOT_VY, SLOT_VF, SLOT_VH, SLOT_BW, SLOT_PROBA,
- SLOT_PRED, SLOT_P, SLOT_RAW, SLOT_PROB, SLOT_LABEL, SLOT_X, SLOT_VX) = range(18)
-NUM_SLOTS = 18
+ SLOT_PRED, SLOT_P, SLOT_RAW, SLOT_PROB, SLOT_LABEL, SLOT_X, SLOT_VX, SLOT_BAG) = range(19)
+NUM_SLOTS = 19
 # se_gbm_update flags
 UPD_RESIDUAL, UPD_NEWTON, UPD_LOSS = 1, 2, 4
 # enum se_agg_kind
@@ -77,8 +77,10 @@ PROTOTYPES = {
     "se_copy_slot": [_vp, _i32, _i32],
     "se_fill_synthetic": [_vp, _i32, _i32, _u64, _d, _d, _i64, _i64],
     "se_slot_sum": [_vp, _i32, _i64, _dp],
+    "se_quantile": [_vp, _i32, _i32, _i64, _d, _dp],
     "se_gbm_configure": [_vp, _i64, _i64, _i32, _i32, _d, _i32],
     "se_gbm_set_loss_param": [_vp, _d],
+    "se_gbm_set_bag": [_vp, _i32],
     "se_gbm_pseudo_residuals": [_vp, _i32, _dp],
     "se_gbm_linesearch_eval": [_vp, _dp, _dp, _dp],
     "se_gbm_linesearch_stats": [_vp, _dp],

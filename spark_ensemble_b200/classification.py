@@ -16,7 +16,7 @@ from .ensemble import DataFrame, fit_dummy_classifier, java_string_hash, subspac
 from .gbm_engine import GBMEngine
 from .params import (Param, Params, ParamValidators, boosting_params, gbm_params, random_uid,
                      shared_classifier_params, shared_predictor_params, subbag_params)
-from .regression import _extract_instances, _split_validation
+from .regression import _extract_instances, _split_validation, bag_counts
 
 _CLS_LOSSES = ("logloss", "exponential", "bernoulli")  # GBMClassifier.scala:102-103
 _CLS_INIT = ("uniform", "prior")                        # :104-106
@@ -97,11 +97,10 @@ class GBMClassifier(Params):
         dim = num_classes if loss == "logloss" else 1  # GBMLoss.scala:198,270,295
         if dim == 1 and num_classes != 2:
             raise ValueError(f"loss {loss} is binary; got numClasses={num_classes}")
-        if self("subsampleRatio") != 1.0 or self("replacement"):
-            raise NotImplementedError("row sub-sampling (subsampleRatio < 1 or replacement) needs Spark's RDD.sample")
         learner = self("baseLearner")
         num_learners = self("numBaseLearners")
         seed = self("seed")
+        counts = bag_counts(n, self("subsampleRatio"), self("replacement"), seed)  # :329-331
         subspaces = [subspace(self("subspaceRatio"), num_features, seed + i) for i in range(num_learners)]
         newton = self("updates").lower() == "newton"  # every classification loss HasHessian (:338)
 
@@ -122,6 +121,9 @@ class GBMClassifier(Params):
             eng.load(y, w, init_raw, yv, init_raw if with_validation else None)
             if bool(self("residentFeatures")):
                 eng.load_features(X, Xv)
+            if counts is not None:
+                ctx.gbm_set_bag(counts)
+                in_bag = counts > 0
             best = ctx.gbm_mean_loss(validation=True) if with_validation else 0.0  # :315-320
             models, weights, history = [], [], []
             eng.residuals(newton)
@@ -132,7 +134,11 @@ class GBMClassifier(Params):
                 imodels = []
                 for j in range(dim):  # one regressor per dimension (:377-411; Futures in the reference)
                     fit_w = wout[j] if newton else w
-                    imodels.append(learner.fit(X[:, sub], r[j], fit_w))
+                    if counts is None:
+                        imodels.append(learner.fit(X[:, sub], r[j], fit_w))
+                    else:
+                        bw = counts[in_bag] if fit_w is None else counts[in_bag] * fit_w[in_bag]
+                        imodels.append(learner.fit(X[in_bag][:, sub], r[j][in_bag], bw))
                 for j in range(dim):
                     eng.set_direction_from_model(j, imodels[j], sub, X)
                 if self("optimizedWeights"):  # :413-431

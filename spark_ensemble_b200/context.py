@@ -171,6 +171,20 @@ class Context:
         self._ck(self._lib.se_slot_sum(self._h, slot, count, C.byref(v)))
         return v.value
 
+    def quantile(self, slot: int, q: float, count: int | None = None) -> float:
+        """Exact q-quantile (ceil(q·N)-th smallest, global) of a [n] slot."""
+        if count is None:
+            _, count, _ = self.layout(slot)
+        v = C.c_double()
+        self._ck(self._lib.se_quantile(self._h, 0, slot, count, float(q), C.byref(v)))
+        return v.value
+
+    def gbm_abs_residual_quantile(self, q: float) -> float:
+        """Exact q-quantile of |y − F| over the train rows (huber δ)."""
+        v = C.c_double()
+        self._ck(self._lib.se_quantile(self._h, 1, 0, 0, float(q), C.byref(v)))
+        return v.value
+
     # ---- GBM
     def gbm_configure(self, n_train: int, n_valid: int, dim: int, loss, param: float = 0.0,
                       has_weights: bool = False):
@@ -181,6 +195,14 @@ class Context:
 
     def gbm_set_loss_param(self, param: float):
         self._ck(self._lib.se_gbm_set_loss_param(self._h, float(param)))
+
+    def gbm_set_bag(self, counts):
+        """Upload bag multiplicities (row sub-sampling); None disables."""
+        if counts is None:
+            self._ck(self._lib.se_gbm_set_bag(self._h, 0))
+            return
+        self._ck(self._lib.se_gbm_set_bag(self._h, 1))
+        self.upload(N.SLOT_BAG, np.ascontiguousarray(counts, dtype=np.float32))
 
     def gbm_pseudo_residuals(self, newton: bool = False):
         sh = np.zeros(max(self.dim, 1))

@@ -74,7 +74,8 @@ NcclApi& nccl() {
 
 thread_local std::string g_last_error;
 
-constexpr int kScal = 128;          // doubles in the device/host scalar blocks
+constexpr int kScal = 512;          // doubles in the device/host scalar blocks
+constexpr int kScalHist = 192;      // 256-bin radix-select histogram
 constexpr int kScalRound = 64;      // offset of the async squared-round results
 constexpr int kScalHost = 96;       // offset used by se_comm_allreduce_host
 constexpr int kSmallBytes = 1 << 20;  // small device scratch: weights, init, tree arrays, factors
@@ -111,6 +112,7 @@ struct se_ctx {
     int dim = 1, loss = 0;
     double param = 0.0;
     bool has_w = false;
+    bool use_bag = false;
     double wsum = 0.0;
     bool wsum_valid = false;
     double n_global = 0.0, nv_global = 0.0;
@@ -332,7 +334,15 @@ int ensure_counts(se_ctx* ctx) {
 int ensure_wsum(se_ctx* ctx) {
   if (ctx->gbm.wsum_valid) return SE_OK;
   SE_TRY(ensure_counts(ctx));
-  if (!ctx->gbm.has_w) {
+  if (ctx->gbm.use_bag) {
+    // weightSum over the bag: Σ c_i·w_i (GBMLoss.scala:65 adds instance.weight once per sampled copy)
+    SE_TRY(need_slot(ctx, SE_SLOT_BAG, 1, ctx->gbm.n, "bag multiplicities"));
+    SE_LAUNCH(ctx, launch_dot(ctx->slot[SE_SLOT_BAG].d, ctx->gbm.has_w ? ctx->slot[SE_SLOT_W].d : nullptr,
+                              ctx->gbm.n, red_ws(ctx), ctx->ctas_per_sm, ctx->sms, ctx->stream));
+    double s = 0.0;
+    SE_TRY(fetch_scalars(ctx, 0, 1, &s));
+    ctx->gbm.wsum = s;
+  } else if (!ctx->gbm.has_w) {
     ctx->gbm.wsum = ctx->gbm.n_global;
   } else {
     SE_TRY(need_slot(ctx, SE_SLOT_W, 1, ctx->gbm.n, "instance weights"));
@@ -353,6 +363,7 @@ GbmArgs gbm_args(se_ctx* ctx, bool validation) {
   a.F = ctx->slot[validation ? SE_SLOT_VF : SE_SLOT_F].d;
   a.h = ctx->slot[validation ? SE_SLOT_VH : SE_SLOT_H].d;
   a.w = (!validation && g.has_w) ? ctx->slot[SE_SLOT_W].d : nullptr;
+  a.bag = (!validation && g.use_bag) ? ctx->slot[SE_SLOT_BAG].d : nullptr;
   a.r = validation ? nullptr : ctx->slot[SE_SLOT_R].d;
   a.wout = validation ? nullptr : ctx->slot[SE_SLOT_WOUT].d;
   a.n = validation ? g.nv : g.n;
@@ -755,7 +766,7 @@ int se_upload(se_ctx* ctx, int slot, const float* host, int64_t count, int64_t o
   if (!ctx || !host) return fail(ctx, SE_ERR_ARG, "null argument");
   SE_REQUIRE(ctx, slot >= 0 && slot < SE_NUM_SLOTS, SE_ERR_ARG, "bad slot %d", slot);
   SE_CUDA(ctx, cudaSetDevice(ctx->device));
-  if (slot == SE_SLOT_W) ctx->gbm.wsum_valid = false;
+  if (slot == SE_SLOT_W || slot == SE_SLOT_BAG) ctx->gbm.wsum_valid = false;
   SE_TRY(for_segments(ctx, ctx->slot[slot], count, offset, [&](float* d, int64_t done, int64_t len) {
     SE_CUDA(ctx, cudaMemcpyAsync(d, host + done, sizeof(float) * len, cudaMemcpyHostToDevice, ctx->stream));
     return SE_OK;
@@ -769,7 +780,7 @@ int se_upload_f64(se_ctx* ctx, int slot, const double* host, int64_t count, int6
   if (!ctx || !host) return fail(ctx, SE_ERR_ARG, "null argument");
   SE_REQUIRE(ctx, slot >= 0 && slot < SE_NUM_SLOTS, SE_ERR_ARG, "bad slot %d", slot);
   SE_CUDA(ctx, cudaSetDevice(ctx->device));
-  if (slot == SE_SLOT_W) ctx->gbm.wsum_valid = false;
+  if (slot == SE_SLOT_W || slot == SE_SLOT_BAG) ctx->gbm.wsum_valid = false;
   // narrow on the host (halves PCIe bytes) through pinned staging, in chunks
   const int64_t chunk = 1 << 22;
   SE_TRY(ensure_stage(ctx, sizeof(float) * (size_t)chunk));
@@ -809,7 +820,7 @@ int se_fill(se_ctx* ctx, int slot, float value, int64_t count, int64_t offset) {
   if (!ctx) return fail(nullptr, SE_ERR_ARG, "null context");
   SE_REQUIRE(ctx, slot >= 0 && slot < SE_NUM_SLOTS, SE_ERR_ARG, "bad slot %d", slot);
   SE_CUDA(ctx, cudaSetDevice(ctx->device));
-  if (slot == SE_SLOT_W) ctx->gbm.wsum_valid = false;
+  if (slot == SE_SLOT_W || slot == SE_SLOT_BAG) ctx->gbm.wsum_valid = false;
   return for_segments(ctx, ctx->slot[slot], count, offset, [&](float* d, int64_t, int64_t len) {
     SE_LAUNCH(ctx, launch_fill(d, value, len, ctx->sms, ctx->stream));
     return SE_OK;
@@ -833,7 +844,7 @@ int se_fill_synthetic(se_ctx* ctx, int slot, int kind, uint64_t seed, double a, 
   SE_REQUIRE(ctx, slot >= 0 && slot < SE_NUM_SLOTS, SE_ERR_ARG, "bad slot %d", slot);
   SE_REQUIRE(ctx, kind >= 0 && kind <= 3, SE_ERR_ARG, "bad synthetic kind %d", kind);
   SE_CUDA(ctx, cudaSetDevice(ctx->device));
-  if (slot == SE_SLOT_W) ctx->gbm.wsum_valid = false;
+  if (slot == SE_SLOT_W || slot == SE_SLOT_BAG) ctx->gbm.wsum_valid = false;
   return for_segments(ctx, ctx->slot[slot], count, offset, [&](float* d, int64_t done, int64_t len) {
     SE_LAUNCH(ctx, launch_fill_synthetic(d, kind, seed, a, b, len, offset + done, ctx->sms, ctx->stream));
     return SE_OK;
@@ -850,6 +861,53 @@ int se_slot_sum(se_ctx* ctx, int slot, int64_t count, double* out) {
   return fetch_scalars(ctx, 0, 1, out);
 }
 
+int se_quantile(se_ctx* ctx, int which, int slot, int64_t count, double q, double* out) {
+  if (!ctx || !out) return fail(ctx, SE_ERR_ARG, "null argument");
+  SE_REQUIRE(ctx, q >= 0.0 && q <= 1.0, SE_ERR_ARG, "quantile %g outside [0,1]", q);
+  const float *a = nullptr, *b = nullptr;
+  int64_t n = count;
+  if (which == 1) {
+    SE_REQUIRE(ctx, ctx->gbm.on && ctx->gbm.dim == 1, SE_ERR_STATE, "|y - F| quantile needs a dim-1 GBM problem");
+    a = ctx->slot[SE_SLOT_Y].d;
+    b = ctx->slot[SE_SLOT_F].d;
+    n = ctx->gbm.n;
+  } else {
+    SE_REQUIRE(ctx, slot >= 0 && slot < SE_NUM_SLOTS, SE_ERR_ARG, "bad slot %d", slot);
+    const SlotBuf& s = ctx->slot[slot];
+    SE_REQUIRE(ctx, s.d && s.rows == 1 && count <= s.cols, SE_ERR_STATE, "slot %d is not a [n] vector of >= %lld", slot, (long long)count);
+    a = s.d;
+  }
+  SE_TRY(begin(ctx));
+  double total = (double)n;
+  SE_TRY(se_comm_allreduce_host(ctx, &total, 1));
+  SE_REQUIRE(ctx, total >= 1.0, SE_ERR_ARG, "quantile of an empty column");
+  // 1-based target rank: ceil(q·N), at least 1
+  double rank = ceil(q * total);
+  if (rank < 1.0) rank = 1.0;
+  uint32_t prefix = 0, mask = 0;
+  double hist[256];
+  for (int shift = 24; shift >= 0; shift -= 8) {
+    SE_CUDA(ctx, cudaMemsetAsync(ctx->d_scal + kScalHist, 0, sizeof(double) * 256, ctx->stream));
+    SE_LAUNCH_T(ctx, SE_KF_OTHER, launch_radix_hist(a, b, n, prefix, mask, shift, ctx->d_scal + kScalHist, ctx->sms, ctx->stream));
+    SE_TRY(fetch_scalars(ctx, kScalHist, 256, hist));
+    double cum = 0.0;
+    int bin = 255;
+    for (int i = 0; i < 256; ++i) {
+      if (cum + hist[i] >= rank) { bin = i; break; }
+      cum += hist[i];
+    }
+    rank -= cum;
+    prefix |= (uint32_t)bin << shift;
+    mask |= 0xFFu << shift;
+  }
+  // invert the order-preserving key
+  const uint32_t bits = (prefix & 0x80000000u) ? (prefix & 0x7FFFFFFFu) : ~prefix;
+  float v;
+  memcpy(&v, &bits, sizeof(v));
+  *out = (double)v;
+  return SE_OK;
+}
+
 // ---- GBM ---------------------------------------------------------------------------------------
 int se_gbm_configure(se_ctx* ctx, int64_t n_train, int64_t n_valid, int dim, int loss, double param,
                      int has_weights) {
@@ -862,6 +920,7 @@ int se_gbm_configure(se_ctx* ctx, int64_t n_train, int64_t n_valid, int dim, int
   auto& g = ctx->gbm;
   g.on = true; g.n = n_train; g.nv = n_valid; g.dim = dim; g.loss = loss; g.param = param;
   g.has_w = has_weights != 0;
+  g.use_bag = false;
   g.wsum_valid = false; g.counts_valid = false;
   SE_TRY(slot_alloc2d(ctx, SE_SLOT_Y, 1, n_train));
   SE_TRY(slot_alloc2d(ctx, SE_SLOT_F, dim, n_train));
@@ -880,6 +939,16 @@ int se_gbm_set_loss_param(se_ctx* ctx, double param) {
   if (!ctx) return fail(nullptr, SE_ERR_ARG, "null context");
   SE_REQUIRE(ctx, ctx->gbm.on, SE_ERR_STATE, "se_gbm_configure first");
   ctx->gbm.param = param;
+  return SE_OK;
+}
+
+int se_gbm_set_bag(se_ctx* ctx, int on) {
+  if (!ctx) return fail(nullptr, SE_ERR_ARG, "null context");
+  SE_REQUIRE(ctx, ctx->gbm.on, SE_ERR_STATE, "se_gbm_configure first");
+  SE_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (on) SE_TRY(slot_alloc2d(ctx, SE_SLOT_BAG, 1, ctx->gbm.n));
+  ctx->gbm.use_bag = on != 0;
+  ctx->gbm.wsum_valid = false;
   return SE_OK;
 }
 

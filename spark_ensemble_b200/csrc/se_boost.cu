@@ -177,6 +177,25 @@ __global__ void __launch_bounds__(kBlock) sum_kernel(const float* x, int64_t n, 
   block_reduce_publish<1>(acc, ws);
 }
 
+__global__ void __launch_bounds__(kBlock) dot_kernel(const float* a, const float* b, int64_t n, const RedWs ws) {
+  double acc[1] = {0.0};
+  const int64_t n4 = n >> 2;
+  for (int64_t g = (int64_t)blockIdx.x * kBlock + threadIdx.x; g < n4; g += (int64_t)gridDim.x * kBlock) {
+    const float4 va = ld_stream4(a + 4 * g);
+    if (b) {
+      const float4 vb = ld_stream4(b + 4 * g);
+      acc[0] += (double)va.x * vb.x + (double)va.y * vb.y + (double)va.z * vb.z + (double)va.w * vb.w;
+    } else {
+      acc[0] += (double)va.x + (double)va.y + (double)va.z + (double)va.w;
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+    const int64_t i = (n4 << 2) + threadIdx.x;
+    acc[0] += b ? (double)a[i] * b[i] : (double)a[i];
+  }
+  block_reduce_publish<1>(acc, ws);
+}
+
 // ---- AdaBoost.R2 -----------------------------------------------------------------------------------
 // loss(e) for e = |y - pred| / maxError in [0,1] (regression/BoostingRegressor.scala:97-106)
 __device__ __forceinline__ float r2_loss(int loss_type, float e) {
@@ -258,6 +277,11 @@ cudaError_t launch_boost_discrete_error(const BoostArgs& a, int ctas_per_sm, int
 }
 cudaError_t launch_boost_discrete_update(const BoostArgs& a, int ctas_per_sm, int sms, cudaStream_t s) {
   boost_discrete_update_kernel<<<grid_for(a.n >> 2, kBlock, ctas_per_sm, sms), kBlock, 0, s>>>(a);
+  return cudaGetLastError();
+}
+cudaError_t launch_dot(const float* a, const float* b, int64_t n, const RedWs& ws, int ctas_per_sm, int sms,
+                       cudaStream_t s) {
+  dot_kernel<<<grid_for(n >> 2, kBlock, ctas_per_sm, sms), kBlock, 0, s>>>(a, b, n, ws);
   return cudaGetLastError();
 }
 cudaError_t launch_sum(const float* x, int64_t n, const RedWs& ws, int ctas_per_sm, int sms,

@@ -62,24 +62,28 @@ __global__ void __launch_bounds__(kBlock, LossTune<LOSS>::kMinCtas) gbm_scalar_k
   if (T::kWriteF && a.dev_stats != nullptr) coef = device_step(a);
   const float param = a.param;
   const bool has_w = (a.w != nullptr);
+  // bag multiplicities (row sub-sampling, GBMRegressor.scala:357-359): the line search and newton's Σh run on
+  // the bag (reference quirk 4), i.e. every per-row term of those sums is multiplied by the row's count
+  constexpr bool kBagMode = (MODE == GBM_EVAL) || T::kNewton;
+  const bool has_bag = kBagMode && (a.bag != nullptr);
   double acc[2] = {0.0, 0.0};
 
   const int64_t n4 = a.n >> 2;
   constexpr int64_t tile = (int64_t)kBlock * U;
   const int64_t ntiles = (n4 + tile - 1) / tile;
 
-  auto row = [&](float y, float F, float h, float w, float& Fo, float& ro, float& wo, float& l_acc,
+  auto row = [&](float y, float F, float h, float w, float c, float& Fo, float& ro, float& wo, float& l_acc,
                  float& x_acc) {
     const float p = T::kReadH ? fmaf(coef, h, F) : F;
     const LGH o = eval_loss<LOSS>(y, p, param);
     if (T::kWriteF) Fo = p;
-    if (T::kSumLoss) l_acc += o.l;
-    if (MODE == GBM_EVAL) x_acc = fmaf(h, o.g, x_acc);
+    if (T::kSumLoss) l_acc += (MODE == GBM_EVAL) ? c * o.l : o.l;
+    if (MODE == GBM_EVAL) x_acc = fmaf(c * h, o.g, x_acc);
     if (T::kNewton) {
       const float hc = fmaxf(o.h, 1e-2f);   // GBMRegressor.scala:371
       ro = -o.g / hc;                       // :377
       wo = 0.5f * hc * w;                   // :379 (× 1/S applied by launch_scale_rows)
-      x_acc += hc;
+      x_acc = fmaf(c, hc, x_acc);
     } else if (T::kWriteR) {
       ro = -o.g;                            // :383
     }
@@ -90,7 +94,7 @@ __global__ void __launch_bounds__(kBlock, LossTune<LOSS>::kMinCtas) gbm_scalar_k
   // thousands of distinct 2 MB pages live at once)
   for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
     const int64_t base = t * tile + threadIdx.x;
-    float4 vy[U], vF[U], vh[U], vw[U];
+    float4 vy[U], vF[U], vh[U], vw[U], vb[U];
     bool ok[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
@@ -101,6 +105,7 @@ __global__ void __launch_bounds__(kBlock, LossTune<LOSS>::kMinCtas) gbm_scalar_k
         vF[u] = T::kWriteF ? ld_rw4(a.F + 4 * g) : ld_stream4(a.F + 4 * g);
         if (T::kReadH) vh[u] = ld_stream4(a.h + 4 * g);
         if (T::kNewton && has_w) vw[u] = ld_stream4(a.w + 4 * g);
+        if (has_bag) vb[u] = ld_stream4(a.bag + 4 * g);
       }
     }
 #pragma unroll
@@ -112,7 +117,8 @@ __global__ void __launch_bounds__(kBlock, LossTune<LOSS>::kMinCtas) gbm_scalar_k
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const float w = (T::kNewton && has_w) ? f4at(vw[u], e) : 1.0f;
-        row(f4at(vy[u], e), f4at(vF[u], e), T::kReadH ? f4at(vh[u], e) : 0.f, w, f4at(oF, e),
+        const float c = has_bag ? f4at(vb[u], e) : 1.0f;
+        row(f4at(vy[u], e), f4at(vF[u], e), T::kReadH ? f4at(vh[u], e) : 0.f, w, c, f4at(oF, e),
             f4at(oR, e), f4at(oW, e), l_acc, x_acc);
       }
       if (T::kWriteF) st_stream4(a.F + 4 * g, oF);
@@ -126,8 +132,9 @@ __global__ void __launch_bounds__(kBlock, LossTune<LOSS>::kMinCtas) gbm_scalar_k
   if (blockIdx.x == 0 && threadIdx.x < (a.n & 3)) {
     const int64_t i = (n4 << 2) + threadIdx.x;
     const float w = (T::kNewton && has_w) ? a.w[i] : 1.0f;
+    const float c = has_bag ? a.bag[i] : 1.0f;
     float Fo = 0.f, ro = 0.f, wo = 0.f, l_acc = 0.f, x_acc = 0.f;
-    row(a.y[i], a.F[i], T::kReadH ? a.h[i] : 0.f, w, Fo, ro, wo, l_acc, x_acc);
+    row(a.y[i], a.F[i], T::kReadH ? a.h[i] : 0.f, w, c, Fo, ro, wo, l_acc, x_acc);
     if (T::kWriteF) a.F[i] = Fo;
     if (T::kWriteR) a.r[i] = ro;
     if (T::kNewton) a.wout[i] = wo;
@@ -140,13 +147,14 @@ __global__ void __launch_bounds__(kBlock, LossTune<LOSS>::kMinCtas) gbm_scalar_k
 // squared loss: the three sufficient statistics of the line-search parabola, one pass (12 B/row)
 __global__ void __launch_bounds__(kBlock) gbm_sq_stats_kernel(const GbmArgs a) {
   constexpr int U = U_SCALAR;
+  const bool has_bag = (a.bag != nullptr);
   double acc[3] = {0.0, 0.0, 0.0};
   const int64_t n4 = a.n >> 2;
   constexpr int64_t tile = (int64_t)kBlock * U;
   const int64_t ntiles = (n4 + tile - 1) / tile;
   for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
     const int64_t base = t * tile + threadIdx.x;
-    float4 vy[U], vF[U], vh[U];
+    float4 vy[U], vF[U], vh[U], vb[U];
     bool ok[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
@@ -156,6 +164,7 @@ __global__ void __launch_bounds__(kBlock) gbm_sq_stats_kernel(const GbmArgs a) {
         vy[u] = ld_stream4(a.y + 4 * g);
         vF[u] = ld_stream4(a.F + 4 * g);
         vh[u] = ld_stream4(a.h + 4 * g);
+        if (has_bag) vb[u] = ld_stream4(a.bag + 4 * g);
       }
     }
 #pragma unroll
@@ -165,9 +174,10 @@ __global__ void __launch_bounds__(kBlock) gbm_sq_stats_kernel(const GbmArgs a) {
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const float d = f4at(vy[u], e) - f4at(vF[u], e), h = f4at(vh[u], e);
-        s0 = fmaf(d, d, s0);
-        s1 = fmaf(h, d, s1);
-        s2 = fmaf(h, h, s2);
+        const float c = has_bag ? f4at(vb[u], e) : 1.0f;
+        s0 = fmaf(c * d, d, s0);
+        s1 = fmaf(c * h, d, s1);
+        s2 = fmaf(c * h, h, s2);
       }
       acc[0] += (double)s0;
       acc[1] += (double)s1;
@@ -177,9 +187,10 @@ __global__ void __launch_bounds__(kBlock) gbm_sq_stats_kernel(const GbmArgs a) {
   if (blockIdx.x == 0 && threadIdx.x < (a.n & 3)) {
     const int64_t i = (n4 << 2) + threadIdx.x;
     const float d = a.y[i] - a.F[i], h = a.h[i];
-    acc[0] += (double)(d * d);
-    acc[1] += (double)(h * d);
-    acc[2] += (double)(h * h);
+    const float c = has_bag ? a.bag[i] : 1.0f;
+    acc[0] += (double)(c * d * d);
+    acc[1] += (double)(c * h * d);
+    acc[2] += (double)(c * h * h);
   }
   block_reduce_publish<3>(acc, a.ws);
 }
@@ -204,7 +215,15 @@ __global__ void __launch_bounds__(kBlock) gbm_logloss_kernel(const GbmArgs a) {
        g += (int64_t)gridDim.x * kBlock) {
     const int64_t i0 = g * VEC;
     const bool full = (i0 + VEC <= a.n);
-    float p[KMAX][VEC], hh[KMAX][VEC], yv[VEC], wv[VEC];
+    float p[KMAX][VEC], hh[KMAX][VEC], yv[VEC], wv[VEC], cv[VEC];
+    constexpr bool kBagMode = (MODE == GBM_EVAL) || T::kNewton;
+    const bool has_bag = kBagMode && (a.bag != nullptr);
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) cv[e] = 1.0f;
+    if (has_bag) {
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) cv[e] = (i0 + e < a.n) ? a.bag[i0 + e] : 0.f;
+    }
     // ---- loads
     if (VEC == 4 && full) {
       const float4 t = ld_stream4(a.y + i0);
@@ -276,18 +295,18 @@ __global__ void __launch_bounds__(kBlock) gbm_logloss_kernel(const GbmArgs a) {
       }
       const float lse = m + log1p_pos(srest);
       const float inv_s = rcp_approx(1.0f + srest);
-      if (T::kSumLoss && in) acc[0] += (double)(lse - py);  // -Σ y_k (p_k - lse)  :206-221
+      if (T::kSumLoss && in) acc[0] += (double)(((MODE == GBM_EVAL) ? cv[e] : 1.0f) * (lse - py));  // -Σ y_k (p_k - lse)  :206-221
 #pragma unroll
       for (int k = 0; k < KMAX; ++k) {
         if (k < K) {
           const float sm = ex[k] * inv_s;                    // exp(p_k - lse)
           const float gk = sm - ((k == yi) ? 1.0f : 0.0f);   // :223-238
-          if (MODE == GBM_EVAL && in) acc[1 + k] += (double)(hh[k][e] * gk);  // :66-72
+          if (MODE == GBM_EVAL && in) acc[1 + k] += (double)(cv[e] * hh[k][e] * gk);  // :66-72
           if (T::kNewton) {
             const float hc = fmaxf(sm * (1.0f - sm), 1e-2f);  // :240-256, GBMClassifier.scala:342
             outR[k][e] = -gk / hc;                            // :362
             outW[k][e] = 0.5f * hc * wv[e];                   // :364 (× 1/S_k later)
-            if (in) acc[1 + k] += (double)hc;
+            if (in) acc[1 + k] += (double)(cv[e] * hc);
           } else if (T::kWriteR) {
             outR[k][e] = -gk;                                 // :371
           }

@@ -127,6 +127,7 @@ __global__ void __launch_bounds__(kRows) gbm_logloss_staged_kernel(const GbmArgs
     const bool in = row < a.n;
     const float yv = in ? ld_stream1(a.y + row) : 0.f;
     const float wv = (T::kNewton && has_w && in) ? ld_stream1(a.w + row) : 1.0f;
+    const float cv = (T::kPerClassAcc && a.bag != nullptr && in) ? ld_stream1(a.bag + row) : 1.0f;  // bag multiplicity
     mbar_wait(&bars[stage], two_stage ? ((it >> 1) & 1) : (it & 1));
     float* sF = stage_base + (size_t)stage * stage_floats + tid;
     const float* sH = sF + K * kRows;
@@ -151,7 +152,7 @@ __global__ void __launch_bounds__(kRows) gbm_logloss_staged_kernel(const GbmArgs
     }
     const float lse = m + log1p_pos(srest);
     const float inv_s = rcp_approx(1.0f + srest);
-    if (T::kSumLoss && in) acc_loss += (double)(lse - py);  // GBMLoss.scala:206-221
+    if (T::kSumLoss && in) acc_loss += (double)(((MODE == GBM_EVAL) ? cv : 1.0f) * (lse - py));  // GBMLoss.scala:206-221
     // pass 3: per-class outputs
     if (T::kPerClassAcc || T::kWriteF || T::kWriteR) {
 #pragma unroll
@@ -161,11 +162,11 @@ __global__ void __launch_bounds__(kRows) gbm_logloss_staged_kernel(const GbmArgs
           const float p = T::kReadH ? fmaf(s_coef[k], hk, sF[k * kRows]) : sF[k * kRows];
           const float sm = ex2_approx((p - m) * kLog2e) * inv_s;   // exp(p_k - lse)
           const float gk = sm - ((k == yi) ? 1.0f : 0.0f);         // :223-238
-          if (MODE == GBM_EVAL) sF[k * kRows] = in ? hk * gk : 0.f;  // :66-72 (summed per class below)
+          if (MODE == GBM_EVAL) sF[k * kRows] = in ? cv * hk * gk : 0.f;  // :66-72 (summed per class below)
           if (T::kWriteF && in) a.F[k * ld + row] = p;
           if (T::kNewton) {
             const float hc = fmaxf(sm * (1.0f - sm), 1e-2f);       // :240-256, GBMClassifier.scala:342
-            sF[k * kRows] = in ? hc : 0.f;
+            sF[k * kRows] = in ? cv * hc : 0.f;
             if (in) {
               a.r[k * ld + row] = -gk / hc;                        // :362
               a.wout[k * ld + row] = 0.5f * hc * wv;               // :364 (x 1/S_k later)

@@ -25,6 +25,7 @@ enum GbmMode {
 struct GbmArgs {
   const float* y = nullptr;
   const float* w = nullptr;  // nullable: unit weights
+  const float* bag = nullptr;  // nullable: per-row bag multiplicities (RDD.sample counts) for line search / newton S
   float* F = nullptr;
   const float* h = nullptr;
   float* r = nullptr;
@@ -70,6 +71,9 @@ cudaError_t launch_boost_discrete_error(const BoostArgs& a, int ctas_per_sm, int
 cudaError_t launch_boost_discrete_update(const BoostArgs& a, int ctas_per_sm, int sms, cudaStream_t s); // out[0]=Σw'
 cudaError_t launch_sum(const float* x, int64_t n, const RedWs& ws, int ctas_per_sm, int sms,
                        cudaStream_t s);  // out[0]
+// out[0] = Σ a_i·b_i (b nullable: Σ a_i)
+cudaError_t launch_dot(const float* a, const float* b, int64_t n, const RedWs& ws, int ctas_per_sm, int sms,
+                       cudaStream_t s);
 // AdaBoost.R2 (regression/BoostingRegressor.scala:225-263). loss_type 0 exponential, 1 linear, 2 squared.
 struct BoostRegArgs {
   const float* y = nullptr;
@@ -118,6 +122,12 @@ cudaError_t launch_tree_predict(const TreeArgs& a, int sms, cudaStream_t s);
 cudaError_t launch_linear_predict(const float* X, int64_t n, int64_t ld, int n_coef,
                                   const float* coef, const int32_t* cols, float intercept,
                                   float* out, int sms, cudaStream_t s);
+
+// ---- exact quantile by radix select (se_util.cu) ---------------------------------------------
+// One pass: histogram (256 bins, fp64 counts in `hist`) of byte `shift/8` of the order-preserving key of each
+// value whose higher bytes equal `prefix` (mask = bits above the byte).  value = a[i], or |a[i] - b[i]| when b.
+cudaError_t launch_radix_hist(const float* a, const float* b, int64_t n, uint32_t prefix, uint32_t mask,
+                              int shift, double* hist, int sms, cudaStream_t s);
 
 // ---- utilities (se_util.cu) ------------------------------------------------------------------
 cudaError_t launch_fill(float* p, float v, int64_t n, int sms, cudaStream_t s);

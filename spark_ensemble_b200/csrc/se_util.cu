@@ -45,6 +45,28 @@ __global__ void __launch_bounds__(kBlock) scale_copy_kernel(const float* s, floa
     d[i] = s[i] * scale;
 }
 
+// order-preserving map float -> uint32 (negative values reversed, positives offset)
+__device__ __forceinline__ uint32_t float_key(float v) {
+  const uint32_t u = __float_as_uint(v);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+__global__ void __launch_bounds__(kBlock) radix_hist_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                                           int64_t n, uint32_t prefix, uint32_t mask, int shift,
+                                                           double* __restrict__ hist) {
+  __shared__ unsigned int sh[256];
+  sh[threadIdx.x] = 0;  // kBlock == 256
+  __syncthreads();
+  for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += (int64_t)gridDim.x * kBlock) {
+    float v = ld_stream1(a + i);
+    if (b) v = fabsf(v - ld_stream1(b + i));
+    const uint32_t key = float_key(v);
+    if ((key & mask) == prefix) atomicAdd(&sh[(key >> shift) & 0xFFu], 1u);
+  }
+  __syncthreads();
+  if (sh[threadIdx.x]) atomicAdd(&hist[threadIdx.x], (double)sh[threadIdx.x]);
+}
+
 inline int grid1(int64_t n, int sms) {
   int64_t need = (n + kBlock - 1) / kBlock;
   if (need < 1) need = 1;
@@ -54,6 +76,11 @@ inline int grid1(int64_t n, int sms) {
 
 }  // namespace
 
+cudaError_t launch_radix_hist(const float* a, const float* b, int64_t n, uint32_t prefix, uint32_t mask,
+                              int shift, double* hist, int sms, cudaStream_t s) {
+  radix_hist_kernel<<<grid1(n, sms), kBlock, 0, s>>>(a, b, n, prefix, mask, shift, hist);
+  return cudaGetLastError();
+}
 cudaError_t launch_fill(float* p, float v, int64_t n, int sms, cudaStream_t s) {
   fill_kernel<<<grid1(n, sms), kBlock, 0, s>>>(p, v, n);
   return cudaGetLastError();

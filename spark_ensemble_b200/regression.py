@@ -29,6 +29,18 @@ def _extract_instances(est: Params, dataset: DataFrame):
     return X, y, w
 
 
+def bag_counts(n: int, subsample_ratio: float, replacement: bool, seed: int):
+    """Multiplicity of every train row in `RDD.sample(replacement, ratio, seed)`; None when the bag is the
+    whole set.  Spark's sampler is partition- and RNG-specific; on a Spark host the mask comes from Spark —
+    here numpy draws it (Bernoulli(ratio) without, Poisson(ratio) with replacement), once, because the
+    reference passes the same seed every round (quirk 3)."""
+    if subsample_ratio == 1.0 and not replacement:
+        return None
+    rng = np.random.default_rng(seed & 0xFFFFFFFF)
+    c = rng.poisson(subsample_ratio, n) if replacement else (rng.random(n) < subsample_ratio)
+    return c.astype(np.float32)
+
+
 def _split_validation(est: Params, dataset: DataFrame):
     vc = est("validationIndicatorCol") if est.isDefined("validationIndicatorCol") else ""
     if vc:
@@ -64,11 +76,9 @@ class GBMRegressor(Params):
         loss = self("loss").lower()
         updates = self("updates").lower()
         learner = self("baseLearner")
-        if self("subsampleRatio") != 1.0 or self("replacement"):
-            # RDD.sample is Spark-RNG-defined: row sub-sampling stays on the Spark side
-            raise NotImplementedError("row sub-sampling (subsampleRatio < 1 or replacement) needs Spark's RDD.sample")
         num_learners = self("numBaseLearners")
         seed = self("seed")
+        counts = bag_counts(n, self("subsampleRatio"), self("replacement"), seed)  # same bag every round (:357-359)
         subspaces = [subspace(self("subspaceRatio"), num_features, seed + i) for i in range(num_learners)]  # :282-284
 
         # init model :287-303
@@ -95,6 +105,9 @@ class GBMRegressor(Params):
             on_device_models = bool(self("residentFeatures"))
             if on_device_models:
                 eng.load_features(X, Xv)
+            if counts is not None:
+                ctx.gbm_set_bag(counts)
+                in_bag = counts > 0
             best = ctx.gbm_mean_loss(validation=True) if with_validation else 0.0  # :330-335
 
             models, weights = [], []
@@ -102,15 +115,18 @@ class GBMRegressor(Params):
             eng.residuals(newton)  # residuals of F0; later rounds get them fused with the update
             i = v = 0
             while i < num_learners and v < self("numRounds"):  # :340
-                if loss == "huber":  # :342-353 (approxQuantile restated as the exact quantile)
-                    F = ctx.download(N.SLOT_F).astype(np.float64)
-                    param = exact_quantile(np.abs(y - F), self("alpha"))
+                if loss == "huber":  # :342-353: δ = α-quantile of |y − F| (approxQuantile -> exact radix select on device)
+                    param = ctx.gbm_abs_residual_quantile(self("alpha"))
                     ctx.gbm_set_loss_param(param)
                     eng.residuals(False)
                 sub = subspaces[i]
                 r, wout = eng.fetch_residuals(newton)
                 fit_w = wout[0] if newton else w
-                model = learner.fit(X[:, sub], r[0], fit_w)  # third party :387-396
+                if counts is None:
+                    model = learner.fit(X[:, sub], r[0], fit_w)  # third party :387-396
+                else:  # the base learner sees the bag: row i with multiplicity c_i (== weight c_i·w_i)
+                    bw = counts[in_bag] if fit_w is None else counts[in_bag] * fit_w[in_bag]
+                    model = learner.fit(X[in_bag][:, sub], r[0][in_bag], bw)
                 eng.set_direction_from_model(0, model, sub, X)
                 if self("optimizedWeights"):  # :398-425
                     alpha, _, _ = eng.line_search_brent(self("tol"), self("maxIter"))

@@ -95,6 +95,20 @@ def main():
     out, eo, so = orc.samme_r_update(Kc, yb, wb, sw, P)
     assert abs(e - eo) <= RT * eo and abs(s - so) <= RT * so, (e, eo, s, so)
     assert np.max(np.abs(ctx.download(N.SLOT_BW) - out[s0:s1]) / out[s0:s1]) <= RT
+    # exact quantile (radix select, histograms all-reduced) and AdaBoost.R2's max-allreduce across shards
+    from spark_ensemble_b200.ensemble import exact_quantile
+    v = rng.standard_normal(n).astype(np.float32)
+    ctx.alloc(N.SLOT_Y, s1 - s0)
+    ctx.upload(N.SLOT_Y, v[s0:s1])
+    for q in (0.1, 0.5, 0.9):
+        assert ctx.quantile(N.SLOT_Y, q) == exact_quantile(v, q)
+    pr = (v + 0.3 * rng.standard_normal(n)).astype(np.float32)
+    ctx.boostreg_configure(s1 - s0)
+    ctx.upload(N.SLOT_Y, v[s0:s1]); ctx.upload(N.SLOT_PRED, pr[s0:s1]); ctx.upload(N.SLOT_BW, wb[s0:s1])
+    mx = ctx.boostreg_max_error()
+    assert abs(mx - orc.r2_max_error(v, pr)) <= 1e-6 * mx
+    e2 = ctx.boostreg_error(sw, "exponential", mx)
+    assert abs(e2 - orc.r2_estimator_error("exponential", v, pr, wb, sw, mx)) <= RT * e2
     dist.barrier()
     if rank == 0:
         print(f"MGPU_PARITY_OK world={world}")

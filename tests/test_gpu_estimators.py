@@ -282,3 +282,20 @@ def test_boosting_regressor_adaboost_r2(oracle, loss_type, voting):
     np.testing.assert_allclose(pred, ref, rtol=1e-5, atol=1e-5 * np.abs(ref).mean())
     rmse = lambda p: float(np.sqrt(np.mean((p - y) ** 2)))
     assert rmse(pred) < rmse(DecisionTreeRegressor(maxDepth=5).fit(X, y).predict(X)) * 1.05
+
+
+def test_gbm_regressor_with_row_subsampling():
+    """subsampleRatio < 1 / replacement: line search on the bag, update on all rows (reference quirk 4)."""
+    from spark_ensemble_b200 import DataFrame
+    from spark_ensemble_b200.learners import DecisionTreeRegressor
+    from spark_ensemble_b200.regression import GBMRegressor
+    X, y = _cpusmall()
+    base = GBMRegressor().setBaseLearner(DecisionTreeRegressor(maxDepth=4)).setNumBaseLearners(6).setLearningRate(0.5)
+    full = base.copy().fit(DataFrame(features=X, label=y))
+    for ratio, repl in ((0.5, False), (1.0, True)):
+        m = base.copy().setSubsampleRatio(ratio).setReplacement(repl).fit(DataFrame(features=X, label=y))
+        assert m.numModels == 6
+        losses = [h["trainLoss"] for h in m.trainingHistory]
+        assert losses[-1] < losses[0]
+        # a bagged fit still tracks the full fit's loss closely on this dataset
+        assert losses[-1] < 1.5 * full.trainingHistory[-1]["trainLoss"]

@@ -551,3 +551,61 @@ def test_agg_boosting_regressor(ctx, oracle, rng, M, n):
     ctx.upload(N.SLOT_P, P)
     ctx.agg_run(a)
     close(ctx.download(N.SLOT_RAW), oracle.agg_weighted_mean(P, a.astype(np.float32).astype(np.float64)), scale=0.1)
+
+
+@pytest.mark.parametrize("n", [1, 2, 1000, 100003])
+def test_exact_quantile_radix_select(ctx, rng, n):
+    """se_quantile == the ceil(q·N)-th smallest value, bit-exact."""
+    from spark_ensemble_b200 import _native as N
+    from spark_ensemble_b200.ensemble import exact_quantile
+    v = f32(rng.standard_normal(n) * 3)
+    v[: n // 5] = np.round(v[: n // 5])  # many duplicates, zeros of both signs
+    if n > 10:
+        v[3], v[4] = 0.0, -0.0
+    ctx.alloc(N.SLOT_Y, n)
+    ctx.upload(N.SLOT_Y, v)
+    for q in (0.0, 0.1, 0.5, 0.9, 0.999, 1.0):
+        assert ctx.quantile(N.SLOT_Y, q) == exact_quantile(v, q), (n, q)
+    F = f32(rng.standard_normal(n))
+    ctx.gbm_configure(n, 0, 1, "huber", 1.0, False)
+    ctx.upload(N.SLOT_Y, v); ctx.upload(N.SLOT_F, F)
+    for q in (0.5, 0.9):
+        assert ctx.gbm_abs_residual_quantile(q) == exact_quantile(np.abs(v - F), q)
+
+
+@pytest.mark.parametrize("name", ["squared", "bernoulli", "logloss2", "logloss9"])
+def test_bag_multiplicities(ctx, oracle, rng, name):
+    """Row sub-sampling: with bag counts c_i the line-search sums and newton's Σh equal the
+    reference's sums over the materialised bag (rows repeated c_i times); update/residuals stay on all rows."""
+    from spark_ensemble_b200 import _native as N
+    n = 20011
+    K = int(name[7:]) if name.startswith("logloss") else 5
+    lname = "logloss" if name.startswith("logloss") else name
+    dim, par, y, F, h, w = setup_gbm(ctx, rng, lname, n, True, K=K)
+    c = rng.poisson(1.0, n).astype(np.float32)
+    ctx.gbm_set_bag(c)
+    rep = np.repeat(np.arange(n), c.astype(int))  # the materialised bag
+    yb, wb, Fb, hb = y[rep], w[rep], np.ascontiguousarray(F[:, rep]), np.ascontiguousarray(h[:, rep])
+    lid = O.LOSS_IDS[lname]
+    alpha = rng.random(dim) + 0.3
+    lg, gg = ctx.gbm_linesearch_eval(alpha)
+    lo, go = oracle.linesearch_eval(lid, par, yb, wb, Fb, hb, alpha)
+    assert lg == pytest.approx(lo, rel=RTOL)
+    close(gg, go, rtol=RTOL, scale=float(np.max(np.abs(go))))
+    if lname == "squared":
+        st = ctx.gbm_linesearch_stats()
+        d = yb.astype(np.float64) - Fb[0]
+        close(st, [np.sum(d * d), np.sum(hb[0] * d), np.sum(hb[0].astype(np.float64) ** 2), np.sum(wb.astype(np.float64))])
+    S = ctx.gbm_pseudo_residuals(newton=True)
+    _, _, So = oracle.pseudo_residuals(lid, par, dim, yb, wb, Fb, True)
+    close(S, So, rtol=RTOL)
+    ro, _, _ = oracle.pseudo_residuals(lid, par, dim, y, w, F, True)  # residuals themselves: every row
+    close(ctx.download(N.SLOT_R).reshape(dim, n), ro, rtol=RTOL, scale=1.0)
+    step = rng.random(dim) * 0.3
+    ls, _ = ctx.gbm_update(step, residual=True, loss=True)
+    Fo = F.astype(np.float64).copy()
+    oracle.update(Fo, h, step)
+    assert ls / n == pytest.approx(oracle.mean_loss(lid, par, dim, y, Fo), rel=RTOL)  # full train set
+    ctx.gbm_set_bag(None)
+    lg2, _ = ctx.gbm_linesearch_eval(alpha)
+    assert lg2 == pytest.approx(oracle.linesearch_eval(lid, par, y, w, Fo, h, alpha)[0], rel=RTOL)

@@ -99,13 +99,15 @@ def test_dummy_init_models():
     assert u.predictRaw(np.zeros((4, 2))).shape == (4, 3)
 
 
-def test_row_subsampling_is_rejected_loudly():
-    from spark_ensemble_b200 import DataFrame
-    from spark_ensemble_b200.learners import DecisionTreeRegressor
-    from spark_ensemble_b200.regression import GBMRegressor
-    df = DataFrame(features=np.zeros((8, 2), dtype=np.float32), label=np.zeros(8))
-    with pytest.raises(NotImplementedError):
-        GBMRegressor().setBaseLearner(DecisionTreeRegressor()).setSubsampleRatio(0.5).fit(df)
+def test_bag_counts_same_every_round():
+    """Reference quirk 3: RDD.sample gets the same seed every round => one bag per fit."""
+    from spark_ensemble_b200.regression import bag_counts
+    assert bag_counts(100, 1.0, False, 7) is None
+    a, b = bag_counts(10000, 0.6, False, 7), bag_counts(10000, 0.6, False, 7)
+    np.testing.assert_array_equal(a, b)
+    assert set(np.unique(a)) <= {0.0, 1.0} and abs(a.mean() - 0.6) < 0.03
+    c = bag_counts(10000, 1.0, True, 7)
+    assert c.max() >= 2 and abs(c.mean() - 1.0) < 0.05  # Poisson(1) bootstrap
 
 
 def test_tree_arrays_threshold_rounding():
