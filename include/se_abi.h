@@ -122,6 +122,10 @@ SE_API int se_host_free(void* ptr);
 #define SE_COMM_ID_BYTES 128
 SE_API int se_comm_unique_id(void* out, int bytes);
 SE_API int se_comm_init(se_ctx* ctx, int nranks, int rank, const void* id, int bytes);
+/* 1 when the fused NVLink all-reduce is active: every rank's mailbox is mapped into every process with CUDA
+ * IPC and the last CTA of each reducing kernel exchanges the per-GPU sums over peer memory itself (no separate
+ * NCCL launch).  0: NCCL all-reduce after the kernel (fallback when IPC mapping fails or SE_P2P_ALLREDUCE=0). */
+SE_API int se_comm_p2p_active(const se_ctx* ctx, int* active);
 SE_API int se_comm_destroy(se_ctx* ctx);
 SE_API int se_comm_info(const se_ctx* ctx, int* nranks, int* rank);
 /* sum-allreduce `count` doubles held on the host across ranks (no-op without a communicator) */

@@ -61,6 +61,7 @@ PROTOTYPES = {
     "se_host_free": [_vp],
     "se_comm_unique_id": [_vp, _i32],
     "se_comm_init": [_vp, _i32, _i32, _vp, _i32],
+    "se_comm_p2p_active": [_vp, C.POINTER(_i32)],
     "se_comm_destroy": [_vp],
     "se_comm_info": [_vp, C.POINTER(_i32), C.POINTER(_i32)],
     "se_comm_allreduce_host": [_vp, _dp, _i32],

@@ -91,6 +91,11 @@ class Context:
         buf = C.create_string_buffer(uid, N.COMM_ID_BYTES) if uid is not None else None
         self._ck(self._lib.se_comm_init(self._h, nranks, rank, buf, N.COMM_ID_BYTES if uid else 0))
 
+    def comm_p2p_active(self) -> bool:
+        v = C.c_int()
+        self._ck(self._lib.se_comm_p2p_active(self._h, C.byref(v)))
+        return bool(v.value)
+
     def comm_destroy(self):
         self._ck(self._lib.se_comm_destroy(self._h))
 

@@ -34,6 +34,7 @@ struct NcclApi {
   int (*CommInitRank)(nccl_comm_t*, int, nccl_uid_t, int) = nullptr;
   int (*CommDestroy)(nccl_comm_t) = nullptr;
   int (*AllReduce)(const void*, void*, size_t, int, int, nccl_comm_t, cudaStream_t) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, nccl_comm_t, cudaStream_t) = nullptr;
   const char* (*GetErrorString)(int) = nullptr;
   int (*GetVersion)(int*) = nullptr;
   bool ok = false;
@@ -42,6 +43,7 @@ struct NcclApi {
 constexpr int kNcclFloat64 = 8;  // ncclDouble
 constexpr int kNcclSum = 0;
 constexpr int kNcclMax = 2;
+constexpr int kNcclChar = 0;
 
 NcclApi& nccl() {
   static NcclApi api;
@@ -65,6 +67,7 @@ NcclApi& nccl() {
   SE_SYM(CommInitRank, "ncclCommInitRank")
   SE_SYM(CommDestroy, "ncclCommDestroy")
   SE_SYM(AllReduce, "ncclAllReduce")
+  SE_SYM(AllGather, "ncclAllGather")
   SE_SYM(GetErrorString, "ncclGetErrorString")
   SE_SYM(GetVersion, "ncclGetVersion")
 #undef SE_SYM
@@ -135,6 +138,15 @@ struct se_ctx {
   } boostreg;
   nccl_comm_t comm = nullptr;
   int nranks = 1, rank = 0;
+  // fused NVLink all-reduce: mailboxes of all ranks mapped into this process with CUDA IPC
+  bool p2p = false;
+  double* mbox_local = nullptr;
+  std::vector<void*> mbox_peers;      // opened IPC mappings (index = rank; own entry = mbox_local)
+  double** d_mbox_table = nullptr;    // device copy of the pointer table
+  int* d_p2p_err = nullptr;           // device alias of h_p2p_err (mapped pinned host memory: no copy to poll it)
+  int* h_p2p_err = nullptr;
+  unsigned long long red_seq = 0;
+  bool last_reduce_global = false;    // the kernel just launched already produced cross-GPU sums
   std::string err;
   // stopwatch + per-kernel-family timing
   cudaEvent_t tm0 = nullptr, tm1 = nullptr;
@@ -237,17 +249,32 @@ int end(se_ctx* ctx) {
   return SE_OK;
 }
 
-RedWs red_ws(se_ctx* ctx, int out_offset = 0) {
+// exchange = true: the launched kernel ends in block_reduce_publish/peer_exchange (sum); it then performs
+// the cross-GPU reduction itself over peer memory and the NCCL all-reduce is skipped.
+RedWs red_ws(se_ctx* ctx, int out_offset = 0, bool exchange = true) {
   RedWs ws;
   ws.partials = ctx->d_partials;
   ws.counter = ctx->d_counter;
   ws.out = ctx->d_scal + out_offset;
+  ctx->last_reduce_global = false;
+  if (exchange && ctx->p2p && ctx->nranks > 1) {
+    ws.mbox = ctx->d_mbox_table;
+    ws.nranks = ctx->nranks;
+    ws.rank = ctx->rank;
+    ws.seq = ++ctx->red_seq;
+    ws.err = ctx->d_p2p_err;
+    ctx->last_reduce_global = true;
+  }
   return ws;
 }
 
 // all-reduce d_scal[off..off+count) in-stream (no-op without communicator)
 int allreduce_dev(se_ctx* ctx, int off, int count, int op = kNcclSum) {
   if (!ctx->comm || ctx->nranks <= 1) return SE_OK;
+  if (ctx->last_reduce_global && op == kNcclSum) {  // already summed across GPUs inside the kernel
+    ctx->last_reduce_global = false;
+    return SE_OK;
+  }
   NcclApi& api = nccl();
   int rc = api.AllReduce(ctx->d_scal + off, ctx->d_scal + off, (size_t)count, kNcclFloat64, op,
                          ctx->comm, ctx->stream);
@@ -263,6 +290,8 @@ int fetch_scalars(se_ctx* ctx, int off, int count, double* out, int op = kNcclSu
   SE_TRY(end(ctx));
   SE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   for (int i = 0; i < count; ++i) out[i] = ctx->h_scal[off + i];
+  if (ctx->p2p && ctx->h_p2p_err && *reinterpret_cast<volatile int*>(ctx->h_p2p_err))
+    return fail(ctx, SE_ERR_NCCL, "peer-memory all-reduce timed out: a rank did not launch the matching reduction");
   return SE_OK;
 }
 
@@ -370,7 +399,7 @@ GbmArgs gbm_args(se_ctx* ctx, bool validation) {
   a.ld = ctx->slot[validation ? SE_SLOT_VF : SE_SLOT_F].ld;
   a.dim = g.dim;
   a.param = (float)g.param;
-  a.ws = red_ws(ctx);
+  a.ws = red_ws(ctx, 0, /*exchange=*/false);  // armed (sequence number taken) only at reducing launches
   return a;
 }
 
@@ -531,7 +560,14 @@ int se_ctx_destroy(se_ctx* ctx) {
   if (!ctx) return SE_OK;
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-  if (ctx->comm && nccl().ok) nccl().CommDestroy(ctx->comm);
+  if (ctx->comm && nccl().ok) {
+    for (int p = 0; p < (int)ctx->mbox_peers.size(); ++p)
+      if (p != ctx->rank && ctx->mbox_peers[p]) cudaIpcCloseMemHandle(ctx->mbox_peers[p]);
+    if (ctx->mbox_local) cudaFree(ctx->mbox_local);
+    if (ctx->d_mbox_table) cudaFree(ctx->d_mbox_table);
+    if (ctx->h_p2p_err) cudaFreeHost(ctx->h_p2p_err);
+    nccl().CommDestroy(ctx->comm);
+  }
   for (auto& s : ctx->slot)
     if (s.d) cudaFree(s.d);
   if (ctx->d_scal) cudaFree(ctx->d_scal);
@@ -682,7 +718,83 @@ int se_comm_init(se_ctx* ctx, int nranks, int rank, const void* id, int bytes) {
     ctx->comm = nullptr;
     return fail(ctx, SE_ERR_NCCL, "ncclCommInitRank: %s", api.GetErrorString(rc));
   }
+  // ---- peer-memory mailboxes for the fused all-reduce (falls back to NCCL if any rank cannot map them)
+  const char* env = getenv("SE_P2P_ALLREDUCE");
+  int want = (env && atoi(env) == 0) ? 0 : 1;
+  const size_t mbox_bytes = sizeof(double) * (size_t)nranks * 2 * kMboxStride;
+  int ok = want;
+  cudaIpcMemHandle_t mine;
+  memset(&mine, 0, sizeof(mine));
+  if (ok) {
+    ok = cudaMalloc(&ctx->mbox_local, mbox_bytes) == cudaSuccess && cudaMemset(ctx->mbox_local, 0, mbox_bytes) == cudaSuccess &&
+         cudaHostAlloc(&ctx->h_p2p_err, sizeof(int), cudaHostAllocMapped) == cudaSuccess &&
+         cudaHostGetDevicePointer(&ctx->d_p2p_err, ctx->h_p2p_err, 0) == cudaSuccess &&
+         cudaMalloc(&ctx->d_mbox_table, sizeof(double*) * nranks) == cudaSuccess &&
+         cudaIpcGetMemHandle(&mine, ctx->mbox_local) == cudaSuccess;
+    cudaGetLastError();
+  }
+  // exchange the handles (and everyone's readiness) through NCCL
+  const size_t hb = sizeof(cudaIpcMemHandle_t) + 8;
+  std::vector<unsigned char> send(hb, 0), recv(hb * nranks, 0);
+  memcpy(send.data(), &mine, sizeof(mine));
+  send[sizeof(mine)] = (unsigned char)ok;
+  unsigned char *d_send = nullptr, *d_recv = nullptr;
+  SE_CUDA(ctx, cudaMalloc(&d_send, hb));
+  SE_CUDA(ctx, cudaMalloc(&d_recv, hb * nranks));
+  SE_CUDA(ctx, cudaMemcpyAsync(d_send, send.data(), hb, cudaMemcpyHostToDevice, ctx->stream));
+  rc = api.AllGather(d_send, d_recv, hb, kNcclChar, ctx->comm, ctx->stream);
+  if (rc != 0) return fail(ctx, SE_ERR_NCCL, "ncclAllGather: %s", api.GetErrorString(rc));
+  SE_CUDA(ctx, cudaMemcpyAsync(recv.data(), d_recv, hb * nranks, cudaMemcpyDeviceToHost, ctx->stream));
+  SE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  int all_ok = 1;
+  for (int p = 0; p < nranks; ++p) all_ok &= recv[p * hb + sizeof(mine)];
+  ctx->mbox_peers.assign(nranks, nullptr);
+  if (all_ok) {
+    for (int p = 0; p < nranks && all_ok; ++p) {
+      if (p == rank) { ctx->mbox_peers[p] = ctx->mbox_local; continue; }
+      cudaIpcMemHandle_t h;
+      memcpy(&h, recv.data() + p * hb, sizeof(h));
+      void* ptr = nullptr;
+      if (cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { all_ok = 0; cudaGetLastError(); }
+      ctx->mbox_peers[p] = ptr;
+    }
+  }
+  // second round: did every rank manage to open every peer?
+  send[0] = (unsigned char)all_ok;
+  SE_CUDA(ctx, cudaMemcpyAsync(d_send, send.data(), hb, cudaMemcpyHostToDevice, ctx->stream));
+  rc = api.AllGather(d_send, d_recv, hb, kNcclChar, ctx->comm, ctx->stream);
+  if (rc != 0) return fail(ctx, SE_ERR_NCCL, "ncclAllGather: %s", api.GetErrorString(rc));
+  SE_CUDA(ctx, cudaMemcpyAsync(recv.data(), d_recv, hb * nranks, cudaMemcpyDeviceToHost, ctx->stream));
+  SE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  for (int p = 0; p < nranks; ++p) all_ok &= recv[p * hb];
+  cudaFree(d_send);
+  cudaFree(d_recv);
+  if (all_ok) {
+    *ctx->h_p2p_err = 0;
+    SE_CUDA(ctx, cudaMemcpy(ctx->d_mbox_table, ctx->mbox_peers.data(), sizeof(double*) * nranks, cudaMemcpyHostToDevice));
+    ctx->p2p = true;
+    ctx->red_seq = 0;
+  } else {
+    ctx->p2p = false;  // NCCL all-reduce of the scalar block after each reducing kernel
+  }
   return SE_OK;
+}
+
+int se_comm_p2p_active(const se_ctx* ctx, int* active) {
+  if (!ctx || !active) return fail(nullptr, SE_ERR_ARG, "null argument");
+  *active = ctx->p2p ? 1 : 0;
+  return SE_OK;
+}
+
+static void release_p2p(se_ctx* ctx) {
+  for (int p = 0; p < (int)ctx->mbox_peers.size(); ++p)
+    if (p != ctx->rank && ctx->mbox_peers[p]) cudaIpcCloseMemHandle(ctx->mbox_peers[p]);
+  ctx->mbox_peers.clear();
+  if (ctx->mbox_local) cudaFree(ctx->mbox_local);
+  if (ctx->d_mbox_table) cudaFree(ctx->d_mbox_table);
+  if (ctx->h_p2p_err) cudaFreeHost(ctx->h_p2p_err);
+  ctx->mbox_local = nullptr; ctx->d_mbox_table = nullptr; ctx->d_p2p_err = nullptr; ctx->h_p2p_err = nullptr;
+  ctx->p2p = false;
 }
 
 int se_comm_destroy(se_ctx* ctx) {
@@ -690,6 +802,7 @@ int se_comm_destroy(se_ctx* ctx) {
   if (ctx->comm) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    release_p2p(ctx);
     nccl().CommDestroy(ctx->comm);
     ctx->comm = nullptr;
   }
@@ -714,6 +827,7 @@ int se_comm_allreduce_host(se_ctx* ctx, double* values, int count) {
   for (int i = 0; i < count; ++i) ctx->h_scal[kScalHost + i] = values[i];
   SE_CUDA(ctx, cudaMemcpyAsync(ctx->d_scal + kScalHost, ctx->h_scal + kScalHost, sizeof(double) * count,
                                cudaMemcpyHostToDevice, ctx->stream));
+  ctx->last_reduce_global = false;
   SE_TRY(allreduce_dev(ctx, kScalHost, count));
   SE_CUDA(ctx, cudaMemcpyAsync(ctx->h_scal + kScalHost, ctx->d_scal + kScalHost, sizeof(double) * count,
                                cudaMemcpyDeviceToHost, ctx->stream));
@@ -888,6 +1002,7 @@ int se_quantile(se_ctx* ctx, int which, int slot, int64_t count, double q, doubl
   double hist[256];
   for (int shift = 24; shift >= 0; shift -= 8) {
     SE_CUDA(ctx, cudaMemsetAsync(ctx->d_scal + kScalHist, 0, sizeof(double) * 256, ctx->stream));
+    ctx->last_reduce_global = false;  // histogram bins: summed by NCCL
     SE_LAUNCH_T(ctx, SE_KF_OTHER, launch_radix_hist(a, b, n, prefix, mask, shift, ctx->d_scal + kScalHist, ctx->sms, ctx->stream));
     SE_TRY(fetch_scalars(ctx, kScalHist, 256, hist));
     double cum = 0.0;
@@ -977,6 +1092,7 @@ int se_gbm_pseudo_residuals(se_ctx* ctx, int newton, double* sum_hess) {
   SE_TRY(begin(ctx));
   if (newton) SE_TRY(slot_alloc2d(ctx, SE_SLOT_WOUT, ctx->gbm.dim, ctx->gbm.n));
   GbmArgs a = gbm_args(ctx, false);
+  if (newton) a.ws = red_ws(ctx);  // Σ max(H,1e-2): reducing launch
   SE_LAUNCH_T(ctx, SE_KF_RESID, launch_gbm(ctx->gbm.loss, newton ? GBM_RESID_NEWTON : GBM_RESID, a, ctx->ctas_per_sm,
                             ctx->sms, ctx->stream));
   if (newton) SE_TRY(newton_finish(ctx, sum_hess));
@@ -991,6 +1107,7 @@ int se_gbm_linesearch_eval(se_ctx* ctx, const double* alpha, double* loss, doubl
   const int dim = ctx->gbm.dim;
   GbmArgs a = gbm_args(ctx, false);
   for (int j = 0; j < dim; ++j) a.coef[j] = (float)alpha[j];
+  a.ws = red_ws(ctx);
   SE_LAUNCH_T(ctx, SE_KF_EVAL, launch_gbm(ctx->gbm.loss, GBM_EVAL, a, ctx->ctas_per_sm, ctx->sms, ctx->stream));
   double s[1 + kMaxDim];
   SE_TRY(fetch_scalars(ctx, 0, 1 + dim, s));
@@ -1007,6 +1124,7 @@ int se_gbm_linesearch_stats(se_ctx* ctx, double* stats4) {
   SE_TRY(ensure_wsum(ctx));
   SE_TRY(begin(ctx));
   GbmArgs a = gbm_args(ctx, false);
+  a.ws = red_ws(ctx);
   SE_LAUNCH_T(ctx, SE_KF_SQ_STATS, launch_gbm(SE_LOSS_SQUARED, GBM_SQ_STATS, a, ctx->ctas_per_sm, ctx->sms, ctx->stream));
   SE_TRY(fetch_scalars(ctx, 0, 3, stats4));
   stats4[3] = ctx->gbm.wsum;
@@ -1023,6 +1141,7 @@ int se_gbm_update(se_ctx* ctx, const double* step, int flags, double* loss_sum, 
   GbmArgs a = gbm_args(ctx, false);
   for (int j = 0; j < ctx->gbm.dim; ++j) a.coef[j] = (float)step[j];
   const int mode = newton ? GBM_UPDATE_NEWTON : ((flags & SE_UPD_RESIDUAL) ? GBM_UPDATE_RESID : GBM_UPDATE);
+  a.ws = red_ws(ctx);
   SE_LAUNCH_T(ctx, SE_KF_UPDATE, launch_gbm(ctx->gbm.loss, mode, a, ctx->ctas_per_sm, ctx->sms, ctx->stream));
   if (newton) {
     SE_TRY(newton_finish(ctx, sum_hess));
@@ -1040,6 +1159,7 @@ int se_gbm_mean_loss(se_ctx* ctx, int which, double* out) {
   SE_TRY(ensure_counts(ctx));
   SE_TRY(begin(ctx));
   GbmArgs a = gbm_args(ctx, which == 1);
+  a.ws = red_ws(ctx);
   SE_LAUNCH_T(ctx, SE_KF_MEAN_LOSS, launch_gbm(ctx->gbm.loss, GBM_MEAN_LOSS, a, ctx->ctas_per_sm, ctx->sms, ctx->stream));
   double s = 0.0;
   SE_TRY(fetch_scalars(ctx, 0, 1, &s));
@@ -1054,6 +1174,7 @@ int se_gbm_update_validation(se_ctx* ctx, const double* step, double* mean_loss)
   SE_TRY(begin(ctx));
   GbmArgs a = gbm_args(ctx, true);
   for (int j = 0; j < ctx->gbm.dim; ++j) a.coef[j] = (float)step[j];
+  a.ws = red_ws(ctx);
   SE_LAUNCH_T(ctx, SE_KF_UPDATE, launch_gbm(ctx->gbm.loss, GBM_UPDATE, a, ctx->ctas_per_sm, ctx->sms, ctx->stream));
   double s = 0.0;
   SE_TRY(fetch_scalars(ctx, 0, 1, &s));
@@ -1218,7 +1339,7 @@ int se_boostreg_configure(se_ctx* ctx, int64_t n) {
   return SE_OK;
 }
 
-static BoostRegArgs boostreg_args(se_ctx* ctx, double sum_w, int loss_type, double max_error) {
+static BoostRegArgs boostreg_args(se_ctx* ctx, double sum_w, int loss_type, double max_error, bool exchange = true) {
   BoostRegArgs a;
   a.y = ctx->slot[SE_SLOT_Y].d;
   a.pred = ctx->slot[SE_SLOT_PRED].d;
@@ -1227,7 +1348,7 @@ static BoostRegArgs boostreg_args(se_ctx* ctx, double sum_w, int loss_type, doub
   a.loss_type = loss_type;
   a.inv_sum_w = (float)(1.0 / sum_w);
   a.inv_max_err = (max_error == 0.0) ? 1.0f : (float)(1.0 / max_error);
-  a.ws = red_ws(ctx);
+  a.ws = red_ws(ctx, 0, exchange);
   return a;
 }
 
@@ -1235,7 +1356,7 @@ int se_boostreg_max_error(se_ctx* ctx, double* max_error) {
   if (!ctx || !max_error) return fail(ctx, SE_ERR_ARG, "null argument");
   SE_REQUIRE(ctx, ctx->boostreg.on, SE_ERR_STATE, "se_boostreg_configure first");
   SE_TRY(begin(ctx));
-  BoostRegArgs a = boostreg_args(ctx, 1.0, 0, 0.0);
+  BoostRegArgs a = boostreg_args(ctx, 1.0, 0, 0.0, /*exchange=*/false);  // max-reduction: NCCL max afterwards
   SE_LAUNCH_T(ctx, SE_KF_OTHER, launch_boostreg_max(a, ctx->ctas_per_sm, ctx->sms, ctx->stream));
   return fetch_scalars(ctx, 0, 1, max_error, kNcclMax);
 }

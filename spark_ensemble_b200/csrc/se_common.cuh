@@ -99,18 +99,82 @@ __device__ __forceinline__ void block_max_publish(double v, double* partials, un
 }
 
 // Reduction workspace owned by the context: partials[kMaxGridPartials][nred], a self-resetting
-// ticket counter, and the output scalar block.
+// ticket counter, and the output scalar block.  With a peer-memory communicator attached (nranks > 1,
+// mbox != nullptr) the kernel that reduces ALSO performs the cross-GPU sum itself (see peer_exchange).
+constexpr int kMboxPayload = 40;   // doubles per mailbox row (>= kMaxRed)
+constexpr int kMboxStride = 48;    // doubles per row: payload + sequence word + padding (384 B)
 struct RedWs {
   double* partials;
   unsigned int* counter;
-  double* out;  // [nred] global (per-GPU) sums
+  double* out;  // [nred] sums: per-GPU, or global when the peer exchange is active
+  // ---- fused NVLink all-reduce (one process per GPU, mailboxes mapped with CUDA IPC)
+  double* const* mbox = nullptr;   // device table [nranks]: base of every rank's mailbox [nranks][2][kMboxStride]
+  int nranks = 1, rank = 0;
+  unsigned long long seq = 0;      // reduction sequence number (same on every rank), >= 1
+  int* err = nullptr;              // set to 1 if a peer never showed up (bounded spin)
 };
+
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_sys_f64(double* p, double v) {
+  asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+__device__ __forceinline__ double ld_relaxed_sys_f64(const double* p) {
+  double v;
+  asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// Cross-GPU sum of `nred` per-GPU totals, executed by warp 0 of the LAST CTA of the reducing kernel —
+// the collective is part of the kernel, not a separate NCCL launch:
+//   1. every lane p < nranks stores this GPU's totals into rank p's mailbox row [my rank][seq parity] with
+//      plain P2P stores over NVLink, then publishes them with a release store of the sequence number;
+//   2. it then spins (acquire loads, bounded) on its OWN mailbox until rank p's row carries this sequence;
+//   3. the rows are summed in rank order, so every GPU produces bit-identical results.
+// Rows are double-buffered by sequence parity: a peer can be at most one reduction ahead.
+__device__ __forceinline__ void peer_exchange(const double* tot, int nred, const RedWs& ws) {
+  if (ws.nranks <= 1 || ws.mbox == nullptr) {
+    for (int k = threadIdx.x; k < nred; k += blockDim.x) ws.out[k] = tot[k];
+    return;
+  }
+  if ((threadIdx.x >> 5) != 0) return;
+  const int lane = threadIdx.x & 31;
+  const int par = (int)(ws.seq & 1ull);
+  for (int p = lane; p < ws.nranks; p += 32) {
+    double* row = ws.mbox[p] + (size_t)(ws.rank * 2 + par) * kMboxStride;
+    for (int k = 0; k < nred; ++k) st_relaxed_sys_f64(row + k, tot[k]);
+    st_release_sys_u64(reinterpret_cast<unsigned long long*>(row + kMboxPayload), ws.seq);
+  }
+  bool ok = true;
+  for (int p = lane; p < ws.nranks; p += 32) {
+    const double* row = ws.mbox[ws.rank] + (size_t)(p * 2 + par) * kMboxStride;
+    const long long t0 = clock64();
+    while (ld_acquire_sys_u64(reinterpret_cast<const unsigned long long*>(row + kMboxPayload)) != ws.seq) {
+      if (clock64() - t0 > 6000000000ll) { ok = false; break; }  // ~3 s: a peer never launched
+    }
+  }
+  ok = __all_sync(0xffffffffu, ok);
+  for (int k = lane; k < nred; k += 32) {
+    double sum = 0.0;
+    for (int p = 0; p < ws.nranks; ++p)
+      sum += ld_relaxed_sys_f64(ws.mbox[ws.rank] + (size_t)(p * 2 + par) * kMboxStride + k);
+    ws.out[k] = ok ? sum : __longlong_as_double(0x7ff8000000000000ll);
+  }
+  if (!ok && lane == 0 && ws.err) *ws.err = 1;
+}
 
 // Block-reduce NRED per-thread fp64 accumulators, publish the block partial, and let the last CTA
 // to arrive reduce all partials in a fixed order (deterministic for a fixed launch configuration).
 template <int NRED>
 __device__ __forceinline__ void block_reduce_publish(double (&acc)[NRED], const RedWs& ws) {
   __shared__ double sm[NRED][kBlock / 32];
+  __shared__ double tot[NRED];
   __shared__ bool is_last;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
@@ -150,9 +214,11 @@ __device__ __forceinline__ void block_reduce_publish(double (&acc)[NRED], const 
     for (int k = 0; k < NRED; ++k) {
       double v = (lane < kBlock / 32) ? sm[k][lane] : 0.0;
       v = warp_sum(v);
-      if (lane == 0) ws.out[k] = v;
+      if (lane == 0) tot[k] = v;
     }
   }
+  __syncthreads();
+  peer_exchange(tot, NRED, ws);  // per-GPU totals -> ws.out (summed across GPUs when a peer communicator is attached)
 }
 
 // ---- counter-based synthetic generator (bench / tests): identical integer stream on host -----

@@ -195,6 +195,7 @@ __global__ void __launch_bounds__(kRows) gbm_logloss_staged_kernel(const GbmArgs
   if (T::kReduce) {
     // Σloss: block reduction over 4 warps; per-class sums are already block-level in s_acc.
     __shared__ double sm_red[kRows / 32];
+    __shared__ double s_tot[NRED];
     __shared__ bool is_last;
     const int lane = tid & 31, warp = tid >> 5;
     {
@@ -208,6 +209,7 @@ __global__ void __launch_bounds__(kRows) gbm_logloss_staged_kernel(const GbmArgs
       a.ws.partials[(size_t)blockIdx.x * NRED] = v;
     }
     if (T::kPerClassAcc && tid < KMAX) a.ws.partials[(size_t)blockIdx.x * NRED + 1 + tid] = (tid < K) ? s_acc[tid] : 0.0;
+    __threadfence();  // every writer publishes its partials before the ticket is taken
     __syncthreads();
     if (tid == 0) {
       __threadfence();
@@ -222,8 +224,10 @@ __global__ void __launch_bounds__(kRows) gbm_logloss_staged_kernel(const GbmArgs
       double v = 0.0;
       for (unsigned int b = lane; b < gridDim.x; b += 32) v += __ldcg(&a.ws.partials[(size_t)b * NRED + k]);
       v = warp_sum(v);
-      if (lane == 0) a.ws.out[k] = v;  // out[0] = Σloss, out[1 + k] per class (register-kernel convention)
+      if (lane == 0) s_tot[k] = v;  // [0] = Σloss, [1 + k] per class (register-kernel convention)
     }
+    __syncthreads();
+    peer_exchange(s_tot, NRED, a.ws);
   }
 }
 

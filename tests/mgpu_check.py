@@ -31,6 +31,9 @@ def main():
     dist.broadcast(uid, 0)
     ctx.comm_init(world, rank, bytes(uid.cpu().numpy().tobytes()))
     assert ctx.comm_info() == (world, rank)
+    p2p = ctx.comm_p2p_active()
+    if os.environ.get("SE_P2P_ALLREDUCE", "1") != "0" and os.environ.get("SE_REQUIRE_P2P") == "1":
+        assert p2p, "fused peer-memory all-reduce expected to be active"
     orc = O.Oracle()
     rng = np.random.default_rng(11)
     n, nv, K = 200_003, 50_001, 5
@@ -111,7 +114,7 @@ def main():
     assert abs(e2 - orc.r2_estimator_error("exponential", v, pr, wb, sw, mx)) <= RT * e2
     dist.barrier()
     if rank == 0:
-        print(f"MGPU_PARITY_OK world={world}")
+        print(f"MGPU_PARITY_OK world={world} p2p_allreduce={p2p}")
     ctx.close()
     dist.destroy_process_group()
 

@@ -412,10 +412,15 @@ def test_multi_gpu_sharded_parity():
         pytest.skip("needs >= 2 GPUs")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     world = 2
-    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
-                          "--master-addr", "127.0.0.1", "--master-port", "29533",
-                          os.path.join(root, "tests", "mgpu_check.py")], capture_output=True, text=True, timeout=600)
-    assert out.returncode == 0 and "MGPU_PARITY_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
+    # once with the fused peer-memory all-reduce (default), once forcing the NCCL fallback
+    for port, p2p in ((29533, "1"), (29537, "0")):
+        env = dict(os.environ, SE_P2P_ALLREDUCE=p2p, SE_REQUIRE_P2P="1")
+        out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+                              "--master-addr", "127.0.0.1", "--master-port", str(port),
+                              os.path.join(root, "tests", "mgpu_check.py")], capture_output=True, text=True,
+                             timeout=600, env=env)
+        assert out.returncode == 0 and "MGPU_PARITY_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
+        assert f"p2p_allreduce={p2p == '1'}" in out.stdout
 
 
 @pytest.mark.parametrize("K", [9, 26, 32])
