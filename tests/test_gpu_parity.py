@@ -614,3 +614,38 @@ def test_bag_multiplicities(ctx, oracle, rng, name):
     ctx.gbm_set_bag(None)
     lg2, _ = ctx.gbm_linesearch_eval(alpha)
     assert lg2 == pytest.approx(oracle.linesearch_eval(lid, par, y, w, Fo, h, alpha)[0], rel=RTOL)
+
+
+def test_empty_and_tiny_inputs(ctx, oracle):
+    """Edge cases the domain has: empty shards (a rank may own zero rows), single rows, zero models."""
+    from spark_ensemble_b200 import _native as N
+    # empty GBM shard: every entry point runs, sums are 0, nothing crashes
+    ctx.gbm_configure(0, 0, 1, "squared", 0.0, False)
+    ctx.gbm_pseudo_residuals(False)
+    ls, _ = ctx.gbm_update([0.5], residual=True, loss=True)
+    assert ls == 0.0
+    s = ctx.gbm_linesearch_stats()
+    assert list(s[:3]) == [0.0, 0.0, 0.0]
+    ctx.gbm_configure(0, 0, 3, "logloss", 0.0, False)
+    ls, _ = ctx.gbm_update(np.ones(3), residual=True, loss=True)
+    assert ls == 0.0
+    ctx.gbm_configure(0, 0, 9, "logloss", 0.0, False)  # staged (TMA) kernel with no tiles
+    ls, _ = ctx.gbm_update(np.ones(9), residual=True, loss=True)
+    assert ls == 0.0
+    # empty boosting shard
+    ctx.boost_configure(0, 3, True)
+    assert ctx.slot_sum(N.SLOT_BW) == 0.0
+    e, s2 = ctx.boost_real_update(1.0)
+    assert (e, s2) == (0.0, 0.0)
+    # single row through every GBM loss
+    for name in ("squared", "absolute", "huber", "quantile", "bernoulli", "exponential"):
+        ctx.gbm_configure(1, 0, 1, name, 0.5, False)
+        ctx.upload(N.SLOT_Y, [1.0]); ctx.upload(N.SLOT_F, [0.25]); ctx.upload(N.SLOT_H, [0.5])
+        l, g = ctx.gbm_linesearch_eval([2.0])
+        lo, go = oracle.linesearch_eval(O.LOSS_IDS[name], 0.5, np.array([1.0]), None, np.array([[0.25]]),
+                                        np.array([[0.5]]), [2.0])
+        assert l == pytest.approx(lo, rel=RTOL) and g[0] == pytest.approx(go[0], rel=RTOL, abs=1e-7)
+    # aggregation over zero rows
+    ctx.agg_configure(N.AGG_GBM_REGRESSOR, 3, 0, 1, 0, 0)
+    ctx.agg_run([1.0, 1.0, 1.0], [0.0])
+    assert ctx.download(N.SLOT_RAW).size == 0
