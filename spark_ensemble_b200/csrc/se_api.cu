@@ -98,7 +98,7 @@ struct se_ctx {
   bool timing = false;
   double last_ms = 0.0;
   int sms = 148;
-  int ctas_per_sm = 4;
+  int ctas_per_sm = 8;  // upper bound; launchers scale the grid down for small shards (se_gbm.cu grid_for)
   int64_t launches = 0;
   SlotBuf slot[SE_NUM_SLOTS];
   double* d_scal = nullptr;

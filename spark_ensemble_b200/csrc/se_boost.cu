@@ -15,12 +15,20 @@ namespace {
 constexpr float kSparkEps = 2.220446049250313e-16f;  // Spark ml.impl.Utils.EPSILON (2^-52)
 constexpr int KU = 8;                                // classes loaded per batch (8 x 16 B in flight)
 
-inline int grid_for(int64_t items, int64_t per_cta, int ctas_per_sm, int sms) {
-  int64_t need = (items + per_cta - 1) / per_cta;
-  if (need < 1) need = 1;
+// Persistent grid: a multiple of the SM count, up to `ctas_per_sm` CTAs per SM, but never so many that a CTA
+// gets fewer than ~8 work units (tiles).  Measured on B200 (squared loss): at 100 M rows 8 CTAs/SM beats 2
+// (K1 0.97 vs 0.93 of the HBM peak: later waves rebalance the tail), at 10 M rows 2 beats 8 (0.82 vs 0.77:
+// fewer, longer-lived CTAs amortise ramp-up and the per-CTA reduction epilogue).
+inline int grid_for(int64_t work_items, int64_t per_cta, int ctas_per_sm, int sms) {
+  int64_t units = (work_items + per_cta - 1) / per_cta;
+  if (units < 1) units = 1;
+  if (ctas_per_sm > 4) ctas_per_sm = 4;  // light grid-stride kernels (all CTAs resident): 4/SM measured best
   int64_t cap = (int64_t)ctas_per_sm * sms;
-  if (cap > kMaxGridPartials) cap = kMaxGridPartials;
-  return (int)(need < cap ? need : cap);
+  if (cap > kMaxGridPartials) cap = (kMaxGridPartials / sms) * sms;
+  int64_t want = (units / 8 / sms) * sms;  // >= 8 units per CTA, whole multiples of the SM count
+  if (want < sms) want = sms;
+  if (want > cap) want = cap;
+  return (int)(units < want ? units : want);
 }
 
 // Σ_k code_k log max(p_k, ε) with code_y = 1, code_{k≠y} = -1/(K-1)  (BoostingClassifier.scala:218-224)
@@ -103,13 +111,15 @@ __global__ void __launch_bounds__(kBlock) boost_real_kernel(const BoostArgs a) {
 __global__ void __launch_bounds__(kBlock) boost_discrete_error_kernel(const BoostArgs a) {
   double acc[1] = {0.0};
   const int64_t n4 = a.n >> 2;
-  constexpr int U = 4;  // 12 independent 16 B loads per thread in flight
-  const int64_t stride = (int64_t)gridDim.x * kBlock;
-  for (int64_t g0 = (int64_t)blockIdx.x * kBlock + threadIdx.x; g0 < n4; g0 += stride * U) {
+  constexpr int U = 4;  // 12 independent 16 B loads per thread in flight, contiguous tiles like the GBM kernels
+  constexpr int64_t tile = (int64_t)kBlock * U;
+  const int64_t ntiles = (n4 + tile - 1) / tile;
+  for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    const int64_t base = t * tile + threadIdx.x;
     float4 vy[U], vp[U], vw[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const int64_t g = g0 + u * stride;
+      const int64_t g = base + (int64_t)u * kBlock;
       if (g < n4) {
         vy[u] = ld_stream4(a.y + 4 * g);
         vp[u] = ld_stream4(a.pred + 4 * g);
@@ -118,7 +128,7 @@ __global__ void __launch_bounds__(kBlock) boost_discrete_error_kernel(const Boos
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      if (g0 + u * stride < n4) {
+      if (base + (int64_t)u * kBlock < n4) {
         float e4 = 0.f;
 #pragma unroll
         for (int e = 0; e < 4; ++e)
