@@ -11,6 +11,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -45,11 +46,16 @@ constexpr int kNcclSum = 0;
 constexpr int kNcclMax = 2;
 constexpr int kNcclChar = 0;
 
+void nccl_load(NcclApi& api);
+
 NcclApi& nccl() {
   static NcclApi api;
-  static bool tried = false;
-  if (tried) return api;
-  tried = true;
+  static std::once_flag once;
+  std::call_once(once, [] { nccl_load(api); });
+  return api;
+}
+
+void nccl_load(NcclApi& api) {
   const char* names[] = {getenv("SE_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
   for (const char* nm : names) {
     if (!nm || !*nm) continue;
@@ -57,12 +63,13 @@ NcclApi& nccl() {
     if (api.handle) break;
   }
   if (!api.handle) {
-    api.why = std::string("dlopen(libnccl.so.2) failed: ") + (dlerror() ? dlerror() : "?");
-    return api;
+    const char* de = dlerror();
+    api.why = std::string("dlopen(libnccl.so.2) failed: ") + (de ? de : "?");
+    return;
   }
 #define SE_SYM(field, name)                                                     \
   api.field = reinterpret_cast<decltype(api.field)>(dlsym(api.handle, name));   \
-  if (!api.field) { api.why = std::string("missing symbol ") + name; return api; }
+  if (!api.field) { api.why = std::string("missing symbol ") + name; return; }
   SE_SYM(GetUniqueId, "ncclGetUniqueId")
   SE_SYM(CommInitRank, "ncclCommInitRank")
   SE_SYM(CommDestroy, "ncclCommDestroy")
@@ -72,7 +79,6 @@ NcclApi& nccl() {
   SE_SYM(GetVersion, "ncclGetVersion")
 #undef SE_SYM
   api.ok = true;
-  return api;
 }
 
 thread_local std::string g_last_error;
@@ -743,7 +749,11 @@ int se_comm_init(se_ctx* ctx, int nranks, int rank, const void* id, int bytes) {
   SE_CUDA(ctx, cudaMalloc(&d_recv, hb * nranks));
   SE_CUDA(ctx, cudaMemcpyAsync(d_send, send.data(), hb, cudaMemcpyHostToDevice, ctx->stream));
   rc = api.AllGather(d_send, d_recv, hb, kNcclChar, ctx->comm, ctx->stream);
-  if (rc != 0) return fail(ctx, SE_ERR_NCCL, "ncclAllGather: %s", api.GetErrorString(rc));
+  if (rc != 0) {
+    cudaFree(d_send);
+    cudaFree(d_recv);
+    return fail(ctx, SE_ERR_NCCL, "ncclAllGather: %s", api.GetErrorString(rc));
+  }
   SE_CUDA(ctx, cudaMemcpyAsync(recv.data(), d_recv, hb * nranks, cudaMemcpyDeviceToHost, ctx->stream));
   SE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   int all_ok = 1;

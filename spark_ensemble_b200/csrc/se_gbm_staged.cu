@@ -133,31 +133,26 @@ __global__ void __launch_bounds__(kRows) gbm_logloss_staged_kernel(const GbmArgs
     const float* sH = sF + K * kRows;
     const int yi = (int)yv;
 
-    // pass 1: p_k = F_k + c_k h_k, max / first argmax
-    float m = -INFINITY;
-    int am = 0;
+    // pass A (online soft-max, one sweep over the classes): running max m and s = Σ_k exp(p_k - m), rescaled
+    // whenever the max moves — no separate max pass; p_y picked up on the way.
+    float m = -INFINITY, ssum = 0.f, py = 0.f;
 #pragma unroll 4
     for (int k = 0; k < K; ++k) {
-      const float p = T::kReadH ? fmaf(s_coef[k], sH[k * kRows], sF[k * kRows]) : sF[k * kRows];
-      if (p > m) { m = p; am = k; }
-    }
-    // pass 2: Σ_{k != argmax} exp(p_k - m), p_y
-    float srest = 0.f, py = 0.f;
-#pragma unroll 4
-    for (int k = 0; k < K; ++k) {
-      const float p = T::kReadH ? fmaf(s_coef[k], sH[k * kRows], sF[k * kRows]) : sF[k * kRows];
-      const float e = ex2_approx((p - m) * kLog2e);
-      srest += (k != am) ? e : 0.f;
+      const float p = T::kReadH ? fmaf(s_coef[k], sH[k * kRows], sF[k * kRows]) : sF[k * kRows];  // GBMLoss.scala:56-59
+      const float mn = fmaxf(m, p);
+      ssum = fmaf(ssum, ex2_approx((m - mn) * kLog2e), ex2_approx((p - mn) * kLog2e));
+      m = mn;
       py = (k == yi) ? p : py;
     }
-    const float lse = m + log1p_pos(srest);
-    const float inv_s = rcp_approx(1.0f + srest);
+    // ssum >= 1 (the max term contributes exactly 1): log Σ exp(p_k) = m + log1p(ssum - 1)
+    const float lse = m + log1p_pos(ssum - 1.0f);
+    const float inv_s = rcp_approx(ssum);
     if (T::kSumLoss && in) acc_loss += (double)(((MODE == GBM_EVAL) ? cv : 1.0f) * (lse - py));  // GBMLoss.scala:206-221
-    // pass 3: per-class outputs
+    // pass B: per-class outputs (no per-class registers: sums go through shared memory)
     if (T::kPerClassAcc || T::kWriteF || T::kWriteR) {
-#pragma unroll
-      for (int k = 0; k < KMAX; ++k) {
-        if (k < K) {
+#pragma unroll 4
+      for (int k = 0; k < K; ++k) {
+        {
           const float hk = T::kReadH ? sH[k * kRows] : 0.f;
           const float p = T::kReadH ? fmaf(s_coef[k], hk, sF[k * kRows]) : sF[k * kRows];
           const float sm = ex2_approx((p - m) * kLog2e) * inv_s;   // exp(p_k - lse)
