@@ -252,6 +252,17 @@ class Context:
                                                    C.byref(a), C.byref(l), C.byref(ne)))
         return a.value, l.value, ne.value
 
+    def gbm_linesearch_eval2(self, alpha: float):
+        l, d1, d2 = C.c_double(), C.c_double(), C.c_double()
+        self._ck(self._lib.se_gbm_linesearch_eval2(self._h, float(alpha), C.byref(l), C.byref(d1), C.byref(d2)))
+        return l.value, d1.value, d2.value
+
+    def gbm_linesearch_newton(self, lo=0.0, hi=100.0, start=1.0, rel=1e-6, abs_tol=1e-6, max_eval=100):
+        a, l, ne = C.c_double(), C.c_double(), C.c_int()
+        self._ck(self._lib.se_gbm_linesearch_newton(self._h, lo, hi, start, rel, abs_tol, max_eval,
+                                                    C.byref(a), C.byref(l), C.byref(ne)))
+        return a.value, l.value, ne.value
+
     def gbm_round_squared_async(self, learning_rate: float = 1.0):
         self._ck(self._lib.se_gbm_round_squared_async(self._h, float(learning_rate)))
 

@@ -1232,6 +1232,55 @@ int se_gbm_linesearch_brent(se_ctx* ctx, double lo, double hi, double start, dou
   return SE_OK;
 }
 
+int se_gbm_linesearch_eval2(se_ctx* ctx, double alpha, double* loss, double* d1, double* d2) {
+  if (!ctx || !loss || !d1 || !d2) return fail(ctx, SE_ERR_ARG, "null argument");
+  SE_REQUIRE(ctx, ctx->gbm.on && ctx->gbm.dim == 1 && ctx->gbm.loss != SE_LOSS_LOGLOSS, SE_ERR_STATE, "needs a dim-1 scalar loss");
+  SE_TRY(ensure_wsum(ctx));
+  SE_TRY(begin(ctx));
+  GbmArgs a = gbm_args(ctx, false);
+  a.coef[0] = (float)alpha;
+  a.ws = red_ws(ctx);
+  SE_LAUNCH_T(ctx, SE_KF_EVAL, launch_gbm(ctx->gbm.loss, GBM_EVAL, a, ctx->ctas_per_sm, ctx->sms, ctx->stream));
+  double s[3];
+  SE_TRY(fetch_scalars(ctx, 0, 3, s));
+  *loss = s[0] / ctx->gbm.wsum;
+  *d1 = s[1] / ctx->gbm.wsum;
+  *d2 = s[2] / ctx->gbm.wsum;
+  return SE_OK;
+}
+
+int se_gbm_linesearch_newton(se_ctx* ctx, double lo, double hi, double start, double rel, double abs_tol,
+                             int max_eval, double* alpha, double* loss, int* n_eval) {
+  if (!ctx || !alpha) return fail(ctx, SE_ERR_ARG, "null argument");
+  SE_REQUIRE(ctx, ctx->gbm.on && ctx->gbm.dim == 1, SE_ERR_STATE, "Newton line search needs dim == 1");
+  SE_REQUIRE(ctx, loss_has_hessian(ctx->gbm.loss), SE_ERR_ARG, "loss %d has no hessian: use the Brent line search", ctx->gbm.loss);
+  if (lo > hi) { const double t = lo; lo = hi; hi = t; }
+  double a = lo, b = hi;
+  double x = fmin(fmax(start, a), b);
+  double f = NAN;
+  int evals = 0;
+  for (;;) {
+    if (evals >= max_eval) return fail(ctx, SE_ERR_OPT, "Newton line search exceeded MaxEval(%d)", max_eval);
+    double d1, d2;
+    SE_TRY(se_gbm_linesearch_eval2(ctx, x, &f, &d1, &d2));
+    ++evals;
+    // the objective is convex along the line: the sign of the slope brackets the minimiser
+    if (d1 > 0.0) b = x; else a = x;
+    if ((x <= lo && d1 >= 0.0) || (x >= hi && d1 <= 0.0) || d1 == 0.0) break;  // boundary or stationary
+    double xn = (d2 > 0.0) ? x - d1 / d2 : 0.5 * (a + b);
+    // a Newton step that leaves the interval through an end that has not been evaluated yet: try that end
+    // (a boundary minimum is then confirmed in one pass instead of ~20 bisections); otherwise bisect
+    if (xn <= a) xn = (a == lo && x != lo) ? lo : 0.5 * (a + b);
+    else if (xn >= b) xn = (b == hi && x != hi) ? hi : 0.5 * (a + b);
+    if (fabs(xn - x) <= rel * fabs(x) + abs_tol) break;  // x is within tolerance of the minimiser
+    x = xn;
+  }
+  *alpha = x;
+  if (loss) *loss = f;
+  if (n_eval) *n_eval = evals;
+  return SE_OK;
+}
+
 int se_gbm_round_squared_async(se_ctx* ctx, double learning_rate) {
   if (!ctx) return fail(nullptr, SE_ERR_ARG, "null context");
   SE_REQUIRE(ctx, ctx->gbm.on && ctx->gbm.loss == SE_LOSS_SQUARED, SE_ERR_STATE, "squared loss only");

@@ -66,19 +66,23 @@ __global__ void __launch_bounds__(kBlock, LossTune<LOSS>::kMinCtas) gbm_scalar_k
   // the bag (reference quirk 4), i.e. every per-row term of those sums is multiplied by the row's count
   constexpr bool kBagMode = (MODE == GBM_EVAL) || T::kNewton;
   const bool has_bag = kBagMode && (a.bag != nullptr);
-  double acc[2] = {0.0, 0.0};
+  // [0] Σloss, [1] Σ h·g (eval) or Σ max(H,1e-2) (newton), [2] Σ h²·H (eval: curvature of the line-search objective)
+  double acc[3] = {0.0, 0.0, 0.0};
 
   const int64_t n4 = a.n >> 2;
   constexpr int64_t tile = (int64_t)kBlock * U;
   const int64_t ntiles = (n4 + tile - 1) / tile;
 
   auto row = [&](float y, float F, float h, float w, float c, float& Fo, float& ro, float& wo, float& l_acc,
-                 float& x_acc) {
+                 float& x_acc, float& z_acc) {
     const float p = T::kReadH ? fmaf(coef, h, F) : F;
     const LGH o = eval_loss<LOSS>(y, p, param);
     if (T::kWriteF) Fo = p;
     if (T::kSumLoss) l_acc += (MODE == GBM_EVAL) ? c * o.l : o.l;
-    if (MODE == GBM_EVAL) x_acc = fmaf(c * h, o.g, x_acc);
+    if (MODE == GBM_EVAL) {
+      x_acc = fmaf(c * h, o.g, x_acc);
+      z_acc = fmaf(c * h * h, o.h, z_acc);
+    }
     if (T::kNewton) {
       const float hc = fmaxf(o.h, 1e-2f);   // GBMRegressor.scala:371
       ro = -o.g / hc;                       // :377
@@ -113,19 +117,20 @@ __global__ void __launch_bounds__(kBlock, LossTune<LOSS>::kMinCtas) gbm_scalar_k
       if (!ok[u]) continue;
       const int64_t g = base + (int64_t)u * kBlock;
       float4 oF, oR, oW;
-      float l_acc = 0.f, x_acc = 0.f;
+      float l_acc = 0.f, x_acc = 0.f, z_acc = 0.f;
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const float w = (T::kNewton && has_w) ? f4at(vw[u], e) : 1.0f;
         const float c = has_bag ? f4at(vb[u], e) : 1.0f;
         row(f4at(vy[u], e), f4at(vF[u], e), T::kReadH ? f4at(vh[u], e) : 0.f, w, c, f4at(oF, e),
-            f4at(oR, e), f4at(oW, e), l_acc, x_acc);
+            f4at(oR, e), f4at(oW, e), l_acc, x_acc, z_acc);
       }
       if (T::kWriteF) st_stream4(a.F + 4 * g, oF);
       if (T::kWriteR) st_stream4(a.r + 4 * g, oR);
       if (T::kNewton) st_stream4(a.wout + 4 * g, oW);
       if (T::kSumLoss) acc[0] += (double)l_acc;
       if (MODE == GBM_EVAL || T::kNewton) acc[1] += (double)x_acc;
+      if (MODE == GBM_EVAL) acc[2] += (double)z_acc;
     }
   }
   // scalar tail (n % 4 rows)
@@ -133,15 +138,16 @@ __global__ void __launch_bounds__(kBlock, LossTune<LOSS>::kMinCtas) gbm_scalar_k
     const int64_t i = (n4 << 2) + threadIdx.x;
     const float w = (T::kNewton && has_w) ? a.w[i] : 1.0f;
     const float c = has_bag ? a.bag[i] : 1.0f;
-    float Fo = 0.f, ro = 0.f, wo = 0.f, l_acc = 0.f, x_acc = 0.f;
-    row(a.y[i], a.F[i], T::kReadH ? a.h[i] : 0.f, w, c, Fo, ro, wo, l_acc, x_acc);
+    float Fo = 0.f, ro = 0.f, wo = 0.f, l_acc = 0.f, x_acc = 0.f, z_acc = 0.f;
+    row(a.y[i], a.F[i], T::kReadH ? a.h[i] : 0.f, w, c, Fo, ro, wo, l_acc, x_acc, z_acc);
     if (T::kWriteF) a.F[i] = Fo;
     if (T::kWriteR) a.r[i] = ro;
     if (T::kNewton) a.wout[i] = wo;
     if (T::kSumLoss) acc[0] += (double)l_acc;
     if (MODE == GBM_EVAL || T::kNewton) acc[1] += (double)x_acc;
+    if (MODE == GBM_EVAL) acc[2] += (double)z_acc;
   }
-  if (T::kReduce) block_reduce_publish<2>(acc, a.ws);
+  if (T::kReduce) block_reduce_publish<3>(acc, a.ws);
 }
 
 // squared loss: the three sufficient statistics of the line-search parabola, one pass (12 B/row)

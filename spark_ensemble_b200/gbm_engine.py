@@ -92,6 +92,13 @@ class GBMEngine:
         alpha, loss, n_eval = self.ctx.gbm_linesearch_brent(0.0, 100.0, 1.0, tol, tol, max_iter)
         return alpha, loss, n_eval
 
+    def line_search_newton(self, tol: float, max_iter: int):
+        """Opt-in (Param lineSearch="newton"): safeguarded Newton on the same objective and interval, using the
+        curvature Σ h²·H returned by the evaluation pass; ~5 passes instead of Brent's 20-40.  Same minimiser to
+        the same tolerance, different iterates (not the reference's optimiser)."""
+        alpha, loss, n_eval = self.ctx.gbm_linesearch_newton(0.0, 100.0, 1.0, tol, tol, max_iter)
+        return alpha, loss, n_eval
+
     def line_search_lbfgsb(self, tol: float, max_iter: int):
         """GBMClassifier.scala:290-292,427: L-BFGS-B on [0,inf)^dim from 1, m=10.  Breeze's LBFGSB is
         third party; SciPy's L-BFGS-B (the original Byrd-Lu-Nocedal code) stands in on this host."""

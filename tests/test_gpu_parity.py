@@ -649,3 +649,35 @@ def test_empty_and_tiny_inputs(ctx, oracle):
     ctx.agg_configure(N.AGG_GBM_REGRESSOR, 3, 0, 1, 0, 0)
     ctx.agg_run([1.0, 1.0, 1.0], [0.0])
     assert ctx.download(N.SLOT_RAW).size == 0
+
+
+@pytest.mark.parametrize("name", ["squared", "bernoulli", "exponential", "logcosh"])
+def test_newton_line_search_matches_brent(ctx, oracle, rng, name):
+    """Opt-in curvature line search: derivatives of the objective match the oracle (finite differences of the
+    fp64 objective), and the minimiser agrees with Brent's to optimiser tolerance in far fewer passes."""
+    from spark_ensemble_b200 import _native as N
+    n = 50021
+    dim, par, y, F, h, w = setup_gbm(ctx, rng, name, n, True)
+    lid = O.LOSS_IDS[name]
+    r, _, _ = oracle.pseudo_residuals(lid, par, 1, y, None, F, False)
+    h = f32(0.7 * r + 0.2 * rng.standard_normal((1, n)))
+    ctx.upload(N.SLOT_H, h)
+    f = lambda a: oracle.linesearch_eval(lid, par, y, w, F, h, [a])
+    l, d1, d2 = ctx.gbm_linesearch_eval2(0.8)
+    lo, go = f(0.8)
+    assert l == pytest.approx(lo, rel=RTOL) and d1 == pytest.approx(go[0], rel=1e-4, abs=1e-8)
+    eps = 1e-4
+    fd2 = (f(0.8 + eps)[1][0] - f(0.8 - eps)[1][0]) / (2 * eps)
+    assert d2 == pytest.approx(fd2, rel=1e-3)
+    an, ln, nn = ctx.gbm_linesearch_newton()
+    ab, lb, nb = ctx.gbm_linesearch_brent()
+    # the fp32-evaluated objective is flat to ~1e-7 relative around its minimum, so Brent's abscissa is only
+    # defined to ~sqrt(noise/curvature); compare the objective reached (fp64 oracle) and the abscissa loosely
+    assert f(an)[0] <= f(ab)[0] * (1 + 1e-7)
+    assert abs(an - ab) <= 2e-3 * max(1.0, abs(ab))
+    assert abs(f(an)[1][0]) <= 1e-4 * max(1.0, abs(f(0.0)[1][0]))  # stationary point of the oracle objective
+    assert ln == pytest.approx(lb, rel=1e-6)
+    assert nn <= 12 and nn < nb  # quadratic convergence, then a few steps at the fp32 noise floor of the slope
+    ctx.gbm_configure(64, 0, 1, "absolute", 0.0, False)
+    with pytest.raises(ValueError):
+        ctx.gbm_linesearch_newton()
