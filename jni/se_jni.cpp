@@ -161,6 +161,39 @@ SE_JNI(jdouble, boostDiscreteUpdate)(JNIEnv* env, jclass, jlong h, jdouble sumW,
   return s;
 }
 
+// ---- BoostingRegressor (AdaBoost.R2), quantiles, row sub-sampling, opt-in Newton line search ----------
+SE_JNI(void, boostregConfigure)(JNIEnv* env, jclass, jlong h, jlong n) { raise(env, H(h), se_boostreg_configure(H(h), n)); }
+SE_JNI(jdouble, boostregMaxError)(JNIEnv* env, jclass, jlong h) {
+  double v = 0.0;
+  raise(env, H(h), se_boostreg_max_error(H(h), &v));
+  return v;
+}
+SE_JNI(jdouble, boostregError)(JNIEnv* env, jclass, jlong h, jdouble sumW, jint lossType, jdouble maxError) {
+  double v = 0.0;
+  raise(env, H(h), se_boostreg_error(H(h), sumW, lossType, maxError, &v));
+  return v;
+}
+SE_JNI(jdouble, boostregUpdate)(JNIEnv* env, jclass, jlong h, jdouble sumW, jint lossType, jdouble maxError, jdouble beta) {
+  double v = 0.0;
+  raise(env, H(h), se_boostreg_update(H(h), sumW, lossType, maxError, beta, &v));
+  return v;
+}
+SE_JNI(jdouble, quantile)(JNIEnv* env, jclass, jlong h, jint which, jint slot, jlong count, jdouble q) {
+  double v = 0.0;
+  raise(env, H(h), se_quantile(H(h), which, slot, count, q, &v));
+  return v;
+}
+SE_JNI(void, gbmSetBag)(JNIEnv* env, jclass, jlong h, jboolean on) { raise(env, H(h), se_gbm_set_bag(H(h), on ? 1 : 0)); }
+SE_JNI(jdoubleArray, gbmLinesearchNewton)(JNIEnv* env, jclass, jlong h, jdouble lo, jdouble hi, jdouble start, jdouble tol,
+                                          jint maxEval) {
+  double out[2] = {0, 0};
+  int ne = 0;
+  if (raise(env, H(h), se_gbm_linesearch_newton(H(h), lo, hi, start, tol, tol, maxEval, &out[0], &out[1], &ne))) return nullptr;
+  jdoubleArray r = env->NewDoubleArray(2);
+  env->SetDoubleArrayRegion(r, 0, 2, out);
+  return r;  // (alpha, objective)
+}
+
 SE_JNI(void, aggConfigure)(JNIEnv* env, jclass, jlong h, jint kind, jint numModels, jint numClasses, jint dim,
                            jint loss, jlong n) {
   raise(env, H(h), se_agg_configure(H(h), kind, numModels, numClasses, dim, loss, n));

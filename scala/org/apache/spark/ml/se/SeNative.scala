@@ -13,7 +13,7 @@ object SeNative {
   // enum se_slot / se_loss / se_agg_kind / update flags (include/se_abi.h)
   object Slot { val Y = 0; val W = 1; val F = 2; val H = 3; val R = 4; val WOUT = 5; val VY = 6; val VF = 7
     val VH = 8; val BW = 9; val PROBA = 10; val PRED = 11; val P = 12; val RAW = 13; val PROB = 14
-    val LABEL = 15; val X = 16; val VX = 17 }
+    val LABEL = 15; val X = 16; val VX = 17; val BAG = 18 }
   object Loss { val Squared = 0; val Absolute = 1; val Huber = 2; val Quantile = 3; val LogCosh = 4
     val ScaledLogCosh = 5; val Bernoulli = 6; val Exponential = 7; val LogLoss = 8 }
   object Upd { val Residual = 1; val Newton = 2; val Loss = 4 }
@@ -43,6 +43,16 @@ object SeNative {
   @native def boostRealUpdate(ctx: Long, sumWeights: Double): Array[Double] // (estimatorError, sumWeights')
   @native def boostDiscreteError(ctx: Long, sumWeights: Double): Double
   @native def boostDiscreteUpdate(ctx: Long, sumWeights: Double, beta: Double): Double
+
+  // BoostingRegressor (AdaBoost.R2): lossType 0 exponential, 1 linear, 2 squared
+  @native def boostregConfigure(ctx: Long, n: Long): Unit
+  @native def boostregMaxError(ctx: Long): Double
+  @native def boostregError(ctx: Long, sumWeights: Double, lossType: Int, maxError: Double): Double
+  @native def boostregUpdate(ctx: Long, sumWeights: Double, lossType: Int, maxError: Double, beta: Double): Double
+  // exact quantile (which = 0: slot values, 1: |y - F|), row sub-sampling multiplicities, opt-in Newton line search
+  @native def quantile(ctx: Long, which: Int, slot: Int, count: Long, q: Double): Double
+  @native def gbmSetBag(ctx: Long, on: Boolean): Unit
+  @native def gbmLinesearchNewton(ctx: Long, lo: Double, hi: Double, start: Double, tol: Double, maxEval: Int): Array[Double]
 
   @native def aggConfigure(ctx: Long, kind: Int, numModels: Int, numClasses: Int, dim: Int, loss: Int,
       n: Long): Unit
