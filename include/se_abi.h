@@ -141,6 +141,12 @@ SE_API int se_slot_free(se_ctx* ctx, int slot);
 SE_API int se_slot_info(const se_ctx* ctx, int slot, void** device_ptr, int64_t* count);
 SE_API int se_upload(se_ctx* ctx, int slot, const float* host, int64_t count, int64_t offset);
 SE_API int se_upload_f64(se_ctx* ctx, int slot, const double* host, int64_t count, int64_t offset);
+/* Ingest of a feature partition: `host` is ROW-major [n_rows][d] (the layout of Spark's dense
+ * feature vectors); it lands in rows [row_offset, row_offset + n_rows) of the COLUMN-major [d][n] slot
+ * (SE_SLOT_X / SE_SLOT_VX).  Chunked and double buffered: chunk c+1 is staged into pinned memory (or copied
+ * straight from `host` when it is already page-locked) while chunk c is in flight over PCIe and chunk c-1 is
+ * being transposed on the device by a 32x32 shared-memory tile kernel. */
+SE_API int se_upload_rowmajor(se_ctx* ctx, int slot, const float* host, int64_t n_rows, int d, int64_t row_offset);
 SE_API int se_download(se_ctx* ctx, int slot, float* host, int64_t count, int64_t offset);
 /* download slot*scale (e.g. BoostingClassifier.scala:186 weight = boostingWeight / sumWeights) */
 SE_API int se_download_scaled(se_ctx* ctx, int slot, double scale, float* host, int64_t count, int64_t offset);

@@ -6,7 +6,7 @@
 // (GetPrimitiveArrayCritical); device memory is owned by the se_ctx.
 //
 // Not compiled in this image: there is no JDK here (no <jni.h>).  Build where a JDK exists with
-//   g++ -O2 -fPIC -shared -I$JAVA_HOME/include -I$JAVA_HOME/include/linux -Iinclude \
+//   g++ -O2 -fPIC -shared -I$JAVA_HOME/include -I$JAVA_HOME/include/linux -Iinclude (continued)
 //       jni/se_jni.cpp -Lspark_ensemble_b200/lib -lse_b200 -o libse_jni.so
 #if defined(__has_include)
 #if __has_include(<jni.h>)

@@ -72,6 +72,7 @@ PROTOTYPES = {
     "se_slot_info": [_vp, _i32, C.POINTER(_vp), C.POINTER(_i64)],
     "se_upload": [_vp, _i32, _fp, _i64, _i64],
     "se_upload_f64": [_vp, _i32, _dp, _i64, _i64],
+    "se_upload_rowmajor": [_vp, _i32, _fp, _i64, _i32, _i64],
     "se_download": [_vp, _i32, _fp, _i64, _i64],
     "se_download_scaled": [_vp, _i32, _d, _fp, _i64, _i64],
     "se_fill": [_vp, _i32, _f, _i64, _i64],

@@ -137,6 +137,12 @@ class Context:
         a = N.as_f32(host)
         self._ck(self._lib.se_upload(self._h, slot, N.fptr(a.reshape(-1)), a.size, offset))
 
+    def upload_rowmajor(self, slot: int, features, row_offset: int = 0):
+        """Row-major [n_rows, d] partition -> rows [row_offset, ...) of the column-major [d][n] slot."""
+        a = N.as_f32(features)
+        assert a.ndim == 2
+        self._ck(self._lib.se_upload_rowmajor(self._h, slot, N.fptr(a.reshape(-1)), a.shape[0], a.shape[1], row_offset))
+
     def download(self, slot: int, count: int | None = None, offset: int = 0, scale: float | None = None,
                  out: np.ndarray | None = None) -> np.ndarray:
         r, c, _ = self.layout(slot)

@@ -920,6 +920,82 @@ int se_upload_f64(se_ctx* ctx, int slot, const double* host, int64_t count, int6
   return SE_OK;
 }
 
+int se_upload_rowmajor(se_ctx* ctx, int slot, const float* host, int64_t n_rows, int d, int64_t row_offset) {
+  if (!ctx || (!host && n_rows > 0)) return fail(ctx, SE_ERR_ARG, "null argument");
+  SE_REQUIRE(ctx, slot >= 0 && slot < SE_NUM_SLOTS, SE_ERR_ARG, "bad slot %d", slot);
+  const SlotBuf& X = ctx->slot[slot];
+  SE_REQUIRE(ctx, X.d && X.rows == d, SE_ERR_STATE, "slot %d must be allocated as [%d][n] (has [%lld][%lld])", slot, d,
+             (long long)X.rows, (long long)X.cols);
+  SE_REQUIRE(ctx, n_rows >= 0 && row_offset >= 0 && row_offset + n_rows <= X.cols, SE_ERR_ARG,
+             "rows [%lld,+%lld) outside the slot's %lld rows", (long long)row_offset, (long long)n_rows, (long long)X.cols);
+  if (n_rows == 0) return SE_OK;
+  SE_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int64_t ld = X.rows > 1 ? X.ld : X.cols;
+  // ~32 MB chunks, whole rows, multiple of 32 rows
+  int64_t chunk_rows = (int64_t)(32u << 20) / ((int64_t)d * (int64_t)sizeof(float));
+  chunk_rows = (chunk_rows / 32) * 32;
+  if (chunk_rows < 32) chunk_rows = 32;
+  if (chunk_rows > n_rows) chunk_rows = n_rows;
+  const size_t chunk_bytes = (size_t)chunk_rows * d * sizeof(float);
+  cudaPointerAttributes attr;
+  const bool pinned_src = (cudaPointerGetAttributes(&attr, host) == cudaSuccess && attr.type == cudaMemoryTypeHost);
+  cudaGetLastError();
+  float* dstage[2] = {nullptr, nullptr};
+  float* hstage[2] = {nullptr, nullptr};
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t copied[2] = {nullptr, nullptr}, consumed[2] = {nullptr, nullptr};
+  int rc = SE_OK;
+  auto cleanup = [&]() {
+    if (copy_stream) { cudaStreamSynchronize(copy_stream); cudaStreamDestroy(copy_stream); }
+    cudaStreamSynchronize(ctx->stream);
+    for (int i = 0; i < 2; ++i) {
+      if (dstage[i]) cudaFree(dstage[i]);
+      if (hstage[i]) cudaFreeHost(hstage[i]);
+      if (copied[i]) cudaEventDestroy(copied[i]);
+      if (consumed[i]) cudaEventDestroy(consumed[i]);
+    }
+  };
+#define SE_ING(call)                                                                            \
+  do {                                                                                          \
+    cudaError_t e__ = (call);                                                                   \
+    if (e__ != cudaSuccess) {                                                                   \
+      rc = fail(ctx, SE_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+      cleanup();                                                                                \
+      return rc;                                                                                \
+    }                                                                                           \
+  } while (0)
+  SE_ING(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; ++i) {
+    SE_ING(cudaMalloc(&dstage[i], chunk_bytes));
+    if (!pinned_src) SE_ING(cudaMallocHost(&hstage[i], chunk_bytes));
+    SE_ING(cudaEventCreateWithFlags(&copied[i], cudaEventDisableTiming));
+    SE_ING(cudaEventCreateWithFlags(&consumed[i], cudaEventDisableTiming));
+  }
+  int64_t done = 0;
+  for (int c = 0; done < n_rows; ++c) {
+    const int b = c & 1;
+    const int64_t rows = (n_rows - done < chunk_rows) ? n_rows - done : chunk_rows;
+    const size_t bytes = (size_t)rows * d * sizeof(float);
+    if (c >= 2) SE_ING(cudaEventSynchronize(consumed[b]));  // staging buffers of chunk c-2 are free again
+    const float* src = host + done * d;
+    if (!pinned_src) {
+      memcpy(hstage[b], src, bytes);  // overlaps the DMA of chunk c-1 and the transpose of chunk c-2
+      src = hstage[b];
+    }
+    SE_ING(cudaMemcpyAsync(dstage[b], src, bytes, cudaMemcpyHostToDevice, copy_stream));
+    SE_ING(cudaEventRecord(copied[b], copy_stream));
+    SE_ING(cudaStreamWaitEvent(ctx->stream, copied[b], 0));
+    cudaError_t le = launch_transpose_rows(dstage[b], rows, d, X.d, ld, row_offset + done, ctx->stream);
+    ctx->launches++;
+    if (le != cudaSuccess) SE_ING(le);
+    SE_ING(cudaEventRecord(consumed[b], ctx->stream));
+    done += rows;
+  }
+#undef SE_ING
+  cleanup();
+  return SE_OK;
+}
+
 int se_download(se_ctx* ctx, int slot, float* host, int64_t count, int64_t offset) {
   if (!ctx || !host) return fail(ctx, SE_ERR_ARG, "null argument");
   SE_REQUIRE(ctx, slot >= 0 && slot < SE_NUM_SLOTS, SE_ERR_ARG, "bad slot %d", slot);

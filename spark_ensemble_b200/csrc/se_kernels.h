@@ -129,6 +129,10 @@ cudaError_t launch_linear_predict(const float* X, int64_t n, int64_t ld, int n_c
 cudaError_t launch_radix_hist(const float* a, const float* b, int64_t n, uint32_t prefix, uint32_t mask,
                               int shift, double* hist, int sms, cudaStream_t s);
 
+// ---- ingest (se_util.cu): row-major host chunk [rows][d] -> column-major X[d][ld] rows [row0, row0+rows)
+cudaError_t launch_transpose_rows(const float* src, int64_t rows, int d, float* X, int64_t ld, int64_t row0,
+                                  cudaStream_t s);
+
 // ---- utilities (se_util.cu) ------------------------------------------------------------------
 cudaError_t launch_fill(float* p, float v, int64_t n, int sms, cudaStream_t s);
 cudaError_t launch_fill_synthetic(float* p, int kind, uint64_t seed, double a, double b, int64_t n,

@@ -67,6 +67,29 @@ __global__ void __launch_bounds__(kBlock) radix_hist_kernel(const float* __restr
   if (sh[threadIdx.x]) atomicAdd(&hist[threadIdx.x], (double)sh[threadIdx.x]);
 }
 
+// 32x32 shared-memory tile transpose: reads coalesced along the feature axis of the row-major chunk,
+// writes coalesced along the row axis of the column-major matrix
+__global__ void __launch_bounds__(256) transpose_rows_kernel(const float* __restrict__ src, int64_t rows, int d,
+                                                             float* __restrict__ X, int64_t ld, int64_t row0) {
+  __shared__ float tile[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  const int64_t r0 = (int64_t)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+#pragma unroll
+  for (int j = ty; j < 32; j += 8) {
+    const int64_t r = r0 + j;
+    const int c = c0 + tx;
+    tile[j][tx] = (r < rows && c < d) ? src[r * d + c] : 0.f;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = ty; j < 32; j += 8) {
+    const int c = c0 + j;
+    const int64_t r = r0 + tx;
+    if (c < d && r < rows) X[(int64_t)c * ld + row0 + r] = tile[tx][j];
+  }
+}
+
 inline int grid1(int64_t n, int sms) {
   int64_t need = (n + kBlock - 1) / kBlock;
   if (need < 1) need = 1;
@@ -79,6 +102,13 @@ inline int grid1(int64_t n, int sms) {
 cudaError_t launch_radix_hist(const float* a, const float* b, int64_t n, uint32_t prefix, uint32_t mask,
                               int shift, double* hist, int sms, cudaStream_t s) {
   radix_hist_kernel<<<grid1(n, sms), kBlock, 0, s>>>(a, b, n, prefix, mask, shift, hist);
+  return cudaGetLastError();
+}
+cudaError_t launch_transpose_rows(const float* src, int64_t rows, int d, float* X, int64_t ld, int64_t row0,
+                                  cudaStream_t s) {
+  if (rows <= 0 || d <= 0) return cudaSuccess;
+  dim3 grid((unsigned)((rows + 31) / 32), (unsigned)((d + 31) / 32));
+  transpose_rows_kernel<<<grid, 256, 0, s>>>(src, rows, d, X, ld, row0);
   return cudaGetLastError();
 }
 cudaError_t launch_fill(float* p, float v, int64_t n, int sms, cudaStream_t s) {

@@ -48,11 +48,11 @@ class GBMEngine:
         c = self.ctx
         X = np.asarray(X)
         c.alloc(N.SLOT_X, X.shape[1], X.shape[0])
-        c.upload(N.SLOT_X, np.ascontiguousarray(X.T, dtype=np.float32))
+        c.upload_rowmajor(N.SLOT_X, X)  # transposed on the device, chunked + double buffered
         if Xv is not None and self.nv > 0:
             Xv = np.asarray(Xv)
             c.alloc(N.SLOT_VX, Xv.shape[1], Xv.shape[0])
-            c.upload(N.SLOT_VX, np.ascontiguousarray(Xv.T, dtype=np.float32))
+            c.upload_rowmajor(N.SLOT_VX, Xv)
         self._x_resident = True
 
     # ---- per-round pieces

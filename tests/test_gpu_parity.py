@@ -681,3 +681,20 @@ def test_newton_line_search_matches_brent(ctx, oracle, rng, name):
     ctx.gbm_configure(64, 0, 1, "absolute", 0.0, False)
     with pytest.raises(ValueError):
         ctx.gbm_linesearch_newton()
+
+
+@pytest.mark.parametrize("n,d", [(1, 1), (33, 12), (1000, 128), (300_001, 64)])
+def test_rowmajor_ingest(ctx, rng, n, d):
+    """se_upload_rowmajor: row-major feature partitions land transposed in the column-major slot (bit-exact),
+    including appends at a row offset and chunk boundaries (the 300k x 64 case spans three 32 MB chunks)."""
+    from spark_ensemble_b200 import _native as N
+    X = f32(rng.standard_normal((n, d)))
+    ctx.alloc(N.SLOT_X, d, n)
+    ctx.fill(N.SLOT_X, -7.0)
+    split = n // 3
+    ctx.upload_rowmajor(N.SLOT_X, X[:split], 0)          # two Spark partitions appended one after the other
+    ctx.upload_rowmajor(N.SLOT_X, X[split:], split)
+    got = ctx.download(N.SLOT_X).reshape(d, n)
+    np.testing.assert_array_equal(got, X.T)
+    with pytest.raises(ValueError):
+        ctx.upload_rowmajor(N.SLOT_X, X, 1)  # runs past the slot
