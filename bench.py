@@ -263,8 +263,8 @@ def main():
         ctx.sync()
 
     def step():
-        alpha, _, _ = ctx.gbm_linesearch_brent(0.0, 100.0, 1.0, tol, tol, max_iter)
-        loss_sum, _ = ctx.gbm_update([lr * alpha], residual=True, newton=False, loss=True)
+        # Brent line search + fused update/residual/loss: one call through the C ABI (se_gbm_round)
+        alpha, loss_sum, _ = ctx.gbm_round(lr, True, tol, max_iter, residual=True)
         return alpha, loss_sum
 
     # clocks are sampled from the first warm-up step to the end of the e2e loop: the device-resident timed

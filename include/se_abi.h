@@ -203,6 +203,11 @@ SE_API int se_gbm_update_validation(se_ctx* ctx, const double* step, double* mea
  * se_gbm_linesearch_stats (one pass, identical objective values up to rounding). */
 SE_API int se_gbm_linesearch_brent(se_ctx* ctx, double lo, double hi, double start, double rel,
                             double abs_tol, int max_eval, double* alpha, double* loss, int* n_eval);
+/* One boosting round for dim == 1 in a single call (GBMRegressor.scala:398-442): Brent line search
+ * (optimized != 0; else alpha = 1), weight = learning_rate·alpha, then se_gbm_update(weight, flags).
+ * Same results as se_gbm_linesearch_brent + se_gbm_update; saves the host round-trips between them. */
+SE_API int se_gbm_round(se_ctx* ctx, double learning_rate, int optimized, double tol, int max_iter, int flags,
+                        double* alpha, double* loss_sum, int* n_eval);
 /* Opt-in fast line search for dim == 1 losses with a hessian (squared, bernoulli, exponential, logcosh): each
  * pass also returns the curvature Σ h²·H, and a safeguarded Newton iteration on [lo,hi] converges in ~4-6
  * passes instead of Brent's 20-40.  NOT the reference's optimiser: it returns a minimiser within the same

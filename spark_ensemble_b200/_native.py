@@ -90,6 +90,7 @@ PROTOTYPES = {
     "se_gbm_mean_loss": [_vp, _i32, _dp],
     "se_gbm_update_validation": [_vp, _dp, _dp],
     "se_gbm_linesearch_brent": [_vp, _d, _d, _d, _d, _d, _i32, _dp, _dp, C.POINTER(_i32)],
+    "se_gbm_round": [_vp, _d, _i32, _d, _i32, _i32, _dp, _dp, C.POINTER(_i32)],
     "se_gbm_linesearch_eval2": [_vp, _d, _dp, _dp, _dp],
     "se_gbm_linesearch_newton": [_vp, _d, _d, _d, _d, _d, _i32, _dp, _dp, C.POINTER(_i32)],
     "se_gbm_round_squared_async": [_vp, _d],

@@ -258,6 +258,15 @@ class Context:
                                                    C.byref(a), C.byref(l), C.byref(ne)))
         return a.value, l.value, ne.value
 
+    def gbm_round(self, learning_rate: float, optimized: bool = True, tol: float = 1e-6, max_iter: int = 100,
+                  residual: bool = True, newton: bool = False):
+        """Line search + update in one native call (dim 1). Returns (alpha, train_loss_sum, n_eval)."""
+        flags = (N.UPD_RESIDUAL if residual else 0) | (N.UPD_NEWTON if newton else 0) | N.UPD_LOSS
+        a, l, ne = C.c_double(), C.c_double(), C.c_int()
+        self._ck(self._lib.se_gbm_round(self._h, float(learning_rate), int(optimized), float(tol), int(max_iter), flags,
+                                        C.byref(a), C.byref(l), C.byref(ne)))
+        return a.value, l.value, ne.value
+
     def gbm_linesearch_eval2(self, alpha: float):
         l, d1, d2 = C.c_double(), C.c_double(), C.c_double()
         self._ck(self._lib.se_gbm_linesearch_eval2(self._h, float(alpha), C.byref(l), C.byref(d1), C.byref(d2)))

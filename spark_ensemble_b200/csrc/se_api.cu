@@ -1308,6 +1308,20 @@ int se_gbm_linesearch_brent(se_ctx* ctx, double lo, double hi, double start, dou
   return SE_OK;
 }
 
+int se_gbm_round(se_ctx* ctx, double learning_rate, int optimized, double tol, int max_iter, int flags,
+                 double* alpha, double* loss_sum, int* n_eval) {
+  if (!ctx) return fail(nullptr, SE_ERR_ARG, "null context");
+  SE_REQUIRE(ctx, ctx->gbm.on && ctx->gbm.dim == 1, SE_ERR_STATE, "se_gbm_round needs dim == 1");
+  double a = 1.0, obj = 0.0;
+  int ne = 0;
+  if (optimized) SE_TRY(se_gbm_linesearch_brent(ctx, 0.0, 100.0, 1.0, tol, tol, max_iter, &a, &obj, &ne));
+  const double step = learning_rate * a;
+  SE_TRY(se_gbm_update(ctx, &step, flags, loss_sum, nullptr));
+  if (alpha) *alpha = a;
+  if (n_eval) *n_eval = ne;
+  return SE_OK;
+}
+
 int se_gbm_linesearch_eval2(se_ctx* ctx, double alpha, double* loss, double* d1, double* d2) {
   if (!ctx || !loss || !d1 || !d2) return fail(ctx, SE_ERR_ARG, "null argument");
   SE_REQUIRE(ctx, ctx->gbm.on && ctx->gbm.dim == 1 && ctx->gbm.loss != SE_LOSS_LOGLOSS, SE_ERR_STATE, "needs a dim-1 scalar loss");

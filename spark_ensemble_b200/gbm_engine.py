@@ -127,7 +127,6 @@ class GBMEngine:
         """h (host) -> device; line search; F += lr·α·h fused with next residuals and loss; residuals
         (the next base learner's labels) -> host.  Returns (alpha, train_loss_sum)."""
         self.ctx.upload(N.SLOT_H, h_host)
-        alpha, _, _ = self.line_search_brent(tol, max_iter)
-        loss_sum, _ = self.ctx.gbm_update([learning_rate * alpha], residual=True, newton=False, loss=True)
+        alpha, loss_sum, _ = self.ctx.gbm_round(learning_rate, True, tol, max_iter, residual=True)
         self.ctx.download(N.SLOT_R, out=r_out)
         return alpha, loss_sum

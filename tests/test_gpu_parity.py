@@ -698,3 +698,21 @@ def test_rowmajor_ingest(ctx, rng, n, d):
     np.testing.assert_array_equal(got, X.T)
     with pytest.raises(ValueError):
         ctx.upload_rowmajor(N.SLOT_X, X, 1)  # runs past the slot
+
+
+def test_gbm_round_single_call(ctx, oracle, rng):
+    """se_gbm_round == se_gbm_linesearch_brent + se_gbm_update."""
+    from spark_ensemble_b200 import _native as N
+    n = 30011
+    for name in ("squared", "bernoulli"):
+        dim, par, y, F, h, w = setup_gbm(ctx, rng, name, n)
+        a1, l1, ne1 = ctx.gbm_round(0.5, True, 1e-6, 100, residual=True)
+        F1, r1 = ctx.download(N.SLOT_F).copy(), ctx.download(N.SLOT_R).copy()
+        ctx.upload(N.SLOT_F, F)
+        a2, _, ne2 = ctx.gbm_linesearch_brent()
+        l2, _ = ctx.gbm_update([0.5 * a2], residual=True, loss=True)
+        assert (a1, ne1) == (a2, ne2) and l1 == l2
+        np.testing.assert_array_equal(F1, ctx.download(N.SLOT_F))
+        np.testing.assert_array_equal(r1, ctx.download(N.SLOT_R))
+        a3, l3, ne3 = ctx.gbm_round(0.5, False)
+        assert (a3, ne3) == (1.0, 0)
