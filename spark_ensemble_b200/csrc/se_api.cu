@@ -153,6 +153,8 @@ struct se_ctx {
   int* h_p2p_err = nullptr;
   unsigned long long red_seq = 0;
   bool last_reduce_global = false;    // the kernel just launched already produced cross-GPU sums
+  unsigned pass_parity = 0;           // alternates the tile direction of consecutive GBM passes (L2 reuse)
+  bool alternate = true;
   std::string err;
   // stopwatch + per-kernel-family timing
   cudaEvent_t tm0 = nullptr, tm1 = nullptr;
@@ -405,6 +407,7 @@ GbmArgs gbm_args(se_ctx* ctx, bool validation) {
   a.ld = ctx->slot[validation ? SE_SLOT_VF : SE_SLOT_F].ld;
   a.dim = g.dim;
   a.param = (float)g.param;
+  a.reverse = (ctx->alternate && !validation) ? (int)(ctx->pass_parity++ & 1u) : 0;
   a.ws = red_ws(ctx, 0, /*exchange=*/false);  // armed (sequence number taken) only at reducing launches
   return a;
 }
@@ -541,6 +544,7 @@ int se_ctx_create(int device, se_ctx** out) {
   cudaDeviceProp prop;
   SE_CREATE_CUDA(cudaGetDeviceProperties(&prop, device));
   ctx->sms = prop.multiProcessorCount;
+  if (const char* s = getenv("SE_ALTERNATE_PASSES")) ctx->alternate = atoi(s) != 0;
   if (const char* s = getenv("SE_CTAS_PER_SM")) {
     const int v = atoi(s);
     if (v >= 1 && v <= 16) ctx->ctas_per_sm = v;

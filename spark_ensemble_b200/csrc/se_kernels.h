@@ -39,6 +39,8 @@ struct GbmArgs {
   const double* dev_stats = nullptr;
   float lr = 1.f;
   int stages = 2;  // staged logloss kernel: shared-memory stages (1 or 2)
+  int reverse = 0; // walk the tiles from the end: consecutive passes alternate direction so the tail of one
+                   // pass (still in the 126 MB L2) is the head of the next
   RedWs ws{};
 };
 
