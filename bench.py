@@ -5,7 +5,8 @@
 
 Workload (config.workload): one GBMRegressor boosting iteration, squared loss, on N_rows x 128 fp32
 synthetic rows per GPU (default 100 M x 128, the configuration the metric is quoted on):
-    line search  (Brent, commons-math3 semantics, over the one-pass sufficient statistics  — K2, 12 B/row)
+    line search  (Brent, commons-math3 semantics, over the one-pass sufficient statistics  — K2, 8 B/row:
+                  the residual r = y - F left by the previous fused update, and h)
   + F += lr*alpha*h fused with next-round pseudo-residuals and train loss                  — K1, 20 B/row
 i.e. regression/GBMRegressor.scala:398-442 + :368-385 of the reference, per round.
 `value`  = rows/s with y, F, h (and the 128-column feature matrix) resident in HBM.
@@ -35,7 +36,7 @@ sys.path.insert(0, ROOT)
 
 METRIC = "boosting-iter rows/sec (grad+update)"
 BYTES_K1 = 20  # y,F,h read + F',r written, fp32
-BYTES_K2 = 12  # y,F,h read
+BYTES_K2 = 8   # squared-loss statistics read the current residual r = y - F and h (12 when r is stale: y,F,h)
 
 
 def _ncu_traffic(rows: int):

@@ -122,6 +122,7 @@ struct se_ctx {
     double param = 0.0;
     bool has_w = false;
     bool use_bag = false;
+    bool r_current = false;  // SE_SLOT_R holds -g(y, F) of the CURRENT F (squared loss: y - F)
     double wsum = 0.0;
     bool wsum_valid = false;
     double n_global = 0.0, nv_global = 0.0;
@@ -876,7 +877,13 @@ int se_slot_free(se_ctx* ctx, int slot) {
 int se_slot_info(const se_ctx* ctx, int slot, void** device_ptr, int64_t* count) {
   if (!ctx) return fail(nullptr, SE_ERR_ARG, "null context");
   if (slot < 0 || slot >= SE_NUM_SLOTS) return fail(nullptr, SE_ERR_ARG, "bad slot %d", slot);
-  if (device_ptr) *device_ptr = ctx->slot[slot].d;
+  if (device_ptr) {
+    *device_ptr = ctx->slot[slot].d;
+    // the caller may write through the raw pointer: drop everything cached about the slot's contents
+    se_ctx* mctx = const_cast<se_ctx*>(ctx);
+    if (slot == SE_SLOT_Y || slot == SE_SLOT_F || slot == SE_SLOT_R) mctx->gbm.r_current = false;
+    if (slot == SE_SLOT_W || slot == SE_SLOT_BAG) mctx->gbm.wsum_valid = false;
+  }
   if (count) *count = ctx->slot[slot].rows * ctx->slot[slot].cols;
   return SE_OK;
 }
@@ -895,6 +902,7 @@ int se_upload(se_ctx* ctx, int slot, const float* host, int64_t count, int64_t o
   SE_REQUIRE(ctx, slot >= 0 && slot < SE_NUM_SLOTS, SE_ERR_ARG, "bad slot %d", slot);
   SE_CUDA(ctx, cudaSetDevice(ctx->device));
   if (slot == SE_SLOT_W || slot == SE_SLOT_BAG) ctx->gbm.wsum_valid = false;
+  if (slot == SE_SLOT_Y || slot == SE_SLOT_F || slot == SE_SLOT_R) ctx->gbm.r_current = false;
   SE_TRY(for_segments(ctx, ctx->slot[slot], count, offset, [&](float* d, int64_t done, int64_t len) {
     SE_CUDA(ctx, cudaMemcpyAsync(d, host + done, sizeof(float) * len, cudaMemcpyHostToDevice, ctx->stream));
     return SE_OK;
@@ -909,6 +917,7 @@ int se_upload_f64(se_ctx* ctx, int slot, const double* host, int64_t count, int6
   SE_REQUIRE(ctx, slot >= 0 && slot < SE_NUM_SLOTS, SE_ERR_ARG, "bad slot %d", slot);
   SE_CUDA(ctx, cudaSetDevice(ctx->device));
   if (slot == SE_SLOT_W || slot == SE_SLOT_BAG) ctx->gbm.wsum_valid = false;
+  if (slot == SE_SLOT_Y || slot == SE_SLOT_F || slot == SE_SLOT_R) ctx->gbm.r_current = false;
   // narrow on the host (halves PCIe bytes) through pinned staging, in chunks
   const int64_t chunk = 1 << 22;
   SE_TRY(ensure_stage(ctx, sizeof(float) * (size_t)chunk));
@@ -1025,6 +1034,7 @@ int se_fill(se_ctx* ctx, int slot, float value, int64_t count, int64_t offset) {
   SE_REQUIRE(ctx, slot >= 0 && slot < SE_NUM_SLOTS, SE_ERR_ARG, "bad slot %d", slot);
   SE_CUDA(ctx, cudaSetDevice(ctx->device));
   if (slot == SE_SLOT_W || slot == SE_SLOT_BAG) ctx->gbm.wsum_valid = false;
+  if (slot == SE_SLOT_Y || slot == SE_SLOT_F || slot == SE_SLOT_R) ctx->gbm.r_current = false;
   return for_segments(ctx, ctx->slot[slot], count, offset, [&](float* d, int64_t, int64_t len) {
     SE_LAUNCH(ctx, launch_fill(d, value, len, ctx->sms, ctx->stream));
     return SE_OK;
@@ -1037,6 +1047,7 @@ int se_copy_slot(se_ctx* ctx, int dst_slot, int src_slot) {
              SE_ERR_ARG, "bad slot");
   const SlotBuf &d = ctx->slot[dst_slot], &s = ctx->slot[src_slot];
   SE_REQUIRE(ctx, d.d && s.d && d.rows == s.rows && d.cols == s.cols, SE_ERR_STATE, "slot shapes differ");
+  if (dst_slot == SE_SLOT_Y || dst_slot == SE_SLOT_F || dst_slot == SE_SLOT_R) ctx->gbm.r_current = false;
   SE_CUDA(ctx, cudaSetDevice(ctx->device));
   SE_CUDA(ctx, cudaMemcpyAsync(d.d, s.d, sizeof(float) * (size_t)(s.rows * s.ld), cudaMemcpyDeviceToDevice, ctx->stream));
   return SE_OK;
@@ -1049,6 +1060,7 @@ int se_fill_synthetic(se_ctx* ctx, int slot, int kind, uint64_t seed, double a, 
   SE_REQUIRE(ctx, kind >= 0 && kind <= 3, SE_ERR_ARG, "bad synthetic kind %d", kind);
   SE_CUDA(ctx, cudaSetDevice(ctx->device));
   if (slot == SE_SLOT_W || slot == SE_SLOT_BAG) ctx->gbm.wsum_valid = false;
+  if (slot == SE_SLOT_Y || slot == SE_SLOT_F || slot == SE_SLOT_R) ctx->gbm.r_current = false;
   return for_segments(ctx, ctx->slot[slot], count, offset, [&](float* d, int64_t done, int64_t len) {
     SE_LAUNCH(ctx, launch_fill_synthetic(d, kind, seed, a, b, len, offset + done, ctx->sms, ctx->stream));
     return SE_OK;
@@ -1126,6 +1138,7 @@ int se_gbm_configure(se_ctx* ctx, int64_t n_train, int64_t n_valid, int dim, int
   g.on = true; g.n = n_train; g.nv = n_valid; g.dim = dim; g.loss = loss; g.param = param;
   g.has_w = has_weights != 0;
   g.use_bag = false;
+  g.r_current = false;
   g.wsum_valid = false; g.counts_valid = false;
   SE_TRY(slot_alloc2d(ctx, SE_SLOT_Y, 1, n_train));
   SE_TRY(slot_alloc2d(ctx, SE_SLOT_F, dim, n_train));
@@ -1144,6 +1157,7 @@ int se_gbm_set_loss_param(se_ctx* ctx, double param) {
   if (!ctx) return fail(nullptr, SE_ERR_ARG, "null context");
   SE_REQUIRE(ctx, ctx->gbm.on, SE_ERR_STATE, "se_gbm_configure first");
   ctx->gbm.param = param;
+  ctx->gbm.r_current = false;
   return SE_OK;
 }
 
@@ -1186,6 +1200,7 @@ int se_gbm_pseudo_residuals(se_ctx* ctx, int newton, double* sum_hess) {
   SE_LAUNCH_T(ctx, SE_KF_RESID, launch_gbm(ctx->gbm.loss, newton ? GBM_RESID_NEWTON : GBM_RESID, a, ctx->ctas_per_sm,
                             ctx->sms, ctx->stream));
   if (newton) SE_TRY(newton_finish(ctx, sum_hess));
+  ctx->gbm.r_current = true;  // squared loss: r = y - F for gradient and newton (h = 1) alike
   return end(ctx);
 }
 
@@ -1214,6 +1229,7 @@ int se_gbm_linesearch_stats(se_ctx* ctx, double* stats4) {
   SE_TRY(ensure_wsum(ctx));
   SE_TRY(begin(ctx));
   GbmArgs a = gbm_args(ctx, false);
+  a.stats_from_r = ctx->gbm.r_current ? 1 : 0;
   a.ws = red_ws(ctx);
   SE_LAUNCH_T(ctx, SE_KF_SQ_STATS, launch_gbm(SE_LOSS_SQUARED, GBM_SQ_STATS, a, ctx->ctas_per_sm, ctx->sms, ctx->stream));
   SE_TRY(fetch_scalars(ctx, 0, 3, stats4));
@@ -1233,6 +1249,7 @@ int se_gbm_update(se_ctx* ctx, const double* step, int flags, double* loss_sum, 
   const int mode = newton ? GBM_UPDATE_NEWTON : ((flags & SE_UPD_RESIDUAL) ? GBM_UPDATE_RESID : GBM_UPDATE);
   a.ws = red_ws(ctx);
   SE_LAUNCH_T(ctx, SE_KF_UPDATE, launch_gbm(ctx->gbm.loss, mode, a, ctx->ctas_per_sm, ctx->sms, ctx->stream));
+  ctx->gbm.r_current = (mode != GBM_UPDATE);  // the fused modes refresh R from the new F
   if (newton) {
     SE_TRY(newton_finish(ctx, sum_hess));
     if (loss_sum) *loss_sum = ctx->h_scal[0];
@@ -1380,6 +1397,7 @@ int se_gbm_round_squared_async(se_ctx* ctx, double learning_rate) {
   SE_REQUIRE(ctx, ctx->gbm.on && ctx->gbm.loss == SE_LOSS_SQUARED, SE_ERR_STATE, "squared loss only");
   SE_TRY(begin(ctx));
   GbmArgs a = gbm_args(ctx, false);
+  a.stats_from_r = ctx->gbm.r_current ? 1 : 0;
   a.ws = red_ws(ctx, kScalRound);  // stats -> d_scal[64..66]
   SE_LAUNCH_T(ctx, SE_KF_SQ_STATS, launch_gbm(SE_LOSS_SQUARED, GBM_SQ_STATS, a, ctx->ctas_per_sm, ctx->sms, ctx->stream));
   SE_TRY(allreduce_dev(ctx, kScalRound, 3));
@@ -1389,6 +1407,7 @@ int se_gbm_round_squared_async(se_ctx* ctx, double learning_rate) {
   u.ws = red_ws(ctx, kScalRound + 8);  // Σloss -> d_scal[72]
   SE_LAUNCH_T(ctx, SE_KF_UPDATE, launch_gbm(SE_LOSS_SQUARED, GBM_UPDATE_RESID, u, ctx->ctas_per_sm, ctx->sms, ctx->stream));
   SE_TRY(allreduce_dev(ctx, kScalRound + 8, 1));
+  ctx->gbm.r_current = true;
   return end(ctx);
 }
 

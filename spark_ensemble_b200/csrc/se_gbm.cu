@@ -152,6 +152,10 @@ __global__ void __launch_bounds__(kBlock, LossTune<LOSS>::kMinCtas) gbm_scalar_k
 }
 
 // squared loss: the three sufficient statistics of the line-search parabola, one pass (12 B/row)
+// FROM_R: the residual slot already holds r = y - F for the current F (squared loss: r = -g, written by the
+// previous fused update or by se_gbm_pseudo_residuals), so the statistics Σr², Σh·r, Σh² need r and h only:
+// 8 B/row instead of 12.  Bit-identical: r was computed as the same fp32 difference y - F.
+template <bool FROM_R>
 __global__ void __launch_bounds__(kBlock) gbm_sq_stats_kernel(const GbmArgs a) {
   constexpr int U = U_SCALAR;
   const bool has_bag = (a.bag != nullptr);
@@ -169,8 +173,12 @@ __global__ void __launch_bounds__(kBlock) gbm_sq_stats_kernel(const GbmArgs a) {
       const int64_t g = base + (int64_t)u * kBlock;
       ok[u] = g < n4;
       if (ok[u]) {
-        vy[u] = ld_stream4(a.y + 4 * g);
-        vF[u] = ld_stream4(a.F + 4 * g);
+        if (FROM_R) {
+          vy[u] = ld_stream4(a.r + 4 * g);
+        } else {
+          vy[u] = ld_stream4(a.y + 4 * g);
+          vF[u] = ld_stream4(a.F + 4 * g);
+        }
         vh[u] = ld_stream4(a.h + 4 * g);
         if (has_bag) vb[u] = ld_stream4(a.bag + 4 * g);
       }
@@ -181,7 +189,7 @@ __global__ void __launch_bounds__(kBlock) gbm_sq_stats_kernel(const GbmArgs a) {
       float s0 = 0.f, s1 = 0.f, s2 = 0.f;
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        const float d = f4at(vy[u], e) - f4at(vF[u], e), h = f4at(vh[u], e);
+        const float d = FROM_R ? f4at(vy[u], e) : f4at(vy[u], e) - f4at(vF[u], e), h = f4at(vh[u], e);
         const float c = has_bag ? f4at(vb[u], e) : 1.0f;
         s0 = fmaf(c * d, d, s0);
         s1 = fmaf(c * h, d, s1);
@@ -194,7 +202,7 @@ __global__ void __launch_bounds__(kBlock) gbm_sq_stats_kernel(const GbmArgs a) {
   }
   if (blockIdx.x == 0 && threadIdx.x < (a.n & 3)) {
     const int64_t i = (n4 << 2) + threadIdx.x;
-    const float d = a.y[i] - a.F[i], h = a.h[i];
+    const float d = FROM_R ? a.r[i] : a.y[i] - a.F[i], h = a.h[i];
     const float c = has_bag ? a.bag[i] : 1.0f;
     acc[0] += (double)(c * d * d);
     acc[1] += (double)(c * h * d);
@@ -434,7 +442,8 @@ cudaError_t launch_gbm(int loss, int mode, const GbmArgs& a, int ctas_per_sm, in
   if (mode == GBM_SQ_STATS) {
     if (loss != SE_LOSS_SQUARED) return cudaErrorInvalidValue;
     const int grid = grid_for(a.n >> 2, (int64_t)kBlock * U_SCALAR, ctas_per_sm, sms);
-    gbm_sq_stats_kernel<<<grid, kBlock, 0, st>>>(a);
+    if (a.stats_from_r) gbm_sq_stats_kernel<true><<<grid, kBlock, 0, st>>>(a);
+    else gbm_sq_stats_kernel<false><<<grid, kBlock, 0, st>>>(a);
     return cudaGetLastError();
   }
   if (loss != SE_LOSS_LOGLOSS) {

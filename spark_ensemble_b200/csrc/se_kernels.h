@@ -39,6 +39,7 @@ struct GbmArgs {
   const double* dev_stats = nullptr;
   float lr = 1.f;
   int stages = 2;  // staged logloss kernel: shared-memory stages (1 or 2)
+  int stats_from_r = 0;  // squared-loss statistics read the current residual slot r = y - F (8 B/row) instead of y, F (12 B/row)
   int reverse = 0; // walk the tiles from the end: consecutive passes alternate direction so the tail of one
                    // pass (still in the 126 MB L2) is the head of the next
   RedWs ws{};

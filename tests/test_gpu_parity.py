@@ -716,3 +716,28 @@ def test_gbm_round_single_call(ctx, oracle, rng):
         np.testing.assert_array_equal(r1, ctx.download(N.SLOT_R))
         a3, l3, ne3 = ctx.gbm_round(0.5, False)
         assert (a3, ne3) == (1.0, 0)
+
+
+def test_squared_stats_from_residual_slot(ctx, oracle, rng):
+    """Squared loss: when R holds the current residual (after pseudo_residuals or a fused update) the line-search
+    statistics are read from (r, h) — 8 B/row — and are bit-identical to the (y, F, h) pass; any write to
+    Y/F/R falls back to the 12 B/row pass."""
+    from spark_ensemble_b200 import _native as N
+    n = 100003
+    dim, par, y, F, h, w = setup_gbm(ctx, rng, "squared", n, True)
+    s_yfh = ctx.gbm_linesearch_stats()           # R stale: y, F, h
+    ctx.gbm_pseudo_residuals(False)
+    s_r = ctx.gbm_linesearch_stats()             # R current: r, h
+    np.testing.assert_array_equal(s_r, s_yfh)
+    ls, _ = ctx.gbm_update([0.3], residual=True, loss=True)
+    s_r2 = ctx.gbm_linesearch_stats()            # fused update refreshed R
+    Fo = F.astype(np.float64).copy(); oracle.update(Fo, h, [0.3])
+    d = y.astype(np.float64) - Fo[0]; hh = h[0].astype(np.float64)
+    close(s_r2[:3], [np.sum(d * d), np.sum(hh * d), np.sum(hh * hh)])
+    Fnow = ctx.download(N.SLOT_F)
+    ctx.upload(N.SLOT_F, Fnow)                   # same values, but the write invalidates the cache
+    np.testing.assert_array_equal(ctx.gbm_linesearch_stats(), s_r2)
+    ctx.gbm_update([0.1], residual=False, loss=True)   # plain update: R is stale again
+    s3 = ctx.gbm_linesearch_stats()
+    oracle.update(Fo, h, [0.1]); d = y.astype(np.float64) - Fo[0]
+    close(s3[:3], [np.sum(d * d), np.sum(hh * d), np.sum(hh * hh)])
