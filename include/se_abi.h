@@ -185,7 +185,9 @@ SE_API int se_gbm_pseudo_residuals(se_ctx* ctx, int newton, double* sum_hess);
  * grad[dim] = gradSum/weightSum (grad may be NULL).  One streaming pass over Y,F,H. */
 SE_API int se_gbm_linesearch_eval(se_ctx* ctx, const double* alpha, double* loss, double* grad);
 /* squared loss only: the three sufficient statistics of the line-search parabola in one pass,
- * stats = {Σ(y-F)², Σh(y-F), Σh², weightSum}; objective(α) = (s0 - 2α s1 + α² s2) / (2 s3). */
+ * stats = {Σ(y-F)², Σh(y-F), Σh², weightSum}; objective(α) = (s0 - 2α s1 + α² s2) / (2 s3).
+ * When SE_SLOT_R is current (after se_gbm_pseudo_residuals or a fused update) the pass reads r = y-F and h only
+ * (8 B/row, bit-identical); any write to Y/F/R through this ABI reverts to reading y, F, h (12 B/row). */
 SE_API int se_gbm_linesearch_stats(se_ctx* ctx, double* stats4);
 /* F_j += step_j·H_j (GBMRegressor.scala:437-441; GBMClassifier.scala:437-448), fused with what the
  * next round needs: flags select extra outputs computed from the NEW F in the same pass. */

@@ -88,17 +88,70 @@ __global__ void __launch_bounds__(kBlock) agg_sum_kernel(const float* __restrict
   }
 }
 
-// Vote histogram: A_c = Σ_{m: vote_m == c} a_m (a_m = 1 when a == nullptr).  One row per thread,
-// per-thread histogram in shared memory laid out [K][kBlock] (conflict-free).
-__global__ void __launch_bounds__(kBlock) agg_votes_kernel(const float* __restrict__ votes, int64_t n,
-                                                          int64_t ld, int M, int K,
-                                                          const float* __restrict__ a,
-                                                          float* __restrict__ out, int64_t ld_out) {
+// Per-row epilogue on the C per-class sums t_c (from shared memory or from the RAW slot): raw, prob, label.
+struct FinArgs {
+  int kind, C, K, dim, loss, M;
+  float sum_a;  // Σ a_m (boosting discrete)
+  int64_t n, ld;
+  float* raw;
+  float* prob;
+  float* label;
+};
+
+__device__ __forceinline__ float fin_raw(const FinArgs& f, float t, float mean_t) {
+  switch (f.kind) {
+    case SE_AGG_BOOSTING_REAL:  // (K-1)(L_k − mean L)   BoostingClassifier.scala:355-360
+      return (float)(f.K - 1) * (t - mean_t);
+    case SE_AGG_BOOSTING_DISCRETE:  // +a on the vote, −a/(K-1) elsewhere   :371-376
+      return (t * (float)f.K - f.sum_a) / (float)(f.K - 1);
+    default: return t;
+  }
+}
+
+// get(c) returns the stage-1 sum of class c for this row.  Two sweeps over the classes: (1) raw values with an
+// online max / Σexp / first-argmax, (2) write raw and probability.
+template <class Get>
+__device__ __forceinline__ void finalize_row(const FinArgs& f, int64_t i, Get get) {
+  const int C = f.C;
+  float mean_t = 0.f;
+  if (f.kind == SE_AGG_BOOSTING_REAL) {
+    float s = 0.f;
+    for (int c = 0; c < C; ++c) s += get(c);
+    mean_t = s / (float)C;
+  }
+  const bool softmax = (f.kind == SE_AGG_BOOSTING_REAL || f.kind == SE_AGG_BOOSTING_DISCRETE ||
+                        f.kind == SE_AGG_GBM_CLASSIFIER);
+  // boosting: softmax(raw/(K-1)) (BoostingClassifier.scala:342-346); GBM logloss: softmax(raw) (GBMLoss.scala:258-261)
+  const float sc = (f.kind == SE_AGG_GBM_CLASSIFIER) ? kLog2e : kLog2e / (float)(f.K - 1);
+  float best = -INFINITY, ssum = 0.f;
+  int am = 0;
+  for (int c = 0; c < C; ++c) {
+    const float r = fin_raw(f, get(c), mean_t);
+    if (r > best) am = c;  // Vector.argmax: first maximum
+    const float mn = fmaxf(best, r);
+    if (softmax) ssum = fmaf(ssum, ex2_approx((best - mn) * sc), ex2_approx((r - mn) * sc));
+    best = mn;
+  }
+  f.label[i] = (float)am;
+  const float inv = softmax ? rcp_approx(ssum) : 1.0f / (float)f.M;  // bagging: prob = raw·(1/M) (BaggingClassifier.scala:285-287)
+  for (int c = 0; c < C; ++c) {
+    const float r = fin_raw(f, get(c), mean_t);
+    f.prob[c * f.ld + i] = softmax ? ex2_approx((r - best) * sc) * inv : r * inv;
+    f.raw[c * f.ld + i] = r;
+  }
+}
+
+// Vote histogram: A_c = Σ_{m: vote_m == c} a_m (a_m = 1 when a == nullptr).  One row per thread, per-thread
+// histogram in shared memory laid out [K][kBlock] (conflict-free); the epilogue (raw, probability, argmax)
+// runs straight out of shared memory — no intermediate [K][n] round trip through HBM.
+__global__ void __launch_bounds__(kBlock) agg_votes_kernel(const float* __restrict__ votes, int64_t ld, int M,
+                                                          const float* __restrict__ a, const FinArgs f) {
   extern __shared__ float hist[];  // [K][kBlock]
-  for (int64_t i0 = (int64_t)blockIdx.x * kBlock; i0 < n; i0 += (int64_t)gridDim.x * kBlock) {
+  const int K = f.K;
+  for (int64_t i0 = (int64_t)blockIdx.x * kBlock; i0 < f.n; i0 += (int64_t)gridDim.x * kBlock) {
     const int64_t i = i0 + threadIdx.x;
     for (int c = 0; c < K; ++c) hist[c * kBlock + threadIdx.x] = 0.f;
-    if (i < n) {
+    if (i < f.n) {
       for (int m0 = 0; m0 < M; m0 += MU) {
         float v[MU];
 #pragma unroll
@@ -111,8 +164,34 @@ __global__ void __launch_bounds__(kBlock) agg_votes_kernel(const float* __restri
             if (c >= 0 && c < K) hist[c * kBlock + threadIdx.x] += a ? a[m0 + u] : 1.0f;
           }
       }
-      for (int c = 0; c < K; ++c) out[c * ld_out + i] = hist[c * kBlock + threadIdx.x];
+      finalize_row(f, i, [&](int c) { return hist[c * kBlock + threadIdx.x]; });
     }
+  }
+}
+
+// Stage 2 for the sum-based kinds: per-row epilogue on tmp[C][n] (in RAW) -> raw, prob, label.
+__global__ void __launch_bounds__(kBlock) agg_finalize_kernel(const FinArgs f) {
+  for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < f.n;
+       i += (int64_t)gridDim.x * kBlock) {
+    if (f.kind == SE_AGG_GBM_CLASSIFIER && f.dim == 1 && f.K == 2) {
+      // GBMClassifier.scala:583-584 + GBMLoss.scala:284-289,311-316 (raw(0) = −F)
+      const float res = f.raw[i];
+      const float r0 = -res;
+      // p1 = 1/(1+e^x), p0 = 1 - p1 with x = raw(0) (bernoulli) or -2 raw(0) (exponential); both
+      // formed from t = e^-|x| so the small one keeps full relative precision
+      const float x = (f.loss == SE_LOSS_EXPONENTIAL) ? -2.0f * r0 : r0;
+      const float t = exp_neg_fast(-fabsf(x));
+      const float inv = rcp_approx(1.0f + t);
+      const float p1 = (x >= 0.f) ? t * inv : inv;
+      const float p0 = (x >= 0.f) ? inv : t * inv;
+      f.raw[i] = r0;
+      f.raw[f.ld + i] = res;
+      f.prob[i] = p0;
+      f.prob[f.ld + i] = p1;
+      f.label[i] = (res > r0) ? 1.0f : 0.0f;  // argmax, first maximum on ties
+      continue;
+    }
+    finalize_row(f, i, [&](int c) { return f.raw[c * f.ld + i]; });
   }
 }
 
@@ -146,83 +225,6 @@ __global__ void __launch_bounds__(kWmRows) agg_wmedian_kernel(const float* __res
       if (W >= half) best = v;
     }
     if (in) out[row] = best;
-  }
-}
-
-// Stage 2: per-row epilogue on tmp[C][n] (in RAW) -> raw, prob, label.
-struct FinArgs {
-  int kind, C, K, dim, loss, M;
-  float sum_a;  // Σ a_m (boosting discrete)
-  int64_t n, ld;
-  float* raw;
-  float* prob;
-  float* label;
-};
-
-__device__ __forceinline__ float fin_raw(const FinArgs& f, float t, float mean_t) {
-  switch (f.kind) {
-    case SE_AGG_BOOSTING_REAL:  // (K-1)(L_k − mean L)   BoostingClassifier.scala:355-360
-      return (float)(f.K - 1) * (t - mean_t);
-    case SE_AGG_BOOSTING_DISCRETE:  // +a on the vote, −a/(K-1) elsewhere   :371-376
-      return (t * (float)f.K - f.sum_a) / (float)(f.K - 1);
-    default: return t;
-  }
-}
-
-__global__ void __launch_bounds__(kBlock) agg_finalize_kernel(const FinArgs f) {
-  for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < f.n;
-       i += (int64_t)gridDim.x * kBlock) {
-    if (f.kind == SE_AGG_GBM_CLASSIFIER && f.dim == 1 && f.K == 2) {
-      // GBMClassifier.scala:583-584 + GBMLoss.scala:284-289,311-316 (raw(0) = −F)
-      const float res = f.raw[i];
-      const float r0 = -res;
-      // p1 = 1/(1+e^x), p0 = 1 - p1 with x = raw(0) (bernoulli) or -2 raw(0) (exponential); both
-      // formed from t = e^-|x| so the small one keeps full relative precision
-      const float x = (f.loss == SE_LOSS_EXPONENTIAL) ? -2.0f * r0 : r0;
-      const float t = exp_neg_fast(-fabsf(x));
-      const float inv = rcp_approx(1.0f + t);
-      const float p1 = (x >= 0.f) ? t * inv : inv;
-      const float p0 = (x >= 0.f) ? inv : t * inv;
-      f.raw[i] = r0;
-      f.raw[f.ld + i] = res;
-      f.prob[i] = p0;
-      f.prob[f.ld + i] = p1;
-      f.label[i] = (res > r0) ? 1.0f : 0.0f;  // argmax, first maximum on ties
-      continue;
-    }
-    const int C = f.C;
-    float mean_t = 0.f;
-    if (f.kind == SE_AGG_BOOSTING_REAL) {
-      float s = 0.f;
-      for (int c = 0; c < C; ++c) s += f.raw[c * f.ld + i];
-      mean_t = s / (float)C;
-    }
-    // pass 1: raw, max / argmax
-    float best = -INFINITY;
-    int am = 0;
-    for (int c = 0; c < C; ++c) {
-      const float r = fin_raw(f, f.raw[c * f.ld + i], mean_t);
-      if (r > best) { best = r; am = c; }
-    }
-    f.label[i] = (float)am;
-    const bool softmax = (f.kind == SE_AGG_BOOSTING_REAL || f.kind == SE_AGG_BOOSTING_DISCRETE ||
-                          (f.kind == SE_AGG_GBM_CLASSIFIER));
-    if (softmax) {
-      // boosting: softmax(raw/(K-1)) (:342-346); GBM logloss: softmax(raw) (GBMLoss.scala:258-261)
-      const float sc = (f.kind == SE_AGG_GBM_CLASSIFIER) ? 1.0f : 1.0f / (float)(f.K - 1);
-      float s = 0.f;
-      for (int c = 0; c < C; ++c) s += exp_neg_fast((fin_raw(f, f.raw[c * f.ld + i], mean_t) - best) * sc);
-      const float inv = rcp_approx(s);
-      for (int c = 0; c < C; ++c) {
-        const float r = fin_raw(f, f.raw[c * f.ld + i], mean_t);
-        f.prob[c * f.ld + i] = exp_neg_fast((r - best) * sc) * inv;
-        f.raw[c * f.ld + i] = r;
-      }
-    } else {
-      // bagging: prob = raw · (1/M)   (BaggingClassifier.scala:285-287)
-      const float invM = 1.0f / (float)f.M;
-      for (int c = 0; c < C; ++c) f.prob[c * f.ld + i] = f.raw[c * f.ld + i] * invM;
-    }
   }
 }
 
@@ -290,11 +292,11 @@ cudaError_t launch_agg(const AggArgs& a, int ctas_per_sm, int sms, cudaStream_t 
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
       }
-      agg_votes_kernel<<<grid1, kBlock, smem, st>>>(
-          a.P, a.n, a.ld, a.M, a.K, a.kind == SE_AGG_BOOSTING_DISCRETE ? a.weights : nullptr, a.raw,
-          a.ld_out);
       f.C = a.K;
-      break;
+      f.sum_a = a.sum_weights;
+      agg_votes_kernel<<<grid1, kBlock, smem, st>>>(
+          a.P, a.ld, a.M, a.kind == SE_AGG_BOOSTING_DISCRETE ? a.weights : nullptr, f);
+      return cudaGetLastError();  // epilogue fused: no separate finalize launch
     }
     default: return cudaErrorInvalidValue;
   }

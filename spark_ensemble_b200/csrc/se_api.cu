@@ -1639,7 +1639,8 @@ int se_agg_run(se_ctx* ctx, const double* weights, const double* init) {
   }
   if (used) SE_CUDA(ctx, cudaMemcpyAsync(ctx->d_small, hs, used * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
   SE_LAUNCH_T(ctx, SE_KF_AGG, launch_agg(a, 8, ctx->sms, ctx->stream));
-  if (g.kind >= SE_AGG_GBM_CLASSIFIER && g.kind <= SE_AGG_BOOSTING_DISCRETE) ctx->launches++;  // finalize kernel
+  if (g.kind == SE_AGG_GBM_CLASSIFIER || g.kind == SE_AGG_BAGGING_SOFT || g.kind == SE_AGG_BOOSTING_REAL)
+    ctx->launches++;  // separate finalize kernel (the vote kinds fuse their epilogue)
   return end(ctx);
 }
 
