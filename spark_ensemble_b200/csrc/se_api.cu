@@ -154,6 +154,17 @@ struct se_ctx {
   int* h_p2p_err = nullptr;
   unsigned long long red_seq = 0;
   bool last_reduce_global = false;    // the kernel just launched already produced cross-GPU sums
+  // host mirror of the scalar block (mapped pinned memory written by the reducing kernel's last CTA)
+  double* h_mirror = nullptr;         // [kMboxPayload] + ticket word
+  double* d_mirror = nullptr;         // device alias
+  unsigned long long mirror_ticket = 0;
+  bool mirror_valid = false;
+  int mirror_off = 0;
+  bool use_mirror = true;
+  float* d_ls_u = nullptr;            // line-search view (signed): u = (2y-1)F, v = (2y-1)h
+  float* d_ls_v = nullptr;
+  int64_t ls_cap = 0;
+  bool ls_packed = false;             // evaluations currently read (u, v) instead of (y, F, h)
   unsigned pass_parity = 0;           // alternates the tile direction of consecutive GBM passes (L2 reuse)
   bool alternate = true;
   std::string err;
@@ -246,8 +257,17 @@ int drain_kernel_events(se_ctx* ctx) {
     if (!(cond)) return fail(ctx, code, __VA_ARGS__); \
   } while (0)
 
+// A non-sticky error left behind by an unrelated earlier runtime call (e.g. a query that reported "not ready")
+// must not be mistaken for a failure of the next kernel launch, which is checked with cudaGetLastError().
+void clear_stale_error(const char* where) {
+  const cudaError_t stale = cudaGetLastError();
+  if (stale != cudaSuccess && getenv("SE_DEBUG"))
+    fprintf(stderr, "[se_b200] cleared stale CUDA error at %s: %s\n", where, cudaGetErrorString(stale));
+}
+
 int begin(se_ctx* ctx) {
   if (!ctx) return fail(nullptr, SE_ERR_ARG, "null context");
+  clear_stale_error("begin");
   SE_CUDA(ctx, cudaSetDevice(ctx->device));
   if (ctx->timing) SE_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
   return SE_OK;
@@ -255,6 +275,7 @@ int begin(se_ctx* ctx) {
 
 int end(se_ctx* ctx) {
   if (ctx->timing) SE_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+  if (getenv("SE_DEBUG")) clear_stale_error("end");
   return SE_OK;
 }
 
@@ -266,6 +287,16 @@ RedWs red_ws(se_ctx* ctx, int out_offset = 0, bool exchange = true) {
   ws.counter = ctx->d_counter;
   ws.out = ctx->d_scal + out_offset;
   ctx->last_reduce_global = false;
+  ctx->mirror_valid = false;
+  // results can be mirrored to the host by the kernel itself when they are final on this GPU: single GPU, or
+  // the fused peer exchange (with the NCCL fallback the all-reduce still has to run after the kernel)
+  if (exchange && ctx->use_mirror && ctx->h_mirror && (ctx->nranks <= 1 || ctx->p2p)) {
+    ws.host_out = ctx->d_mirror;
+    ws.host_flag = reinterpret_cast<volatile unsigned long long*>(ctx->d_mirror + kMboxPayload);
+    ws.host_ticket = ++ctx->mirror_ticket;
+    ctx->mirror_valid = true;
+    ctx->mirror_off = out_offset;
+  }
   if (exchange && ctx->p2p && ctx->nranks > 1) {
     ws.mbox = ctx->d_mbox_table;
     ws.nranks = ctx->nranks;
@@ -293,6 +324,29 @@ int allreduce_dev(se_ctx* ctx, int off, int count, int op = kNcclSum) {
 
 // (all-reduce and) bring d_scal[off..off+count) to the host; synchronises the stream
 int fetch_scalars(se_ctx* ctx, int off, int count, double* out, int op = kNcclSum) {
+  if (ctx->mirror_valid && ctx->mirror_off == off && op == kNcclSum && count <= kMboxPayload) {
+    // poll the ticket the last CTA writes after the sums: no D2H copy, no stream synchronisation
+    ctx->mirror_valid = false;
+    ctx->last_reduce_global = false;
+    SE_TRY(end(ctx));
+    volatile unsigned long long* flag = reinterpret_cast<volatile unsigned long long*>(ctx->h_mirror + kMboxPayload);
+    bool seen = false;
+    for (long spin = 0; spin < 2000000000L; ++spin) {
+      if (*flag == ctx->mirror_ticket) { seen = true; break; }
+      if ((spin & 0xFFFFF) == 0xFFFFF && cudaStreamQuery(ctx->stream) != cudaErrorNotReady) {  // finished or failed
+        seen = (*flag == ctx->mirror_ticket);
+        break;
+      }
+    }
+    if (!seen) {
+      SE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+      if (*flag != ctx->mirror_ticket) return fail(ctx, SE_ERR_CUDA, "reduction results never reached the host mirror");
+    }
+    for (int i = 0; i < count; ++i) out[i] = ctx->h_mirror[i];
+    if (ctx->p2p && ctx->h_p2p_err && *reinterpret_cast<volatile int*>(ctx->h_p2p_err))
+      return fail(ctx, SE_ERR_NCCL, "peer-memory all-reduce timed out: a rank did not launch the matching reduction");
+    return SE_OK;
+  }
   SE_TRY(allreduce_dev(ctx, off, count, op));
   SE_CUDA(ctx, cudaMemcpyAsync(ctx->h_scal + off, ctx->d_scal + off, sizeof(double) * count,
                                cudaMemcpyDeviceToHost, ctx->stream));
@@ -559,6 +613,10 @@ int se_ctx_create(int device, se_ctx** out) {
   SE_CREATE_CUDA(cudaMalloc(&ctx->d_partials, sizeof(double) * (size_t)kMaxGridPartials * kMaxRed));
   SE_CREATE_CUDA(cudaMalloc(&ctx->d_counter, sizeof(unsigned int)));
   SE_CREATE_CUDA(cudaMemset(ctx->d_counter, 0, sizeof(unsigned int)));
+  SE_CREATE_CUDA(cudaHostAlloc(&ctx->h_mirror, sizeof(double) * (kMboxPayload + 8), cudaHostAllocMapped));
+  memset(ctx->h_mirror, 0, sizeof(double) * (kMboxPayload + 8));
+  SE_CREATE_CUDA(cudaHostGetDevicePointer(&ctx->d_mirror, ctx->h_mirror, 0));
+  if (const char* s = getenv("SE_HOST_MIRROR")) ctx->use_mirror = atoi(s) != 0;
   SE_CREATE_CUDA(cudaMalloc(&ctx->d_small, kSmallBytes));
   SE_CREATE_CUDA(cudaMallocHost(&ctx->h_small, kSmallBytes));
   SE_CREATE_CUDA(cudaDeviceSynchronize());
@@ -586,6 +644,9 @@ int se_ctx_destroy(se_ctx* ctx) {
   if (ctx->d_partials) cudaFree(ctx->d_partials);
   if (ctx->d_counter) cudaFree(ctx->d_counter);
   if (ctx->d_small) cudaFree(ctx->d_small);
+  if (ctx->h_mirror) cudaFreeHost(ctx->h_mirror);
+  if (ctx->d_ls_u) cudaFree(ctx->d_ls_u);
+  if (ctx->d_ls_v) cudaFree(ctx->d_ls_v);
   if (ctx->h_small) cudaFreeHost(ctx->h_small);
   if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
   if (ctx->tm0) cudaEventDestroy(ctx->tm0);
@@ -1212,8 +1273,15 @@ int se_gbm_linesearch_eval(se_ctx* ctx, const double* alpha, double* loss, doubl
   const int dim = ctx->gbm.dim;
   GbmArgs a = gbm_args(ctx, false);
   for (int j = 0; j < dim; ++j) a.coef[j] = (float)alpha[j];
+  if (ctx->ls_packed) {  // inside se_gbm_linesearch_brent: bit-identical 8 B/row view
+    a.y = nullptr;
+    a.F = ctx->d_ls_u;
+    a.h = ctx->d_ls_v;
+  }
   a.ws = red_ws(ctx);
-  SE_LAUNCH_T(ctx, SE_KF_EVAL, launch_gbm(ctx->gbm.loss, GBM_EVAL, a, ctx->ctas_per_sm, ctx->sms, ctx->stream));
+  // Brent consumes the objective value only: skip the gradient/curvature arithmetic when nobody asked for it
+  const int eval_mode = (!grad && ctx->gbm.loss != SE_LOSS_LOGLOSS) ? GBM_EVAL_LOSS : GBM_EVAL;
+  SE_LAUNCH_T(ctx, SE_KF_EVAL, launch_gbm(ctx->gbm.loss, eval_mode, a, ctx->ctas_per_sm, ctx->sms, ctx->stream));
   double s[1 + kMaxDim];
   SE_TRY(fetch_scalars(ctx, 0, 1 + dim, s));
   // lossSum is accumulated `dim` times per row in the reference (GBMLoss.scala:60-64)
@@ -1322,8 +1390,29 @@ int se_gbm_linesearch_brent(se_ctx* ctx, double lo, double hi, double start, dou
     if (rc != SE_OK) return fail(ctx, rc, "Brent exceeded MaxEval(%d)", max_eval);
     return SE_OK;
   }
+  // Binary scalar losses depend on (2y-1)(F + αh) only: one 20 B/row pass builds u = (2y-1)F, v = (2y-1)h and
+  // every one of Brent's 20-40 evaluations then reads 8 B/row instead of 12 — same values bit for bit
+  // (multiplying by ±1 is exact and fma is sign-symmetric).
+  const bool pack = (ctx->gbm.loss == SE_LOSS_BERNOULLI || ctx->gbm.loss == SE_LOSS_EXPONENTIAL) && max_eval >= 8 &&
+                    getenv("SE_NO_LS_PACK") == nullptr;
+  if (pack) {
+    SE_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (ctx->ls_cap < ctx->gbm.n) {
+      if (ctx->d_ls_u) cudaFree(ctx->d_ls_u);
+      if (ctx->d_ls_v) cudaFree(ctx->d_ls_v);
+      ctx->d_ls_u = ctx->d_ls_v = nullptr;
+      ctx->ls_cap = 0;
+      SE_CUDA(ctx, cudaMalloc(&ctx->d_ls_u, sizeof(float) * (size_t)(ctx->gbm.n + 32)));
+      SE_CUDA(ctx, cudaMalloc(&ctx->d_ls_v, sizeof(float) * (size_t)(ctx->gbm.n + 32)));
+      ctx->ls_cap = ctx->gbm.n;
+    }
+    SE_LAUNCH_T(ctx, SE_KF_OTHER, launch_gbm_pack_signed(ctx->slot[SE_SLOT_Y].d, ctx->slot[SE_SLOT_F].d, ctx->slot[SE_SLOT_H].d,
+                                                         ctx->d_ls_u, ctx->d_ls_v, ctx->gbm.n, ctx->sms, ctx->stream));
+    ctx->ls_packed = true;
+  }
   EvalClosure c{ctx, SE_OK};
   int rc = brent_impl(eval_cb, &c, lo, hi, start, rel, abs_tol, max_eval, alpha, loss, n_eval);
+  ctx->ls_packed = false;
   if (c.rc != SE_OK) return c.rc;
   if (rc != SE_OK) return fail(ctx, rc, "Brent exceeded MaxEval(%d)", max_eval);
   return SE_OK;

@@ -112,6 +112,11 @@ struct RedWs {
   int nranks = 1, rank = 0;
   unsigned long long seq = 0;      // reduction sequence number (same on every rank), >= 1
   int* err = nullptr;              // set to 1 if a peer never showed up (bounded spin)
+  // ---- host mirror: the final sums are also stored into mapped pinned host memory, followed by a ticket, so
+  // the host can pick them up by polling one cache line instead of a D2H copy + stream synchronisation
+  double* host_out = nullptr;
+  volatile unsigned long long* host_flag = nullptr;
+  unsigned long long host_ticket = 0;
 };
 
 __device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v) {
@@ -140,7 +145,15 @@ __device__ __forceinline__ double ld_relaxed_sys_f64(const double* p) {
 // Rows are double-buffered by sequence parity: a peer can be at most one reduction ahead.
 __device__ __forceinline__ void peer_exchange(const double* tot, int nred, const RedWs& ws) {
   if (ws.nranks <= 1 || ws.mbox == nullptr) {
-    for (int k = threadIdx.x; k < nred; k += blockDim.x) ws.out[k] = tot[k];
+    for (int k = threadIdx.x; k < nred; k += blockDim.x) {
+      ws.out[k] = tot[k];
+      if (ws.host_out) ws.host_out[k] = tot[k];
+    }
+    if (ws.host_out) {
+      __threadfence_system();  // every writer orders its mirror stores before the barrier ...
+      __syncthreads();         // (all threads of the last CTA reach this point together)
+      if (threadIdx.x == 0) *ws.host_flag = ws.host_ticket;  // ... so the ticket is the last thing the host sees
+    }
     return;
   }
   if ((threadIdx.x >> 5) != 0) return;
@@ -164,9 +177,16 @@ __device__ __forceinline__ void peer_exchange(const double* tot, int nred, const
     double sum = 0.0;
     for (int p = 0; p < ws.nranks; ++p)
       sum += ld_relaxed_sys_f64(ws.mbox[ws.rank] + (size_t)(p * 2 + par) * kMboxStride + k);
-    ws.out[k] = ok ? sum : __longlong_as_double(0x7ff8000000000000ll);
+    const double res = ok ? sum : __longlong_as_double(0x7ff8000000000000ll);
+    ws.out[k] = res;
+    if (ws.host_out) ws.host_out[k] = res;
   }
   if (!ok && lane == 0 && ws.err) *ws.err = 1;
+  if (ws.host_out) {
+    __threadfence_system();
+    __syncwarp();
+    if (lane == 0) *ws.host_flag = ws.host_ticket;
+  }
 }
 
 // Block-reduce NRED per-thread fp64 accumulators, publish the block partial, and let the last CTA

@@ -35,13 +35,13 @@ struct LossTune {
 
 template <int MODE>
 struct ModeTraits {
-  static constexpr bool kReadH = (MODE == GBM_EVAL || MODE == GBM_UPDATE ||
+  static constexpr bool kReadH = (MODE == GBM_EVAL || MODE == GBM_EVAL_LOSS || MODE == GBM_UPDATE ||
                                   MODE == GBM_UPDATE_RESID || MODE == GBM_UPDATE_NEWTON);
   static constexpr bool kWriteF = (MODE == GBM_UPDATE || MODE == GBM_UPDATE_RESID ||
                                    MODE == GBM_UPDATE_NEWTON);
   static constexpr bool kNewton = (MODE == GBM_RESID_NEWTON || MODE == GBM_UPDATE_NEWTON);
   static constexpr bool kWriteR = (MODE == GBM_RESID || MODE == GBM_UPDATE_RESID || kNewton);
-  static constexpr bool kSumLoss = (MODE == GBM_EVAL || kWriteF || MODE == GBM_MEAN_LOSS);
+  static constexpr bool kSumLoss = (MODE == GBM_EVAL || MODE == GBM_EVAL_LOSS || kWriteF || MODE == GBM_MEAN_LOSS);
   static constexpr bool kReduce = kSumLoss || kNewton;
 };
 
@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(kBlock, LossTune<LOSS>::kMinCtas) gbm_scalar_k
   const bool has_w = (a.w != nullptr);
   // bag multiplicities (row sub-sampling, GBMRegressor.scala:357-359): the line search and newton's Σh run on
   // the bag (reference quirk 4), i.e. every per-row term of those sums is multiplied by the row's count
-  constexpr bool kBagMode = (MODE == GBM_EVAL) || T::kNewton;
+  constexpr bool kBagMode = (MODE == GBM_EVAL) || (MODE == GBM_EVAL_LOSS) || T::kNewton;
   const bool has_bag = kBagMode && (a.bag != nullptr);
   // [0] Σloss, [1] Σ h·g (eval) or Σ max(H,1e-2) (newton), [2] Σ h²·H (eval: curvature of the line-search objective)
   double acc[3] = {0.0, 0.0, 0.0};
@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(kBlock, LossTune<LOSS>::kMinCtas) gbm_scalar_k
     const float p = T::kReadH ? fmaf(coef, h, F) : F;
     const LGH o = eval_loss<LOSS>(y, p, param);
     if (T::kWriteF) Fo = p;
-    if (T::kSumLoss) l_acc += (MODE == GBM_EVAL) ? c * o.l : o.l;
+    if (T::kSumLoss) l_acc += (MODE == GBM_EVAL || MODE == GBM_EVAL_LOSS) ? c * o.l : o.l;
     if (MODE == GBM_EVAL) {
       x_acc = fmaf(c * h, o.g, x_acc);
       z_acc = fmaf(c * h * h, o.h, z_acc);
@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(kBlock, LossTune<LOSS>::kMinCtas) gbm_scalar_k
       const int64_t g = base + (int64_t)u * kBlock;
       ok[u] = g < n4;
       if (ok[u]) {
-        vy[u] = ld_stream4(a.y + 4 * g);
+        vy[u] = a.y ? ld_stream4(a.y + 4 * g) : make_float4(1.f, 1.f, 1.f, 1.f);  // y == nullptr: signed view, label 1
         vF[u] = T::kWriteF ? ld_rw4(a.F + 4 * g) : ld_stream4(a.F + 4 * g);
         if (T::kReadH) vh[u] = ld_stream4(a.h + 4 * g);
         if (T::kNewton && has_w) vw[u] = ld_stream4(a.w + 4 * g);
@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(kBlock, LossTune<LOSS>::kMinCtas) gbm_scalar_k
     const float w = (T::kNewton && has_w) ? a.w[i] : 1.0f;
     const float c = has_bag ? a.bag[i] : 1.0f;
     float Fo = 0.f, ro = 0.f, wo = 0.f, l_acc = 0.f, x_acc = 0.f, z_acc = 0.f;
-    row(a.y[i], a.F[i], T::kReadH ? a.h[i] : 0.f, w, c, Fo, ro, wo, l_acc, x_acc, z_acc);
+    row(a.y ? a.y[i] : 1.0f, a.F[i], T::kReadH ? a.h[i] : 0.f, w, c, Fo, ro, wo, l_acc, x_acc, z_acc);
     if (T::kWriteF) a.F[i] = Fo;
     if (T::kWriteR) a.r[i] = ro;
     if (T::kNewton) a.wout[i] = wo;
@@ -360,6 +360,30 @@ __global__ void __launch_bounds__(kBlock) gbm_logloss_kernel(const GbmArgs a) {
   if (T::kReduce) block_reduce_publish<NRED>(acc, a.ws);
 }
 
+__global__ void __launch_bounds__(kBlock) pack_signed_kernel(const float* __restrict__ y, const float* __restrict__ F,
+                                                            const float* __restrict__ h, float* __restrict__ u,
+                                                            float* __restrict__ v, int64_t n) {
+  const int64_t n4 = n >> 2;
+  for (int64_t g = (int64_t)blockIdx.x * kBlock + threadIdx.x; g < n4; g += (int64_t)gridDim.x * kBlock) {
+    const float4 vy = ld_stream4(y + 4 * g), vF = ld_stream4(F + 4 * g), vh = ld_stream4(h + 4 * g);
+    float4 ou, ov;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float ye = 2.0f * f4at(vy, e) - 1.0f;  // GBMLoss.scala:272,297
+      f4at(ou, e) = ye * f4at(vF, e);
+      f4at(ov, e) = ye * f4at(vh, e);
+    }
+    st_stream4(u + 4 * g, ou);
+    st_stream4(v + 4 * g, ov);
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+    const int64_t i = (n4 << 2) + threadIdx.x;
+    const float ye = 2.0f * y[i] - 1.0f;
+    u[i] = ye * F[i];
+    v[i] = ye * h[i];
+  }
+}
+
 __global__ void __launch_bounds__(kBlock) scale_rows_kernel(float* a, int64_t n, int64_t ld, int dim,
                                                             const float* factors) {
   for (int j = 0; j < dim; ++j) {
@@ -411,6 +435,7 @@ cudaError_t launch_scalar_loss(int mode, const GbmArgs& a, int ctas_per_sm, int 
     SE_CASE(GBM_UPDATE_RESID)
     SE_CASE(GBM_UPDATE_NEWTON)
     SE_CASE(GBM_MEAN_LOSS)
+    SE_CASE(GBM_EVAL_LOSS)
 #undef SE_CASE
     default: return cudaErrorInvalidValue;
   }
@@ -474,6 +499,12 @@ cudaError_t launch_gbm(int loss, int mode, const GbmArgs& a, int ctas_per_sm, in
   if (K <= 8) return launch_logloss_k<8, 4>(mode, a, grid_for((a.n + 3) / 4, kBlock, ctas_per_sm, sms), st);
   if (K <= 16) return launch_logloss_k<16, 1>(mode, a, grid_for(a.n, kBlock, ctas_per_sm, sms), st);
   return launch_logloss_k<32, 1>(mode, a, grid_for(a.n, kBlock, ctas_per_sm, sms), st);
+}
+
+cudaError_t launch_gbm_pack_signed(const float* y, const float* F, const float* h, float* u, float* v, int64_t n,
+                                   int sms, cudaStream_t st) {
+  pack_signed_kernel<<<grid_for(n >> 2, kBlock, 4, sms), kBlock, 0, st>>>(y, F, h, u, v, n);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_scale_rows(float* a, int64_t n, int64_t ld, int dim, const float* factors,

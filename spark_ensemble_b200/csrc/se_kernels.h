@@ -19,7 +19,8 @@ enum GbmMode {
   GBM_UPDATE_RESID = 4,  // + R = -g(y,F')
   GBM_UPDATE_NEWTON = 5, // + R = -g/hc, WOUT = 1/2 hc w, Σhc
   GBM_MEAN_LOSS = 6,     // Σloss(y,F)
-  GBM_SQ_STATS = 7       // squared: Σ(y-F)², Σh(y-F), Σh²
+  GBM_SQ_STATS = 7,      // squared: Σ(y-F)², Σh(y-F), Σh²
+  GBM_EVAL_LOSS = 8      // p = F + a h : Σloss only (Brent needs the objective value, not its gradient)
 };
 
 struct GbmArgs {
@@ -49,6 +50,10 @@ struct GbmArgs {
 // logloss: [0]=Σloss, [1..K]=Σ h_j g_j  or Σhc_j
 cudaError_t launch_gbm(int loss, int mode, const GbmArgs& a, int ctas_per_sm, int sms,
                        cudaStream_t stream);
+// line-search view for the binary scalar losses: u = (2y-1)·F, v = (2y-1)·h (exact sign flips), so that every
+// Brent evaluation reads two arrays instead of three (launch_gbm GBM_EVAL with y == nullptr, F = u, h = v)
+cudaError_t launch_gbm_pack_signed(const float* y, const float* F, const float* h, float* u, float* v, int64_t n,
+                                   int sms, cudaStream_t stream);
 // LogLoss(K) through shared-memory staging (TMA bulk copies, double buffered): wide K (se_gbm_staged.cu)
 cudaError_t launch_gbm_logloss_staged(int mode, const GbmArgs& a, int sms, cudaStream_t stream);
 // WOUT[j][i] *= 0.5/S_j was folded: scale rows of a [dim][n] array by per-row factors

@@ -741,3 +741,24 @@ def test_squared_stats_from_residual_slot(ctx, oracle, rng):
     s3 = ctx.gbm_linesearch_stats()
     oracle.update(Fo, h, [0.1]); d = y.astype(np.float64) - Fo[0]
     close(s3[:3], [np.sum(d * d), np.sum(hh * d), np.sum(hh * hh)])
+
+
+@pytest.mark.parametrize("name", ["bernoulli", "exponential"])
+@pytest.mark.parametrize("weighted_bag", [False, True])
+def test_brent_packed_line_search_view_is_bit_identical(ctx, oracle, rng, name, weighted_bag, monkeypatch):
+    """se_gbm_linesearch_brent evaluates the binary losses on the signed view u=(2y-1)F, v=(2y-1)h (8 B/row):
+    same alpha, objective and evaluation count as the plain (y, F, h) evaluations, bit for bit."""
+    from spark_ensemble_b200 import _native as N
+    n = 40013
+    dim, par, y, F, h, w = setup_gbm(ctx, rng, name, n, weighted_bag)
+    r, _, _ = oracle.pseudo_residuals(O.LOSS_IDS[name], par, 1, y, None, F, False)
+    h = f32(0.6 * r + 0.2 * rng.standard_normal((1, n)))
+    ctx.upload(N.SLOT_H, h)
+    if weighted_bag:
+        ctx.gbm_set_bag(rng.poisson(1.0, n).astype(np.float32))
+    packed = ctx.gbm_linesearch_brent()
+    monkeypatch.setenv("SE_NO_LS_PACK", "1")
+    plain = ctx.gbm_linesearch_brent()
+    monkeypatch.delenv("SE_NO_LS_PACK")
+    assert packed == plain
+    assert packed[2] >= 8
