@@ -279,6 +279,13 @@ SE_API int se_tree_predict(se_ctx* ctx, int which, int n_nodes, const int32_t* f
                     const float* threshold, const int32_t* left, const int32_t* right,
                     const float* value, const int32_t* subspace, int n_subspace, int out_slot,
                     int out_row);
+/* Classification tree: every node carries a vector of n_out values (`values` is [n_nodes][n_out], e.g. the leaf's
+ * class probabilities = predictProbability); rows 0..n_out-1 of out_slot ([n_out][n]) are written.  Feeds
+ * SE_SLOT_PROBA for SAMME.R (BoostingClassifier.scala:199-200) without moving K x n probabilities over PCIe. */
+SE_API int se_tree_predict_multi(se_ctx* ctx, int which, int n_nodes, const int32_t* feature,
+                                 const float* threshold, const int32_t* left, const int32_t* right,
+                                 const float* values, int n_out, const int32_t* subspace, int n_subspace,
+                                 int out_slot);
 /* linear model: out = intercept + Σ_j coef[j]·X[subspace[j]] */
 SE_API int se_linear_predict(se_ctx* ctx, int which, int n_coef, const float* coef, float intercept,
                       const int32_t* subspace, int out_slot, int out_row);

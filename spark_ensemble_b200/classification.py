@@ -248,6 +248,10 @@ class BoostingClassifier(Params):
         ctx = Context(self.device)
         try:
             ctx.boost_configure(n, K, real)
+            resident = bool(self("residentFeatures"))
+            if resident:  # column-major X in HBM: fitted trees are evaluated on device (no K x n upload per round)
+                ctx.alloc(N.SLOT_X, X.shape[1], n)
+                ctx.upload_rowmajor(N.SLOT_X, X)
             ctx.upload(N.SLOT_Y, y)
             ctx.upload(N.SLOT_BW, np.ones(n) if w is None else w)  # boostingWeights = instances.map(_.weight) :168
             sum_w = ctx.slot_sum(N.SLOT_BW)  # :175
@@ -258,15 +262,23 @@ class BoostingClassifier(Params):
                 if real:  # SAMME.R :198-230
                     if not hasattr(model, "predictProbability"):
                         raise RuntimeError('algorithm "real" is not compatible with base learner')  # :261-263
-                    P = model.predictProbability(X)
-                    ctx.upload(N.SLOT_PROBA, np.ascontiguousarray(P.T, dtype=np.float32))
+                    t = model.tree_arrays() if resident else None
+                    if t is not None:
+                        ctx.tree_predict_multi(t, N.SLOT_PROBA)
+                    else:
+                        P = model.predictProbability(X)
+                        ctx.upload(N.SLOT_PROBA, np.ascontiguousarray(P.T, dtype=np.float32))
                     err, new_sum = ctx.boost_real_update(sum_w)
                     if err <= 0:
                         done = True
                     est_weights.append(1.0)  # :212
                     models.append(model)
                 else:  # SAMME :231-260
-                    ctx.upload(N.SLOT_PRED, model.predict(X))
+                    t = model.tree_arrays() if resident else None
+                    if t is not None:
+                        ctx.tree_predict(t, N.SLOT_PRED, 0)
+                    else:
+                        ctx.upload(N.SLOT_PRED, model.predict(X))
                     err = ctx.boost_discrete_error(sum_w)
                     if err <= 0:
                         done = True
@@ -291,8 +303,9 @@ class BoostingClassifier(Params):
 
 
 _pboost = [Param("algorithm", "algorithm, (case-insensitive). Supported options: discrete,real",
-                 lambda v: v.lower() in ("discrete", "real"), str)]
-_BOOST_DEFAULTS = {**_d, **_dc, **_db, "algorithm": "discrete",
+                 lambda v: v.lower() in ("discrete", "real"), str),
+           Param("residentFeatures", "evaluate base models on device over the HBM-resident feature matrix", convert=bool)]
+_BOOST_DEFAULTS = {**_d, **_dc, **_db, "algorithm": "discrete", "residentFeatures": False,
                    "seed": java_string_hash("org.apache.spark.ml.classification.BoostingClassifier")}
 BoostingClassifier._declare(_p + _pc + _pb + _pboost + [Param("seed", "random seed", convert=int)], _BOOST_DEFAULTS)
 

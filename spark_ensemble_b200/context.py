@@ -349,6 +349,19 @@ class Context:
                                            N.iptr(r), N.fptr(v), None if sub is None else N.iptr(sub),
                                            0 if sub is None else sub.size, out_slot, out_row))
 
+    def tree_predict_multi(self, tree: dict, out_slot: int, validation: bool = False, subspace=None):
+        """Classification tree: tree["values"] is [n_nodes, K] (leaf class probabilities) -> K rows of out_slot."""
+        f = np.ascontiguousarray(tree["feature"], dtype=np.int32)
+        t = np.ascontiguousarray(tree["threshold"], dtype=np.float32)
+        l = np.ascontiguousarray(tree["left"], dtype=np.int32)
+        r = np.ascontiguousarray(tree["right"], dtype=np.int32)
+        v = np.ascontiguousarray(tree["values"], dtype=np.float32)
+        sub = None if subspace is None else np.ascontiguousarray(subspace, dtype=np.int32)
+        self._ck(self._lib.se_tree_predict_multi(self._h, int(validation), f.size, N.iptr(f), N.fptr(t), N.iptr(l),
+                                                 N.iptr(r), N.fptr(v.reshape(-1)), v.shape[1],
+                                                 None if sub is None else N.iptr(sub), 0 if sub is None else sub.size,
+                                                 out_slot))
+
     def linear_predict(self, coef, intercept: float, out_slot: int, out_row: int = 0,
                        validation: bool = False, subspace=None):
         c = np.ascontiguousarray(coef, dtype=np.float32)

@@ -1734,17 +1734,19 @@ int se_agg_run(se_ctx* ctx, const double* weights, const double* init) {
 }
 
 // ---- on-device base models ---------------------------------------------------------------------
-int se_tree_predict(se_ctx* ctx, int which, int n_nodes, const int32_t* feature, const float* threshold,
-                    const int32_t* left, const int32_t* right, const float* value,
-                    const int32_t* subspace, int n_subspace, int out_slot, int out_row) {
+static int tree_predict_impl(se_ctx* ctx, int which, int n_nodes, const int32_t* feature, const float* threshold,
+                             const int32_t* left, const int32_t* right, const float* value, int n_out,
+                             const int32_t* subspace, int n_subspace, int out_slot, int out_row) {
   if (!ctx || !feature || !threshold || !left || !right || !value) return fail(ctx, SE_ERR_ARG, "null argument");
-  SE_REQUIRE(ctx, n_nodes >= 1 && (size_t)n_nodes * 20 <= (size_t)kSmallBytes && n_nodes * 20 <= 200 * 1024,
-             SE_ERR_ARG, "tree of %d nodes not supported", n_nodes);
+  SE_REQUIRE(ctx, n_out >= 1 && n_out <= 4096, SE_ERR_ARG, "bad leaf width %d", n_out);
+  const size_t bytes = (size_t)n_nodes * (16 + 4 * (size_t)n_out);
+  SE_REQUIRE(ctx, n_nodes >= 1 && bytes <= (size_t)kSmallBytes && (size_t)n_nodes * 20 <= 200 * 1024,
+             SE_ERR_ARG, "tree of %d nodes x %d outputs not supported", n_nodes, n_out);
   SE_REQUIRE(ctx, out_slot >= 0 && out_slot < SE_NUM_SLOTS, SE_ERR_ARG, "bad out slot");
   const SlotBuf& X = ctx->slot[which ? SE_SLOT_VX : SE_SLOT_X];
   const SlotBuf& O = ctx->slot[out_slot];
   SE_REQUIRE(ctx, X.d, SE_ERR_STATE, "feature matrix slot not allocated");
-  SE_REQUIRE(ctx, O.d && out_row >= 0 && out_row < O.rows && O.cols == X.cols, SE_ERR_STATE, "output slot shape mismatch");
+  SE_REQUIRE(ctx, O.d && O.cols == X.cols && out_row >= 0 && out_row + n_out <= O.rows, SE_ERR_STATE, "output slot shape mismatch");
   SE_TRY(begin(ctx));
   SE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   int32_t* hf = reinterpret_cast<int32_t*>(ctx->h_small);
@@ -1762,9 +1764,11 @@ int se_tree_predict(se_ctx* ctx, int which, int n_nodes, const int32_t* feature,
       SE_REQUIRE(ctx, f >= 0 && f < X.rows, SE_ERR_ARG, "node %d: column %d outside X with %lld columns", i, f, (long long)X.rows);
       SE_REQUIRE(ctx, left[i] >= 0 && left[i] < n_nodes && right[i] >= 0 && right[i] < n_nodes, SE_ERR_ARG, "node %d: bad child", i);
     }
-    hf[i] = f; ht[i] = threshold[i]; hl[i] = left[i]; hr[i] = right[i]; hv[i] = value[i];
+    hf[i] = f; ht[i] = threshold[i]; hl[i] = left[i]; hr[i] = right[i];
   }
-  SE_CUDA(ctx, cudaMemcpyAsync(ctx->d_small, ctx->h_small, (size_t)n_nodes * 20, cudaMemcpyHostToDevice, ctx->stream));
+  memcpy(hv, value, sizeof(float) * (size_t)n_nodes * n_out);
+  SE_CUDA(ctx, cudaMemcpyAsync(ctx->d_small, ctx->h_small, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  if (out_slot == SE_SLOT_F || out_slot == SE_SLOT_R || out_slot == SE_SLOT_Y) ctx->gbm.r_current = false;
   TreeArgs t;
   t.X = X.d; t.n = X.cols; t.ld = X.rows > 1 ? X.ld : X.cols; t.n_nodes = n_nodes;
   t.feature = reinterpret_cast<const int32_t*>(ctx->d_small);
@@ -1772,9 +1776,25 @@ int se_tree_predict(se_ctx* ctx, int which, int n_nodes, const int32_t* feature,
   t.left = reinterpret_cast<const int32_t*>(t.threshold + n_nodes);
   t.right = t.left + n_nodes;
   t.value = reinterpret_cast<const float*>(t.right + n_nodes);
-  t.out = O.d + (int64_t)out_row * (O.rows > 1 ? O.ld : O.cols);
+  t.n_out = n_out;
+  t.ld_out = O.rows > 1 ? O.ld : O.cols;
+  t.out = O.d + (int64_t)out_row * t.ld_out;
   SE_LAUNCH_T(ctx, SE_KF_TREE, launch_tree_predict(t, ctx->sms, ctx->stream));
   return end(ctx);
+}
+
+int se_tree_predict(se_ctx* ctx, int which, int n_nodes, const int32_t* feature, const float* threshold,
+                    const int32_t* left, const int32_t* right, const float* value,
+                    const int32_t* subspace, int n_subspace, int out_slot, int out_row) {
+  return tree_predict_impl(ctx, which, n_nodes, feature, threshold, left, right, value, 1, subspace, n_subspace,
+                           out_slot, out_row);
+}
+
+int se_tree_predict_multi(se_ctx* ctx, int which, int n_nodes, const int32_t* feature, const float* threshold,
+                          const int32_t* left, const int32_t* right, const float* values, int n_out,
+                          const int32_t* subspace, int n_subspace, int out_slot) {
+  return tree_predict_impl(ctx, which, n_nodes, feature, threshold, left, right, values, n_out, subspace, n_subspace,
+                           out_slot, 0);
 }
 
 int se_linear_predict(se_ctx* ctx, int which, int n_coef, const float* coef, float intercept,

@@ -123,8 +123,10 @@ struct TreeArgs {
   const float* threshold = nullptr;
   const int32_t* left = nullptr;
   const int32_t* right = nullptr;
-  const float* value = nullptr;
-  float* out = nullptr;
+  const float* value = nullptr;      // [n_nodes][n_out]
+  float* out = nullptr;              // n_out rows of stride ld_out
+  int n_out = 1;                     // 1: regression value / label; K: class-probability vector of the leaf
+  int64_t ld_out = 0;
 };
 cudaError_t launch_tree_predict(const TreeArgs& a, int sms, cudaStream_t s);
 cudaError_t launch_linear_predict(const float* X, int64_t n, int64_t ld, int n_coef,

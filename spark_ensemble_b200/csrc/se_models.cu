@@ -24,12 +24,13 @@ __global__ void __launch_bounds__(kBlock) tree_predict_kernel(const TreeArgs a) 
   int32_t* s_left = reinterpret_cast<int32_t*>(s_thr + a.n_nodes);
   int32_t* s_right = s_left + a.n_nodes;
   float* s_val = reinterpret_cast<float*>(s_right + a.n_nodes);
+  const bool scalar = (a.n_out == 1);
   for (int i = threadIdx.x; i < a.n_nodes; i += kBlock) {
     s_feat[i] = a.feature[i];
     s_thr[i] = a.threshold[i];
     s_left[i] = a.left[i];
     s_right[i] = a.right[i];
-    s_val[i] = a.value[i];
+    if (scalar) s_val[i] = a.value[i];
   }
   __syncthreads();
   const int64_t ngroups = (a.n + TV - 1) / TV;
@@ -59,7 +60,20 @@ __global__ void __launch_bounds__(kBlock) tree_predict_kernel(const TreeArgs a) 
           any |= live[e];
         }
     }
-    if (i0 + TV <= a.n) {
+    if (!scalar) {
+      // leaf vectors (class probabilities of a classification tree): one coalesced row store per class
+      for (int k = 0; k < a.n_out; ++k) {
+        if (i0 + TV <= a.n) {
+          st_stream4(a.out + (int64_t)k * a.ld_out + i0,
+                     make_float4(__ldg(a.value + node[0] * a.n_out + k), __ldg(a.value + node[1] * a.n_out + k),
+                                 __ldg(a.value + node[2] * a.n_out + k), __ldg(a.value + node[3] * a.n_out + k)));
+        } else {
+#pragma unroll
+          for (int e = 0; e < TV; ++e)
+            if (i0 + e < a.n) a.out[(int64_t)k * a.ld_out + i0 + e] = __ldg(a.value + node[e] * a.n_out + k);
+        }
+      }
+    } else if (i0 + TV <= a.n) {
       st_stream4(a.out + i0, make_float4(s_val[node[0]], s_val[node[1]], s_val[node[2]], s_val[node[3]]));
     } else {
 #pragma unroll

@@ -78,6 +78,18 @@ class DecisionTreeClassificationModel(_Model):
     def predict(self, X) -> np.ndarray:
         return np.argmax(self.predictProbability(X), axis=1).astype(np.float64)
 
+    def tree_arrays(self):
+        """Array form with per-node class-probability vectors ("values" [n_nodes, K]) and the predicted label
+        ("value" [n_nodes]) so both predictProbability and predict can be evaluated on device."""
+        d = _tree_arrays(self.sk)
+        v = self.sk.tree_.value[:, 0, :].astype(np.float64)
+        v = v / np.maximum(v.sum(axis=1, keepdims=True), 1e-300)
+        full = np.zeros((v.shape[0], self.numClasses))
+        full[:, self.sk.classes_.astype(int)] = v
+        d["values"] = full.astype(np.float32)
+        d["value"] = np.argmax(full, axis=1).astype(np.float32)
+        return d
+
 
 class DecisionTreeClassifier:
     """Stand-in for org.apache.spark.ml.classification.DecisionTreeClassifier."""

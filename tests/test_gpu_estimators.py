@@ -299,3 +299,19 @@ def test_gbm_regressor_with_row_subsampling():
         assert losses[-1] < losses[0]
         # a bagged fit still tracks the full fit's loss closely on this dataset
         assert losses[-1] < 1.5 * full.trainingHistory[-1]["trainLoss"]
+
+
+@pytest.mark.parametrize("algorithm", ["discrete", "real"])
+def test_boosting_classifier_resident_features(algorithm):
+    """Base trees evaluated on device (se_tree_predict / se_tree_predict_multi) give the same fit as host predict."""
+    from spark_ensemble_b200 import DataFrame
+    from spark_ensemble_b200.classification import BoostingClassifier
+    from spark_ensemble_b200.learners import DecisionTreeClassifier
+    X, y = _letter(3000)
+    base = BoostingClassifier().setBaseLearner(DecisionTreeClassifier(maxDepth=6)).setNumBaseLearners(4).setAlgorithm(algorithm)
+    host = base.copy().fit(DataFrame(features=X, label=y))
+    dev = base.copy().setResidentFeatures(True).fit(DataFrame(features=X, label=y))
+    assert host.numModels == dev.numModels
+    for a, b in zip(host.trainingHistory, dev.trainingHistory):
+        assert a["estimatorError"] == pytest.approx(b["estimatorError"], rel=1e-6, abs=1e-9)
+        assert a["sumWeights"] == pytest.approx(b["sumWeights"], rel=1e-6)

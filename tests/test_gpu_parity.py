@@ -762,3 +762,23 @@ def test_brent_packed_line_search_view_is_bit_identical(ctx, oracle, rng, name, 
     monkeypatch.delenv("SE_NO_LS_PACK")
     assert packed == plain
     assert packed[2] >= 8
+
+
+def test_tree_predict_multi_class_probabilities(ctx, rng):
+    """Classification trees on device: leaf class-probability vectors -> SE_SLOT_PROBA, leaf labels -> SE_SLOT_PRED."""
+    from spark_ensemble_b200 import _native as N
+    from spark_ensemble_b200.learners import DecisionTreeClassifier
+    n, d, K = 20011, 10, 7
+    X = f32(rng.standard_normal((n, d)))
+    yv = (np.abs(X[:, 0] * 2 + X[:, 3]).astype(int) % K).astype(np.float64)
+    yv[yv == 5] = 4  # class 5 never occurs: sklearn's classes_ is a subset
+    m = DecisionTreeClassifier(maxDepth=7).fit(X, yv, None, num_classes=K)
+    t = m.tree_arrays()
+    ctx.alloc(N.SLOT_X, d, n)
+    ctx.upload_rowmajor(N.SLOT_X, X)
+    ctx.alloc(N.SLOT_PROBA, K, n)
+    ctx.tree_predict_multi(t, N.SLOT_PROBA)
+    np.testing.assert_allclose(ctx.download(N.SLOT_PROBA), m.predictProbability(X).T.astype(np.float32), rtol=1e-6)
+    ctx.alloc(N.SLOT_PRED, n)
+    ctx.tree_predict(t, N.SLOT_PRED, 0)
+    np.testing.assert_array_equal(ctx.download(N.SLOT_PRED), m.predict(X).astype(np.float32))
