@@ -43,7 +43,10 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true")
     ap.add_argument("--out", default=None)
+    ap.add_argument("--only", default="", help="comma list of sections: scalar,logloss,boost,agg (default: all)")
     args = ap.parse_args()
+    only = set(x for x in args.only.split(",") if x)
+    want = lambda sec: not only or sec in only
     scale = 0.1 if args.quick else 1.0
     pk = peak()
     ctx = Context(0)
@@ -56,7 +59,7 @@ def main():
         print(f"{name:34s} {cfg:38s} n={n:>11d} {bpr:5d} B/row {ms:9.4f} ms {gbs:8.1f} GB/s {gbs / pk:6.3f}", flush=True)
 
     # ---- GBM scalar losses
-    for loss, n in (("squared", int(10e6)), ("squared", int(100e6 * scale)), ("bernoulli", int(50e6 * scale)),
+    for loss, n in () if not want("scalar") else (("squared", int(10e6)), ("squared", int(100e6 * scale)), ("bernoulli", int(50e6 * scale)),
                     ("exponential", int(50e6 * scale)), ("absolute", int(50e6 * scale)), ("logcosh", int(50e6 * scale))):
         ctx.gbm_configure(n, 0, 1, loss, 0.9, False)
         if loss in ("bernoulli", "exponential"):
@@ -75,7 +78,8 @@ def main():
             rec("K1 newton (r, w', S)", cfg, n, 24, timed(ctx, "update", lambda: ctx.gbm_update([1e-3], newton=True, loss=True)))
 
     # ---- LogLoss(K)
-    for K, n in ((2, int(50e6 * scale)), (8, int(20e6 * scale)), (26, int(10e6 * scale))):
+    for K, n in () if not want("logloss") else ((2, int(50e6 * scale)), (8, int(20e6 * scale)), (16, int(10e6 * scale)),
+                                                (26, int(10e6 * scale))):
         ctx.gbm_configure(n, 0, K, "logloss", 0.0, False)
         ctx.fill_synthetic(N.SLOT_Y, "randint", 1, 0, K)
         ctx.fill_synthetic(N.SLOT_F, "normal", 2, 0, 0.5)
@@ -84,42 +88,47 @@ def main():
         rec("K2 linesearch_eval", cfg, n, 4 * (2 * K + 1), timed(ctx, "eval", lambda: ctx.gbm_linesearch_eval(np.full(K, 0.7))))
         rec("K1 update+resid+loss", cfg, n, 4 * (4 * K + 1),
             timed(ctx, "update", lambda: ctx.gbm_update(np.full(K, 1e-3), residual=True, loss=True)))
+        rec("pseudo_residuals", cfg, n, 4 * (2 * K + 1), timed(ctx, "resid", lambda: ctx.gbm_pseudo_residuals(False)))
+        rec("K1 newton (r, w', S)", cfg, n, 4 * (5 * K + 1),
+            timed(ctx, "update", lambda: ctx.gbm_update(np.full(K, 1e-3), newton=True, loss=True)))
     for s in (N.SLOT_F, N.SLOT_H, N.SLOT_R, N.SLOT_WOUT):
         ctx.free(s)
 
-    # ---- SAMME.R / SAMME (config 4: K = 26)
-    K, n = 26, int(100e6 * scale)
-    ctx.boost_configure(n, K, True)
-    ctx.fill_synthetic(N.SLOT_Y, "randint", 1, 0, K)
-    ctx.fill_synthetic(N.SLOT_PROBA, "uniform", 2, 0.001, 0.08)
-    def samme_r():
+    if want("boost"):
+        # ---- SAMME.R / SAMME (config 4: K = 26)
+        K, n = 26, int(100e6 * scale)
+        ctx.boost_configure(n, K, True)
+        ctx.fill_synthetic(N.SLOT_Y, "randint", 1, 0, K)
+        ctx.fill_synthetic(N.SLOT_PROBA, "uniform", 2, 0.001, 0.08)
+        def samme_r():
+            ctx.fill(N.SLOT_BW, 1.0)
+            ctx.boost_real_update(float(n))
+        rec("K3 SAMME.R update", f"K={K}", n, 4 * K + 12, timed(ctx, "boost_real", samme_r, reps=5))
+        ctx.free(N.SLOT_PROBA)
+        ctx.boost_configure(n, K, False)
+        ctx.fill_synthetic(N.SLOT_PRED, "randint", 3, 0, K)
         ctx.fill(N.SLOT_BW, 1.0)
-        ctx.boost_real_update(float(n))
-    rec("K3 SAMME.R update", f"K={K}", n, 4 * K + 12, timed(ctx, "boost_real", samme_r, reps=5))
-    ctx.free(N.SLOT_PROBA)
-    ctx.boost_configure(n, K, False)
-    ctx.fill_synthetic(N.SLOT_PRED, "randint", 3, 0, K)
-    ctx.fill(N.SLOT_BW, 1.0)
-    rec("K3' SAMME error", f"K={K}", n, 12, timed(ctx, "boost_err", lambda: ctx.boost_discrete_error(float(n))))
-    rec("K3' SAMME update", f"K={K}", n, 16, timed(ctx, "boost_upd", lambda: ctx.boost_discrete_update(1.0, 1.0)))
+        rec("K3' SAMME error", f"K={K}", n, 12, timed(ctx, "boost_err", lambda: ctx.boost_discrete_error(float(n))))
+        rec("K3' SAMME update", f"K={K}", n, 16, timed(ctx, "boost_upd", lambda: ctx.boost_discrete_update(1.0, 1.0)))
 
-    # ---- aggregation (config 5: M = 512)
-    for kind, name, M, K, n in ((N.AGG_BAGGING_REGRESSOR, "bagging mean", 512, 0, int(6.25e6 * scale)),
-                                (N.AGG_GBM_REGRESSOR, "gbm weighted sum", 512, 0, int(6.25e6 * scale)),
-                                (N.AGG_GBM_REGRESSOR, "gbm weighted sum", 100, 0, int(25e6 * scale)),
-                                (N.AGG_BOOSTING_REAL, "boosting real", 10, 26, int(10e6 * scale)),
-                                (N.AGG_BAGGING_HARD, "bagging hard vote", 64, 26, int(10e6 * scale))):
-        ctx.agg_configure(kind, M, max(K, 2), 1, 0, n)
-        if kind == N.AGG_BAGGING_HARD:
-            ctx.fill_synthetic(N.SLOT_P, "randint", 5, 0, K)
-        else:
-            ctx.fill_synthetic(N.SLOT_P, "uniform", 5, 0.01, 1.0)
-        w = np.full(M, 1.0 / M)
-        width = K if kind == N.AGG_BOOSTING_REAL else 1
-        C = K if K else 1
-        bpr = 4 * M * width + 4 * C * (1 if kind in (N.AGG_GBM_REGRESSOR, N.AGG_BAGGING_REGRESSOR) else 3)
-        rec("K4 aggregation", f"{name} M={M}" + (f" K={K}" if K else ""), n, bpr,
-            timed(ctx, "agg", lambda: ctx.agg_run(w if kind == N.AGG_GBM_REGRESSOR else None, [0.1]), reps=5))
+    if want("agg"):
+        # ---- aggregation (config 5: M = 512)
+        for kind, name, M, K, n in ((N.AGG_BAGGING_REGRESSOR, "bagging mean", 512, 0, int(6.25e6 * scale)),
+                                    (N.AGG_GBM_REGRESSOR, "gbm weighted sum", 512, 0, int(6.25e6 * scale)),
+                                    (N.AGG_GBM_REGRESSOR, "gbm weighted sum", 100, 0, int(25e6 * scale)),
+                                    (N.AGG_BOOSTING_REAL, "boosting real", 10, 26, int(10e6 * scale)),
+                                    (N.AGG_BAGGING_HARD, "bagging hard vote", 64, 26, int(10e6 * scale))):
+            ctx.agg_configure(kind, M, max(K, 2), 1, 0, n)
+            if kind == N.AGG_BAGGING_HARD:
+                ctx.fill_synthetic(N.SLOT_P, "randint", 5, 0, K)
+            else:
+                ctx.fill_synthetic(N.SLOT_P, "uniform", 5, 0.01, 1.0)
+            w = np.full(M, 1.0 / M)
+            width = K if kind == N.AGG_BOOSTING_REAL else 1
+            C = K if K else 1
+            bpr = 4 * M * width + 4 * C * (1 if kind in (N.AGG_GBM_REGRESSOR, N.AGG_BAGGING_REGRESSOR) else 3)
+            rec("K4 aggregation", f"{name} M={M}" + (f" K={K}" if K else ""), n, bpr,
+                timed(ctx, "agg", lambda: ctx.agg_run(w if kind == N.AGG_GBM_REGRESSOR else None, [0.1]), reps=5))
     ctx.close()
     if args.out:
         json.dump({"peak_gbs": pk, "rows": rows}, open(args.out, "w"), indent=1)

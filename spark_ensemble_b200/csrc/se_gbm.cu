@@ -486,13 +486,13 @@ cudaError_t launch_gbm(int loss, int mode, const GbmArgs& a, int ctas_per_sm, in
   }
   const int K = a.dim;
   if (K < 1 || K > kMaxDim) return cudaErrorInvalidValue;
-  // K classes per row in registers up to `staged_min_k - 1`; wider K goes through shared-memory staging
+  // K classes per row in registers up to `staged_min_k - 1`; wider K goes through the TMA-tiled kernels (se_gbm_tiled.cu)
   static const int staged_min_k = [] {
     const char* e = getenv("SE_LOGLOSS_STAGED_MIN_K");
     const int v = e ? atoi(e) : 5;
     return v < 2 ? 2 : v;
   }();
-  if (K >= staged_min_k) return launch_gbm_logloss_staged(mode, a, sms, st);
+  if (K >= staged_min_k) return launch_gbm_logloss_tiled(mode, a, sms, st);
   if (ctas_per_sm > 4) ctas_per_sm = 4;  // register-resident K <= 4 kernels: 4 CTAs/SM measured best
   if (K <= 2) return launch_logloss_k<2, 4>(mode, a, grid_for((a.n + 3) / 4, kBlock, ctas_per_sm, sms), st);
   if (K <= 4) return launch_logloss_k<4, 4>(mode, a, grid_for((a.n + 3) / 4, kBlock, ctas_per_sm, sms), st);

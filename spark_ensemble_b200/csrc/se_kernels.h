@@ -39,7 +39,7 @@ struct GbmArgs {
   // squared-loss device-resident step: step = lr * clip(stats[1]/stats[2], 0, 100) when non-null
   const double* dev_stats = nullptr;
   float lr = 1.f;
-  int stages = 2;  // staged logloss kernel: shared-memory stages (1 or 2)
+  int stages = 1;  // tiled logloss kernel: shared-memory stages (1, or 2 for experiments)
   int stats_from_r = 0;  // squared-loss statistics read the current residual slot r = y - F (8 B/row) instead of y, F (12 B/row)
   int reverse = 0; // walk the tiles from the end: consecutive passes alternate direction so the tail of one
                    // pass (still in the 126 MB L2) is the head of the next
@@ -54,8 +54,8 @@ cudaError_t launch_gbm(int loss, int mode, const GbmArgs& a, int ctas_per_sm, in
 // Brent evaluation reads two arrays instead of three (launch_gbm GBM_EVAL with y == nullptr, F = u, h = v)
 cudaError_t launch_gbm_pack_signed(const float* y, const float* F, const float* h, float* u, float* v, int64_t n,
                                    int sms, cudaStream_t stream);
-// LogLoss(K) through shared-memory staging (TMA bulk copies, double buffered): wide K (se_gbm_staged.cu)
-cudaError_t launch_gbm_logloss_staged(int mode, const GbmArgs& a, int sms, cudaStream_t stream);
+// LogLoss(K), wide K: 2-D TMA tiles of 256 rows x K classes, four rows per thread (se_gbm_tiled.cu)
+cudaError_t launch_gbm_logloss_tiled(int mode, const GbmArgs& a, int sms, cudaStream_t stream);
 // WOUT[j][i] *= 0.5/S_j was folded: scale rows of a [dim][n] array by per-row factors
 cudaError_t launch_scale_rows(float* a, int64_t n, int64_t ld, int dim, const float* factors,
                               int sms, cudaStream_t stream);

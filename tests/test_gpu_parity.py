@@ -424,9 +424,9 @@ def test_multi_gpu_sharded_parity():
 
 
 @pytest.mark.parametrize("K", [9, 26, 32])
-@pytest.mark.parametrize("n", [1, 127, 128, 129, 40961])
-def test_logloss_wide_k_staged_kernels(ctx, oracle, rng, K, n):
-    """LogLoss with K > 8 runs through the TMA/shared-memory staged kernels (se_gbm_staged.cu): every mode,
+@pytest.mark.parametrize("n", [1, 127, 129, 255, 256, 257, 40961])
+def test_logloss_wide_k_tiled_kernels(ctx, oracle, rng, K, n):
+    """LogLoss with K >= 5 runs through the TMA-tiled kernels (se_gbm_tiled.cu, 256-row tiles): every mode,
     tile tails included."""
     from spark_ensemble_b200 import _native as N
     dim, par, y, F, h, w = setup_gbm(ctx, rng, "logloss", n, True, K=K)
@@ -629,7 +629,7 @@ def test_empty_and_tiny_inputs(ctx, oracle):
     ctx.gbm_configure(0, 0, 3, "logloss", 0.0, False)
     ls, _ = ctx.gbm_update(np.ones(3), residual=True, loss=True)
     assert ls == 0.0
-    ctx.gbm_configure(0, 0, 9, "logloss", 0.0, False)  # staged (TMA) kernel with no tiles
+    ctx.gbm_configure(0, 0, 9, "logloss", 0.0, False)  # TMA-tiled kernel with no tiles
     ls, _ = ctx.gbm_update(np.ones(9), residual=True, loss=True)
     assert ls == 0.0
     # empty boosting shard
