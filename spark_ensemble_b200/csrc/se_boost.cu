@@ -5,8 +5,11 @@
 // passes over zipped RDDs per round; here SAMME.R is ONE pass (P[K][n] read once: 4K+8 B read, 4 B
 // written per row) that also produces both scalars, and SAMME is the two passes its data dependence
 // (β needs the error first) requires.  Weights are updated in place.
+#include <stdlib.h>
+
 #include "se_kernels.h"
 #include "se_loss.cuh"
+#include "se_tma.cuh"
 
 namespace se {
 
@@ -105,6 +108,88 @@ __global__ void __launch_bounds__(kBlock) boost_real_kernel(const BoostArgs a) {
     acc[1] += (double)wo;
   }
   block_reduce_publish<2>(acc, a.ws);
+}
+
+// SAMME.R through TMA tiles (K >= 5): the register-streaming kernel above keeps 8 x 16 B of P per thread in
+// registers (99 registers, 2 CTAs/SM, ~64 KB of loads in flight per SM; ncu: long-scoreboard bound at 0.82 of the
+// HBM roofline, K = 26).  Here a 2-warp CTA owns a 256-row x K tile of P that arrives as one 2-D tensor-map box
+// (`cp.async.bulk.tensor.2d`, rows past n zero-filled), up to 8 CTAs per SM keep ~200 KB in flight, and a thread
+// walks the classes of its four rows with 128-bit shared-memory reads: first-maximum argmax, Σ_k lg2 max(p, ε);
+// log p_y is picked from the tile afterwards.  Same arithmetic as boost_real_kernel (BoostingClassifier.scala:198-230).
+constexpr int kRT = 64;        // threads per CTA
+constexpr int kRR = 4 * kRT;   // rows per tile
+
+__global__ void __launch_bounds__(kRT) boost_real_tiled_kernel(const BoostArgs a, const __grid_constant__ CUtensorMap mapP) {
+  extern __shared__ __align__(128) unsigned char smem_dyn[];
+  float* tileP = reinterpret_cast<float*>(smem_dyn + ((128u - (smem_u32(smem_dyn) & 127u)) & 127u));
+  __shared__ __align__(8) uint64_t bar;
+  const int K = a.K;
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const float inv_km1 = 1.0f / (float)(K - 1);
+  const float scale = -((float)(K - 1) / (float)K);
+  const int64_t ntiles = (a.n + kRR - 1) / kRR;
+  double acc[2] = {0.0, 0.0};
+  uint32_t it = 0;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+    if (tid == 0) {  // the other resident CTAs of the SM cover this tile's load latency
+      mbar_expect_tx(&bar, (uint32_t)(K * kRR * sizeof(float)));
+      tma_load_tile(tileP, &mapP, (int)(tile * kRR), &bar);
+    }
+    const int64_t row0 = tile * kRR + 4 * tid;
+    const bool any_in = row0 < a.n, all_in = row0 + 3 < a.n;
+    // slots are padded to 32 floats: 128-bit accesses at a 4-aligned row below n stay inside them
+    const float4 vy = any_in ? ld_stream4(a.y + row0) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 vw = any_in ? ld_rw4(a.w + row0) : make_float4(0.f, 0.f, 0.f, 0.f);
+    int yi[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) yi[e] = (int)f4at(vy, e);
+    mbar_wait(&bar, it & 1);
+    const float* sP = tileP + 4 * tid;
+    float best[4], sum_lg[4];
+    int am[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) best[e] = -INFINITY, sum_lg[e] = 0.f, am[e] = 0;
+#pragma unroll 2
+    for (int k = 0; k < K; ++k) {
+      const float4 p = *reinterpret_cast<const float4*>(sP + k * kRR);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float pe = f4at(p, e);
+        if (pe > best[e]) best[e] = pe, am[e] = k;  // Vector.argmax: first maximum
+        sum_lg[e] += lg2_approx(fmaxf(pe, kSparkEps));
+      }
+    }
+    float4 out;
+    float err4 = 0.f, sum4 = 0.f;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const bool in = row0 + e < a.n;
+      const int yc = min(max(yi[e], 0), K - 1);
+      const float log_y = lg2_approx(fmaxf(sP[yc * kRR + e], kSparkEps)) * kLn2;
+      const float wn = f4at(vw, e) * a.inv_sum_w;  // :186
+      const float loss = (1.0f + inv_km1) * log_y - inv_km1 * (sum_lg[e] * kLn2);  // :218-224
+      const float wo = wn * exp_fast(scale * loss);                                // :226
+      f4at(out, e) = wo;
+      err4 += (in && am[e] != yi[e]) ? wn : 0.f;                                   // :202-209
+      sum4 += in ? wo : 0.f;
+    }
+    if (all_in) {
+      st_stream4(a.w + row0, out);
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        if (row0 + e < a.n) a.w[row0 + e] = f4at(out, e);
+    }
+    acc[0] += (double)err4;
+    acc[1] += (double)sum4;
+    __syncthreads();  // everyone is done with the tile before it is refilled
+  }
+  block_reduce_publish<2, kRT>(acc, a.ws);
 }
 
 // SAMME: est_err = Σ wₙ·1[pred ≠ y]  (:232-242)
@@ -278,6 +363,24 @@ cudaError_t launch_boostreg_update(const BoostRegArgs& a, int ctas_per_sm, int s
 }
 
 cudaError_t launch_boost_real(const BoostArgs& a, int ctas_per_sm, int sms, cudaStream_t s) {
+  static const int tiled_min_k = [] { const char* e = getenv("SE_SAMME_TILED_MIN_K"); return e ? atoi(e) : 5; }();
+  const size_t tile_bytes = (size_t)a.K * kRR * sizeof(float);
+  if (a.K >= tiled_min_k && a.n > 0 && a.n < (int64_t)0x7fffff00 && tile_bytes <= 200 * 1024) {
+    CUtensorMap mapP;
+    cudaError_t e = make_tile_map(&mapP, a.proba, a.n, a.ld, a.K, kRR);
+    if (e != cudaSuccess) return e;
+    const size_t smem = tile_bytes + 128;
+    int per_sm = (int)((228 * 1024) / (smem + 1536));  // + static shared memory and the 1 KB the system reserves
+    if (per_sm > 8) per_sm = 8;
+    const int64_t ntiles = (a.n + kRR - 1) / kRR;
+    int64_t cap = (int64_t)per_sm * sms;
+    if (cap > kMaxGridPartials) cap = kMaxGridPartials;
+    const int grid = (int)(ntiles < cap ? ntiles : cap);
+    e = cudaFuncSetAttribute(boost_real_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    boost_real_tiled_kernel<<<grid, kRT, smem, s>>>(a, mapP);
+    return cudaGetLastError();
+  }
   boost_real_kernel<<<grid_for(a.n >> 2, kBlock, ctas_per_sm, sms), kBlock, 0, s>>>(a);
   return cudaGetLastError();
 }

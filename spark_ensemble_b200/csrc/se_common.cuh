@@ -191,9 +191,9 @@ __device__ __forceinline__ void peer_exchange(const double* tot, int nred, const
 
 // Block-reduce NRED per-thread fp64 accumulators, publish the block partial, and let the last CTA
 // to arrive reduce all partials in a fixed order (deterministic for a fixed launch configuration).
-template <int NRED>
+template <int NRED, int BLOCK = kBlock>
 __device__ __forceinline__ void block_reduce_publish(double (&acc)[NRED], const RedWs& ws) {
-  __shared__ double sm[NRED][kBlock / 32];
+  __shared__ double sm[NRED][BLOCK / 32];
   __shared__ double tot[NRED];
   __shared__ bool is_last;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -206,7 +206,7 @@ __device__ __forceinline__ void block_reduce_publish(double (&acc)[NRED], const 
   if (warp == 0) {
 #pragma unroll
     for (int k = 0; k < NRED; ++k) {
-      double v = (lane < kBlock / 32) ? sm[k][lane] : 0.0;
+      double v = (lane < BLOCK / 32) ? sm[k][lane] : 0.0;
       v = warp_sum(v);
       if (lane == 0) ws.partials[(size_t)blockIdx.x * NRED + k] = v;
     }
@@ -219,11 +219,11 @@ __device__ __forceinline__ void block_reduce_publish(double (&acc)[NRED], const 
   __syncthreads();
   if (!is_last) return;
   __threadfence();
-  // fixed-order accumulation over blocks: thread t takes blocks t, t+kBlock, ...
+  // fixed-order accumulation over blocks: thread t takes blocks t, t+BLOCK, ...
 #pragma unroll
   for (int k = 0; k < NRED; ++k) {
     double v = 0.0;
-    for (unsigned int b = threadIdx.x; b < gridDim.x; b += kBlock)
+    for (unsigned int b = threadIdx.x; b < gridDim.x; b += BLOCK)
       v += __ldcg(&ws.partials[(size_t)b * NRED + k]);
     v = warp_sum(v);
     if (lane == 0) sm[k][warp] = v;
@@ -232,7 +232,7 @@ __device__ __forceinline__ void block_reduce_publish(double (&acc)[NRED], const 
   if (warp == 0) {
 #pragma unroll
     for (int k = 0; k < NRED; ++k) {
-      double v = (lane < kBlock / 32) ? sm[k][lane] : 0.0;
+      double v = (lane < BLOCK / 32) ? sm[k][lane] : 0.0;
       v = warp_sum(v);
       if (lane == 0) tot[k] = v;
     }

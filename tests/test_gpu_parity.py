@@ -230,9 +230,10 @@ def test_multi_round_drift(ctx, oracle, rng):
 
 
 # ------------------------------------------------------------------ BoostingClassifier
-@pytest.mark.parametrize("K", [2, 3, 26])
-@pytest.mark.parametrize("n", [2, 4097, 50001])
+@pytest.mark.parametrize("K", [2, 3, 5, 9, 26])
+@pytest.mark.parametrize("n", [2, 255, 256, 257, 4097, 50001])
 def test_samme_r_update(ctx, oracle, rng, K, n):
+    """K < 5: register-streaming kernel; K >= 5: TMA-tiled kernel (256-row tiles, tails included)."""
     from spark_ensemble_b200 import _native as N
     y = f32(rng.integers(0, K, n))
     Z = rng.standard_normal((K, n))
