@@ -117,18 +117,24 @@ def main():
                                     (N.AGG_GBM_REGRESSOR, "gbm weighted sum", 512, 0, int(6.25e6 * scale)),
                                     (N.AGG_GBM_REGRESSOR, "gbm weighted sum", 100, 0, int(25e6 * scale)),
                                     (N.AGG_BOOSTING_REAL, "boosting real", 10, 26, int(10e6 * scale)),
-                                    (N.AGG_BAGGING_HARD, "bagging hard vote", 64, 26, int(10e6 * scale))):
+                                    (N.AGG_BAGGING_HARD, "bagging hard vote", 64, 26, int(10e6 * scale)),
+                                    (N.AGG_BAGGING_SOFT, "bagging soft vote", 16, 26, int(10e6 * scale)),
+                                    (N.AGG_BAGGING_SOFT, "bagging soft vote", 64, 2, int(25e6 * scale)),
+                                    (N.AGG_BOOSTING_DISCRETE, "boosting discrete", 64, 26, int(10e6 * scale)),
+                                    (N.AGG_BOOSTING_REG_MEDIAN, "weighted median", 32, 0, int(25e6 * scale))):
             ctx.agg_configure(kind, M, max(K, 2), 1, 0, n)
-            if kind == N.AGG_BAGGING_HARD:
+            if kind in (N.AGG_BAGGING_HARD, N.AGG_BOOSTING_DISCRETE):
                 ctx.fill_synthetic(N.SLOT_P, "randint", 5, 0, K)
             else:
                 ctx.fill_synthetic(N.SLOT_P, "uniform", 5, 0.01, 1.0)
             w = np.full(M, 1.0 / M)
-            width = K if kind == N.AGG_BOOSTING_REAL else 1
+            width = K if kind in (N.AGG_BOOSTING_REAL, N.AGG_BAGGING_SOFT) else 1
             C = K if K else 1
-            bpr = 4 * M * width + 4 * C * (1 if kind in (N.AGG_GBM_REGRESSOR, N.AGG_BAGGING_REGRESSOR) else 3)
+            regr = kind in (N.AGG_GBM_REGRESSOR, N.AGG_BAGGING_REGRESSOR, N.AGG_BOOSTING_REG_MEDIAN)
+            bpr = 4 * M * width + (4 * C if regr else 4 * (2 * C + 1))  # classifiers write raw, prob [C] and the label
             rec("K4 aggregation", f"{name} M={M}" + (f" K={K}" if K else ""), n, bpr,
-                timed(ctx, "agg", lambda: ctx.agg_run(w if kind == N.AGG_GBM_REGRESSOR else None, [0.1]), reps=5))
+                timed(ctx, "agg", lambda: ctx.agg_run(w if kind in (N.AGG_GBM_REGRESSOR, N.AGG_BOOSTING_DISCRETE,
+                                                                   N.AGG_BOOSTING_REG_MEDIAN) else None, [0.1]), reps=5))
     ctx.close()
     if args.out:
         json.dump({"peak_gbs": pk, "rows": rows}, open(args.out, "w"), indent=1)
