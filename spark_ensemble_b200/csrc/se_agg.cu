@@ -36,7 +36,12 @@ __global__ void __launch_bounds__(kBlock) agg_sum_kernel(const float* __restrict
   for (int64_t g = (int64_t)blockIdx.x * kBlock + threadIdx.x; g < n4;
        g += (int64_t)gridDim.x * kBlock) {
     for (int c = 0; c < width; ++c) {
-      float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0;
+      // every batch of MU models is summed in fp32 (two short chains) and folded into fp64 accumulators: the
+      // rounding error stays at the magnitude of one batch instead of growing with M (M = 512 in config 5)
+      // (up to two batches there is nothing to gain: plain fp32 carry)
+      const bool wide = M > 2 * MU;
+      double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0;
+      float4 carry = make_float4(0.f, 0.f, 0.f, 0.f);
       for (int m0 = 0; m0 < M; m0 += MU) {
         float4 v[MU];
         float wv[MU];
@@ -49,6 +54,7 @@ __global__ void __launch_bounds__(kBlock) agg_sum_kernel(const float* __restrict
             wv[u] = a ? a[(int64_t)m * width + c] : 1.0f;
           }
         }
+        float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0;
 #pragma unroll
         for (int u = 0; u < MU; ++u) {
           if (m0 + u < M) {
@@ -62,10 +68,18 @@ __global__ void __launch_bounds__(kBlock) agg_sum_kernel(const float* __restrict
             s.z = fmaf(wv[u], x.z, s.z); s.w = fmaf(wv[u], x.w, s.w);
           }
         }
+        if (wide) {
+          d0 += (double)(s0.x + s1.x); d1 += (double)(s0.y + s1.y);
+          d2 += (double)(s0.z + s1.z); d3 += (double)(s0.w + s1.w);
+        } else {
+          carry.x += s0.x + s1.x; carry.y += s0.y + s1.y; carry.z += s0.z + s1.z; carry.w += s0.w + s1.w;
+        }
       }
-      const float b = init ? init[c] : 0.f;
-      float4 r = make_float4(b + (s0.x + s1.x), b + (s0.y + s1.y), b + (s0.z + s1.z), b + (s0.w + s1.w));
-      if (post_div != 0.f) { r.x /= post_div; r.y /= post_div; r.z /= post_div; r.w /= post_div; }
+      if (!wide) { d0 = (double)carry.x; d1 = (double)carry.y; d2 = (double)carry.z; d3 = (double)carry.w; }
+      const double b = init ? (double)init[c] : 0.0;
+      d0 += b; d1 += b; d2 += b; d3 += b;
+      if (post_div != 0.f) { const double pd = (double)post_div; d0 /= pd; d1 /= pd; d2 /= pd; d3 /= pd; }
+      const float4 r = make_float4((float)d0, (float)d1, (float)d2, (float)d3);
       st_stream4(out + c * ld_out + 4 * g, r);
     }
   }
@@ -74,16 +88,15 @@ __global__ void __launch_bounds__(kBlock) agg_sum_kernel(const float* __restrict
   if (blockIdx.x == 0 && threadIdx.x < tail) {
     const int64_t i = (n4 << 2) + threadIdx.x;
     for (int c = 0; c < width; ++c) {
-      float s = 0.f;
+      double sd = init ? (double)init[c] : 0.0;
       for (int m = 0; m < M; ++m) {
         const int64_t rowi = cols ? (int64_t)cols[m] : (int64_t)m * width + c;
         float x = P[rowi * ld + i];
         if (LOGP) x = log_fast(fmaxf(x, kSparkEps));
-        s = fmaf(a ? a[(int64_t)m * width + c] : 1.0f, x, s);
+        sd += (double)((a ? a[(int64_t)m * width + c] : 1.0f) * x);
       }
-      float r = (init ? init[c] : 0.f) + s;
-      if (post_div != 0.f) r /= post_div;
-      out[c * ld_out + i] = r;
+      if (post_div != 0.f) sd /= (double)post_div;
+      out[c * ld_out + i] = (float)sd;
     }
   }
 }
@@ -91,20 +104,24 @@ __global__ void __launch_bounds__(kBlock) agg_sum_kernel(const float* __restrict
 // Per-row epilogue on the C per-class sums t_c (from shared memory or from the RAW slot): raw, prob, label.
 struct FinArgs {
   int kind, C, K, dim, loss, M;
-  float sum_a;  // Σ a_m (boosting discrete)
+  double sum_a;  // Σ a_m (boosting discrete)
   int64_t n, ld;
   float* raw;
   float* prob;
   float* label;
 };
 
-__device__ __forceinline__ float fin_raw(const FinArgs& f, float t, float mean_t) {
+// raw value from the stage-1 sum.  Real: the mean is a shift common to all classes (soft-max invariant), so fp32 is
+// enough once the mean itself was accumulated in fp64; discrete: K·A_k − Σa subtracts nearly equal numbers and is
+// formed in fp64 before the single rounding to the fp32 output.
+template <class T>
+__device__ __forceinline__ float fin_raw(const FinArgs& f, T t, float mean_t) {
   switch (f.kind) {
     case SE_AGG_BOOSTING_REAL:  // (K-1)(L_k − mean L)   BoostingClassifier.scala:355-360
-      return (float)(f.K - 1) * (t - mean_t);
+      return (float)(f.K - 1) * ((float)t - mean_t);
     case SE_AGG_BOOSTING_DISCRETE:  // +a on the vote, −a/(K-1) elsewhere   :371-376
-      return (t * (float)f.K - f.sum_a) / (float)(f.K - 1);
-    default: return t;
+      return (float)(((double)t * (double)f.K - f.sum_a) / (double)(f.K - 1));
+    default: return (float)t;
   }
 }
 
@@ -115,9 +132,9 @@ __device__ __forceinline__ void finalize_row(const FinArgs& f, int64_t i, Get ge
   const int C = f.C;
   float mean_t = 0.f;
   if (f.kind == SE_AGG_BOOSTING_REAL) {
-    float s = 0.f;
-    for (int c = 0; c < C; ++c) s += get(c);
-    mean_t = s / (float)C;
+    double s = 0.0;
+    for (int c = 0; c < C; ++c) s += (double)get(c);
+    mean_t = (float)(s / (double)C);
   }
   const bool softmax = (f.kind == SE_AGG_BOOSTING_REAL || f.kind == SE_AGG_BOOSTING_DISCRETE ||
                         f.kind == SE_AGG_GBM_CLASSIFIER);
@@ -144,13 +161,15 @@ __device__ __forceinline__ void finalize_row(const FinArgs& f, int64_t i, Get ge
 // Vote histogram: A_c = Σ_{m: vote_m == c} a_m (a_m = 1 when a == nullptr).  One row per thread, per-thread
 // histogram in shared memory laid out [K][kBlock] (conflict-free); the epilogue (raw, probability, argmax)
 // runs straight out of shared memory — no intermediate [K][n] round trip through HBM.
+template <typename HT>  // float: unweighted counts (exact); double: weighted votes (error independent of M)
 __global__ void __launch_bounds__(kBlock) agg_votes_kernel(const float* __restrict__ votes, int64_t ld, int M,
                                                           const float* __restrict__ a, const FinArgs f) {
-  extern __shared__ float hist[];  // [K][kBlock]
+  extern __shared__ __align__(8) unsigned char hist_raw[];
+  HT* hist = reinterpret_cast<HT*>(hist_raw);  // [K][kBlock]
   const int K = f.K;
   for (int64_t i0 = (int64_t)blockIdx.x * kBlock; i0 < f.n; i0 += (int64_t)gridDim.x * kBlock) {
     const int64_t i = i0 + threadIdx.x;
-    for (int c = 0; c < K; ++c) hist[c * kBlock + threadIdx.x] = 0.f;
+    for (int c = 0; c < K; ++c) hist[c * kBlock + threadIdx.x] = (HT)0;
     if (i < f.n) {
       for (int m0 = 0; m0 < M; m0 += MU) {
         float v[MU];
@@ -161,7 +180,7 @@ __global__ void __launch_bounds__(kBlock) agg_votes_kernel(const float* __restri
         for (int u = 0; u < MU; ++u)
           if (m0 + u < M) {
             const int c = (int)v[u];
-            if (c >= 0 && c < K) hist[c * kBlock + threadIdx.x] += a ? a[m0 + u] : 1.0f;
+            if (c >= 0 && c < K) hist[c * kBlock + threadIdx.x] += (HT)(a ? a[m0 + u] : 1.0f);
           }
       }
       finalize_row(f, i, [&](int c) { return hist[c * kBlock + threadIdx.x]; });
@@ -243,7 +262,7 @@ cudaError_t launch_agg(const AggArgs& a, int ctas_per_sm, int sms, cudaStream_t 
   FinArgs f{};
   f.kind = a.kind; f.K = a.K; f.dim = a.dim; f.loss = a.loss; f.M = a.M;
   f.n = a.n; f.ld = a.ld_out; f.raw = a.raw; f.prob = a.prob; f.label = a.label;
-  f.sum_a = 0.f;
+  f.sum_a = 0.0;
   switch (a.kind) {
     case SE_AGG_GBM_REGRESSOR:
       agg_sum_kernel<false><<<grid4, kBlock, 0, st>>>(a.P, a.n, a.ld, a.M, 1, a.weights, a.init,
@@ -255,7 +274,7 @@ cudaError_t launch_agg(const AggArgs& a, int ctas_per_sm, int sms, cudaStream_t 
       return cudaGetLastError();
     case SE_AGG_BOOSTING_REG_MEAN:  // dot(predictions, weights) / Σ weights  (BoostingRegressor.scala:339-342)
       agg_sum_kernel<false><<<grid4, kBlock, 0, st>>>(a.P, a.n, a.ld, a.M, 1, a.weights, nullptr,
-                                                       nullptr, a.sum_weights, a.raw, a.ld_out);
+                                                       nullptr, (float)a.sum_weights, a.raw, a.ld_out);
       return cudaGetLastError();
     case SE_AGG_BOOSTING_REG_MEDIAN: {
       const size_t smem = (size_t)a.M * sizeof(double) + (size_t)a.M * kWmRows * sizeof(float);
@@ -285,17 +304,17 @@ cudaError_t launch_agg(const AggArgs& a, int ctas_per_sm, int sms, cudaStream_t 
       break;
     case SE_AGG_BAGGING_HARD:
     case SE_AGG_BOOSTING_DISCRETE: {
-      const size_t smem = (size_t)a.K * kBlock * sizeof(float);
+      const bool weighted = (a.kind == SE_AGG_BOOSTING_DISCRETE);
+      const size_t smem = (size_t)a.K * kBlock * (weighted ? sizeof(double) : sizeof(float));
       if (smem > 200 * 1024) return cudaErrorInvalidValue;
+      auto kern = weighted ? agg_votes_kernel<double> : agg_votes_kernel<float>;
       if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(agg_votes_kernel,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
       }
       f.C = a.K;
       f.sum_a = a.sum_weights;
-      agg_votes_kernel<<<grid1, kBlock, smem, st>>>(
-          a.P, a.ld, a.M, a.kind == SE_AGG_BOOSTING_DISCRETE ? a.weights : nullptr, f);
+      kern<<<grid1, kBlock, smem, st>>>(a.P, a.ld, a.M, weighted ? a.weights : nullptr, f);
       return cudaGetLastError();  // epilogue fused: no separate finalize launch
     }
     default: return cudaErrorInvalidValue;

@@ -1707,9 +1707,9 @@ int se_agg_run(se_ctx* ctx, const double* weights, const double* init) {
   if (uses_w) {
     SE_REQUIRE(ctx, weights || g.M == 0, SE_ERR_ARG, "weights required for this aggregation kind");
     double sw = 0.0;
-    for (int i = 0; i < nw; ++i) { hs[i] = (float)weights[i]; sw += weights[i]; }
+    for (int i = 0; i < nw; ++i) { hs[i] = (float)weights[i]; sw += (double)hs[i]; }  // Σ of what the device sees
     a.weights = reinterpret_cast<const float*>(ctx->d_small);
-    a.sum_weights = (float)sw;
+    a.sum_weights = sw;
     used = (size_t)nw;
   }
   if ((g.kind == SE_AGG_GBM_REGRESSOR || g.kind == SE_AGG_GBM_CLASSIFIER) && init) {

@@ -109,7 +109,7 @@ struct AggArgs {
   const float* init = nullptr;     // device [dim]
   int M = 0, K = 0, dim = 1, loss = 0;
   int64_t n = 0, ld = 0, ld_out = 0;
-  float sum_weights = 0.f;  // Σ a_m (boosting discrete epilogue, boosting-regressor mean)
+  double sum_weights = 0.0;  // Σ a_m of the fp32-narrowed weights (boosting discrete epilogue, boosting-regressor mean)
   const double* weights64 = nullptr;  // device [M] fp64 (weighted median cumulative sums)
 };
 cudaError_t launch_agg(const AggArgs& a, int ctas_per_sm, int sms, cudaStream_t s);
