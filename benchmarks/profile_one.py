@@ -51,6 +51,12 @@ elif what == "tree":
             "left": np.where(leaf, 0, 2 * idx + 1), "right": np.where(leaf, 0, 2 * idx + 2), "value": np.linspace(-1, 1, nn)}
     for _ in range(3):
         ctx.tree_predict(tree, N.SLOT_H, 0)
+elif what == "wmedian":
+    M = 32
+    ctx.agg_configure(N.AGG_BOOSTING_REG_MEDIAN, M, 2, 1, 0, n)
+    ctx.fill_synthetic(N.SLOT_P, "uniform", 5, 0.01, 1.0)
+    for _ in range(3):
+        ctx.agg_run(np.full(M, 1.0 / M))
 elif what == "votes":
     M, K = 64, 26
     ctx.agg_configure(N.AGG_BAGGING_HARD, M, K, 1, 0, n)

@@ -18,7 +18,7 @@ LIBDIR = os.path.join(HERE, "lib")
 OBJDIR = os.path.join(LIBDIR, "obj")
 LIB = os.path.join(LIBDIR, "libse_b200.so")
 SOURCES = ["se_api.cu", "se_gbm.cu", "se_gbm_tiled.cu", "se_boost.cu", "se_agg.cu", "se_models.cu", "se_util.cu"]
-HEADERS = ["se_common.cuh", "se_kernels.h", "se_loss.cuh", os.path.join("..", "..", "include", "se_abi.h")]
+HEADERS = ["se_common.cuh", "se_kernels.h", "se_loss.cuh", "se_tma.cuh", os.path.join("..", "..", "include", "se_abi.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",

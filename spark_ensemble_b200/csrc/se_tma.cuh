@@ -68,7 +68,8 @@ inline cudaError_t make_tile_map(CUtensorMap* m, const float* base, int64_t n, i
   auto enc = tensor_map_encoder();
   if (enc == nullptr) return cudaErrorNotSupported;
   const cuuint64_t gdim[2] = {(cuuint64_t)n, (cuuint64_t)K};
-  const cuuint64_t gstride[1] = {(cuuint64_t)ld * sizeof(float)};
+  // a one-row array has no meaningful stride (1-D slots are unpadded): any multiple of 16 B satisfies the encoder
+  const cuuint64_t gstride[1] = {K > 1 ? (cuuint64_t)ld * sizeof(float) : (((cuuint64_t)ld * sizeof(float) + 15) / 16) * 16};
   const cuuint32_t box[2] = {(cuuint32_t)tile_rows, (cuuint32_t)K};
   const cuuint32_t estride[2] = {1, 1};
   const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estride,
