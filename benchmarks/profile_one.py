@@ -57,6 +57,12 @@ elif what == "wmedian":
     ctx.fill_synthetic(N.SLOT_P, "uniform", 5, 0.01, 1.0)
     for _ in range(3):
         ctx.agg_run(np.full(M, 1.0 / M))
+elif what == "agg_real":
+    M, K = 10, 26
+    ctx.agg_configure(N.AGG_BOOSTING_REAL, M, K, 1, 0, n)
+    ctx.fill_synthetic(N.SLOT_P, "uniform", 5, 0.01, 1.0)
+    for _ in range(3):
+        ctx.agg_run()
 elif what == "votes":
     M, K = 64, 26
     ctx.agg_configure(N.AGG_BAGGING_HARD, M, K, 1, 0, n)

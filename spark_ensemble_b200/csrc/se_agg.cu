@@ -11,6 +11,8 @@
 // All of them are one streaming pass over the stacked base-model outputs P (the only large operand:
 // 4·M·width B/row) followed by a tiny per-row epilogue.  Stage 1 (sum / vote histogram) is the
 // HBM-bound kernel; stage 2 (finalize) touches only C values per row.
+#include <stdlib.h>
+
 #include "se_kernels.h"
 #include "se_loss.cuh"
 #include "se_tma.cuh"
@@ -184,8 +186,223 @@ __global__ void __launch_bounds__(kBlock) agg_votes_kernel(const float* __restri
             if (c >= 0 && c < K) hist[c * kBlock + threadIdx.x] += (HT)(a ? a[m0 + u] : 1.0f);
           }
       }
-      finalize_row(f, i, [&](int c) { return hist[c * kBlock + threadIdx.x]; });
+      // epilogue out of the thread's own histogram column, which doubles as fp32 scratch (ncu on the generic
+      // two-sweep finalize_row: ~55 instructions per class; this form: 8 for plain votes, ~25 with the soft-max)
+      HT* col = hist + threadIdx.x;
+      float best = -INFINITY;
+      int am = 0;
+      if (f.kind == SE_AGG_BAGGING_HARD) {
+        const float inv = 1.0f / (float)f.M;  // prob = raw·(1/M)  (BaggingClassifier.scala:285-287)
+        for (int c = 0; c < K; ++c) {
+          const float r = (float)col[c * kBlock];
+          if (r > best) best = r, am = c;  // Vector.argmax: first maximum
+          f.raw[c * f.ld + i] = r;
+          f.prob[c * f.ld + i] = r * inv;
+        }
+      } else {
+        const float sc = kLog2e / (float)(f.K - 1);  // prob = softmax(raw/(K-1))  (BoostingClassifier.scala:342-346)
+        for (int c = 0; c < K; ++c) {
+          const float r = fin_raw(f, col[c * kBlock], 0.f);
+          if (r > best) best = r, am = c;
+          f.raw[c * f.ld + i] = r;
+          *reinterpret_cast<float*>(col + c * kBlock) = r;
+        }
+        float ssum = 0.f;
+        for (int c = 0; c < K; ++c) {
+          float* sp = reinterpret_cast<float*>(col + c * kBlock);
+          const float e = ex2_approx((*sp - best) * sc);
+          ssum += e;
+          *sp = e;
+        }
+        const float inv = rcp_approx(ssum);
+        for (int c = 0; c < K; ++c) f.prob[c * f.ld + i] = *reinterpret_cast<const float*>(col + c * kBlock) * inv;
+      }
+      f.label[i] = (float)am;
     }
+  }
+}
+
+// ------------------------------------------------------------------ class-wide sums through TMA tiles
+// For the classifiers every row needs all C class sums before its epilogue (argmax, soft-max).  The streaming path
+// (agg_sum_kernel + agg_finalize_kernel) round-trips a [C][n] intermediate through HBM and, per ncu, is
+// instruction-bound: 15.8 instructions per element in stage 1 and 55 per (row, class) in the epilogue.  Here a W-warp
+// CTA owns 128 W rows; the stacked model outputs arrive as 2-D tensor-map TMA boxes of G models x C classes x 128 W
+// rows; a thread owns four rows and keeps the C x 4 sums of the current batch of <= 8 models in REGISTERS (one 128-bit
+// shared-memory read and 4 FMAs — plus 4 lg2 for SAMME.R — per class and model); each batch is folded into the
+// tile's running totals [C][128 W] in shared memory (own columns only), and the epilogue runs out of shared memory
+// with 128-bit stores: P is read once, nothing is re-read.  Latency is covered by the other resident CTAs (up to 8
+// per SM), not by per-CTA double buffering.
+// W warps per CTA: 32 W threads, tiles of 128 W rows
+constexpr int kAggMaxStages = 4;
+
+struct ClassTileArgs {
+  int M, C;          // models, classes
+  int G;             // models per TMA box
+  int stages;
+  int logp;          // f = log max(p, eps) (boosting real)
+  const float* a;    // weights [M][C] (GBM classifier) or null
+  const float* init; // [C] or null
+};
+
+// epilogue of four rows whose C stage-1 sums sit in T[c * kAR + j] (this thread's own columns)
+template <int kAR>
+__device__ __forceinline__ void finalize_tile4(const FinArgs& f, float* T, int64_t row0) {
+  const int C = f.C;
+  const bool all_in = row0 + 3 < f.n;
+  auto store4 = [&](float* base, const float4& v) {
+    if (all_in) {
+      st_stream4(base + row0, v);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (row0 + j < f.n) base[row0 + j] = f4at(v, j);
+    }
+  };
+  float4 mean = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (f.kind == SE_AGG_BOOSTING_REAL) {
+    double m0 = 0.0, m1 = 0.0, m2 = 0.0, m3 = 0.0;
+    for (int c = 0; c < C; ++c) {
+      const float4 t = *reinterpret_cast<const float4*>(T + c * kAR);
+      m0 += (double)t.x, m1 += (double)t.y, m2 += (double)t.z, m3 += (double)t.w;
+    }
+    const double ic = 1.0 / (double)C;
+    mean = make_float4((float)(m0 * ic), (float)(m1 * ic), (float)(m2 * ic), (float)(m3 * ic));
+  }
+  const bool softmax = (f.kind == SE_AGG_BOOSTING_REAL || f.kind == SE_AGG_GBM_CLASSIFIER);
+  const float sc = (f.kind == SE_AGG_GBM_CLASSIFIER) ? kLog2e : kLog2e / (float)(f.K - 1);
+  // pass 1: raw (kept in the tile, written to HBM), max and first argmax
+  float4 best = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+  float4 am = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int c = 0; c < C; ++c) {
+    const float4 t = *reinterpret_cast<const float4*>(T + c * kAR);
+    float4 r;
+    r.x = fin_raw(f, t.x, mean.x), r.y = fin_raw(f, t.y, mean.y), r.z = fin_raw(f, t.z, mean.z), r.w = fin_raw(f, t.w, mean.w);
+    const float cf = (float)c;  // Vector.argmax: first maximum
+    if (r.x > best.x) best.x = r.x, am.x = cf;
+    if (r.y > best.y) best.y = r.y, am.y = cf;
+    if (r.z > best.z) best.z = r.z, am.z = cf;
+    if (r.w > best.w) best.w = r.w, am.w = cf;
+    *reinterpret_cast<float4*>(T + c * kAR) = r;
+    store4(f.raw + c * f.ld, r);
+  }
+  store4(f.label, am);
+  if (softmax) {
+    float4 ssum = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int c = 0; c < C; ++c) {
+      const float4 r = *reinterpret_cast<const float4*>(T + c * kAR);
+      float4 e;
+      e.x = ex2_approx((r.x - best.x) * sc), e.y = ex2_approx((r.y - best.y) * sc);
+      e.z = ex2_approx((r.z - best.z) * sc), e.w = ex2_approx((r.w - best.w) * sc);
+      ssum.x += e.x, ssum.y += e.y, ssum.z += e.z, ssum.w += e.w;
+      *reinterpret_cast<float4*>(T + c * kAR) = e;
+    }
+    const float4 inv = make_float4(rcp_approx(ssum.x), rcp_approx(ssum.y), rcp_approx(ssum.z), rcp_approx(ssum.w));
+    for (int c = 0; c < C; ++c) {
+      const float4 e = *reinterpret_cast<const float4*>(T + c * kAR);
+      store4(f.prob + c * f.ld, make_float4(e.x * inv.x, e.y * inv.y, e.z * inv.z, e.w * inv.w));
+    }
+  } else {
+    const float inv = 1.0f / (float)f.M;  // bagging: prob = raw·(1/M) (BaggingClassifier.scala:285-287)
+    for (int c = 0; c < C; ++c) {
+      const float4 r = *reinterpret_cast<const float4*>(T + c * kAR);
+      store4(f.prob + c * f.ld, make_float4(r.x * inv, r.y * inv, r.z * inv, r.w * inv));
+    }
+  }
+}
+
+// dynamic shared memory (128-byte aligned): [stages][G*C][kAR] floats, then the running totals [C][kAR]
+template <int CMAX, int W>
+__global__ void __launch_bounds__(32 * W) agg_class_tile_kernel(const ClassTileArgs ta, const FinArgs f,
+                                                             const __grid_constant__ CUtensorMap mapP) {
+  constexpr int kAT = 32 * W, kAR = 128 * W;
+  extern __shared__ __align__(128) unsigned char smem_dyn[];
+  float* ring = reinterpret_cast<float*>(smem_dyn + ((128u - (smem_u32(smem_dyn) & 127u)) & 127u));
+  __shared__ __align__(8) uint64_t full[kAggMaxStages];
+  const int C = ta.C, M = ta.M, S = ta.stages;
+  const int box_rows = ta.G * C;
+  const int stage_floats = box_rows * kAR;
+  const int tid = threadIdx.x;
+  float* total = ring + (size_t)S * stage_floats + 4 * tid;  // this thread's four columns
+  if (tid == 0) {
+    for (int s = 0; s < S; ++s) mbar_init(&full[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  (void)kAT;
+  const int64_t ntiles = (f.n + kAR - 1) / kAR;
+  const int64_t my_tiles = (ntiles > blockIdx.x) ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const int steps = (M + ta.G - 1) / ta.G;            // boxes per tile
+  const int64_t nbox = my_tiles * steps;              // boxes this CTA consumes, in order
+  auto issue = [&](int64_t q, int stage) {            // one elected thread
+    const int64_t tile = blockIdx.x + (q / steps) * gridDim.x;
+    const int step = (int)(q % steps);
+    mbar_expect_tx(&full[stage], (uint32_t)(stage_floats * sizeof(float)));
+    tma_load_tile_at(ring + (size_t)stage * stage_floats, &mapP, (int)(tile * kAR), step * box_rows, &full[stage]);
+  };
+  if (tid == 0)
+    for (int s = 0; s < S && s < nbox; ++s) issue(s, s);
+
+  const float fold_scale = ta.logp ? kLn2 : 1.0f;  // logs are summed in the lg2 domain
+  int stage = 0;
+  uint32_t phase = 0;
+  int64_t q = 0;
+  for (int64_t ti = 0; ti < my_tiles; ++ti) {
+    const int64_t row0 = (blockIdx.x + ti * gridDim.x) * kAR + 4 * tid;
+    float4 acc[CMAX];
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c) acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+    int in_batch = 0;
+    bool first_fold = true;
+    for (int step = 0; step < steps; ++step, ++q) {
+      mbar_wait(&full[stage], phase);
+      const float* box = ring + (size_t)stage * stage_floats + 4 * tid;
+      const int m0 = step * ta.G;
+      const int gcount = min(ta.G, M - m0);
+      for (int g = 0; g < gcount; ++g) {
+        const float* bg = box + g * C * kAR;
+        const float* wg = ta.a ? ta.a + (int64_t)(m0 + g) * C : nullptr;
+#pragma unroll
+        for (int c = 0; c < CMAX; ++c) {
+          if (c < C) {
+            float4 x = *reinterpret_cast<const float4*>(bg + c * kAR);
+            if (ta.logp) {
+              x.x = lg2_approx(fmaxf(x.x, kSparkEps)), x.y = lg2_approx(fmaxf(x.y, kSparkEps));
+              x.z = lg2_approx(fmaxf(x.z, kSparkEps)), x.w = lg2_approx(fmaxf(x.w, kSparkEps));
+            }
+            const float wv = wg ? __ldg(wg + c) : 1.0f;
+            acc[c].x = fmaf(wv, x.x, acc[c].x), acc[c].y = fmaf(wv, x.y, acc[c].y);
+            acc[c].z = fmaf(wv, x.z, acc[c].z), acc[c].w = fmaf(wv, x.w, acc[c].w);
+          }
+        }
+      }
+      __syncthreads();  // every thread is done with the box: the stage can be refilled
+      if (tid == 0 && q + S < nbox) issue(q + S, stage);
+      if (++stage == S) stage = 0, phase ^= 1;
+      in_batch += gcount;
+      if (in_batch >= 8 || step == steps - 1) {
+        // fold the batch into the running totals: the rounding error stays at the magnitude of one batch
+#pragma unroll
+        for (int c = 0; c < CMAX; ++c) {
+          if (c < C) {
+            float4 t;
+            if (first_fold) {
+              const float b = ta.init ? __ldg(ta.init + c) : 0.f;
+              t = make_float4(b, b, b, b);
+            } else {
+              t = *reinterpret_cast<const float4*>(total + c * kAR);
+            }
+            t.x = fmaf(acc[c].x, fold_scale, t.x), t.y = fmaf(acc[c].y, fold_scale, t.y);
+            t.z = fmaf(acc[c].z, fold_scale, t.z), t.w = fmaf(acc[c].w, fold_scale, t.w);
+            *reinterpret_cast<float4*>(total + c * kAR) = t;
+            acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+        first_fold = false;
+        in_batch = 0;
+      }
+    }
+    if (row0 < f.n) finalize_tile4<kAR>(f, total, row0);
   }
 }
 
@@ -372,6 +589,62 @@ inline int grid_rows(int64_t items, int64_t per_cta, int ctas_per_sm, int sms) {
   return (int)(need < cap ? need : cap);
 }
 
+// class-wide sum kinds through the tile kernel (2 <= C <= 32 classes, the tile and >= 2 stages fit in shared memory)
+cudaError_t try_launch_agg_class_tile(const AggArgs& a, const FinArgs& f0, int sms, cudaStream_t st, bool* launched) {
+  *launched = false;
+  static const int enabled = [] { const char* e = getenv("SE_AGG_TILE"); return e ? atoi(e) : 1; }();
+  if (!enabled || a.M < 1 || a.n < 1 || a.n >= (int64_t)0x7fffff00) return cudaSuccess;
+  // one warp per CTA (128-row tiles), one stage: shared memory bounds occupancy and what counts is the number of
+  // boxes in flight per SM (measured, boosting-real M=10 K=26: 1 warp x 1 stage 2.75 ms, 2 warps x 1 stage 2.78,
+  // 2 warps x 2 stages 4.32, 2 warps x 4 stages 8.59; streaming path 3.01)
+  constexpr int warps = 1;
+  const int kAT = 32 * warps, kAR = 128 * warps;
+  ClassTileArgs ta{};
+  FinArgs f = f0;
+  ta.M = a.M;
+  switch (a.kind) {
+    case SE_AGG_GBM_CLASSIFIER:
+      if (a.dim < 2) return cudaSuccess;  // binary dim-1 form: two outputs from one sum (streaming path)
+      ta.C = a.dim; ta.a = a.weights; ta.init = a.init; break;
+    case SE_AGG_BAGGING_SOFT: ta.C = a.K; break;
+    case SE_AGG_BOOSTING_REAL: ta.C = a.K; ta.logp = 1; break;
+    default: return cudaSuccess;
+  }
+  const int C = ta.C;
+  if (C < 2 || C > 32) return cudaSuccess;
+  f.C = C;
+  ta.G = 32 / C;
+  if (ta.G > a.M) ta.G = a.M;
+  if (ta.G > 8) ta.G = 8;
+  const int box_rows = ta.G * C;
+  const size_t stage_bytes = (size_t)box_rows * kAR * sizeof(float);
+  const size_t total_bytes = (size_t)C * kAR * sizeof(float);
+  static const int forced_stages = [] { const char* e = getenv("SE_AGG_TILE_STAGES"); return e ? atoi(e) : 0; }();
+  const int stages = forced_stages >= 1 && forced_stages <= kAggMaxStages ? forced_stages : 1;
+  const size_t smem = total_bytes + stages * stage_bytes + 128;
+  ta.stages = stages;
+  CUtensorMap mapP;
+  cudaError_t e = make_tile_map_rows(&mapP, a.P, a.n, a.ld, (int64_t)a.M * C, kAR, box_rows);
+  if (e != cudaSuccess) return e;
+  int per_sm = (int)((228 * 1024) / (smem + 1280));
+  if (per_sm > 16) per_sm = 16;
+  if (per_sm < 1) return cudaSuccess;
+  const int64_t ntiles = (a.n + kAR - 1) / kAR;
+  const int64_t cap = (int64_t)per_sm * sms;
+  const int grid = (int)(ntiles < cap ? ntiles : cap);
+#define SE_CT(CM)                                                                                        \
+  {                                                                                                      \
+    auto kern = agg_class_tile_kernel<CM, warps>;                                                        \
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);              \
+    if (e != cudaSuccess) return e;                                                                      \
+    kern<<<grid, kAT, smem, st>>>(ta, f, mapP);                                                          \
+  }
+  if (C <= 4) SE_CT(4) else if (C <= 8) SE_CT(8) else if (C <= 16) SE_CT(16) else SE_CT(32)
+#undef SE_CT
+  *launched = true;
+  return cudaGetLastError();
+}
+
 }  // namespace
 
 cudaError_t launch_agg(const AggArgs& a, int ctas_per_sm, int sms, cudaStream_t st) {
@@ -381,6 +654,11 @@ cudaError_t launch_agg(const AggArgs& a, int ctas_per_sm, int sms, cudaStream_t 
   f.kind = a.kind; f.K = a.K; f.dim = a.dim; f.loss = a.loss; f.M = a.M;
   f.n = a.n; f.ld = a.ld_out; f.raw = a.raw; f.prob = a.prob; f.label = a.label;
   f.sum_a = 0.0;
+  {
+    bool launched = false;
+    const cudaError_t e = try_launch_agg_class_tile(a, f, sms, st, &launched);
+    if (e != cudaSuccess || launched) return e;
+  }
   switch (a.kind) {
     case SE_AGG_GBM_REGRESSOR:
       agg_sum_kernel<false><<<grid4, kBlock, 0, st>>>(a.P, a.n, a.ld, a.M, 1, a.weights, a.init,

@@ -43,6 +43,15 @@ __device__ __forceinline__ void tma_load_tile(void* dst, const CUtensorMap* map,
       "l"(map), "r"(row0), "r"(0), "r"(smem_u32(bar))
       : "memory");
 }
+// box starting at (row0, first_row) of a [rows][ld] array
+__device__ __forceinline__ void tma_load_tile_at(void* dst, const CUtensorMap* map, int row0, int first_row,
+                                                 uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::
+          "r"(smem_u32(dst)),
+      "l"(map), "r"(row0), "r"(first_row), "r"(smem_u32(bar))
+      : "memory");
+}
 // generic-proxy accesses to a stage are ordered before the async-proxy (TMA) refill of the same bytes
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
@@ -63,19 +72,24 @@ inline PFN_cuTensorMapEncodeTiled_v12000 tensor_map_encoder() {
   return fn;
 }
 
-// [K][ld] fp32, rows [0, n) valid: boxes of [K][tile_rows]; reads past n are zero-filled
-inline cudaError_t make_tile_map(CUtensorMap* m, const float* base, int64_t n, int64_t ld, int K, int tile_rows) {
+// general form: the array has `rows` rows of stride ld; boxes are [box_rows][tile_cols]
+inline cudaError_t make_tile_map_rows(CUtensorMap* m, const float* base, int64_t n, int64_t ld, int64_t rows,
+                                      int tile_cols, int box_rows) {
   auto enc = tensor_map_encoder();
   if (enc == nullptr) return cudaErrorNotSupported;
-  const cuuint64_t gdim[2] = {(cuuint64_t)n, (cuuint64_t)K};
+  const cuuint64_t gdim[2] = {(cuuint64_t)n, (cuuint64_t)rows};
   // a one-row array has no meaningful stride (1-D slots are unpadded): any multiple of 16 B satisfies the encoder
-  const cuuint64_t gstride[1] = {K > 1 ? (cuuint64_t)ld * sizeof(float) : (((cuuint64_t)ld * sizeof(float) + 15) / 16) * 16};
-  const cuuint32_t box[2] = {(cuuint32_t)tile_rows, (cuuint32_t)K};
+  const cuuint64_t gstride[1] = {rows > 1 ? (cuuint64_t)ld * sizeof(float) : (((cuuint64_t)ld * sizeof(float) + 15) / 16) * 16};
+  const cuuint32_t box[2] = {(cuuint32_t)tile_cols, (cuuint32_t)box_rows};
   const cuuint32_t estride[2] = {1, 1};
   const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estride,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
+}
+// [K][ld] fp32, rows [0, n) valid: boxes of [K][tile_rows]; reads past n are zero-filled
+inline cudaError_t make_tile_map(CUtensorMap* m, const float* base, int64_t n, int64_t ld, int K, int tile_rows) {
+  return make_tile_map_rows(m, base, n, ld, K, tile_rows, K);
 }
 
 }  // namespace se
