@@ -798,10 +798,24 @@ def test_squared_stats_from_residual_slot(ctx, oracle, rng):
 
 @pytest.mark.parametrize("name", ["bernoulli", "exponential"])
 @pytest.mark.parametrize("weighted_bag", [False, True])
-def test_brent_packed_line_search_view_is_bit_identical(ctx, oracle, rng, name, weighted_bag, monkeypatch):
+def test_brent_packed_line_search_view_is_bit_identical(oracle, rng, name, weighted_bag, monkeypatch):
     """se_gbm_linesearch_brent evaluates the binary losses on the signed view u=(2y-1)F, v=(2y-1)h (8 B/row):
-    same alpha, objective and evaluation count as the plain (y, F, h) evaluations, bit for bit."""
+    same alpha, objective and evaluation count as the plain (y, F, h) evaluations, bit for bit.
+
+    Consecutive passes normally walk the tiles in alternating directions (L2 reuse), which changes which CTA owns
+    which tile and therefore the last bits of the fp64 sums; the comparison runs in its own context with the
+    alternation switched off (SE_ALTERNATE_PASSES=0, read at context creation) so both searches see one direction."""
     from spark_ensemble_b200 import _native as N
+    from spark_ensemble_b200.context import Context
+    monkeypatch.setenv("SE_ALTERNATE_PASSES", "0")
+    ctx = Context(0)
+    try:
+        _packed_vs_plain(ctx, oracle, rng, name, weighted_bag, monkeypatch, N)
+    finally:
+        ctx.close()
+
+
+def _packed_vs_plain(ctx, oracle, rng, name, weighted_bag, monkeypatch, N):
     n = 40013
     dim, par, y, F, h, w = setup_gbm(ctx, rng, name, n, weighted_bag)
     r, _, _ = oracle.pseudo_residuals(O.LOSS_IDS[name], par, 1, y, None, F, False)
