@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(kBlock, LossTune<LOSS>::kMinCtas) gbm_scalar_k
     }
     if (T::kNewton) {
       const float hc = fmaxf(o.h, 1e-2f);   // GBMRegressor.scala:371
-      ro = -o.g / hc;                       // :377
+      ro = -o.g * rcp_approx(hc);                      // :377
       wo = 0.5f * hc * w;                   // :379 (× 1/S applied by launch_scale_rows)
       x_acc = fmaf(c, hc, x_acc);
     } else if (T::kWriteR) {
@@ -284,10 +284,16 @@ __global__ void __launch_bounds__(kBlock) gbm_logloss_kernel(const GbmArgs a) {
     }
     // ---- per-row math
     float outR[KMAX][VEC], outW[KMAX][VEC];
+    // the VEC rows of a group are summed in fp32 and converted to fp64 once per group: the float->double
+    // conversions share the SFU pipe with ex2/lg2/rcp (ncu, K = 2 eval: 46 % XU utilisation, 101 instructions per row
+    // with one conversion per row and class)
+    float g_loss = 0.f, g_cls[KMAX];
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) g_cls[k] = 0.f;
 #pragma unroll
     for (int e = 0; e < VEC; ++e) {
       const bool in = (i0 + e < a.n);
-      const int yi = (int)yv[e];
+      const float yf = yv[e];  // labels are compared as floats (exact small integers): no float->int conversion
       float m = -INFINITY;
       int am = 0;
 #pragma unroll
@@ -306,28 +312,34 @@ __global__ void __launch_bounds__(kBlock) gbm_logloss_kernel(const GbmArgs a) {
         if (k < K) {
           ex[k] = ex2_approx((p[k][e] - m) * kLog2e);
           if (k != am) srest += ex[k];
-          if (k == yi) py = p[k][e];
+          if (yf == (float)k) py = p[k][e];
         }
       }
       const float lse = m + log1p_pos(srest);
       const float inv_s = rcp_approx(1.0f + srest);
-      if (T::kSumLoss && in) acc[0] += (double)(((MODE == GBM_EVAL) ? cv[e] : 1.0f) * (lse - py));  // -Σ y_k (p_k - lse)  :206-221
+      if (T::kSumLoss && in) g_loss += ((MODE == GBM_EVAL) ? cv[e] : 1.0f) * (lse - py);  // -Σ y_k (p_k - lse)  :206-221
 #pragma unroll
       for (int k = 0; k < KMAX; ++k) {
         if (k < K) {
           const float sm = ex[k] * inv_s;                    // exp(p_k - lse)
-          const float gk = sm - ((k == yi) ? 1.0f : 0.0f);   // :223-238
-          if (MODE == GBM_EVAL && in) acc[1 + k] += (double)(cv[e] * hh[k][e] * gk);  // :66-72
+          const float gk = sm - ((yf == (float)k) ? 1.0f : 0.0f);   // :223-238
+          if (MODE == GBM_EVAL && in) g_cls[k] = fmaf(cv[e] * hh[k][e], gk, g_cls[k]);  // :66-72
           if (T::kNewton) {
             const float hc = fmaxf(sm * (1.0f - sm), 1e-2f);  // :240-256, GBMClassifier.scala:342
-            outR[k][e] = -gk / hc;                            // :362
+            outR[k][e] = -gk * rcp_approx(hc);                           // :362
             outW[k][e] = 0.5f * hc * wv[e];                   // :364 (× 1/S_k later)
-            if (in) acc[1 + k] += (double)(cv[e] * hc);
+            if (in) g_cls[k] = fmaf(cv[e], hc, g_cls[k]);
           } else if (T::kWriteR) {
             outR[k][e] = -gk;                                 // :371
           }
         }
       }
+    }
+    if (T::kSumLoss) acc[0] += (double)g_loss;
+    if (MODE == GBM_EVAL || T::kNewton) {
+#pragma unroll
+      for (int k = 0; k < KMAX; ++k)
+        if (k < K) acc[1 + k] += (double)g_cls[k];
     }
     // ---- stores
     if (VEC == 4 && full) {

@@ -208,7 +208,7 @@ __global__ void __launch_bounds__(32 * W) gbm_logloss_tiled_kernel(const GbmArgs
           const float sm = f4at(e, j) * inv_s[j];
           const float gk = sm - ((k == yi[j]) ? 1.0f : 0.0f);
           const float hc = fmaxf(sm * (1.0f - sm), 1e-2f);
-          f4at(rr, j) = -gk / hc;
+          f4at(rr, j) = -gk * rcp_approx(hc);
           f4at(ww, j) = 0.5f * hc * f4at(w4, j);
           f4at(hh, j) = f4at(c4, j) * hc;
         }
