@@ -79,6 +79,19 @@ def main():
                                  "ms_per_round": 1e3 * dt / rounds, "rows_per_s": n * rounds / dt,
                                  "evals_per_round": evals / rounds}
         print(name + "_newton", res[name + "_newton"], flush=True)
+        if loss == "squared":
+            # opt-in device-resident round: closed-form alpha on the device, two launches, no host synchronisation
+            for _ in range(3):
+                ctx.gbm_round_squared_async(0.1)
+            ctx.sync()
+            t0 = time.perf_counter()
+            for _ in range(rounds):
+                ctx.gbm_round_squared_async(0.1)
+            ctx.sync()
+            dt = time.perf_counter() - t0
+            res[name + "_async"] = {"config": f"{loss} {n} rows, {rounds} rounds, device-resident closed-form step",
+                                    "ms_per_round": 1e3 * dt / rounds, "rows_per_s": n * rounds / dt}
+            print(name + "_async", res[name + "_async"], flush=True)
     for s in (N.SLOT_F, N.SLOT_H, N.SLOT_R):
         ctx.free(s)
     # ---- C4
