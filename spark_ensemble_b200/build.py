@@ -17,8 +17,10 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 OBJDIR = os.path.join(LIBDIR, "obj")
 LIB = os.path.join(LIBDIR, "libse_b200.so")
-SOURCES = ["se_api.cu", "se_gbm.cu", "se_gbm_tiled.cu", "se_boost.cu", "se_agg.cu", "se_models.cu", "se_util.cu"]
-HEADERS = ["se_common.cuh", "se_kernels.h", "se_loss.cuh", "se_tma.cuh", os.path.join("..", "..", "include", "se_abi.h")]
+SOURCES = ["se_api.cu", "se_gbm.cu", "se_gbm_tiled.cu", "se_brent.cu", "se_boost.cu", "se_agg.cu", "se_models.cu", "se_util.cu"]
+# the device Brent must round every multiply and add separately to reproduce the host line search bit for bit
+EXTRA_FLAGS = {"se_brent.cu": ["-fmad=false"]}
+HEADERS = ["se_common.cuh", "se_kernels.h", "se_loss.cuh", "se_tma.cuh", "se_brent.h", os.path.join("..", "..", "include", "se_abi.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
@@ -52,7 +54,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     def compile_one(job):
         s, o = job
-        cmd = [nvcc] + NVCC_FLAGS + ["-c", s, "-o", o]
+        cmd = [nvcc] + NVCC_FLAGS + EXTRA_FLAGS.get(os.path.basename(s), []) + ["-c", s, "-o", o]
         if verbose:
             print(" ".join(cmd), flush=True)
         subprocess.check_call(cmd)

@@ -16,6 +16,8 @@
 #include <vector>
 
 #include "../../include/se_abi.h"
+#define SE_BRENT_HOST_ONLY
+#include "se_brent.h"
 #include "se_kernels.h"
 #include "se_loss.cuh"
 
@@ -467,88 +469,12 @@ GbmArgs gbm_args(se_ctx* ctx, bool validation) {
   return a;
 }
 
-// ---- Brent, commons-math3 3.6.1 BrentOptimizer semantics (call site GBMRegressor.scala:311,413-421).
-// Golden-section fallback, parabolic interpolation when the fit lies inside the bracket and is
-// shrinking, never evaluates closer than tol1 = rel*|x| + abs to a previous abscissa, stops when
-// |x - mid| <= 2*tol1 - (hi-lo)/2; returns the best point evaluated.
-bool within_one_ulp(double a, double b) {
-  return a == b || (!isnan(a) && !isnan(b) && nextafter(a, b) == b);
-}
-
+// ---- Brent (se_brent.h): host wrapper over the shared host/device template
 int brent_impl(se_fn1 f, void* user, double lo, double hi, double start, double rel, double abs_tol,
                int max_eval, double* x_out, double* f_out, int* n_eval) {
-  static const double kGolden = 0.5 * (3.0 - sqrt(5.0));
-  double left = lo < hi ? lo : hi, right = lo < hi ? hi : lo;
-  double x = start, w = start, v = start;       // best, second best, previous second best
-  double step = 0.0, prev_step = 0.0;           // "d" and "e" of the classic formulation
-  int evals = 0;
-  double fx = f(x, user);
-  ++evals;
-  double fw = fx, fv = fx;
-  double bx = x, bf = fx;                       // best-of-all-evaluations bookkeeping
-  double last_x = x, last_f = fx;
-  bool have_two = false;
-  double before_x = 0.0, before_f = 0.0;
-  int status = SE_OK;
-  auto consider = [&](double cx, double cf) {
-    if (!(bf <= cf)) { bx = cx; bf = cf; }
-  };
-  for (;;) {
-    const double mid = 0.5 * (left + right);
-    const double tol1 = rel * fabs(x) + abs_tol, tol2 = 2.0 * tol1;
-    if (fabs(x - mid) <= tol2 - 0.5 * (right - left)) {
-      if (have_two && before_f <= last_f) consider(before_x, before_f);
-      else consider(last_x, last_f);
-      break;
-    }
-    bool use_golden = true;
-    double u;
-    if (fabs(prev_step) > tol1) {
-      double r = (x - w) * (fx - fv);
-      double q = (x - v) * (fx - fw);
-      double p = (x - v) * q - (x - w) * r;
-      q = 2.0 * (q - r);
-      if (q > 0.0) p = -p; else q = -q;
-      r = prev_step;
-      prev_step = step;
-      if (p > q * (left - x) && p < q * (right - x) && fabs(p) < fabs(0.5 * q * r)) {
-        step = p / q;
-        u = x + step;
-        if (u - left < tol2 || right - u < tol2) step = (x <= mid) ? tol1 : -tol1;
-        use_golden = false;
-      }
-    }
-    if (use_golden) {
-      prev_step = (x < mid) ? right - x : left - x;
-      step = kGolden * prev_step;
-    }
-    u = (fabs(step) < tol1) ? (step >= 0.0 ? x + tol1 : x - tol1) : x + step;
-    if (evals >= max_eval) { status = SE_ERR_OPT; break; }
-    const double fu = f(u, user);
-    ++evals;
-    before_x = last_x; before_f = last_f; have_two = true;
-    last_x = u; last_f = fu;
-    if (before_f <= last_f) consider(before_x, before_f);
-    else consider(last_x, last_f);
-    if (fu <= fx) {
-      if (u < x) right = x; else left = x;
-      v = w; fv = fw;
-      w = x; fw = fx;
-      x = u; fx = fu;
-    } else {
-      if (u < x) left = u; else right = u;
-      if (fu <= fw || within_one_ulp(w, x)) {
-        v = w; fv = fw;
-        w = u; fw = fu;
-      } else if (fu <= fv || within_one_ulp(v, x) || within_one_ulp(v, w)) {
-        v = u; fv = fu;
-      }
-    }
-  }
-  if (x_out) *x_out = bx;
-  if (f_out) *f_out = bf;
-  if (n_eval) *n_eval = evals;
-  return status;
+  const int rc = brent_core([&](double x) { return f(x, user); }, lo, hi, start, rel, abs_tol, max_eval, x_out, f_out,
+                            n_eval);
+  return rc == kBrentOk ? SE_OK : SE_ERR_OPT;
 }
 
 }  // namespace
@@ -1368,14 +1294,8 @@ double eval_cb(double x, void* user) {
   if (c->rc == SE_OK) c->rc = se_gbm_linesearch_eval(c->ctx, &x, &l, nullptr);
   return l;
 }
-struct Parabola {
-  double s0, s1, s2, ws;
-};
-double parabola_cb(double x, void* user) {
-  const Parabola* p = static_cast<const Parabola*>(user);
-  // Σ (y-F-αh)²/2 / Σw
-  return (p->s0 - 2.0 * x * p->s1 + x * x * p->s2) / (2.0 * p->ws);
-}
+using Parabola = BrentParabola;
+double parabola_cb(double x, void* user) { return (*static_cast<const Parabola*>(user))(x); }
 }  // namespace
 
 int se_gbm_linesearch_brent(se_ctx* ctx, double lo, double hi, double start, double rel, double abs_tol,
@@ -1418,10 +1338,59 @@ int se_gbm_linesearch_brent(se_ctx* ctx, double lo, double hi, double start, dou
   return SE_OK;
 }
 
+namespace {
+// Squared loss: statistics kernel -> Brent on the device over the exact parabola (se_brent.cu, same template and
+// rounding as the host line search) -> fused update reading alpha from device memory.  Three launches back to back,
+// one host synchronisation per round (for alpha, the evaluation count and the train loss) instead of two.  Opt-in
+// (SE_DEVICE_BRENT=1, see se_gbm_round).
+int round_squared_device_brent(se_ctx* ctx, double learning_rate, double tol, int max_iter, int flags, double* alpha,
+                               double* loss_sum, int* n_eval) {
+  SE_TRY(ensure_wsum(ctx));
+  SE_TRY(begin(ctx));
+  GbmArgs a = gbm_args(ctx, false);
+  a.stats_from_r = ctx->gbm.r_current ? 1 : 0;
+  a.ws = red_ws(ctx, kScalRound);  // stats -> d_scal[kScalRound..+2], summed across GPUs
+  SE_LAUNCH_T(ctx, SE_KF_SQ_STATS, launch_gbm(SE_LOSS_SQUARED, GBM_SQ_STATS, a, ctx->ctas_per_sm, ctx->sms, ctx->stream));
+  SE_TRY(allreduce_dev(ctx, kScalRound, 3));
+  double* out_dev = ctx->d_scal + kScalRound + 4;
+  const bool mirror = ctx->use_mirror && ctx->h_mirror && (ctx->nranks <= 1 || ctx->p2p);
+  constexpr int kMirrorBrent = 32;  // mirror slots [32..34]: above what any reducing kernel writes before its ticket
+  SE_LAUNCH(ctx, launch_brent_parabola(ctx->d_scal + kScalRound, ctx->gbm.wsum, 0.0, 100.0, 1.0, tol, tol, max_iter,
+                                       out_dev, mirror ? ctx->d_mirror + kMirrorBrent : nullptr, ctx->stream));
+  GbmArgs u = gbm_args(ctx, false);
+  u.dev_alpha = out_dev;
+  u.lr64 = learning_rate;
+  const int mode = (flags & SE_UPD_RESIDUAL) ? GBM_UPDATE_RESID : GBM_UPDATE;
+  u.ws = red_ws(ctx);
+  SE_LAUNCH_T(ctx, SE_KF_UPDATE, launch_gbm(SE_LOSS_SQUARED, mode, u, ctx->ctas_per_sm, ctx->sms, ctx->stream));
+  ctx->gbm.r_current = (mode != GBM_UPDATE);
+  double ls = 0.0;
+  SE_TRY(fetch_scalars(ctx, 0, 1, &ls));  // the line-search results were written before this kernel's ticket
+  double res[3];
+  if (mirror) {
+    for (int i = 0; i < 3; ++i) res[i] = ctx->h_mirror[kMirrorBrent + i];
+  } else {
+    SE_CUDA(ctx, cudaMemcpyAsync(res, out_dev, sizeof(res), cudaMemcpyDeviceToHost, ctx->stream));
+    SE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  if (res[2] < 0.0) return fail(ctx, SE_ERR_OPT, "Brent exceeded MaxEval(%d)", max_iter);
+  if (alpha) *alpha = res[0];
+  if (loss_sum) *loss_sum = ls;
+  if (n_eval) *n_eval = (int)res[2];
+  return SE_OK;
+}
+}  // namespace
+
 int se_gbm_round(se_ctx* ctx, double learning_rate, int optimized, double tol, int max_iter, int flags,
                  double* alpha, double* loss_sum, int* n_eval) {
   if (!ctx) return fail(nullptr, SE_ERR_ARG, "null context");
   SE_REQUIRE(ctx, ctx->gbm.on && ctx->gbm.dim == 1, SE_ERR_STATE, "se_gbm_round needs dim == 1");
+  // SE_DEVICE_BRENT=1: the squared-loss line search runs on the device (one host synchronisation per round instead
+  // of two, same iterates bit for bit).  Opt-in: measured 13 us SLOWER per round at 100 M rows on B200 — one GPU
+  // thread needs ~20 us for Brent's ~21 dependent fp64 iterations, more than the host round trip it saves.
+  if (optimized && ctx->gbm.loss == SE_LOSS_SQUARED && !(flags & SE_UPD_NEWTON) && max_iter >= 1 &&
+      getenv("SE_DEVICE_BRENT") != nullptr)
+    return round_squared_device_brent(ctx, learning_rate, tol, max_iter, flags, alpha, loss_sum, n_eval);
   double a = 1.0, obj = 0.0;
   int ne = 0;
   if (optimized) SE_TRY(se_gbm_linesearch_brent(ctx, 0.0, 100.0, 1.0, tol, tol, max_iter, &a, &obj, &ne));

@@ -39,6 +39,9 @@ struct GbmArgs {
   // squared-loss device-resident step: step = lr * clip(stats[1]/stats[2], 0, 100) when non-null
   const double* dev_stats = nullptr;
   float lr = 1.f;
+  // step = (float)(lr64 * *dev_alpha) when non-null: alpha comes from the on-device line search (se_brent.cu)
+  const double* dev_alpha = nullptr;
+  double lr64 = 1.0;
   int stages = 1;  // tiled logloss kernel: shared-memory stages (1, or 2 for experiments)
   int stats_from_r = 0;  // squared-loss statistics read the current residual slot r = y - F (8 B/row) instead of y, F (12 B/row)
   int reverse = 0; // walk the tiles from the end: consecutive passes alternate direction so the tail of one
@@ -59,6 +62,10 @@ cudaError_t launch_gbm_logloss_tiled(int mode, const GbmArgs& a, int sms, cudaSt
 // WOUT[j][i] *= 0.5/S_j was folded: scale rows of a [dim][n] array by per-row factors
 cudaError_t launch_scale_rows(float* a, int64_t n, int64_t ld, int dim, const float* factors,
                               int sms, cudaStream_t stream);
+// squared-loss line search on the device: Brent over the parabola of stats[0..2]; out[0] = alpha, out[1] = objective,
+// out[2] = evaluations (negative: MaxEval exceeded); out_host (mapped pinned memory) is optional
+cudaError_t launch_brent_parabola(const double* stats, double wsum, double lo, double hi, double start, double rel,
+                                  double abs_tol, int max_eval, double* out_dev, double* out_host, cudaStream_t stream);
 // squared-loss round result: out[0] = alpha*, computed on device from stats (for se_gbm_round_result)
 cudaError_t launch_sq_alpha(const double* stats, double* out_alpha, cudaStream_t stream);
 

@@ -771,6 +771,50 @@ def test_gbm_round_single_call(ctx, oracle, rng):
         assert (a3, ne3) == (1.0, 0)
 
 
+def test_device_brent_matches_host_brent(oracle, rng, monkeypatch):
+    """Squared loss: with SE_DEVICE_BRENT=1 se_gbm_round runs Brent on the device over the parabola of the sufficient
+    statistics (se_brent.cu: the same template as the host line search, compiled without multiply-add contraction).
+    alpha, the evaluation count, the train loss and the updated F / R must equal the host line search bit for bit,
+    for interior minima, both interval ends and several tolerances."""
+    from spark_ensemble_b200 import _native as N
+    from spark_ensemble_b200.context import Context
+    monkeypatch.setenv("SE_ALTERNATE_PASSES", "0")  # one tile direction: sums do not depend on the call history
+    c = Context(0)
+    try:
+        n = 50021
+        for case, (scale, shift, tol) in enumerate([(1.0, 0.0, 1e-6), (0.01, 0.0, 1e-6), (-1.0, 0.0, 1e-6),
+                                                    (3.0, 0.5, 1e-9), (1e-3, 0.0, 1e-4), (0.3, -2.0, 1e-12)]):
+            y = f32(rng.standard_normal(n))
+            F = f32(0.3 * rng.standard_normal(n) + shift)
+            h = f32(scale * (y - F) + 0.1 * rng.standard_normal(n))
+            out = []
+            for host in (False, True):
+                c.gbm_configure(n, 0, 1, "squared", 0.0, False)
+                c.upload(N.SLOT_Y, y); c.upload(N.SLOT_F, F); c.upload(N.SLOT_H, h)
+                if host:
+                    monkeypatch.delenv("SE_DEVICE_BRENT", raising=False)
+                else:
+                    monkeypatch.setenv("SE_DEVICE_BRENT", "1")
+                a, l, ne = c.gbm_round(0.7, True, tol, 100, residual=True)
+                out.append((a, l, ne, c.download(N.SLOT_F).copy(), c.download(N.SLOT_R).copy()))
+            monkeypatch.delenv("SE_DEVICE_BRENT", raising=False)
+            (a1, l1, ne1, F1, r1), (a2, l2, ne2, F2, r2) = out
+            assert (a1, ne1, l1) == (a2, ne2, l2), (case, a1, a2, ne1, ne2, l1, l2)
+            np.testing.assert_array_equal(F1, F2)
+            np.testing.assert_array_equal(r1, r2)
+            assert ne1 >= 3
+        # MaxEval exceeded: both paths raise (commons-math: TooManyEvaluationsException)
+        for host in (False, True):
+            c.gbm_configure(n, 0, 1, "squared", 0.0, False)
+            c.upload(N.SLOT_Y, y); c.upload(N.SLOT_F, F); c.upload(N.SLOT_H, h)
+            if not host:
+                monkeypatch.setenv("SE_DEVICE_BRENT", "1")
+            with pytest.raises(N.NativeError):
+                c.gbm_round(0.7, True, 1e-12, 2, residual=True)
+        monkeypatch.delenv("SE_DEVICE_BRENT", raising=False)
+    finally:
+        c.close()
+
 def test_squared_stats_from_residual_slot(ctx, oracle, rng):
     """Squared loss: when R holds the current residual (after pseudo_residuals or a fused update) the line-search
     statistics are read from (r, h) — 8 B/row — and are bit-identical to the (y, F, h) pass; any write to
