@@ -85,10 +85,10 @@ void nccl_load(NcclApi& api) {
 
 thread_local std::string g_last_error;
 
-constexpr int kScal = 512;          // doubles in the device/host scalar blocks
-constexpr int kScalHist = 192;      // 256-bin radix-select histogram
-constexpr int kScalRound = 64;      // offset of the async squared-round results
-constexpr int kScalHost = 96;       // offset used by se_comm_allreduce_host
+constexpr int kScal = 1024;         // doubles in the device/host scalar blocks ([0, 160): generic reductions)
+constexpr int kScalHist = 704;      // 256-bin radix-select histogram
+constexpr int kScalRound = 160;     // offset of the squared-round results (statistics, alpha, loss)
+constexpr int kScalHost = 192;      // offset used by se_comm_allreduce_host (up to kScalHist - kScalHost values)
 constexpr int kSmallBytes = 1 << 20;  // small device scratch: weights, init, tree arrays, factors
 
 struct SlotBuf {
@@ -823,7 +823,7 @@ int se_comm_info(const se_ctx* ctx, int* nranks, int* rank) {
 
 int se_comm_allreduce_host(se_ctx* ctx, double* values, int count) {
   if (!ctx || !values) return fail(nullptr, SE_ERR_ARG, "null argument");
-  SE_REQUIRE(ctx, count >= 0 && count <= kScal - kScalHost, SE_ERR_ARG, "count %d too large", count);
+  SE_REQUIRE(ctx, count >= 0 && count <= kScalHist - kScalHost, SE_ERR_ARG, "count %d too large", count);
   if (!ctx->comm || ctx->nranks <= 1 || count == 0) return SE_OK;
   SE_CUDA(ctx, cudaSetDevice(ctx->device));
   for (int i = 0; i < count; ++i) ctx->h_scal[kScalHost + i] = values[i];
@@ -1456,13 +1456,13 @@ int se_gbm_round_squared_async(se_ctx* ctx, double learning_rate) {
   SE_TRY(begin(ctx));
   GbmArgs a = gbm_args(ctx, false);
   a.stats_from_r = ctx->gbm.r_current ? 1 : 0;
-  a.ws = red_ws(ctx, kScalRound);  // stats -> d_scal[64..66]
+  a.ws = red_ws(ctx, kScalRound);  // stats -> d_scal[kScalRound..+2]
   SE_LAUNCH_T(ctx, SE_KF_SQ_STATS, launch_gbm(SE_LOSS_SQUARED, GBM_SQ_STATS, a, ctx->ctas_per_sm, ctx->sms, ctx->stream));
   SE_TRY(allreduce_dev(ctx, kScalRound, 3));
   GbmArgs u = gbm_args(ctx, false);
   u.dev_stats = ctx->d_scal + kScalRound;
   u.lr = (float)learning_rate;
-  u.ws = red_ws(ctx, kScalRound + 8);  // Σloss -> d_scal[72]
+  u.ws = red_ws(ctx, kScalRound + 8);  // Σloss -> d_scal[kScalRound + 8]
   SE_LAUNCH_T(ctx, SE_KF_UPDATE, launch_gbm(SE_LOSS_SQUARED, GBM_UPDATE_RESID, u, ctx->ctas_per_sm, ctx->sms, ctx->stream));
   SE_TRY(allreduce_dev(ctx, kScalRound + 8, 1));
   ctx->gbm.r_current = true;

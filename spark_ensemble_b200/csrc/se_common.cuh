@@ -14,7 +14,7 @@ namespace se {
 
 constexpr int kBlock = 256;          // threads per CTA for the streaming kernels
 constexpr int kMaxGridPartials = 4096;  // upper bound on gridDim.x of reducing kernels
-constexpr int kMaxRed = 40;          // max number of fp64 sums one kernel reduces (dim <= 32 -> dim+3)
+constexpr int kMaxRed = 72;          // max number of fp64 sums one kernel reduces (dim <= 64 -> dim+1)
 
 // ---- 128-bit streaming global accesses ------------------------------------------------------
 __device__ __forceinline__ float4 ld_stream4(const float* p) {
@@ -101,8 +101,8 @@ __device__ __forceinline__ void block_max_publish(double v, double* partials, un
 // Reduction workspace owned by the context: partials[kMaxGridPartials][nred], a self-resetting
 // ticket counter, and the output scalar block.  With a peer-memory communicator attached (nranks > 1,
 // mbox != nullptr) the kernel that reduces ALSO performs the cross-GPU sum itself (see peer_exchange).
-constexpr int kMboxPayload = 40;   // doubles per mailbox row (>= kMaxRed)
-constexpr int kMboxStride = 48;    // doubles per row: payload + sequence word + padding (384 B)
+constexpr int kMboxPayload = 72;   // doubles per mailbox row (>= kMaxRed)
+constexpr int kMboxStride = 80;    // doubles per row: payload + sequence word + padding (640 B)
 struct RedWs {
   double* partials;
   unsigned int* counter;

@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(32 * W) gbm_logloss_tiled_kernel(const GbmArgs
   __shared__ __align__(16) float s_scale[T::kPerClassAcc ? kTR : 4];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid < K) s_coef[tid] = a.coef[tid];
+  for (int k = tid; k < K; k += kTT) s_coef[k] = a.coef[k];
   if (tid == 0) {
     mbar_init(&bars[0], 1);
     mbar_init(&bars[1], 1);
@@ -364,7 +364,10 @@ cudaError_t launch_gbm_logloss_tiled(int mode, const GbmArgs& a, int sms, cudaSt
   // two warps per CTA (256-row tiles) measured best: one warp / 128 rows loses 2-15 % in the per-class modes
   if (K <= 8) return launch_tiled_k<8, 2>(mode, a, sms, st);
   if (K <= 16) return launch_tiled_k<16, 2>(mode, a, sms, st);
-  return launch_tiled_k<32, 2>(mode, a, sms, st);
+  if (K <= 32) return launch_tiled_k<32, 2>(mode, a, sms, st);
+  // 33..64 classes: 128-row tiles (one warp) so that F and h of a tile still fit next to other CTAs' tiles; the warp
+  // keeps all per-class fp64 sums (64 per lane) in registers
+  return launch_tiled_k<64, 1>(mode, a, sms, st);
 }
 
 }  // namespace se

@@ -8,7 +8,7 @@
 
 namespace se {
 
-constexpr int kMaxDim = 32;  // logloss classes handled in registers
+constexpr int kMaxDim = 64;  // LogLoss classes: per-class sums are reduced by one kernel (kMaxRed, mailbox width)
 
 // ---- GBM (se_gbm.cu) -------------------------------------------------------------------------
 enum GbmMode {

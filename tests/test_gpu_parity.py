@@ -476,7 +476,7 @@ def test_multi_gpu_sharded_parity():
         assert f"p2p_allreduce={p2p == '1'}" in out.stdout
 
 
-@pytest.mark.parametrize("K", [9, 26, 32])
+@pytest.mark.parametrize("K", [9, 26, 32, 33, 64])
 @pytest.mark.parametrize("n", [1, 127, 129, 255, 256, 257, 40961])
 def test_logloss_wide_k_tiled_kernels(ctx, oracle, rng, K, n):
     """LogLoss with K >= 5 runs through the TMA-tiled kernels (se_gbm_tiled.cu, 256-row tiles): every mode,
@@ -565,7 +565,7 @@ def test_abi_utilities(ctx, rng):
     with pytest.raises(ValueError):
         ctx.gbm_configure(10, 0, 3, "squared")  # scalar losses have dim 1
     with pytest.raises(ValueError):
-        ctx.gbm_configure(10, 0, 64, "logloss")  # dim > 32
+        ctx.gbm_configure(10, 0, 65, "logloss")  # dim > 64
 
 
 @pytest.mark.parametrize("loss_type", ["exponential", "linear", "squared"])
