@@ -88,6 +88,7 @@ thread_local std::string g_last_error;
 constexpr int kScal = 1024;         // doubles in the device/host scalar blocks ([0, 160): generic reductions)
 constexpr int kScalHist = 704;      // 256-bin radix-select histogram
 constexpr int kScalRound = 160;     // offset of the squared-round results (statistics, alpha, loss)
+constexpr int64_t kL2HintRows = 16000000;  // 16 B/row of y, F, h, r: up to ~2x the 126 MB L2
 constexpr int kScalHost = 192;      // offset used by se_comm_allreduce_host (up to kScalHist - kScalHost values)
 constexpr int kSmallBytes = 1 << 20;  // small device scratch: weights, init, tree arrays, factors
 
@@ -169,6 +170,7 @@ struct se_ctx {
   bool ls_packed = false;             // evaluations currently read (u, v) instead of (y, F, h)
   unsigned pass_parity = 0;           // alternates the tile direction of consecutive GBM passes (L2 reuse)
   bool alternate = true;
+  int l2_hints = -1;                  // evict_first hints on the GBM streams: -1 by shard size, 0 off, 1 on (SE_L2_HINTS)
   std::string err;
   // stopwatch + per-kernel-family timing
   cudaEvent_t tm0 = nullptr, tm1 = nullptr;
@@ -465,6 +467,8 @@ GbmArgs gbm_args(se_ctx* ctx, bool validation) {
   a.dim = g.dim;
   a.param = (float)g.param;
   a.reverse = (ctx->alternate && !validation) ? (int)(ctx->pass_parity++ & 1u) : 0;
+  // shards whose four per-row arrays (y, F, h, r) are of the order of the L2: evict_first hints (se_common.cuh)
+  a.l2_hints = ctx->l2_hints >= 0 ? ctx->l2_hints : ((validation ? ctx->gbm.nv : ctx->gbm.n) <= kL2HintRows ? 1 : 0);
   a.ws = red_ws(ctx, 0, /*exchange=*/false);  // armed (sequence number taken) only at reducing launches
   return a;
 }
@@ -526,6 +530,7 @@ int se_ctx_create(int device, se_ctx** out) {
   SE_CREATE_CUDA(cudaGetDeviceProperties(&prop, device));
   ctx->sms = prop.multiProcessorCount;
   if (const char* s = getenv("SE_ALTERNATE_PASSES")) ctx->alternate = atoi(s) != 0;
+  if (const char* s = getenv("SE_L2_HINTS")) ctx->l2_hints = atoi(s) != 0 ? 1 : 0;
   if (const char* s = getenv("SE_CTAS_PER_SM")) {
     const int v = atoi(s);
     if (v >= 1 && v <= 16) ctx->ctas_per_sm = v;

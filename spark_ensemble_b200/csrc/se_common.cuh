@@ -51,6 +51,56 @@ __device__ __forceinline__ void st_stream1(float* p, float v) {
   asm volatile("st.global.L1::no_allocate.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
 }
 
+// ---- the same accesses with an explicit L2 eviction policy (createpolicy + .L2::cache_hint) -----------------
+// Measured on B200 (100 M-row squared-loss round, same box, profiles/README.md):
+//  * kernels that WRITE per-row results (K1: read y,F,h, write F,r) run 3 % faster when every access carries an
+//    explicit evict_normal policy than with the plain instructions (0.312 vs 0.322 ms, 0.97 vs 0.945 of the copy
+//    peak), while read-only passes lose 4 % with it (K2 0.142 vs 0.137 ms) — so POL is a template flag set per mode;
+//  * on shards whose four arrays are of the order of the 126 MB L2 (10 M rows: 160 MB) marking what the next pass
+//    does not re-read as evict_first keeps r and h resident between the statistics pass and the update: +8 % per
+//    round; on 100 M-row shards the same hints cost 3 %, so they are enabled by size (se_api.cu gbm_args).
+__device__ __forceinline__ uint64_t l2_policy(bool evict_first) {
+  uint64_t p;
+  if (evict_first) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  else asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ float4 ld_stream4_p(const float* p, uint64_t pol) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ float4 ld_rw4_p(const float* p, uint64_t pol) {
+  float4 v;
+  asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ void st_stream4_p(float* p, const float4& v, uint64_t pol) {
+  asm volatile("st.global.L1::no_allocate.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p), "f"(v.x),
+               "f"(v.y), "f"(v.z), "f"(v.w), "l"(pol)
+               : "memory");
+}
+
+template <bool POL>
+__device__ __forceinline__ float4 ld_s4(const float* p, uint64_t pol) {
+  if constexpr (POL) return ld_stream4_p(p, pol);
+  else return ld_stream4(p);
+}
+template <bool POL>
+__device__ __forceinline__ float4 ld_r4(const float* p, uint64_t pol) {
+  if constexpr (POL) return ld_rw4_p(p, pol);
+  else return ld_rw4(p);
+}
+template <bool POL>
+__device__ __forceinline__ void st_s4(float* p, const float4& v, uint64_t pol) {
+  if constexpr (POL) st_stream4_p(p, v, pol);
+  else st_stream4(p, v);
+}
+
 __device__ __forceinline__ float& f4at(float4& v, int i) { return (&v.x)[i]; }
 __device__ __forceinline__ const float& f4at(const float4& v, int i) { return (&v.x)[i]; }
 

@@ -54,7 +54,9 @@ __device__ __forceinline__ float device_step(const GbmArgs& a) {
 }
 
 // ------------------------------------------------------------------ scalar losses, dim == 1
-template <int LOSS, int MODE>
+// POL: accesses carry an explicit L2 eviction policy (se_common.cuh): always for the modes that write per-row
+// results, for the read-only modes only on L2-sized shards (a.l2_hints)
+template <int LOSS, int MODE, bool POL>
 __global__ void __launch_bounds__(kBlock, LossTune<LOSS>::kMinCtas) gbm_scalar_kernel(const GbmArgs a) {
   using T = ModeTraits<MODE>;
   constexpr int U = LossTune<LOSS>::kU;
@@ -73,6 +75,7 @@ __global__ void __launch_bounds__(kBlock, LossTune<LOSS>::kMinCtas) gbm_scalar_k
   const int64_t n4 = a.n >> 2;
   constexpr int64_t tile = (int64_t)kBlock * U;
   const int64_t ntiles = (n4 + tile - 1) / tile;
+  const uint64_t pol_keep = l2_policy(false), pol_stream = l2_policy(a.l2_hints != 0);
 
   auto row = [&](float y, float F, float h, float w, float c, float& Fo, float& ro, float& wo, float& l_acc,
                  float& x_acc, float& z_acc) {
@@ -107,9 +110,9 @@ __global__ void __launch_bounds__(kBlock, LossTune<LOSS>::kMinCtas) gbm_scalar_k
       const int64_t g = base + (int64_t)u * kBlock;
       ok[u] = g < n4;
       if (ok[u]) {
-        vy[u] = a.y ? ld_stream4(a.y + 4 * g) : make_float4(1.f, 1.f, 1.f, 1.f);  // y == nullptr: signed view, label 1
-        vF[u] = T::kWriteF ? ld_rw4(a.F + 4 * g) : ld_stream4(a.F + 4 * g);
-        if (T::kReadH) vh[u] = ld_stream4(a.h + 4 * g);
+        vy[u] = a.y ? ld_s4<POL>(a.y + 4 * g, pol_stream) : make_float4(1.f, 1.f, 1.f, 1.f);  // y == nullptr: signed view, label 1
+        vF[u] = T::kWriteF ? ld_r4<POL>(a.F + 4 * g, pol_stream) : ld_s4<POL>(a.F + 4 * g, pol_stream);
+        if (T::kReadH) vh[u] = ld_s4<POL>(a.h + 4 * g, T::kWriteF ? pol_stream : pol_keep);  // an update is h's last reader
         if (T::kNewton && has_w) vw[u] = ld_stream4(a.w + 4 * g);
         if (has_bag) vb[u] = ld_stream4(a.bag + 4 * g);
       }
@@ -127,8 +130,8 @@ __global__ void __launch_bounds__(kBlock, LossTune<LOSS>::kMinCtas) gbm_scalar_k
         row(f4at(vy[u], e), f4at(vF[u], e), T::kReadH ? f4at(vh[u], e) : 0.f, w, c, f4at(oF, e),
             f4at(oR, e), f4at(oW, e), l_acc, x_acc, z_acc);
       }
-      if (T::kWriteF) st_stream4(a.F + 4 * g, oF);
-      if (T::kWriteR) st_stream4(a.r + 4 * g, oR);
+      if (T::kWriteF) st_s4<POL>(a.F + 4 * g, oF, pol_stream);
+      if (T::kWriteR) st_s4<POL>(a.r + 4 * g, oR, pol_keep);  // the next statistics pass starts where this one ends
       if (T::kNewton) st_stream4(a.wout + 4 * g, oW);
       if (T::kSumLoss) acc[0] += (double)l_acc;
       if (MODE == GBM_EVAL || T::kNewton) acc[1] += (double)x_acc;
@@ -156,10 +159,11 @@ __global__ void __launch_bounds__(kBlock, LossTune<LOSS>::kMinCtas) gbm_scalar_k
 // FROM_R: the residual slot already holds r = y - F for the current F (squared loss: r = -g, written by the
 // previous fused update or by se_gbm_pseudo_residuals), so the statistics Σr², Σh·r, Σh² need r and h only:
 // 8 B/row instead of 12.  Bit-identical: r was computed as the same fp32 difference y - F.
-template <bool FROM_R>
+template <bool FROM_R, bool POL>
 __global__ void __launch_bounds__(kBlock) gbm_sq_stats_kernel(const GbmArgs a) {
   constexpr int U = U_SCALAR;
   const bool has_bag = (a.bag != nullptr);
+  const uint64_t pol_keep = l2_policy(false), pol_stream = l2_policy(a.l2_hints != 0);
   double acc[3] = {0.0, 0.0, 0.0};
   const int64_t n4 = a.n >> 2;
   constexpr int64_t tile = (int64_t)kBlock * U;
@@ -175,12 +179,12 @@ __global__ void __launch_bounds__(kBlock) gbm_sq_stats_kernel(const GbmArgs a) {
       ok[u] = g < n4;
       if (ok[u]) {
         if (FROM_R) {
-          vy[u] = ld_stream4(a.r + 4 * g);
+          vy[u] = ld_s4<POL>(a.r + 4 * g, pol_stream);  // the update that follows rewrites r without reading it
         } else {
-          vy[u] = ld_stream4(a.y + 4 * g);
-          vF[u] = ld_stream4(a.F + 4 * g);
+          vy[u] = ld_s4<POL>(a.y + 4 * g, pol_keep);
+          vF[u] = ld_s4<POL>(a.F + 4 * g, pol_keep);
         }
-        vh[u] = ld_stream4(a.h + 4 * g);
+        vh[u] = ld_s4<POL>(a.h + 4 * g, pol_keep);      // re-read by the update, from this pass's tail
         if (has_bag) vb[u] = ld_stream4(a.bag + 4 * g);
       }
     }
@@ -439,17 +443,23 @@ cudaError_t launch_scalar_loss(int mode, const GbmArgs& a, int ctas_per_sm, int 
   const int per_sm = LossTune<LOSS>::kHeavy ? (ctas_per_sm > 4 ? ctas_per_sm : 4) : ctas_per_sm;
   const int grid = grid_for(a.n >> 2, (int64_t)kBlock * LossTune<LOSS>::kU, per_sm, sms);
   switch (mode) {
-#define SE_CASE(M) \
-  case M: gbm_scalar_kernel<LOSS, M><<<grid, kBlock, 0, st>>>(a); break;
-    SE_CASE(GBM_RESID)
-    SE_CASE(GBM_RESID_NEWTON)
-    SE_CASE(GBM_EVAL)
-    SE_CASE(GBM_UPDATE)
-    SE_CASE(GBM_UPDATE_RESID)
-    SE_CASE(GBM_UPDATE_NEWTON)
-    SE_CASE(GBM_MEAN_LOSS)
-    SE_CASE(GBM_EVAL_LOSS)
-#undef SE_CASE
+#define SE_CASE_W(M) /* writes per-row results: explicit policy always */ \
+  case M: gbm_scalar_kernel<LOSS, M, true><<<grid, kBlock, 0, st>>>(a); break;
+#define SE_CASE_R(M) /* read-only pass: explicit policy only with the small-shard hints */ \
+  case M:                                                                                  \
+    if (a.l2_hints) gbm_scalar_kernel<LOSS, M, true><<<grid, kBlock, 0, st>>>(a);          \
+    else gbm_scalar_kernel<LOSS, M, false><<<grid, kBlock, 0, st>>>(a);                    \
+    break;
+    SE_CASE_W(GBM_RESID)
+    SE_CASE_W(GBM_RESID_NEWTON)
+    SE_CASE_R(GBM_EVAL)
+    SE_CASE_W(GBM_UPDATE)
+    SE_CASE_W(GBM_UPDATE_RESID)
+    SE_CASE_W(GBM_UPDATE_NEWTON)
+    SE_CASE_R(GBM_MEAN_LOSS)
+    SE_CASE_R(GBM_EVAL_LOSS)
+#undef SE_CASE_W
+#undef SE_CASE_R
     default: return cudaErrorInvalidValue;
   }
   return cudaGetLastError();
@@ -480,8 +490,13 @@ cudaError_t launch_gbm(int loss, int mode, const GbmArgs& a, int ctas_per_sm, in
   if (mode == GBM_SQ_STATS) {
     if (loss != SE_LOSS_SQUARED) return cudaErrorInvalidValue;
     const int grid = grid_for(a.n >> 2, (int64_t)kBlock * U_SCALAR, ctas_per_sm, sms);
-    if (a.stats_from_r) gbm_sq_stats_kernel<true><<<grid, kBlock, 0, st>>>(a);
-    else gbm_sq_stats_kernel<false><<<grid, kBlock, 0, st>>>(a);
+    if (a.stats_from_r) {
+      if (a.l2_hints) gbm_sq_stats_kernel<true, true><<<grid, kBlock, 0, st>>>(a);
+      else gbm_sq_stats_kernel<true, false><<<grid, kBlock, 0, st>>>(a);
+    } else {
+      if (a.l2_hints) gbm_sq_stats_kernel<false, true><<<grid, kBlock, 0, st>>>(a);
+      else gbm_sq_stats_kernel<false, false><<<grid, kBlock, 0, st>>>(a);
+    }
     return cudaGetLastError();
   }
   if (loss != SE_LOSS_LOGLOSS) {
