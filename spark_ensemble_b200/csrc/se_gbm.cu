@@ -518,15 +518,13 @@ cudaError_t launch_gbm(int loss, int mode, const GbmArgs& a, int ctas_per_sm, in
   static const int staged_min_k = [] {
     const char* e = getenv("SE_LOGLOSS_STAGED_MIN_K");
     const int v = e ? atoi(e) : 5;
-    return v < 2 ? 2 : v;
+    return v < 2 ? 2 : (v > 9 ? 9 : v);  // the register kernels exist for K <= 8 only
   }();
   if (K >= staged_min_k) return launch_gbm_logloss_tiled(mode, a, sms, st);
   if (ctas_per_sm > 4) ctas_per_sm = 4;  // register-resident K <= 4 kernels: 4 CTAs/SM measured best
   if (K <= 2) return launch_logloss_k<2, 4>(mode, a, grid_for((a.n + 3) / 4, kBlock, ctas_per_sm, sms), st);
   if (K <= 4) return launch_logloss_k<4, 4>(mode, a, grid_for((a.n + 3) / 4, kBlock, ctas_per_sm, sms), st);
-  if (K <= 8) return launch_logloss_k<8, 4>(mode, a, grid_for((a.n + 3) / 4, kBlock, ctas_per_sm, sms), st);
-  if (K <= 16) return launch_logloss_k<16, 1>(mode, a, grid_for(a.n, kBlock, ctas_per_sm, sms), st);
-  return launch_logloss_k<32, 1>(mode, a, grid_for(a.n, kBlock, ctas_per_sm, sms), st);
+  return launch_logloss_k<8, 4>(mode, a, grid_for((a.n + 3) / 4, kBlock, ctas_per_sm, sms), st);
 }
 
 cudaError_t launch_gbm_pack_signed(const float* y, const float* F, const float* h, float* u, float* v, int64_t n,
