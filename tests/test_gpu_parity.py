@@ -893,3 +893,19 @@ def test_tree_predict_multi_class_probabilities(ctx, rng):
     ctx.alloc(N.SLOT_PRED, n)
     ctx.tree_predict(t, N.SLOT_PRED, 0)
     np.testing.assert_array_equal(ctx.download(N.SLOT_PRED), m.predict(X).astype(np.float32))
+
+
+def test_libsvm_to_device_ingest(ctx, rng, tmp_path):
+    """LIBSVM file -> row blocks -> se_upload_rowmajor -> column-major X in HBM, block boundaries not 32-aligned."""
+    from spark_ensemble_b200 import _native as N
+    from spark_ensemble_b200.io import load_libsvm_to_device
+    n, d = 1003, 12
+    X = np.where(rng.random((n, d)) < 0.6, rng.standard_normal((n, d)), 0.0).astype(np.float32)
+    y = rng.integers(0, 3, n).astype(np.float64)
+    p = tmp_path / "x.svm"
+    with open(p, "w") as fh:
+        for i in range(n):
+            fh.write(f"{float(y[i])!r} " + " ".join(f"{j + 1}:{float(X[i, j])!r}" for j in range(d) if X[i, j] != 0.0) + "\n")
+    labels = load_libsvm_to_device(ctx, N.SLOT_X, str(p), d, block_rows=250)
+    np.testing.assert_array_equal(labels, y)
+    np.testing.assert_array_equal(ctx.download(N.SLOT_X).reshape(d, n), X.T)

@@ -213,3 +213,30 @@ def test_no_product_module_imports_the_oracle():
                 src = open(os.path.join(dirpath, f), errors="replace").read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
                 assert "se_oracle.h" not in src and "liboracle" not in src, f
+
+
+def test_libsvm_reader_blocks_and_errors(tmp_path):
+    """LIBSVM text -> dense fp32 row blocks (1-based ascending indices, comments, blank lines, ragged tail block)."""
+    from spark_ensemble_b200.io import count_libsvm_rows, iter_libsvm_dense
+    rng = np.random.default_rng(3)
+    n, d = 23, 7
+    X = np.where(rng.random((n, d)) < 0.5, rng.standard_normal((n, d)), 0.0).astype(np.float32)
+    y = rng.standard_normal(n)
+    p = tmp_path / "a.svm"
+    with open(p, "w") as fh:
+        fh.write("# header comment\n\n")
+        for i in range(n):
+            feats = " ".join(f"{j + 1}:{float(X[i, j])!r}" for j in range(d) if X[i, j] != 0.0)
+            fh.write(f"{float(y[i])!r} {feats}  # row {i}\n")
+    assert count_libsvm_rows(str(p)) == n
+    blocks = list(iter_libsvm_dense(str(p), d, block_rows=10))
+    assert [len(b[1]) for b in blocks] == [10, 10, 3]
+    np.testing.assert_array_equal(np.concatenate([b[0] for b in blocks]), X)
+    np.testing.assert_array_equal(np.concatenate([b[1] for b in blocks]), y)
+    bad = tmp_path / "b.svm"
+    bad.write_text("1.0 3:1.0 2:2.0\n")
+    with pytest.raises(ValueError, match="ascending"):
+        list(iter_libsvm_dense(str(bad), d))
+    bad.write_text("1.0 9:1.0\n")
+    with pytest.raises(ValueError, match="outside"):
+        list(iter_libsvm_dense(str(bad), d))
