@@ -14,6 +14,12 @@ i.e. regression/GBMRegressor.scala:398-442 + :368-385 of the reference, per roun
            copied host->device and the pseudo-residuals device->host inside the timed region.
 `roofline` is for the dominant kernel K1 (fused update+residual+loss), timed with CUDA events on the
 library's own stream, against MEASURED_PEAKS.json's HBM copy bandwidth.
+`extras.strong_scaling`: the SAME round on a fixed GLOBAL dataset (--strong-rows, default 100 M rows) split over
+the ranks (12.5 M rows per GPU at N=8), measured in the same run after the weak-scaling figure; `extras.strong_c3`:
+BASELINE config 3 (bernoulli, 50 M rows global, Brent line search + update per round) split the same way.
+`parity_ok` / `parity`: after all timed regions every rank downloads its shard, runs one more round on the GPU
+and the fp64 CPU oracle (checker only) on the same data; the GPU's GLOBAL alpha / Σloss (summed across GPUs inside
+the kernels) are compared with the oracle's sums all-reduced over torch.distributed, F / r row by row (1e-5).
 `cpu_baseline` / `--impl reference`: the reference algorithm's CPU restatement (oracle/, OpenMP, fp64:
 one full pass per Brent evaluation as RDDLossFunction does) on the host cores, bounded sample.
 The reference itself is Scala/Spark and cannot run here (no JVM): kind = "port".
@@ -184,6 +190,64 @@ def run_cpu_arm(sample_rows: int, steps: int, warmup: int) -> dict:
             "usable_cpus": cap, "brent_evals_per_round": float(np.mean(evals)), "sample_rows": sample_rows}
 
 
+# ------------------------------------------------------------------ self-check against the oracle (checker only)
+def parity_check(ctx, n, lr, tol, max_iter, world, rank, dist, label):
+    """One extra round on the current device state, replayed by the fp64 oracle on this rank's shard; the
+    line-search objective is summed over ALL ranks' shards through torch.distributed (an independent channel), so
+    the GPU's global alpha / Σloss (in-kernel cross-GPU sums) are checked against the concatenated data."""
+    from oracle import oracle as O
+    from oracle.oracle import Oracle
+    from spark_ensemble_b200 import _native as N
+    t_start = time.perf_counter()
+    orc = Oracle(omp=True)
+    orc.lib.orc_set_num_threads(max(1, _usable_cpus() // max(world, 1)))
+    y32 = ctx.download(N.SLOT_Y)[:n]
+    F32 = ctx.download(N.SLOT_F)[:n]
+    h32 = ctx.download(N.SLOT_H)[:n]
+    alpha_g, loss_g, ne_g = ctx.gbm_round(lr, True, tol, max_iter, residual=True)
+    fused = int(ctx.get_option("last_round_fused"))
+    Fg = ctx.download(N.SLOT_F)[:n]
+    rg = ctx.download(N.SLOT_R)[:n]
+    y = y32.astype(np.float64); F = F32.astype(np.float64).reshape(1, -1); h = h32.astype(np.float64).reshape(1, -1)
+
+    def allsum(vals):
+        v = np.asarray(vals, dtype=np.float64)
+        if dist is None:
+            return v
+        import torch
+        t = torch.tensor(v, dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return t.cpu().numpy()
+
+    n_glob = float(allsum([n])[0])
+
+    def objective(a):  # RDDLossFunction over the concatenated shards: Σ lossSum / Σ weightSum (GBMLoss.scala:50-74)
+        l_local = orc.linesearch_eval(O.SQUARED, 0.0, y, None, F, h, [a])[0] * n
+        return float(allsum([l_local])[0]) / n_glob
+
+    alpha_o, ne_o, st = orc.brent(objective, 0.0, 100.0, 1.0, tol, tol, max_iter)
+    orc.update(F, h, [lr * alpha_g])  # the GPU's step: row-level parity is not blurred by the optimiser tolerance
+    loss_o = float(allsum([orc.mean_loss(O.SQUARED, 0.0, 1, y, F) * n])[0])
+    r_o, _, _ = orc.pseudo_residuals(O.SQUARED, 0.0, 1, y, None, F, False, want_weights=False)
+    f_scale = max(1.0, float(np.abs(F).max()))
+    r_scale = max(1.0, float(np.abs(r_o).max()))
+    f_err = float(np.max(np.abs(Fg - F[0]))) / f_scale
+    r_err = float(np.max(np.abs(rg - r_o[0]))) / r_scale
+    if dist is not None:
+        import torch
+        t = torch.tensor([f_err, r_err], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        f_err, r_err = float(t[0]), float(t[1])
+    a_err = abs(alpha_g - alpha_o)
+    l_err = abs(loss_g - loss_o) / abs(loss_o)
+    ok = bool(st == 0 and a_err <= 1e-5 * max(abs(alpha_o), 1e-3) + 4 * tol and l_err <= 1e-5 and f_err <= 1e-5
+              and r_err <= 1e-5)
+    return {"case": label, "ok": ok, "rows_global": int(n_glob), "rows_per_gpu": int(n), "fused_round": fused,
+            "alpha_gpu": alpha_g, "alpha_oracle": alpha_o, "brent_evals_gpu": ne_g, "brent_evals_oracle": ne_o,
+            "loss_sum_gpu": loss_g, "loss_sum_oracle": loss_o, "loss_rel_err": l_err, "F_max_rel_err": f_err,
+            "r_max_rel_err": r_err, "tolerance": 1e-5, "seconds": time.perf_counter() - t_start}
+
+
 # ------------------------------------------------------------------ main
 def main():
     ap = argparse.ArgumentParser()
@@ -196,6 +260,10 @@ def main():
     ap.add_argument("--features", type=int, default=128)
     ap.add_argument("--cpu-rows", type=int, default=16_000_000, help="bounded CPU sample per step")
     ap.add_argument("--no-features", action="store_true", help="do not materialise the feature matrix")
+    ap.add_argument("--strong-rows", type=int, default=int(os.environ.get("SE_BENCH_STRONG_ROWS", 100_000_000)),
+                    help="GLOBAL rows of the strong-scaling measurement (split over the ranks); 0 disables")
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle self-check after the timed regions")
+    ap.add_argument("--no-extras", action="store_true", help="skip the tree / async / config-3 extras")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -321,6 +389,8 @@ def main():
     # ---------------- extras: device-resident async round, on-device tree direction over X
     extras = {}
     ctx.kernel_timing(False)
+    if args.no_extras:
+        have_x = False
     for _ in range(2):
         ctx.gbm_round_squared_async(lr)
     barrier()
@@ -369,6 +439,63 @@ def main():
                                      "note": "direction = depth-6 tree evaluated on device over the resident feature matrix; "
                                              "pseudo-residuals still go device->host for the (host) base-learner fit"}
 
+    # ---------------- strong scaling: a fixed GLOBAL dataset split over the ranks (same buffers, first rows)
+    def timed_rounds(n_rows, steps, loss="squared"):
+        ctx.gbm_configure(n_rows, 0, 1, loss, 0.0, False)   # re-uses the resident slots (no reallocation)
+        if loss != "squared":
+            ctx.fill_synthetic(N.SLOT_Y, "bernoulli", seed + 7, 0.4, 1.0)
+            ctx.fill(N.SLOT_F, 0.0)
+        ctx.gbm_pseudo_residuals(False)
+        for _ in range(3):
+            ctx.gbm_round(lr if loss == "squared" else 0.1, True, tol, max_iter, residual=True)
+        barrier()
+        ctx.timer_start()
+        t0 = time.perf_counter()
+        evals = 0
+        for _ in range(steps):
+            _, _, ne = ctx.gbm_round(lr if loss == "squared" else 0.1, True, tol, max_iter, residual=True)
+            evals += ne
+        ms_d = ctx.timer_stop()
+        ctx.sync()
+        ms_w = 1e3 * (time.perf_counter() - t0)
+        barrier()
+        m = max(ms_d, ms_w)
+        if dist is not None:
+            import torch
+            t = torch.tensor([m], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            m = float(t.item())
+        return m / steps, evals / steps
+
+    strong = strong_c3 = None
+    if args.strong_rows > 0:
+        ns = min(n, (args.strong_rows // world) // 4 * 4)
+        ms_s, ne_s = timed_rounds(ns, max(args.steps, 20))
+        strong = {"rows_global": ns * world, "rows_per_gpu": ns, "ms_per_step": ms_s, "value": ns * world / (ms_s * 1e-3),
+                  "unit": "rows/s", "one_launch_round": int(ctx.get_option("last_round_fused")),
+                  "brent_evals_per_round": ne_s, "scaling": "strong",
+                  "note": "same round as `value` on a fixed global dataset split over the ranks"}
+    parity = []
+    if not args.no_parity and args.strong_rows > 0:
+        parity.append(parity_check(ctx, ns, lr, tol, max_iter, world, rank, dist, "strong shard (global rows / N per GPU)"))
+    if args.strong_rows > 0 and not args.no_extras:
+        nc3 = min(n, (min(args.strong_rows, 50_000_000) // world) // 4 * 4)
+        ms_c, ne_c = timed_rounds(nc3, 5, loss="bernoulli")
+        strong_c3 = {"rows_global": nc3 * world, "rows_per_gpu": nc3, "ms_per_round": ms_c, "value": nc3 * world / (ms_c * 1e-3),
+                     "unit": "rows/s", "brent_evals_per_round": ne_c, "loss": "bernoulli",
+                     "line_search": {0: "one launch per evaluation", 1: "one persistent launch (device Brent)",
+                                     2: "host Brent over the persistent kernel"}[int(ctx.get_option("ls_mode"))],
+                     "ls_workers": int(ctx.get_option("last_ls_workers")), "l2_hit_ratio_requested": ctx.get_option("last_ls_hit_ratio")}
+    if not args.no_parity:
+        # the weak-scaling configuration itself (full shard per GPU, the round `value` was timed on)
+        ctx.gbm_configure(n, 0, 1, "squared", 0.0, False)
+        ctx.fill_synthetic(N.SLOT_Y, "normal", seed + 1, 0.0, 1.0)
+        ctx.fill(N.SLOT_F, 0.0)
+        ctx.gbm_pseudo_residuals(False)
+        ctx.gbm_round(lr, True, tol, max_iter, residual=True)
+        parity.append(parity_check(ctx, n, lr, tol, max_iter, world, rank, dist, "weak shard (the timed configuration)"))
+    p2p_active = bool(ctx.comm_p2p_active()) if world > 1 else None
+
     if rank != 0:
         ctx.close()
         if dist is not None:
@@ -386,6 +513,8 @@ def main():
     extras["kernel_ms_share_of_step"] = (k1["ms"] + k2["ms"]) / ms_dev if ms_dev > 0 else None
     extras["device_ms_per_step"] = ms_dev / args.steps
     extras["wall_ms_per_step"] = ms_wall / args.steps
+    extras["strong_scaling"] = strong
+    extras["strong_c3"] = strong_c3
 
     cpu = None
     if world == 1:
@@ -401,13 +530,17 @@ def main():
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload, "rows_per_gpu": n, "features": d, "loss": "squared",
                    "l2": "inputs (1.2 GB of y/F/h per GPU) are larger than L2 (126 MB); no flush needed",
-                   "features_resident": have_x, "parallelism": f"rows sharded x{world}, one NCCL allreduce of <=3 doubles per reduction"},
+                   "features_resident": have_x,
+                   "parallelism": (f"rows sharded x{world}; the <=3 fp64 sums of every reduction are exchanged over NVLink peer "
+                                   f"memory by the reducing kernel's last CTA (fused all-reduce, p2p_active={p2p_active}; NCCL only "
+                                   f"bootstraps the IPC handles and is the fallback)") if world > 1 else "single GPU"},
         "clocks": clocks,
         "e2e": {"value": world * n * e2e_steps / (e2e_ms * 1e-3), "unit": "rows/s",
                 "h2d_bytes_per_step": 4 * n, "d2h_bytes_per_step": 4 * n + 8 * 4, "steps": e2e_steps,
                 "ms_per_step": e2e_ms / e2e_steps,
                 "note": "direction h host->device and pseudo-residuals device->host (pinned) every round"},
         "gpu_launches": int(launches),
+        "parity_ok": (all(p["ok"] for p in parity) if parity else None), "parity": parity, "p2p_active": p2p_active,
         "roofline": {"kernel": "gbm_scalar_kernel<squared, UPDATE_RESID> (K1: F update + residual + loss)",
                      "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": _ncu_traffic(n), "peak_source": peak_src, "bytes_per_row": BYTES_K1, "ms_per_launch": k1_ms,

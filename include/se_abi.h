@@ -113,6 +113,16 @@ enum se_kernel_family {
 SE_API int se_ctx_kernel_timing(se_ctx* ctx, int on);
 SE_API int se_ctx_kernel_time(se_ctx* ctx, int family, double* total_ms, int64_t* launches);
 SE_API int se_ctx_kernel_time_reset(se_ctx* ctx);
+/* Tunables and diagnostics by name (doubles).  Settable: "fused_round" (-1 auto by shard size / 0 / 1: squared-loss
+ * round in ONE cooperative launch), "fused_round_max_rows", "fused_ctas_per_sm", "ls_mode" (non-squared Brent line
+ * search: 0 = one launch per evaluation, 1 = one persistent launch with Brent on the device [default], 2 = host Brent
+ * over single-evaluation launches of the persistent kernel — bit-identical to 1, for tests), "ls_resident",
+ * "ls_ctas_per_sm", "l2_persist", "l2_persist_frac", "peer_timeout_ms" (spin bound of the fused peer exchange,
+ * 0 = forever), "alternate_passes", "l2_hints", "ctas_per_sm", "host_mirror".  Read-only: "last_round_fused",
+ * "last_ls_workers", "last_ls_passes", "last_ls_hit_ratio", "last_fused_grid", "l2_persist_max_bytes",
+ * "l2_window_max_bytes".  Unknown keys fail with SE_ERR_ARG. */
+SE_API int se_ctx_set_option(se_ctx* ctx, const char* key, double value);
+SE_API int se_ctx_get_option(const se_ctx* ctx, const char* key, double* value);
 /* pinned (page-locked) host memory for the buffers handed to se_upload/se_download (JNI: wrap in a
  * direct ByteBuffer); pageable memory works too but is staged by the driver */
 SE_API int se_host_alloc(int64_t bytes, void** out);
@@ -126,6 +136,10 @@ SE_API int se_comm_init(se_ctx* ctx, int nranks, int rank, const void* id, int b
  * IPC and the last CTA of each reducing kernel exchanges the per-GPU sums over peer memory itself (no separate
  * NCCL launch).  0: NCCL all-reduce after the kernel (fallback when IPC mapping fails or SE_P2P_ALLREDUCE=0). */
 SE_API int se_comm_p2p_active(const se_ctx* ctx, int* active);
+/* A peer that does not launch the matching reduction within "peer_timeout_ms" (default 120 s; se_ctx_set_option)
+ * makes the waiting rank POISON that reduction in every peer's mailbox, so that all ranks fail the same reduction
+ * with SE_ERR_NCCL instead of disagreeing on its result.  The error is sticky until every rank calls this. */
+SE_API int se_comm_clear_error(se_ctx* ctx);
 SE_API int se_comm_destroy(se_ctx* ctx);
 SE_API int se_comm_info(const se_ctx* ctx, int* nranks, int* rank);
 /* sum-allreduce `count` doubles held on the host across ranks (no-op without a communicator) */

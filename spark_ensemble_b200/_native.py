@@ -57,11 +57,14 @@ PROTOTYPES = {
     "se_ctx_kernel_timing": [_vp, _i32],
     "se_ctx_kernel_time": [_vp, _i32, _dp, C.POINTER(_i64)],
     "se_ctx_kernel_time_reset": [_vp],
+    "se_ctx_set_option": [_vp, C.c_char_p, _d],
+    "se_ctx_get_option": [_vp, C.c_char_p, _dp],
     "se_host_alloc": [_i64, C.POINTER(_vp)],
     "se_host_free": [_vp],
     "se_comm_unique_id": [_vp, _i32],
     "se_comm_init": [_vp, _i32, _i32, _vp, _i32],
     "se_comm_p2p_active": [_vp, C.POINTER(_i32)],
+    "se_comm_clear_error": [_vp],
     "se_comm_destroy": [_vp],
     "se_comm_info": [_vp, C.POINTER(_i32), C.POINTER(_i32)],
     "se_comm_allreduce_host": [_vp, _dp, _i32],

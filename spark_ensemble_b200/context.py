@@ -80,6 +80,15 @@ class Context:
     def kernel_times_reset(self):
         self._ck(self._lib.se_ctx_kernel_time_reset(self._h))
 
+    def set_option(self, key: str, value: float):
+        """Tunables by name (se_ctx_set_option): fused_round, ls_mode, l2_persist, peer_timeout_ms, ..."""
+        self._ck(self._lib.se_ctx_set_option(self._h, key.encode(), float(value)))
+
+    def get_option(self, key: str) -> float:
+        v = C.c_double()
+        self._ck(self._lib.se_ctx_get_option(self._h, key.encode(), C.byref(v)))
+        return v.value
+
     # ---- communicator
     @staticmethod
     def comm_unique_id() -> bytes:
@@ -95,6 +104,9 @@ class Context:
         v = C.c_int()
         self._ck(self._lib.se_comm_p2p_active(self._h, C.byref(v)))
         return bool(v.value)
+
+    def comm_clear_error(self):
+        self._ck(self._lib.se_comm_clear_error(self._h))
 
     def comm_destroy(self):
         self._ck(self._lib.se_comm_destroy(self._h))

@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <math.h>
+#include <sched.h>
 #include <stdarg.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -171,6 +172,29 @@ struct se_ctx {
   unsigned pass_parity = 0;           // alternates the tile direction of consecutive GBM passes (L2 reuse)
   bool alternate = true;
   int l2_hints = -1;                  // evict_first hints on the GBM streams: -1 by shard size, 0 off, 1 on (SE_L2_HINTS)
+  // ---- cooperative whole-round / whole-line-search kernels (se_gbm_fused.cu)
+  FusedSync* d_fsync = nullptr;
+  unsigned long long fused_epoch = 0;
+  int fused_round = -1;               // squared-loss round in one launch: -1 by shard size, 0 off, 1 on
+  int64_t fused_round_max_rows = 40000000;
+  int fused_ctas_per_sm = 3;
+  int ls_mode = 1;                    // non-squared line search: 0 one launch per evaluation (round-1 kernels), 1 one
+                                      // persistent launch (device Brent), 2 host Brent over single-evaluation launches of
+                                      // the persistent kernel (bit-identity check of mode 1)
+  int ls_resident = 1;                // workers keep their first tiles in shared memory
+  int ls_ctas_per_sm = 4;
+  int l2_persist = 1;                 // mark the packed line-search view as L2-persisting
+  size_t l2_persist_max = 0;          // cudaDevAttrMaxPersistingL2CacheSize
+  size_t l2_window_max = 0;           // cudaDevAttrMaxAccessPolicyWindowSize
+  size_t l2_persist_set = 0;          // current cudaLimitPersistingL2CacheSize
+  double l2_persist_frac = 0.75;      // fraction of the persisting carve-out the window is sized for
+  bool l2_persist_dirty = false;      // persisting lines may be resident: reset before unrelated kernels
+  int clock_khz = 1965000;
+  double peer_timeout_ms = 120000.0;  // spin bound of the fused peer exchange (0 = wait forever)
+  // diagnostics of the last call (se_ctx_get_option)
+  int last_round_fused = 0, last_ls_workers = 0, last_ls_resident = 0, last_ls_passes = 0, last_fused_grid = 0;
+  double last_ls_hit_ratio = 0.0;
+  double last_round_stats[3] = {0.0, 0.0, 0.0};
   std::string err;
   // stopwatch + per-kernel-family timing
   cudaEvent_t tm0 = nullptr, tm1 = nullptr;
@@ -307,6 +331,7 @@ RedWs red_ws(se_ctx* ctx, int out_offset = 0, bool exchange = true) {
     ws.rank = ctx->rank;
     ws.seq = ++ctx->red_seq;
     ws.err = ctx->d_p2p_err;
+    ws.timeout_clocks = (long long)(ctx->peer_timeout_ms * (double)ctx->clock_khz);
     ctx->last_reduce_global = true;
   }
   return ws;
@@ -326,6 +351,40 @@ int allreduce_dev(se_ctx* ctx, int off, int count, int op = kNcclSum) {
   return SE_OK;
 }
 
+int check_p2p(se_ctx* ctx) {
+  if (ctx->p2p && ctx->h_p2p_err && *reinterpret_cast<volatile int*>(ctx->h_p2p_err))
+    return fail(ctx, SE_ERR_NCCL, "peer-memory all-reduce failed: a rank did not launch the matching reduction within "
+                "%.0f ms (or gave up on it); se_comm_clear_error() re-arms the communicator", ctx->peer_timeout_ms);
+  return SE_OK;
+}
+
+// Wait until the kernel's last CTA has written the current mirror ticket into mapped host memory.  Spins on the
+// cache line with PAUSE for the first ~100 us (the common case: the kernel is already running), then yields the core
+// between polls so that a long kernel / a slow peer does not burn the driver thread.
+int wait_mirror(se_ctx* ctx) {
+  volatile unsigned long long* flag = reinterpret_cast<volatile unsigned long long*>(ctx->h_mirror + kMboxPayload);
+  for (unsigned long spin = 0;; ++spin) {
+    if (*flag == ctx->mirror_ticket) return SE_OK;
+    if (spin < 20000) {
+#if defined(__x86_64__) || defined(__i386__)
+      __builtin_ia32_pause();
+#endif
+      continue;
+    }
+    if ((spin & 0x3F) == 0) {
+      const cudaError_t q = cudaStreamQuery(ctx->stream);
+      if (q != cudaErrorNotReady) {  // finished or failed
+        if (*flag == ctx->mirror_ticket) return SE_OK;
+        if (q != cudaSuccess) return fail(ctx, SE_ERR_CUDA, "kernel failed before publishing its results: %s", cudaGetErrorString(q));
+        SE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (*flag == ctx->mirror_ticket) return SE_OK;
+        return fail(ctx, SE_ERR_CUDA, "reduction results never reached the host mirror");
+      }
+    }
+    sched_yield();
+  }
+}
+
 // (all-reduce and) bring d_scal[off..off+count) to the host; synchronises the stream
 int fetch_scalars(se_ctx* ctx, int off, int count, double* out, int op = kNcclSum) {
   if (ctx->mirror_valid && ctx->mirror_off == off && op == kNcclSum && count <= kMboxPayload) {
@@ -333,23 +392,9 @@ int fetch_scalars(se_ctx* ctx, int off, int count, double* out, int op = kNcclSu
     ctx->mirror_valid = false;
     ctx->last_reduce_global = false;
     SE_TRY(end(ctx));
-    volatile unsigned long long* flag = reinterpret_cast<volatile unsigned long long*>(ctx->h_mirror + kMboxPayload);
-    bool seen = false;
-    for (long spin = 0; spin < 2000000000L; ++spin) {
-      if (*flag == ctx->mirror_ticket) { seen = true; break; }
-      if ((spin & 0xFFFFF) == 0xFFFFF && cudaStreamQuery(ctx->stream) != cudaErrorNotReady) {  // finished or failed
-        seen = (*flag == ctx->mirror_ticket);
-        break;
-      }
-    }
-    if (!seen) {
-      SE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-      if (*flag != ctx->mirror_ticket) return fail(ctx, SE_ERR_CUDA, "reduction results never reached the host mirror");
-    }
+    SE_TRY(wait_mirror(ctx));
     for (int i = 0; i < count; ++i) out[i] = ctx->h_mirror[i];
-    if (ctx->p2p && ctx->h_p2p_err && *reinterpret_cast<volatile int*>(ctx->h_p2p_err))
-      return fail(ctx, SE_ERR_NCCL, "peer-memory all-reduce timed out: a rank did not launch the matching reduction");
-    return SE_OK;
+    return check_p2p(ctx);
   }
   SE_TRY(allreduce_dev(ctx, off, count, op));
   SE_CUDA(ctx, cudaMemcpyAsync(ctx->h_scal + off, ctx->d_scal + off, sizeof(double) * count,
@@ -357,9 +402,7 @@ int fetch_scalars(se_ctx* ctx, int off, int count, double* out, int op = kNcclSu
   SE_TRY(end(ctx));
   SE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   for (int i = 0; i < count; ++i) out[i] = ctx->h_scal[off + i];
-  if (ctx->p2p && ctx->h_p2p_err && *reinterpret_cast<volatile int*>(ctx->h_p2p_err))
-    return fail(ctx, SE_ERR_NCCL, "peer-memory all-reduce timed out: a rank did not launch the matching reduction");
-  return SE_OK;
+  return check_p2p(ctx);
 }
 
 int slot_alloc2d(se_ctx* ctx, int slot, int64_t rows, int64_t cols) {
@@ -417,8 +460,19 @@ int for_segments(se_ctx* ctx, const SlotBuf& s, int64_t count, int64_t offset, F
   return SE_OK;
 }
 
+// Release L2 lines a previous line search marked as persisting (they would otherwise keep occupying the carve-out
+// while unrelated kernels stream through a smaller L2).
+int release_l2_persist(se_ctx* ctx) {
+  if (!ctx->l2_persist_dirty) return SE_OK;
+  ctx->l2_persist_dirty = false;
+  cudaCtxResetPersistingL2Cache();
+  cudaGetLastError();
+  return SE_OK;
+}
+
 int ensure_counts(se_ctx* ctx) {
   if (ctx->gbm.counts_valid) return SE_OK;
+  SE_CUDA(ctx, cudaSetDevice(ctx->device));  // callers may run before begin(): launches below need the right device
   double v[2] = {(double)ctx->gbm.n, (double)ctx->gbm.nv};
   SE_TRY(se_comm_allreduce_host(ctx, v, 2));
   ctx->gbm.n_global = v[0];
@@ -429,6 +483,7 @@ int ensure_counts(se_ctx* ctx) {
 
 int ensure_wsum(se_ctx* ctx) {
   if (ctx->gbm.wsum_valid) return SE_OK;
+  SE_CUDA(ctx, cudaSetDevice(ctx->device));
   SE_TRY(ensure_counts(ctx));
   if (ctx->gbm.use_bag) {
     // weightSum over the bag: Σ c_i·w_i (GBMLoss.scala:65 adds instance.weight once per sampled copy)
@@ -544,6 +599,20 @@ int se_ctx_create(int device, se_ctx** out) {
   SE_CREATE_CUDA(cudaMalloc(&ctx->d_partials, sizeof(double) * (size_t)kMaxGridPartials * kMaxRed));
   SE_CREATE_CUDA(cudaMalloc(&ctx->d_counter, sizeof(unsigned int)));
   SE_CREATE_CUDA(cudaMemset(ctx->d_counter, 0, sizeof(unsigned int)));
+  SE_CREATE_CUDA(cudaMalloc(&ctx->d_fsync, sizeof(FusedSync)));
+  SE_CREATE_CUDA(cudaMemset(ctx->d_fsync, 0, sizeof(FusedSync)));
+  ctx->clock_khz = prop.clockRate > 0 ? prop.clockRate : 1965000;
+  {
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMaxPersistingL2CacheSize, device) == cudaSuccess && v > 0) ctx->l2_persist_max = (size_t)v;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMaxAccessPolicyWindowSize, device) == cudaSuccess && v > 0) ctx->l2_window_max = (size_t)v;
+    cudaGetLastError();
+  }
+  if (const char* s = getenv("SE_FUSED_ROUND")) ctx->fused_round = atoi(s) != 0 ? 1 : 0;
+  if (const char* s = getenv("SE_LS_MODE")) { const int v = atoi(s); if (v >= 0 && v <= 2) ctx->ls_mode = v; }
+  if (const char* s = getenv("SE_LS_RESIDENT")) ctx->ls_resident = atoi(s) != 0;
+  if (const char* s = getenv("SE_L2_PERSIST")) ctx->l2_persist = atoi(s) != 0;
+  if (const char* s = getenv("SE_PEER_TIMEOUT_MS")) { const double v = atof(s); if (v >= 0.0) ctx->peer_timeout_ms = v; }
   SE_CREATE_CUDA(cudaHostAlloc(&ctx->h_mirror, sizeof(double) * (kMboxPayload + 8), cudaHostAllocMapped));
   memset(ctx->h_mirror, 0, sizeof(double) * (kMboxPayload + 8));
   SE_CREATE_CUDA(cudaHostGetDevicePointer(&ctx->d_mirror, ctx->h_mirror, 0));
@@ -574,10 +643,10 @@ int se_ctx_destroy(se_ctx* ctx) {
   if (ctx->h_scal) cudaFreeHost(ctx->h_scal);
   if (ctx->d_partials) cudaFree(ctx->d_partials);
   if (ctx->d_counter) cudaFree(ctx->d_counter);
+  if (ctx->d_fsync) cudaFree(ctx->d_fsync);
   if (ctx->d_small) cudaFree(ctx->d_small);
   if (ctx->h_mirror) cudaFreeHost(ctx->h_mirror);
-  if (ctx->d_ls_u) cudaFree(ctx->d_ls_u);
-  if (ctx->d_ls_v) cudaFree(ctx->d_ls_v);
+  if (ctx->d_ls_u) cudaFree(ctx->d_ls_u);  // (u, v) share one allocation
   if (ctx->h_small) cudaFreeHost(ctx->h_small);
   if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
   if (ctx->tm0) cudaEventDestroy(ctx->tm0);
@@ -672,6 +741,84 @@ int se_ctx_kernel_time_reset(se_ctx* ctx) {
   SE_CUDA(ctx, cudaSetDevice(ctx->device));
   SE_TRY(drain_kernel_events(ctx));
   for (int i = 0; i < SE_KF_COUNT; ++i) { ctx->kms[i] = 0.0; ctx->kcount[i] = 0; }
+  return SE_OK;
+}
+
+namespace {
+struct OptKey { const char* name; int id; };
+enum { OPT_FUSED_ROUND, OPT_FUSED_MAX_ROWS, OPT_FUSED_CTAS, OPT_LS_MODE, OPT_LS_RESIDENT, OPT_LS_CTAS, OPT_L2_PERSIST,
+       OPT_L2_PERSIST_FRAC, OPT_PEER_TIMEOUT_MS, OPT_ALTERNATE, OPT_L2_HINTS, OPT_CTAS_PER_SM, OPT_HOST_MIRROR,
+       // read-only diagnostics
+       OPT_LAST_ROUND_FUSED, OPT_LAST_LS_WORKERS, OPT_LAST_LS_PASSES, OPT_LAST_LS_HIT_RATIO, OPT_LAST_FUSED_GRID,
+       OPT_L2_PERSIST_MAX, OPT_L2_WINDOW_MAX, OPT_LAST_STAT0, OPT_LAST_STAT1, OPT_LAST_STAT2 };
+const OptKey kOpts[] = {
+  {"fused_round", OPT_FUSED_ROUND}, {"fused_round_max_rows", OPT_FUSED_MAX_ROWS}, {"fused_ctas_per_sm", OPT_FUSED_CTAS},
+  {"ls_mode", OPT_LS_MODE}, {"ls_resident", OPT_LS_RESIDENT}, {"ls_ctas_per_sm", OPT_LS_CTAS}, {"l2_persist", OPT_L2_PERSIST},
+  {"l2_persist_frac", OPT_L2_PERSIST_FRAC}, {"peer_timeout_ms", OPT_PEER_TIMEOUT_MS}, {"alternate_passes", OPT_ALTERNATE},
+  {"l2_hints", OPT_L2_HINTS}, {"ctas_per_sm", OPT_CTAS_PER_SM}, {"host_mirror", OPT_HOST_MIRROR},
+  {"last_round_fused", OPT_LAST_ROUND_FUSED}, {"last_ls_workers", OPT_LAST_LS_WORKERS}, {"last_ls_passes", OPT_LAST_LS_PASSES},
+  {"last_ls_hit_ratio", OPT_LAST_LS_HIT_RATIO}, {"last_fused_grid", OPT_LAST_FUSED_GRID},
+  {"l2_persist_max_bytes", OPT_L2_PERSIST_MAX}, {"l2_window_max_bytes", OPT_L2_WINDOW_MAX},
+  {"last_round_stat0", OPT_LAST_STAT0}, {"last_round_stat1", OPT_LAST_STAT1}, {"last_round_stat2", OPT_LAST_STAT2},
+};
+int opt_id(const char* key) {
+  if (!key) return -1;
+  for (const OptKey& k : kOpts)
+    if (strcmp(k.name, key) == 0) return k.id;
+  return -1;
+}
+}  // namespace
+
+int se_ctx_set_option(se_ctx* ctx, const char* key, double value) {
+  if (!ctx) return fail(nullptr, SE_ERR_ARG, "null context");
+  const int iv = (int)value;
+  switch (opt_id(key)) {
+    case OPT_FUSED_ROUND: ctx->fused_round = value < 0 ? -1 : (iv != 0); break;
+    case OPT_FUSED_MAX_ROWS: ctx->fused_round_max_rows = (int64_t)value; break;
+    case OPT_FUSED_CTAS: SE_REQUIRE(ctx, iv >= 1 && iv <= 8, SE_ERR_ARG, "fused_ctas_per_sm in [1,8]"); ctx->fused_ctas_per_sm = iv; break;
+    case OPT_LS_MODE: SE_REQUIRE(ctx, iv >= 0 && iv <= 2, SE_ERR_ARG, "ls_mode in {0,1,2}"); ctx->ls_mode = iv; break;
+    case OPT_LS_RESIDENT: ctx->ls_resident = iv != 0; break;
+    case OPT_LS_CTAS: SE_REQUIRE(ctx, iv >= 1 && iv <= 8, SE_ERR_ARG, "ls_ctas_per_sm in [1,8]"); ctx->ls_ctas_per_sm = iv; break;
+    case OPT_L2_PERSIST: ctx->l2_persist = iv != 0; break;
+    case OPT_L2_PERSIST_FRAC: SE_REQUIRE(ctx, value > 0.0 && value <= 1.0, SE_ERR_ARG, "l2_persist_frac in (0,1]"); ctx->l2_persist_frac = value; break;
+    case OPT_PEER_TIMEOUT_MS: SE_REQUIRE(ctx, value >= 0.0, SE_ERR_ARG, "peer_timeout_ms >= 0"); ctx->peer_timeout_ms = value; break;
+    case OPT_ALTERNATE: ctx->alternate = iv != 0; break;
+    case OPT_L2_HINTS: ctx->l2_hints = value < 0 ? -1 : (iv != 0); break;
+    case OPT_CTAS_PER_SM: SE_REQUIRE(ctx, iv >= 1 && iv <= 16, SE_ERR_ARG, "ctas_per_sm in [1,16]"); ctx->ctas_per_sm = iv; break;
+    case OPT_HOST_MIRROR: ctx->use_mirror = iv != 0; break;
+    default: return fail(ctx, SE_ERR_ARG, "unknown or read-only option '%s'", key ? key : "(null)");
+  }
+  return SE_OK;
+}
+
+int se_ctx_get_option(const se_ctx* ctx, const char* key, double* value) {
+  if (!ctx || !value) return fail(nullptr, SE_ERR_ARG, "null argument");
+  switch (opt_id(key)) {
+    case OPT_FUSED_ROUND: *value = ctx->fused_round; break;
+    case OPT_FUSED_MAX_ROWS: *value = (double)ctx->fused_round_max_rows; break;
+    case OPT_FUSED_CTAS: *value = ctx->fused_ctas_per_sm; break;
+    case OPT_LS_MODE: *value = ctx->ls_mode; break;
+    case OPT_LS_RESIDENT: *value = ctx->ls_resident; break;
+    case OPT_LS_CTAS: *value = ctx->ls_ctas_per_sm; break;
+    case OPT_L2_PERSIST: *value = ctx->l2_persist; break;
+    case OPT_L2_PERSIST_FRAC: *value = ctx->l2_persist_frac; break;
+    case OPT_PEER_TIMEOUT_MS: *value = ctx->peer_timeout_ms; break;
+    case OPT_ALTERNATE: *value = ctx->alternate; break;
+    case OPT_L2_HINTS: *value = ctx->l2_hints; break;
+    case OPT_CTAS_PER_SM: *value = ctx->ctas_per_sm; break;
+    case OPT_HOST_MIRROR: *value = ctx->use_mirror; break;
+    case OPT_LAST_ROUND_FUSED: *value = ctx->last_round_fused; break;
+    case OPT_LAST_LS_WORKERS: *value = ctx->last_ls_workers; break;
+    case OPT_LAST_LS_PASSES: *value = ctx->last_ls_passes; break;
+    case OPT_LAST_LS_HIT_RATIO: *value = ctx->last_ls_hit_ratio; break;
+    case OPT_LAST_FUSED_GRID: *value = ctx->last_fused_grid; break;
+    case OPT_L2_PERSIST_MAX: *value = (double)ctx->l2_persist_max; break;
+    case OPT_L2_WINDOW_MAX: *value = (double)ctx->l2_window_max; break;
+    case OPT_LAST_STAT0: *value = ctx->last_round_stats[0]; break;
+    case OPT_LAST_STAT1: *value = ctx->last_round_stats[1]; break;
+    case OPT_LAST_STAT2: *value = ctx->last_round_stats[2]; break;
+    default: return fail(const_cast<se_ctx*>(ctx), SE_ERR_ARG, "unknown option '%s'", key ? key : "(null)");
+  }
   return SE_OK;
 }
 
@@ -790,6 +937,15 @@ int se_comm_init(se_ctx* ctx, int nranks, int rank, const void* id, int bytes) {
 int se_comm_p2p_active(const se_ctx* ctx, int* active) {
   if (!ctx || !active) return fail(nullptr, SE_ERR_ARG, "null argument");
   *active = ctx->p2p ? 1 : 0;
+  return SE_OK;
+}
+
+int se_comm_clear_error(se_ctx* ctx) {
+  if (!ctx) return fail(nullptr, SE_ERR_ARG, "null context");
+  SE_CUDA(ctx, cudaSetDevice(ctx->device));
+  SE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (ctx->h_p2p_err) *reinterpret_cast<volatile int*>(ctx->h_p2p_err) = 0;
+  ctx->err.clear();
   return SE_OK;
 }
 
@@ -1132,6 +1288,7 @@ int se_gbm_configure(se_ctx* ctx, int64_t n_train, int64_t n_valid, int dim, int
   g.use_bag = false;
   g.r_current = false;
   g.wsum_valid = false; g.counts_valid = false;
+  release_l2_persist(ctx);
   SE_TRY(slot_alloc2d(ctx, SE_SLOT_Y, 1, n_train));
   SE_TRY(slot_alloc2d(ctx, SE_SLOT_F, dim, n_train));
   SE_TRY(slot_alloc2d(ctx, SE_SLOT_H, dim, n_train));
@@ -1303,6 +1460,101 @@ using Parabola = BrentParabola;
 double parabola_cb(double x, void* user) { return (*static_cast<const Parabola*>(user))(x); }
 }  // namespace
 
+namespace {
+
+int ensure_ls_view(se_ctx* ctx) {
+  if (ctx->ls_cap >= ctx->gbm.n && ctx->d_ls_u) return SE_OK;
+  if (ctx->d_ls_u) cudaFree(ctx->d_ls_u);
+  ctx->d_ls_u = ctx->d_ls_v = nullptr;
+  ctx->ls_cap = 0;
+  // one allocation for both halves: a single L2 access-policy window covers the whole view
+  const size_t half = ((size_t)ctx->gbm.n + 32 + 63) / 64 * 64;
+  SE_CUDA(ctx, cudaMalloc(&ctx->d_ls_u, sizeof(float) * 2 * half));
+  ctx->d_ls_v = ctx->d_ls_u + half;
+  ctx->ls_cap = ctx->gbm.n;
+  return SE_OK;
+}
+
+// One launch of the persistent line-search kernel (se_gbm_fused.cu): the whole Brent search (single == 0) or one
+// evaluation of the objective at `start` with the tile direction of evaluation number `parity + 1` (single == 1).
+int linesearch_persist(se_ctx* ctx, double lo, double hi, double start, double rel, double abs_tol, int max_eval,
+                       int single, int parity, double* alpha, double* loss, int* n_eval) {
+  SE_TRY(ensure_wsum(ctx));
+  SE_TRY(begin(ctx));
+  const int lossid = ctx->gbm.loss;
+  const bool packed = gbm_linesearch_persist_packed(lossid);
+  if (packed) SE_TRY(ensure_ls_view(ctx));
+  LsArgs a;
+  a.y = ctx->slot[SE_SLOT_Y].d;
+  a.F = ctx->slot[SE_SLOT_F].d;
+  a.h = ctx->slot[SE_SLOT_H].d;
+  a.u = ctx->d_ls_u;
+  a.v = ctx->d_ls_v;
+  a.n = ctx->gbm.n;
+  a.param = (float)ctx->gbm.param;
+  a.wsum = ctx->gbm.wsum;
+  a.lo = lo; a.hi = hi; a.start = start; a.rel = rel; a.abs_tol = abs_tol; a.max_eval = max_eval;
+  a.single = single;
+  a.first_parity = parity;
+  a.partials = ctx->d_partials;
+  a.sync = ctx->d_fsync;
+  a.epoch0 = ctx->fused_epoch;
+  ctx->fused_epoch += (unsigned long long)(max_eval > 0 ? max_eval : 1) + 4;
+  a.out = ctx->d_scal + kScalRound + 16;
+  a.ws = red_ws(ctx, kScalRound + 16);  // takes ONE sequence number; the kernel uses seq, seq+1, ... per evaluation
+  const unsigned long long seq0 = ctx->red_seq;
+  LsLaunch cfg;
+  cfg.max_ctas_per_sm = ctx->ls_ctas_per_sm;
+  cfg.resident = ctx->ls_resident;
+  ctx->last_ls_hit_ratio = 0.0;
+  if (packed && !single && ctx->l2_persist && ctx->l2_persist_max > 0 && ctx->l2_window_max > 0) {
+    if (ctx->l2_persist_set != ctx->l2_persist_max) {
+      if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, ctx->l2_persist_max) == cudaSuccess) ctx->l2_persist_set = ctx->l2_persist_max;
+      cudaGetLastError();
+    }
+    if (ctx->l2_persist_set > 0) {
+      size_t bytes = sizeof(float) * (size_t)(ctx->d_ls_v - ctx->d_ls_u) + sizeof(float) * (size_t)ctx->gbm.n;  // [u .. end of v)
+      if (bytes > ctx->l2_window_max) bytes = ctx->l2_window_max;
+      cfg.window_base = ctx->d_ls_u;
+      cfg.window_bytes = bytes;
+      const double want = ctx->l2_persist_frac * (double)ctx->l2_persist_set / (double)bytes;
+      cfg.hit_ratio = (float)(want > 1.0 ? 1.0 : want);
+      ctx->last_ls_hit_ratio = cfg.hit_ratio;
+      ctx->l2_persist_dirty = true;
+    }
+  }
+  int workers = 0;
+  SE_LAUNCH_T(ctx, SE_KF_EVAL, launch_gbm_linesearch_persist(lossid, a, ctx->sms, cfg, ctx->stream, &workers));
+  ctx->last_ls_workers = workers;
+  double res[4] = {0, 0, 0, 0};
+  const int rc = fetch_scalars(ctx, kScalRound + 16, 4, res);
+  // every evaluation consumed one reduction sequence number on every rank (the first was taken by red_ws)
+  const int passes = (int)res[3];
+  if (ctx->p2p && ctx->nranks > 1 && passes > 1) ctx->red_seq = seq0 + (unsigned long long)(passes - 1);
+  ctx->last_ls_passes = passes;
+  if (rc != SE_OK) return rc;
+  if (alpha) *alpha = res[0];
+  if (loss) *loss = res[1];
+  if (n_eval) *n_eval = (int)fabs(res[2]);
+  if (res[2] < 0.0) return fail(ctx, SE_ERR_OPT, "Brent exceeded MaxEval(%d)", max_eval);
+  return SE_OK;
+}
+
+struct PersistEvalClosure {
+  se_ctx* ctx;
+  int rc;
+  int k;  // evaluations so far
+};
+double persist_eval_cb(double x, void* user) {
+  PersistEvalClosure* c = static_cast<PersistEvalClosure*>(user);
+  double l = NAN;
+  if (c->rc == SE_OK) c->rc = linesearch_persist(c->ctx, 0.0, 0.0, x, 1e-6, 1e-6, 1, /*single=*/1, /*parity=*/c->k, nullptr, &l, nullptr);
+  c->k++;
+  return l;
+}
+
+}  // namespace
+
 int se_gbm_linesearch_brent(se_ctx* ctx, double lo, double hi, double start, double rel, double abs_tol,
                             int max_eval, double* alpha, double* loss, int* n_eval) {
   if (!ctx || !alpha) return fail(ctx, SE_ERR_ARG, "null argument");
@@ -1315,22 +1567,29 @@ int se_gbm_linesearch_brent(se_ctx* ctx, double lo, double hi, double start, dou
     if (rc != SE_OK) return fail(ctx, rc, "Brent exceeded MaxEval(%d)", max_eval);
     return SE_OK;
   }
+  // Default: ONE persistent launch runs all of Brent's evaluations on the device (no host round trip and no launch
+  // per evaluation; tiles resident in shared memory / L2 between evaluations) — se_gbm_fused.cu.
+  // (needs in-kernel cross-GPU sums: single GPU or the fused peer exchange, not the NCCL fallback)
+  if (ctx->ls_mode != 0 && !ctx->gbm.use_bag && max_eval >= 1 && gbm_linesearch_persist_supported(ctx->gbm.loss) &&
+      (ctx->nranks <= 1 || ctx->p2p)) {
+    if (ctx->ls_mode == 1) return linesearch_persist(ctx, lo, hi, start, rel, abs_tol, max_eval, 0, 0, alpha, loss, n_eval);
+    // mode 2: the HOST runs the same Brent template and asks the same kernel for one evaluation at a time; the
+    // objective values, hence the iterates, must equal mode 1 bit for bit (tests/test_gpu_parity.py)
+    PersistEvalClosure c{ctx, SE_OK, 0};
+    int rc = brent_impl(persist_eval_cb, &c, lo, hi, start, rel, abs_tol, max_eval, alpha, loss, n_eval);
+    if (c.rc != SE_OK) return c.rc;
+    if (rc != SE_OK) return fail(ctx, rc, "Brent exceeded MaxEval(%d)", max_eval);
+    return SE_OK;
+  }
+  // Round-1 path (one launch + one host poll per evaluation), kept for bags and as the A/B baseline.
   // Binary scalar losses depend on (2y-1)(F + αh) only: one 20 B/row pass builds u = (2y-1)F, v = (2y-1)h and
   // every one of Brent's 20-40 evaluations then reads 8 B/row instead of 12 — same values bit for bit
   // (multiplying by ±1 is exact and fma is sign-symmetric).
   const bool pack = (ctx->gbm.loss == SE_LOSS_BERNOULLI || ctx->gbm.loss == SE_LOSS_EXPONENTIAL) && max_eval >= 8 &&
-                    getenv("SE_NO_LS_PACK") == nullptr;
+                    !ctx->gbm.use_bag && getenv("SE_NO_LS_PACK") == nullptr;
   if (pack) {
     SE_CUDA(ctx, cudaSetDevice(ctx->device));
-    if (ctx->ls_cap < ctx->gbm.n) {
-      if (ctx->d_ls_u) cudaFree(ctx->d_ls_u);
-      if (ctx->d_ls_v) cudaFree(ctx->d_ls_v);
-      ctx->d_ls_u = ctx->d_ls_v = nullptr;
-      ctx->ls_cap = 0;
-      SE_CUDA(ctx, cudaMalloc(&ctx->d_ls_u, sizeof(float) * (size_t)(ctx->gbm.n + 32)));
-      SE_CUDA(ctx, cudaMalloc(&ctx->d_ls_v, sizeof(float) * (size_t)(ctx->gbm.n + 32)));
-      ctx->ls_cap = ctx->gbm.n;
-    }
+    SE_TRY(ensure_ls_view(ctx));
     SE_LAUNCH_T(ctx, SE_KF_OTHER, launch_gbm_pack_signed(ctx->slot[SE_SLOT_Y].d, ctx->slot[SE_SLOT_F].d, ctx->slot[SE_SLOT_H].d,
                                                          ctx->d_ls_u, ctx->d_ls_v, ctx->gbm.n, ctx->sms, ctx->stream));
     ctx->ls_packed = true;
@@ -1386,15 +1645,84 @@ int round_squared_device_brent(se_ctx* ctx, double learning_rate, double tol, in
 }
 }  // namespace
 
+namespace {
+// Squared loss, one cooperative launch per round (se_gbm_fused.cu): statistics -> cross-GPU sum -> Brent -> update +
+// residual + loss -> cross-GPU sum -> host mirror.  One launch and one host poll per round.
+int round_squared_fused(se_ctx* ctx, double learning_rate, double tol, int max_iter, int flags, double* alpha,
+                        double* loss_sum, int* n_eval) {
+  SE_TRY(ensure_wsum(ctx));
+  SE_TRY(begin(ctx));
+  SqRoundArgs a;
+  const auto& g = ctx->gbm;
+  a.y = ctx->slot[SE_SLOT_Y].d;
+  a.F = ctx->slot[SE_SLOT_F].d;
+  a.h = ctx->slot[SE_SLOT_H].d;
+  a.r = ctx->slot[SE_SLOT_R].d;
+  a.bag = g.use_bag ? ctx->slot[SE_SLOT_BAG].d : nullptr;
+  a.n = g.n;
+  a.stats_from_r = g.r_current ? 1 : 0;
+  a.l2_hints = ctx->l2_hints >= 0 ? ctx->l2_hints : (g.n <= kL2HintRows ? 1 : 0);
+  a.lr = learning_rate;
+  a.wsum = g.wsum;
+  a.lo = 0.0; a.hi = 100.0; a.start = 1.0; a.rel = tol; a.abs_tol = tol; a.max_eval = max_iter;
+  a.out = ctx->d_scal + kScalRound;
+  a.ws_a = red_ws(ctx, kScalRound);            // sequence number s (statistics)
+  a.ws_a.host_out = nullptr;                   // the mirror ticket belongs to the SECOND reduction
+  a.ws_a.host_flag = nullptr;
+  if (ctx->mirror_valid) --ctx->mirror_ticket; // red_ws armed the mirror for ws_a: hand the ticket to ws_b instead
+  a.ws_b = red_ws(ctx, kScalRound + 8);        // sequence number s + 1 (loss), host mirror + ticket
+  a.ws_b.partials = ctx->d_partials + (size_t)(kMaxGridPartials / 2) * 4;
+  a.ws_b.counter = &ctx->d_fsync->counter_b;
+  const bool mirror = ctx->mirror_valid;
+  constexpr int kMirrorRound = 32;             // mirror slots [32..38]: above what a reducing kernel writes before its ticket
+  a.host_res = mirror ? ctx->d_mirror + kMirrorRound : nullptr;
+  a.sync = ctx->d_fsync;
+  a.epoch = ++ctx->fused_epoch;
+  const int write_r = (flags & SE_UPD_RESIDUAL) ? 1 : 0;
+  int grid = 0;
+  SE_LAUNCH_T(ctx, SE_KF_UPDATE, launch_gbm_round_sq_fused(a, write_r, ctx->sms, ctx->fused_ctas_per_sm, ctx->stream, &grid));
+  ctx->last_fused_grid = grid;
+  ctx->gbm.r_current = write_r != 0;
+  double ls = 0.0;
+  SE_TRY(fetch_scalars(ctx, kScalRound + 8, 1, &ls));
+  double res[7];
+  if (mirror) {
+    for (int i = 0; i < 7; ++i) res[i] = ctx->h_mirror[kMirrorRound + i];
+  } else {
+    SE_CUDA(ctx, cudaMemcpyAsync(ctx->h_scal + kScalRound, ctx->d_scal + kScalRound, sizeof(double) * 7, cudaMemcpyDeviceToHost, ctx->stream));
+    SE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < 7; ++i) res[i] = ctx->h_scal[kScalRound + i];
+  }
+  for (int i = 0; i < 3; ++i) ctx->last_round_stats[i] = res[i];
+  if (alpha) *alpha = res[4];
+  if (n_eval) *n_eval = (int)fabs(res[6]);
+  if (loss_sum) *loss_sum = ls;
+  if (res[6] < 0.0) return fail(ctx, SE_ERR_OPT, "Brent exceeded MaxEval(%d)", max_iter);
+  return SE_OK;
+}
+}  // namespace
+
 int se_gbm_round(se_ctx* ctx, double learning_rate, int optimized, double tol, int max_iter, int flags,
                  double* alpha, double* loss_sum, int* n_eval) {
   if (!ctx) return fail(nullptr, SE_ERR_ARG, "null context");
   SE_REQUIRE(ctx, ctx->gbm.on && ctx->gbm.dim == 1, SE_ERR_STATE, "se_gbm_round needs dim == 1");
-  // SE_DEVICE_BRENT=1: the squared-loss line search runs on the device (one host synchronisation per round instead
-  // of two, same iterates bit for bit).  Opt-in: measured 13 us SLOWER per round at 100 M rows on B200 — one GPU
-  // thread needs ~20 us for Brent's ~21 dependent fp64 iterations, more than the host round trip it saves.
-  if (optimized && ctx->gbm.loss == SE_LOSS_SQUARED && !(flags & SE_UPD_NEWTON) && max_iter >= 1 &&
-      getenv("SE_DEVICE_BRENT") != nullptr)
+  ctx->last_round_fused = 0;
+  const bool sq_search = optimized && ctx->gbm.loss == SE_LOSS_SQUARED && !(flags & SE_UPD_NEWTON) && max_iter >= 1;
+  if (sq_search) {
+    // commons-math3 BrentOptimizer constructor checks (the host path performs them in brent_impl's caller)
+    SE_REQUIRE(ctx, tol >= 2.0 * 2.220446049250313e-16 && tol > 0.0, SE_ERR_ARG, "tolerance %g too small for Brent", tol);
+    // One cooperative launch per round on shards where the fixed costs matter (default: <= 40 M rows).  With a
+    // communicator it additionally needs the fused peer exchange (an NCCL all-reduce cannot run inside the kernel).
+    const bool can = (ctx->nranks <= 1 || ctx->p2p);
+    const bool want = ctx->fused_round > 0 || (ctx->fused_round < 0 && ctx->gbm.n <= ctx->fused_round_max_rows);
+    if (can && want && getenv("SE_DEVICE_BRENT") == nullptr) {
+      ctx->last_round_fused = 1;
+      return round_squared_fused(ctx, learning_rate, tol, max_iter, flags, alpha, loss_sum, n_eval);
+    }
+  }
+  // SE_DEVICE_BRENT=1: three launches (statistics, one-thread Brent, update) with one host synchronisation; kept as an
+  // experiment switch — the fused round above supersedes it.
+  if (sq_search && getenv("SE_DEVICE_BRENT") != nullptr)
     return round_squared_device_brent(ctx, learning_rate, tol, max_iter, flags, alpha, loss_sum, n_eval);
   double a = 1.0, obj = 0.0;
   int ne = 0;
@@ -1513,6 +1841,7 @@ int se_boost_configure(se_ctx* ctx, int64_t n, int num_classes, int real) {
 }
 
 static BoostArgs boost_args(se_ctx* ctx, double sum_w) {
+  release_l2_persist(ctx);
   BoostArgs a;
   a.y = ctx->slot[SE_SLOT_Y].d;
   a.w = ctx->slot[SE_SLOT_BW].d;
@@ -1575,6 +1904,7 @@ int se_boostreg_configure(se_ctx* ctx, int64_t n) {
 }
 
 static BoostRegArgs boostreg_args(se_ctx* ctx, double sum_w, int loss_type, double max_error, bool exchange = true) {
+  release_l2_persist(ctx);
   BoostRegArgs a;
   a.y = ctx->slot[SE_SLOT_Y].d;
   a.pred = ctx->slot[SE_SLOT_PRED].d;
@@ -1662,6 +1992,7 @@ int se_agg_run(se_ctx* ctx, const double* weights, const double* init) {
   SE_REQUIRE(ctx, ctx->agg.on, SE_ERR_STATE, "se_agg_configure first");
   const auto& g = ctx->agg;
   SE_TRY(begin(ctx));
+  release_l2_persist(ctx);
   AggArgs a;
   a.kind = g.kind; a.M = g.M; a.K = g.K; a.dim = g.dim; a.loss = g.loss; a.n = g.n;
   a.P = ctx->slot[SE_SLOT_P].d; a.ld = ctx->slot[SE_SLOT_P].rows > 1 ? ctx->slot[SE_SLOT_P].ld : ctx->slot[SE_SLOT_P].cols;
@@ -1722,6 +2053,7 @@ static int tree_predict_impl(se_ctx* ctx, int which, int n_nodes, const int32_t*
   SE_REQUIRE(ctx, X.d, SE_ERR_STATE, "feature matrix slot not allocated");
   SE_REQUIRE(ctx, O.d && O.cols == X.cols && out_row >= 0 && out_row + n_out <= O.rows, SE_ERR_STATE, "output slot shape mismatch");
   SE_TRY(begin(ctx));
+  release_l2_persist(ctx);
   SE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   int32_t* hf = reinterpret_cast<int32_t*>(ctx->h_small);
   float* ht = reinterpret_cast<float*>(hf + n_nodes);
@@ -1781,6 +2113,7 @@ int se_linear_predict(se_ctx* ctx, int which, int n_coef, const float* coef, flo
   SE_REQUIRE(ctx, X.d, SE_ERR_STATE, "feature matrix slot not allocated");
   SE_REQUIRE(ctx, O.d && out_row >= 0 && out_row < O.rows && O.cols == X.cols, SE_ERR_STATE, "output slot shape mismatch");
   SE_TRY(begin(ctx));
+  release_l2_persist(ctx);
   SE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   float* hc = reinterpret_cast<float*>(ctx->h_small);
   int32_t* hcol = reinterpret_cast<int32_t*>(hc + n_coef);

@@ -161,7 +161,8 @@ struct RedWs {
   double* const* mbox = nullptr;   // device table [nranks]: base of every rank's mailbox [nranks][2][kMboxStride]
   int nranks = 1, rank = 0;
   unsigned long long seq = 0;      // reduction sequence number (same on every rank), >= 1
-  int* err = nullptr;              // set to 1 if a peer never showed up (bounded spin)
+  int* err = nullptr;              // set to 1 if a peer never showed up (bounded spin) or poisoned the reduction
+  long long timeout_clocks = 0;    // spin bound of the peer exchange in SM clocks (0 = wait forever)
   // ---- host mirror: the final sums are also stored into mapped pinned host memory, followed by a ticket, so
   // the host can pick them up by polling one cache line instead of a D2H copy + stream synchronisation
   double* host_out = nullptr;
@@ -186,13 +187,58 @@ __device__ __forceinline__ double ld_relaxed_sys_f64(const double* p) {
   return v;
 }
 
-// Cross-GPU sum of `nred` per-GPU totals, executed by warp 0 of the LAST CTA of the reducing kernel —
-// the collective is part of the kernel, not a separate NCCL launch:
+// Cross-GPU sum of `nred` per-GPU totals, executed by ONE WARP (all 32 lanes converged) — the collective is part
+// of the reducing kernel, not a separate NCCL launch:
 //   1. every lane p < nranks stores this GPU's totals into rank p's mailbox row [my rank][seq parity] with
 //      plain P2P stores over NVLink, then publishes them with a release store of the sequence number;
-//   2. it then spins (acquire loads, bounded) on its OWN mailbox until rank p's row carries this sequence;
-//   3. the rows are summed in rank order, so every GPU produces bit-identical results.
+//   2. it then spins (acquire loads, bounded by ws.timeout_clocks; 0 = unbounded) on its OWN mailbox until rank p's
+//      row carries this sequence;
+//   3. the rows are summed in rank order, so every GPU produces bit-identical results; emit(k, sum_k) is called by
+//      lane k % 32 for every k < nred.
 // Rows are double-buffered by sequence parity: a peer can be at most one reduction ahead.
+// Failure protocol: a rank that gives up (timeout) or sees a poisoned row overwrites the sequence word of ITS row in
+// every peer's mailbox with seq | kPoisonBit, so that a late peer fails the SAME reduction instead of completing it
+// with a sum its partners never saw; every rank then reports NaN sums + the sticky error flag (-> SE_ERR_NCCL).
+constexpr unsigned long long kPoisonBit = 1ull << 63;
+template <class Emit>
+__device__ __forceinline__ bool peer_allreduce_warp(const double* tot, int nred, const RedWs& ws, Emit emit) {
+  const int lane = threadIdx.x & 31;
+  const int par = (int)(ws.seq & 1ull);
+  for (int p = lane; p < ws.nranks; p += 32) {
+    double* row = ws.mbox[p] + (size_t)(ws.rank * 2 + par) * kMboxStride;
+    for (int k = 0; k < nred; ++k) st_relaxed_sys_f64(row + k, tot[k]);
+    st_release_sys_u64(reinterpret_cast<unsigned long long*>(row + kMboxPayload), ws.seq);
+  }
+  bool ok = true;
+  for (int p = lane; p < ws.nranks; p += 32) {
+    const double* row = ws.mbox[ws.rank] + (size_t)(p * 2 + par) * kMboxStride;
+    const long long t0 = clock64();
+    for (;;) {
+      const unsigned long long s = ld_acquire_sys_u64(reinterpret_cast<const unsigned long long*>(row + kMboxPayload));
+      if (s == ws.seq) break;
+      if (s == (ws.seq | kPoisonBit)) { ok = false; break; }                          // the peer gave up on this one
+      if (ws.timeout_clocks > 0 && clock64() - t0 > ws.timeout_clocks) { ok = false; break; }  // it never launched
+    }
+  }
+  ok = __all_sync(0xffffffffu, ok);
+  if (!ok) {
+    for (int p = lane; p < ws.nranks; p += 32) {
+      double* row = ws.mbox[p] + (size_t)(ws.rank * 2 + par) * kMboxStride;
+      st_release_sys_u64(reinterpret_cast<unsigned long long*>(row + kMboxPayload), ws.seq | kPoisonBit);
+    }
+    if (lane == 0 && ws.err) *ws.err = 1;
+  }
+  for (int k = lane; k < nred; k += 32) {
+    double sum = 0.0;
+    for (int p = 0; p < ws.nranks; ++p)
+      sum += ld_relaxed_sys_f64(ws.mbox[ws.rank] + (size_t)(p * 2 + par) * kMboxStride + k);
+    emit(k, ok ? sum : __longlong_as_double(0x7ff8000000000000ll));
+  }
+  return ok;
+}
+
+// The epilogue of every reducing kernel, executed by the LAST CTA: per-GPU totals -> ws.out (summed across GPUs by
+// warp 0 when a peer communicator is attached), mirrored to mapped host memory + ticket when requested.
 __device__ __forceinline__ void peer_exchange(const double* tot, int nred, const RedWs& ws) {
   if (ws.nranks <= 1 || ws.mbox == nullptr) {
     for (int k = threadIdx.x; k < nred; k += blockDim.x) {
@@ -208,30 +254,10 @@ __device__ __forceinline__ void peer_exchange(const double* tot, int nred, const
   }
   if ((threadIdx.x >> 5) != 0) return;
   const int lane = threadIdx.x & 31;
-  const int par = (int)(ws.seq & 1ull);
-  for (int p = lane; p < ws.nranks; p += 32) {
-    double* row = ws.mbox[p] + (size_t)(ws.rank * 2 + par) * kMboxStride;
-    for (int k = 0; k < nred; ++k) st_relaxed_sys_f64(row + k, tot[k]);
-    st_release_sys_u64(reinterpret_cast<unsigned long long*>(row + kMboxPayload), ws.seq);
-  }
-  bool ok = true;
-  for (int p = lane; p < ws.nranks; p += 32) {
-    const double* row = ws.mbox[ws.rank] + (size_t)(p * 2 + par) * kMboxStride;
-    const long long t0 = clock64();
-    while (ld_acquire_sys_u64(reinterpret_cast<const unsigned long long*>(row + kMboxPayload)) != ws.seq) {
-      if (clock64() - t0 > 6000000000ll) { ok = false; break; }  // ~3 s: a peer never launched
-    }
-  }
-  ok = __all_sync(0xffffffffu, ok);
-  for (int k = lane; k < nred; k += 32) {
-    double sum = 0.0;
-    for (int p = 0; p < ws.nranks; ++p)
-      sum += ld_relaxed_sys_f64(ws.mbox[ws.rank] + (size_t)(p * 2 + par) * kMboxStride + k);
-    const double res = ok ? sum : __longlong_as_double(0x7ff8000000000000ll);
+  peer_allreduce_warp(tot, nred, ws, [&](int k, double res) {
     ws.out[k] = res;
     if (ws.host_out) ws.host_out[k] = res;
-  }
-  if (!ok && lane == 0 && ws.err) *ws.err = 1;
+  });
   if (ws.host_out) {
     __threadfence_system();
     __syncwarp();
@@ -241,8 +267,10 @@ __device__ __forceinline__ void peer_exchange(const double* tot, int nred, const
 
 // Block-reduce NRED per-thread fp64 accumulators, publish the block partial, and let the last CTA
 // to arrive reduce all partials in a fixed order (deterministic for a fixed launch configuration).
+// Returns true in every thread of the CTA that performed the final reduction (its ws.out writes are then complete
+// after a __syncthreads()).
 template <int NRED, int BLOCK = kBlock>
-__device__ __forceinline__ void block_reduce_publish(double (&acc)[NRED], const RedWs& ws) {
+__device__ __forceinline__ bool block_reduce_publish(double (&acc)[NRED], const RedWs& ws) {
   __shared__ double sm[NRED][BLOCK / 32];
   __shared__ double tot[NRED];
   __shared__ bool is_last;
@@ -267,7 +295,7 @@ __device__ __forceinline__ void block_reduce_publish(double (&acc)[NRED], const 
     is_last = (ticket == gridDim.x - 1);
   }
   __syncthreads();
-  if (!is_last) return;
+  if (!is_last) return false;
   __threadfence();
   // fixed-order accumulation over blocks: thread t takes blocks t, t+BLOCK, ...
 #pragma unroll
@@ -289,6 +317,7 @@ __device__ __forceinline__ void block_reduce_publish(double (&acc)[NRED], const 
   }
   __syncthreads();
   peer_exchange(tot, NRED, ws);  // per-GPU totals -> ws.out (summed across GPUs when a peer communicator is attached)
+  return true;
 }
 
 // ---- counter-based synthetic generator (bench / tests): identical integer stream on host -----

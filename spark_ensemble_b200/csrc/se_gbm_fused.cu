@@ -1,0 +1,538 @@
+// se_gbm_fused.cu — whole-round and whole-line-search kernels (sm_100a): the per-round fixed costs (kernel
+// launches, host round trips between the line search and the update, one cross-GPU exchange per launch) are what
+// bounds small row shards — exactly the shards STRONG scaling produces (100 M rows / 8 GPUs = 12.5 M rows = a 53 us
+// round at the HBM roofline).  Two cooperative (co-resident, persistent) kernels remove them:
+//
+//  * gbm_round_sq_fused_kernel — a complete squared-loss boosting round (regression/GBMRegressor.scala:398-442 +
+//    :368-385 of the reference) in ONE launch: statistics pass (8 B/row) -> last CTA folds the partials, sums them
+//    across GPUs over peer memory and runs Brent (se_brent.h, the same template as the host line search) -> the step
+//    is published through an acquire/release flag while every other CTA already has the first update tile's loads in
+//    flight -> fused F update + next pseudo-residuals + loss (20 B/row), walking the tiles in the opposite direction
+//    so that the statistics pass's tail of h is still in the 126 MB L2 -> loss reduction + second exchange + host
+//    mirror.  1 launch, 0 host round trips inside the round, the Brent latency hidden behind the preloads.
+//
+//  * gbm_linesearch_persist_kernel — Brent's <= MaxEval evaluations of the line-search objective
+//    (boosting/GBMLoss.scala:50-74 through RDDLossFunction; GBMRegressor.scala:408-421) for the non-squared scalar
+//    losses in ONE launch: worker CTAs own a fixed set of tiles, keep the first of them in SHARED MEMORY for the whole
+//    search (148 SMs x ~190 KB = 28 MB that never touch HBM again) and stream the rest (the caller marks the packed
+//    view as L2-persisting); a coordinator warp folds the per-CTA partials in a fixed order, performs the cross-GPU
+//    sum, advances Brent and publishes the next abscissa.  The first evaluation of the binary losses also BUILDS the
+//    signed view u = (2y-1)F, v = (2y-1)h (exact sign flips: later evaluations read 8 B/row and are bit-identical to
+//    evaluating on (y, F, h)).
+//
+// This translation unit is compiled with -fmad=false so that Brent executes the same IEEE operations as the host
+// build of the template (bit-identical iterates); the per-row arithmetic below uses explicit fmaf().
+#include "se_brent.h"
+#include "se_kernels.h"
+#include "se_loss.cuh"
+
+namespace se {
+
+namespace {
+
+__device__ __forceinline__ unsigned long long ld_acquire_gpu_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_acquire_gpu_u32(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_gpu_add_u32(unsigned int* p, unsigned int v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// =================================================================================== squared-loss round, one launch
+constexpr int U_SQ = 4;  // float4 groups per thread per tile (as the two-launch kernels)
+
+template <bool WRITE_R>
+__global__ void __launch_bounds__(kBlock, 3) gbm_round_sq_fused_kernel(const SqRoundArgs a) {
+  constexpr int U = U_SQ;
+  __shared__ float s_coef;
+  const int64_t n4 = a.n >> 2;
+  constexpr int64_t tile = (int64_t)kBlock * U;
+  const int64_t ntiles = (n4 + tile - 1) / tile;
+  const int64_t G = gridDim.x;
+  const int64_t cnt = (ntiles > (int64_t)blockIdx.x) ? (ntiles - 1 - blockIdx.x) / G + 1 : 0;  // tiles b, b+G, ...
+  const bool has_bag = (a.bag != nullptr);
+  const uint64_t pol_keep = l2_policy(false), pol_stream = l2_policy(a.l2_hints != 0);
+
+  // ---- phase A: Σ(y-F)², Σh(y-F), Σh² (from the current residual slot when it is valid: 8 B/row)
+  double acc[3] = {0.0, 0.0, 0.0};
+  for (int64_t i = 0; i < cnt; ++i) {
+    const int64_t base = (blockIdx.x + i * G) * tile + threadIdx.x;
+    float4 vy[U], vF[U], vh[U], vb[U];
+    bool ok[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t g = base + (int64_t)u * kBlock;
+      ok[u] = g < n4;
+      if (ok[u]) {
+        if (a.stats_from_r) {
+          vy[u] = ld_rw4_p(a.r + 4 * g, pol_stream);  // r is rewritten by phase B without being read again
+        } else {
+          vy[u] = ld_stream4_p(a.y + 4 * g, pol_keep);
+          vF[u] = ld_rw4_p(a.F + 4 * g, pol_keep);
+        }
+        vh[u] = ld_stream4_p(a.h + 4 * g, pol_keep);   // re-read by phase B, starting from this pass's tail
+        if (has_bag) vb[u] = ld_stream4(a.bag + 4 * g);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (!ok[u]) continue;
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float d = a.stats_from_r ? f4at(vy[u], e) : f4at(vy[u], e) - f4at(vF[u], e), h = f4at(vh[u], e);
+        const float c = has_bag ? f4at(vb[u], e) : 1.0f;
+        s0 = fmaf(c * d, d, s0);
+        s1 = fmaf(c * h, d, s1);
+        s2 = fmaf(c * h, h, s2);
+      }
+      acc[0] += (double)s0;
+      acc[1] += (double)s1;
+      acc[2] += (double)s2;
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (a.n & 3)) {
+    const int64_t i = (n4 << 2) + threadIdx.x;
+    const float d = a.stats_from_r ? a.r[i] : a.y[i] - a.F[i], h = a.h[i];
+    const float c = has_bag ? a.bag[i] : 1.0f;
+    acc[0] += (double)(c * d * d);
+    acc[1] += (double)(c * h * d);
+    acc[2] += (double)(c * h * h);
+  }
+  const bool last = block_reduce_publish<3>(acc, a.ws_a);  // the last CTA also sums across GPUs (peer_exchange)
+  if (last) {
+    __syncthreads();  // a.out[0..2] were written by other threads of this CTA
+    if (threadIdx.x == 0) {
+      const double s0 = a.out[0], s1 = a.out[1], s2 = a.out[2];
+      const BrentParabola f{s0, s1, s2, a.wsum};
+      double x = 1.0, fx = 0.0;
+      int evals = 0;
+      const int rc = brent_core(f, a.lo, a.hi, a.start, a.rel, a.abs_tol, a.max_eval, &x, &fx, &evals);
+      const double ne = (rc == kBrentOk) ? (double)evals : -(double)evals;  // negative: MaxEval exceeded
+      a.out[4] = x, a.out[5] = fx, a.out[6] = ne;
+      if (a.host_res) {  // mapped host memory, above what a reducing kernel writes before its ticket
+        a.host_res[0] = s0, a.host_res[1] = s1, a.host_res[2] = s2;
+        a.host_res[4] = x, a.host_res[5] = fx, a.host_res[6] = ne;
+        __threadfence_system();
+      }
+      // MaxEval exceeded: the host reports SE_ERR_OPT and F must stay untouched (F + 0*h == F, r is recomputed)
+      a.sync->x = (rc == kBrentOk) ? a.lr * x : 0.0;
+      st_release_gpu_u64(&a.sync->flag, a.epoch);
+    }
+  }
+
+  // ---- phase B: F' = F + step*h, r = y - F', Σ (y-F')²/2 — tiles in the opposite direction
+  float4 vy[U], vF[U], vh[U];
+  bool ok[U];
+  auto load_tile = [&](int64_t i) {
+    const int64_t base = (blockIdx.x + i * G) * tile + threadIdx.x;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t g = base + (int64_t)u * kBlock;
+      ok[u] = g < n4;
+      if (ok[u]) {
+        vy[u] = ld_stream4_p(a.y + 4 * g, pol_stream);
+        vF[u] = ld_rw4_p(a.F + 4 * g, pol_stream);
+        vh[u] = ld_stream4_p(a.h + 4 * g, pol_stream);  // the update is h's last reader
+      }
+    }
+  };
+  int64_t i = cnt - 1;
+  if (i >= 0) load_tile(i);  // in flight while the last CTA reduces, exchanges and runs Brent
+  if (threadIdx.x == 0) {
+    while (ld_acquire_gpu_u64(&a.sync->flag) != a.epoch) {}
+    s_coef = (float)a.sync->x;  // same rounding as the host path: (float)(lr * alpha)
+  }
+  __syncthreads();
+  const float coef = s_coef;
+  double accb[1] = {0.0};
+  while (i >= 0) {
+    const int64_t base = (blockIdx.x + i * G) * tile + threadIdx.x;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (!ok[u]) continue;
+      const int64_t g = base + (int64_t)u * kBlock;
+      float4 oF, oR;
+      float l_acc = 0.f;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float p = fmaf(coef, f4at(vh[u], e), f4at(vF[u], e));  // GBMRegressor.scala:434-441
+        const float d = f4at(vy[u], e) - p;
+        f4at(oF, e) = p;
+        f4at(oR, e) = d;                                             // -g(y, F') (:383)
+        l_acc = fmaf(0.5f * d, d, l_acc);                            // GBMLoss.scala:129-137
+      }
+      st_stream4_p(a.F + 4 * g, oF, pol_stream);
+      if (WRITE_R) st_stream4_p(a.r + 4 * g, oR, pol_keep);  // the next statistics pass starts where this one ends
+      accb[0] += (double)l_acc;
+    }
+    --i;
+    if (i >= 0) load_tile(i);
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (a.n & 3)) {
+    const int64_t j = (n4 << 2) + threadIdx.x;
+    const float p = fmaf(coef, a.h[j], a.F[j]);
+    const float d = a.y[j] - p;
+    a.F[j] = p;
+    if (WRITE_R) a.r[j] = d;
+    accb[0] += (double)(0.5f * d * d);
+  }
+  block_reduce_publish<1>(accb, a.ws_b);  // Σloss -> a.ws_b.out (+ cross-GPU sum, host mirror + ticket)
+}
+
+// =================================================================================== persistent line search
+// Tiles hold U float4 groups per thread of NARR arrays: (u, v) for the binary losses, (y, F, h) otherwise.
+template <int LOSS>
+struct LsTraits {
+  static constexpr bool kPacked = (LOSS == SE_LOSS_BERNOULLI || LOSS == SE_LOSS_EXPONENTIAL);
+  static constexpr int kNarr = kPacked ? 2 : 3;
+  static constexpr int kU = 2;
+  static constexpr int kTileBytes = kNarr * kU * kBlock * 16;
+};
+
+template <int LOSS>
+__global__ void __launch_bounds__(kBlock, 4) gbm_linesearch_persist_kernel(const LsArgs a) {
+  using T = LsTraits<LOSS>;
+  constexpr int U = T::kU, NARR = T::kNarr;
+  constexpr bool PACKED = T::kPacked;
+  extern __shared__ float4 s_tiles[];  // [resident][NARR][U][kBlock]
+  __shared__ double s_red[kBlock / 32];
+  __shared__ double s_x;
+  __shared__ int s_cmd;
+  const int W = (int)gridDim.x - 1;  // worker CTAs; the last CTA coordinates
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  if ((int)blockIdx.x == W) {
+    // ------------------------------------------------------------------ coordinator: warp 0, all lanes in lockstep
+    if (warp != 0) return;
+    int e = 0;
+    bool failed = false;
+    auto f = [&](double x) -> double {
+      ++e;
+      if (e > 1) {  // the first abscissa (start / the single point) is known to every worker at launch
+        if (lane == 0) {
+          a.sync->x = x;
+          a.sync->cmd = 0;
+          st_release_gpu_u64(&a.sync->flag, a.epoch0 + (unsigned long long)e);
+        }
+        __syncwarp();
+      }
+      const unsigned int want = (unsigned int)W * (unsigned int)e;
+      while (ld_acquire_gpu_u32(&a.sync->arrive) != want) {}
+      double s = 0.0;
+      for (int b = lane; b < W; b += 32) s += __ldcg(&a.partials[b]);  // fixed order: deterministic sums
+      s = warp_sum(s);
+      s = __shfl_sync(0xffffffffu, s, 0);
+      if (a.ws.nranks > 1 && a.ws.mbox != nullptr) {
+        RedWs ws = a.ws;
+        ws.seq = a.ws.seq + (unsigned long long)(e - 1);
+        double tot = s, g = 0.0;
+        const bool ok = peer_allreduce_warp(&tot, 1, ws, [&](int, double v) { g = v; });
+        s = __shfl_sync(0xffffffffu, g, 0);
+        if (!ok) failed = true;
+      }
+      return s / a.wsum;  // dim == 1: lossSum / weightSum (GBMLoss.scala:60-65)
+    };
+    double x = a.start, fx = 0.0;
+    int evals = 0, rc = kBrentOk;
+    if (a.single) {
+      fx = f(a.start);
+      evals = 1;
+    } else {
+      // a dead peer turns every further sum into NaN: stop the search instead of waiting MaxEval timeouts
+      auto guarded = [&](double xx) -> double { return failed ? __longlong_as_double(0x7ff8000000000000ll) : f(xx); };
+      rc = brent_core(guarded, a.lo, a.hi, a.start, a.rel, a.abs_tol, failed ? 1 : a.max_eval, &x, &fx, &evals);
+    }
+    if (lane == 0) {
+      a.sync->cmd = 1;  // stop
+      a.sync->arrive = 0;
+      st_release_gpu_u64(&a.sync->flag, a.epoch0 + (unsigned long long)(e + 1));
+      const double ne = (rc == kBrentOk) ? (double)evals : -(double)evals;
+      a.out[0] = x, a.out[1] = fx, a.out[2] = ne, a.out[3] = (double)e;
+      if (a.ws.host_out) {
+        a.ws.host_out[0] = x, a.ws.host_out[1] = fx, a.ws.host_out[2] = ne, a.ws.host_out[3] = (double)e;
+        __threadfence_system();
+        *a.ws.host_flag = a.ws.host_ticket;
+      }
+    }
+    return;
+  }
+
+  // -------------------------------------------------------------------- workers
+  const int64_t n4 = a.n >> 2;
+  constexpr int64_t tile = (int64_t)kBlock * U;
+  const int64_t ntiles = (n4 + tile - 1) / tile;
+  const int64_t cnt = (ntiles > (int64_t)blockIdx.x) ? (ntiles - 1 - blockIdx.x) / W + 1 : 0;  // tiles b, b+W, ...
+  const int64_t R = cnt < a.resident_tiles ? cnt : a.resident_tiles;                           // kept in shared memory
+  const float param = a.param;
+  const uint64_t pol_keep = l2_policy(false);
+
+  auto row_loss = [&](float c0, float c1, float c2, float coef) -> float {
+    // PACKED: (u, v): label 1 => (2y-1) == 1;  otherwise (y, F, h)
+    if constexpr (PACKED) return eval_loss<LOSS>(1.0f, fmaf(coef, c1, c0), param).l;
+    else return eval_loss<LOSS>(c0, fmaf(coef, c2, c1), param).l;
+  };
+
+  for (int e = 1;; ++e) {
+    float4 reg[NARR][U];
+    bool ok[U];
+    const int dir = (a.first_parity + e) & 1;
+    const bool first = (e == 1);
+    // issue the loads of the first streamed tile, then wait for the abscissa
+    auto stream_index = [&](int64_t k) { return dir ? (cnt - 1 - k) : (R + k); };  // k-th streamed tile of this pass
+    const int64_t nstream = cnt - R;
+    auto load_tile = [&](int64_t i, bool from_source) {
+      const int64_t base = (blockIdx.x + i * (int64_t)W) * tile + tid;
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int64_t g = base + (int64_t)u * kBlock;
+        ok[u] = g < n4;
+        if (!ok[u]) continue;
+        if (PACKED && !from_source) {
+          reg[0][u] = ld_rw4(a.u + 4 * g);  // written by this very thread in the first evaluation
+          reg[1][u] = ld_rw4(a.v + 4 * g);
+        } else {
+          const float4 y4 = ld_stream4_p(a.y + 4 * g, pol_keep), F4 = ld_stream4_p(a.F + 4 * g, pol_keep),
+                       h4 = ld_stream4_p(a.h + 4 * g, pol_keep);
+          if constexpr (PACKED) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float ye = 2.0f * f4at(y4, q) - 1.0f;  // GBMLoss.scala:272,297
+              f4at(reg[0][u], q) = ye * f4at(F4, q);
+              f4at(reg[1][u], q) = ye * f4at(h4, q);
+            }
+          } else {
+            reg[0][u] = y4; reg[1][u] = F4; reg[NARR - 1][u] = h4;
+          }
+        }
+      }
+    };
+    if (nstream > 0) load_tile(stream_index(0), first || !PACKED);
+    double x;
+    if (first) {
+      x = a.start;
+    } else {
+      if (tid == 0) {
+        while (ld_acquire_gpu_u64(&a.sync->flag) != a.epoch0 + (unsigned long long)e) {}
+        s_cmd = a.sync->cmd;
+        s_x = a.sync->x;
+      }
+      __syncthreads();
+      if (s_cmd) return;
+      x = s_x;
+    }
+    const float coef = (float)x;  // same narrowing as se_gbm_linesearch_eval
+    double acc = 0.0;
+    // streamed tiles (the first one is already in registers)
+    for (int64_t k = 0; k < nstream; ++k) {
+      const int64_t i = stream_index(k);
+      const int64_t base = (blockIdx.x + i * (int64_t)W) * tile + tid;
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (!ok[u]) continue;
+        const int64_t g = base + (int64_t)u * kBlock;
+        if (PACKED && first) {
+          st_stream4_p(a.u + 4 * g, reg[0][u], pol_keep);
+          st_stream4_p(a.v + 4 * g, reg[1][u], pol_keep);
+        }
+        float l = 0.f;
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          l += row_loss(f4at(reg[0][u], q), f4at(reg[1][u], q), f4at(reg[NARR - 1][u], q), coef);
+        acc += (double)l;
+      }
+      if (k + 1 < nstream) load_tile(stream_index(k + 1), first || !PACKED);
+    }
+    // resident tiles: filled in the first evaluation, served from shared memory afterwards
+    for (int64_t i = 0; i < R; ++i) {
+      float4* st = s_tiles + (size_t)i * NARR * U * kBlock;
+      if (first) {
+        load_tile(i, true);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+#pragma unroll
+          for (int c = 0; c < NARR; ++c)
+            if (ok[u]) st[(c * U + u) * kBlock + tid] = reg[c][u];
+        }
+      } else {
+        const int64_t base = (blockIdx.x + i * (int64_t)W) * tile + tid;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          ok[u] = base + (int64_t)u * kBlock < n4;
+#pragma unroll
+          for (int c = 0; c < NARR; ++c)
+            if (ok[u]) reg[c][u] = st[(c * U + u) * kBlock + tid];
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (!ok[u]) continue;
+        float l = 0.f;
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          l += row_loss(f4at(reg[0][u], q), f4at(reg[1][u], q), f4at(reg[NARR - 1][u], q), coef);
+        acc += (double)l;
+      }
+    }
+    if (blockIdx.x == 0 && tid < (a.n & 3)) {  // scalar tail (n % 4 rows), always from the source arrays
+      const int64_t j = (n4 << 2) + tid;
+      if constexpr (PACKED) {
+        const float ye = 2.0f * a.y[j] - 1.0f;
+        acc += (double)row_loss(ye * a.F[j], ye * a.h[j], 0.f, coef);
+      } else {
+        acc += (double)row_loss(a.y[j], a.F[j], a.h[j], coef);
+      }
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) s_red[warp] = acc;
+    __syncthreads();
+    if (warp == 0) {
+      double v = (lane < kBlock / 32) ? s_red[lane] : 0.0;
+      v = warp_sum(v);
+      if (lane == 0) {
+        a.partials[blockIdx.x] = v;
+        __threadfence();
+        red_release_gpu_add_u32(&a.sync->arrive, 1u);
+      }
+    }
+    __syncthreads();  // s_red / s_x / s_cmd are reused by the next evaluation
+  }
+}
+
+template <int LOSS>
+cudaError_t launch_ls(const LsArgs& a0, int sms, const LsLaunch& cfg, cudaStream_t st, int* workers_out) {
+  using T = LsTraits<LOSS>;
+  auto kern = gbm_linesearch_persist_kernel<LOSS>;
+  static int max_smem = -1, blocks_full = -1;
+  static size_t smem_cap = 0;
+  if (max_smem < 0) {
+    int dev = 0, optin = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
+    if (e != cudaSuccess) return e;
+    max_smem = optin;
+    // co-resident CTAs per SM are bounded by registers / threads (4 by __launch_bounds__): share the SM's shared
+    // memory between them
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_full, kern, kBlock, 0);
+    if (e != cudaSuccess) return e;
+    if (blocks_full < 1) return cudaErrorLaunchOutOfResources;
+    int per_sm = 0;
+    cudaDeviceGetAttribute(&per_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
+    smem_cap = (size_t)per_sm;
+  }
+  LsArgs a = a0;
+  int per_sm_ctas = blocks_full > cfg.max_ctas_per_sm ? cfg.max_ctas_per_sm : blocks_full;
+  if (per_sm_ctas < 1) per_sm_ctas = 1;
+  const int64_t ntiles = ((a.n >> 2) + (int64_t)kBlock * T::kU - 1) / ((int64_t)kBlock * T::kU);
+  int64_t workers = (int64_t)per_sm_ctas * sms - 1;
+  if (workers > ntiles) workers = ntiles;
+  if (workers < 1) workers = 1;
+  if (workers > kMaxGridPartials) workers = kMaxGridPartials;
+  // shared-memory budget per CTA: the SM's capacity split between the co-resident CTAs (1 KB reserved per CTA)
+  int64_t budget = (int64_t)smem_cap / per_sm_ctas - 1024 - 256;
+  if (budget > max_smem) budget = max_smem;
+  int64_t resident = cfg.resident ? budget / T::kTileBytes : 0;
+  const int64_t per_cta = (ntiles + workers - 1) / workers;
+  if (resident > per_cta) resident = per_cta;
+  if (resident < 0) resident = 0;
+  a.resident_tiles = (int)resident;
+  const size_t dyn = (size_t)resident * T::kTileBytes;
+  // the occupancy with this much dynamic shared memory must still cover the grid (cooperative launch would fail)
+  int blocks = 0;
+  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, kern, kBlock, dyn);
+  if (e != cudaSuccess) return e;
+  if ((int64_t)blocks * sms < workers + 1) return cudaErrorCooperativeLaunchTooLarge;
+  cudaLaunchConfig_t lc = {};
+  lc.gridDim = dim3((unsigned)(workers + 1));
+  lc.blockDim = dim3(kBlock);
+  lc.dynamicSmemBytes = dyn;
+  lc.stream = st;
+  cudaLaunchAttribute attrs[2];
+  int na = 0;
+  attrs[na].id = cudaLaunchAttributeCooperative;
+  attrs[na].val.cooperative = 1;
+  ++na;
+  if (cfg.window_bytes > 0 && cfg.window_base != nullptr) {
+    attrs[na].id = cudaLaunchAttributeAccessPolicyWindow;
+    attrs[na].val.accessPolicyWindow.base_ptr = cfg.window_base;
+    attrs[na].val.accessPolicyWindow.num_bytes = cfg.window_bytes;
+    attrs[na].val.accessPolicyWindow.hitRatio = cfg.hit_ratio;
+    attrs[na].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    attrs[na].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    ++na;
+  }
+  lc.attrs = attrs;
+  lc.numAttrs = na;
+  if (workers_out) *workers_out = (int)workers;
+  return cudaLaunchKernelEx(&lc, kern, a);
+}
+
+}  // namespace
+
+cudaError_t launch_gbm_round_sq_fused(const SqRoundArgs& a, int write_r, int sms, int max_ctas_per_sm, cudaStream_t st,
+                                      int* grid_out) {
+  static int blocks_r = -1, blocks_n = -1;
+  if (blocks_r < 0) {
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_r, gbm_round_sq_fused_kernel<true>, kBlock, 0);
+    if (e != cudaSuccess) return e;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_n, gbm_round_sq_fused_kernel<false>, kBlock, 0);
+    if (e != cudaSuccess) return e;
+  }
+  int per_sm = write_r ? blocks_r : blocks_n;
+  if (per_sm > max_ctas_per_sm) per_sm = max_ctas_per_sm;
+  if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+  const int64_t ntiles = ((a.n >> 2) + (int64_t)kBlock * U_SQ - 1) / ((int64_t)kBlock * U_SQ);
+  int64_t grid = (int64_t)per_sm * sms;
+  if (grid > ntiles) grid = ntiles;
+  if (grid < 1) grid = 1;
+  if (grid > kMaxGridPartials / 2) grid = kMaxGridPartials / 2;
+  cudaLaunchConfig_t lc = {};
+  lc.gridDim = dim3((unsigned)grid);
+  lc.blockDim = dim3(kBlock);
+  lc.dynamicSmemBytes = 0;
+  lc.stream = st;
+  cudaLaunchAttribute attr;
+  attr.id = cudaLaunchAttributeCooperative;
+  attr.val.cooperative = 1;  // co-residency of all CTAs is what makes the in-kernel flag wait deadlock-free
+  lc.attrs = &attr;
+  lc.numAttrs = 1;
+  if (grid_out) *grid_out = (int)grid;
+  if (write_r) return cudaLaunchKernelEx(&lc, gbm_round_sq_fused_kernel<true>, a);
+  return cudaLaunchKernelEx(&lc, gbm_round_sq_fused_kernel<false>, a);
+}
+
+bool gbm_linesearch_persist_supported(int loss) {
+  switch (loss) {
+    case SE_LOSS_ABSOLUTE: case SE_LOSS_HUBER: case SE_LOSS_QUANTILE: case SE_LOSS_LOGCOSH:
+    case SE_LOSS_SCALED_LOGCOSH: case SE_LOSS_BERNOULLI: case SE_LOSS_EXPONENTIAL: return true;
+    default: return false;
+  }
+}
+
+bool gbm_linesearch_persist_packed(int loss) { return loss == SE_LOSS_BERNOULLI || loss == SE_LOSS_EXPONENTIAL; }
+
+cudaError_t launch_gbm_linesearch_persist(int loss, const LsArgs& a, int sms, const LsLaunch& cfg, cudaStream_t st,
+                                          int* workers_out) {
+  switch (loss) {
+    case SE_LOSS_ABSOLUTE: return launch_ls<SE_LOSS_ABSOLUTE>(a, sms, cfg, st, workers_out);
+    case SE_LOSS_HUBER: return launch_ls<SE_LOSS_HUBER>(a, sms, cfg, st, workers_out);
+    case SE_LOSS_QUANTILE: return launch_ls<SE_LOSS_QUANTILE>(a, sms, cfg, st, workers_out);
+    case SE_LOSS_LOGCOSH: return launch_ls<SE_LOSS_LOGCOSH>(a, sms, cfg, st, workers_out);
+    case SE_LOSS_SCALED_LOGCOSH: return launch_ls<SE_LOSS_SCALED_LOGCOSH>(a, sms, cfg, st, workers_out);
+    case SE_LOSS_BERNOULLI: return launch_ls<SE_LOSS_BERNOULLI>(a, sms, cfg, st, workers_out);
+    case SE_LOSS_EXPONENTIAL: return launch_ls<SE_LOSS_EXPONENTIAL>(a, sms, cfg, st, workers_out);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+}  // namespace se

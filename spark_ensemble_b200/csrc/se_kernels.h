@@ -70,6 +70,73 @@ cudaError_t launch_brent_parabola(const double* stats, double wsum, double lo, d
 // squared-loss round result: out[0] = alpha*, computed on device from stats (for se_gbm_round_result)
 cudaError_t launch_sq_alpha(const double* stats, double* out_alpha, cudaStream_t stream);
 
+// ---- whole-round / whole-line-search cooperative kernels (se_gbm_fused.cu) ----------------------
+// Device-side rendezvous of the cooperative kernels (owned by the context, zero-initialised).
+struct FusedSync {
+  unsigned long long flag;  // epoch published by the coordinating CTA / warp (monotonic across launches)
+  double x;                 // published with the flag: the step (round kernel) or the next abscissa (line search)
+  int cmd;                  // line search: 0 = evaluate x, 1 = stop
+  int pad;
+  unsigned int arrive;      // line search: worker arrival counter (reset by the coordinator)
+  unsigned int counter_b;   // round kernel: ticket of the second (loss) reduction
+};
+
+// One squared-loss boosting round in one launch: statistics -> (cross-GPU sum) -> Brent -> update + residual + loss.
+struct SqRoundArgs {
+  const float* y = nullptr;
+  float* F = nullptr;
+  const float* h = nullptr;
+  float* r = nullptr;
+  const float* bag = nullptr;  // nullable: bag multiplicities for the line-search statistics
+  int64_t n = 0;
+  int stats_from_r = 0;
+  int l2_hints = 0;
+  double lr = 1.0, wsum = 1.0;                                   // learning rate, Σw (objective scale)
+  double lo = 0.0, hi = 100.0, start = 1.0, rel = 1e-6, abs_tol = 1e-6;
+  int max_eval = 100;
+  RedWs ws_a{};  // statistics: out = `out`, no host mirror
+  RedWs ws_b{};  // loss: out = out + 8, host mirror + ticket
+  double* out = nullptr;       // [0..2] statistics, [4] alpha, [5] objective, [6] +-evaluations, [8] Σloss
+  double* host_res = nullptr;  // mapped host copy of out[0..6] (nullable)
+  FusedSync* sync = nullptr;
+  unsigned long long epoch = 0;
+};
+cudaError_t launch_gbm_round_sq_fused(const SqRoundArgs& a, int write_r, int sms, int max_ctas_per_sm, cudaStream_t stream,
+                                      int* grid_out);
+
+// Brent's whole line search for a dim-1 scalar loss in one launch (persistent workers + coordinator warp).
+struct LsArgs {
+  const float* y = nullptr;
+  const float* F = nullptr;
+  const float* h = nullptr;
+  float* u = nullptr;  // binary losses: signed view written by the first evaluation, read by the others
+  float* v = nullptr;
+  int64_t n = 0;
+  float param = 0.f;
+  double wsum = 1.0;
+  double lo = 0.0, hi = 100.0, start = 1.0, rel = 1e-6, abs_tol = 1e-6;
+  int max_eval = 100;
+  int single = 0;        // evaluate the objective at `start` once (host-driven search over the same kernel)
+  int first_parity = 0;  // tile direction of evaluation e is (first_parity + e) & 1
+  int resident_tiles = 0;
+  double* partials = nullptr;
+  FusedSync* sync = nullptr;
+  unsigned long long epoch0 = 0;
+  RedWs ws{};            // peer exchange (seq = sequence of the FIRST evaluation) and host mirror
+  double* out = nullptr; // [0] alpha, [1] objective, [2] +-evaluations (negative: MaxEval exceeded), [3] passes run
+};
+struct LsLaunch {
+  int max_ctas_per_sm = 4;
+  int resident = 1;             // keep each worker's first tiles in shared memory
+  void* window_base = nullptr;  // L2 access-policy window (persisting) over the packed view
+  size_t window_bytes = 0;
+  float hit_ratio = 0.f;
+};
+bool gbm_linesearch_persist_supported(int loss);
+bool gbm_linesearch_persist_packed(int loss);
+cudaError_t launch_gbm_linesearch_persist(int loss, const LsArgs& a, int sms, const LsLaunch& cfg, cudaStream_t stream,
+                                          int* workers_out);
+
 // ---- Boosting (se_boost.cu) ------------------------------------------------------------------
 struct BoostArgs {
   const float* y = nullptr;

@@ -112,6 +112,72 @@ def main():
     assert abs(mx - orc.r2_max_error(v, pr)) <= 1e-6 * mx
     e2 = ctx.boostreg_error(sw, "exponential", mx)
     assert abs(e2 - orc.r2_estimator_error("exponential", v, pr, wb, sw, mx)) <= RT * e2
+    # ---- cooperative kernels across shards: the cross-GPU sums happen INSIDE the running kernel (peer mailboxes)
+    import time
+    if p2p:
+        n2 = 1_000_003
+        for name in ("squared", "bernoulli", "absolute"):
+            lid = O.LOSS_IDS[name]
+            y = (rng.standard_normal(n2) if name != "bernoulli" else (rng.random(n2) < 0.4)).astype(np.float32)
+            F = (0.5 * rng.standard_normal((1, n2))).astype(np.float32)
+            r0, _, _ = orc.pseudo_residuals(lid, 0.0, 1, y, None, F, False)
+            h = (0.6 * r0 + 0.2 * rng.standard_normal((1, n2))).astype(np.float32)
+            s0, s1 = row_partition(n2, world, rank)
+            ctx.gbm_configure(s1 - s0, 0, 1, name, 0.0, False)
+            ctx.upload(N.SLOT_Y, y[s0:s1]); ctx.upload(N.SLOT_F, np.ascontiguousarray(F[:, s0:s1]))
+            ctx.upload(N.SLOT_H, np.ascontiguousarray(h[:, s0:s1]))
+            f = lambda x: orc.linesearch_eval(lid, 0.0, y, None, F, h, [x])[0]
+            ao, neo, st = orc.brent(f)
+            assert st == 0
+            if name == "squared":
+                ctx.set_option("fused_round", 1)
+                a, ls, ne = ctx.gbm_round(0.5, True, 1e-6, 100, residual=True)
+                assert ctx.get_option("last_round_fused") == 1
+                ctx.set_option("fused_round", -1)
+                assert abs(a - ao) <= 1e-5 * abs(ao) + 4e-6, (a, ao)
+                Fo = F.astype(np.float64).copy()
+                orc.update(Fo, h, [0.5 * a])
+                lo = orc.mean_loss(lid, 0.0, 1, y, Fo) * n2
+                assert abs(ls - lo) <= RT * abs(lo), (ls, lo)
+                assert np.max(np.abs(ctx.download(N.SLOT_F) - Fo[0, s0:s1])) <= RT * max(1.0, np.abs(Fo).max())
+                # every rank must hold the SAME alpha bit for bit (rank-ordered sums in the mailboxes)
+                t = torch.tensor([a], dtype=torch.float64, device="cuda")
+                tl = [torch.zeros_like(t) for _ in range(world)]
+                dist.all_gather(tl, t)
+                assert all(float(x) == a for x in tl), [float(x) for x in tl]
+            else:
+                ctx.set_option("ls_mode", 1)
+                dev = ctx.gbm_linesearch_brent()
+                ctx.set_option("ls_mode", 2)
+                host = ctx.gbm_linesearch_brent()
+                ctx.set_option("ls_mode", 1)
+                assert dev == host, (name, dev, host)
+                assert abs(dev[1] - f(ao)) <= RT * abs(f(ao)), (name, dev, f(ao))
+                assert f(dev[0]) <= f(ao) * (1 + 1e-5)
+        # ---- skewed ranks: a late rank inside the (configurable) bound is simply waited for ...
+        ctx.alloc(N.SLOT_BW, 1000)
+        ctx.fill(N.SLOT_BW, 1.0)
+        ctx.set_option("peer_timeout_ms", 20000.0)
+        dist.barrier()
+        if rank == world - 1:
+            time.sleep(4.0)  # longer than round 1's hard-coded 3 s bound
+        assert ctx.slot_sum(N.SLOT_BW) == 1000.0 * world
+        # ... and one beyond it fails the SAME reduction on every rank (poisoned mailbox rows), then recovers
+        ctx.set_option("peer_timeout_ms", 300.0)
+        dist.barrier()
+        if rank == world - 1:
+            time.sleep(2.0)
+        failed = False
+        try:
+            ctx.slot_sum(N.SLOT_BW)
+        except N.NativeError as e:
+            failed = "peer-memory all-reduce failed" in str(e)
+        assert failed, "a reduction whose peer never showed up in time must fail on every rank"
+        dist.barrier()
+        ctx.comm_clear_error()
+        ctx.set_option("peer_timeout_ms", 20000.0)
+        dist.barrier()
+        assert ctx.slot_sum(N.SLOT_BW) == 1000.0 * world
     dist.barrier()
     if rank == 0:
         print(f"MGPU_PARITY_OK world={world} p2p_allreduce={p2p}")

@@ -757,6 +757,7 @@ def test_gbm_round_single_call(ctx, oracle, rng):
     """se_gbm_round == se_gbm_linesearch_brent + se_gbm_update."""
     from spark_ensemble_b200 import _native as N
     n = 30011
+    ctx.set_option("fused_round", 0)  # the one-launch round has its own test (different reduction grids)
     for name in ("squared", "bernoulli"):
         dim, par, y, F, h, w = setup_gbm(ctx, rng, name, n)
         a1, l1, ne1 = ctx.gbm_round(0.5, True, 1e-6, 100, residual=True)
@@ -769,6 +770,7 @@ def test_gbm_round_single_call(ctx, oracle, rng):
         np.testing.assert_array_equal(r1, ctx.download(N.SLOT_R))
         a3, l3, ne3 = ctx.gbm_round(0.5, False)
         assert (a3, ne3) == (1.0, 0)
+    ctx.set_option("fused_round", -1)
 
 
 def test_device_brent_matches_host_brent(oracle, rng, monkeypatch):
@@ -780,6 +782,7 @@ def test_device_brent_matches_host_brent(oracle, rng, monkeypatch):
     from spark_ensemble_b200.context import Context
     monkeypatch.setenv("SE_ALTERNATE_PASSES", "0")  # one tile direction: sums do not depend on the call history
     c = Context(0)
+    c.set_option("fused_round", 0)  # compare the three-launch device search with the two-launch host search
     try:
         n = 50021
         for case, (scale, shift, tol) in enumerate([(1.0, 0.0, 1e-6), (0.01, 0.0, 1e-6), (-1.0, 0.0, 1e-6),
@@ -853,6 +856,7 @@ def test_brent_packed_line_search_view_is_bit_identical(oracle, rng, name, weigh
     from spark_ensemble_b200.context import Context
     monkeypatch.setenv("SE_ALTERNATE_PASSES", "0")
     ctx = Context(0)
+    ctx.set_option("ls_mode", 0)  # the one-launch-per-evaluation path (the persistent search has its own test)
     try:
         _packed_vs_plain(ctx, oracle, rng, name, weighted_bag, monkeypatch, N)
     finally:
@@ -909,3 +913,154 @@ def test_libsvm_to_device_ingest(ctx, rng, tmp_path):
     labels = load_libsvm_to_device(ctx, N.SLOT_X, str(p), d, block_rows=250)
     np.testing.assert_array_equal(labels, y)
     np.testing.assert_array_equal(ctx.download(N.SLOT_X).reshape(d, n), X.T)
+
+
+# ------------------------------------------------------------------ cooperative whole-round / whole-search kernels
+def _host_brent(fn, rel=1e-6, abs_tol=1e-6, max_eval=100):
+    """The product's host Brent (se_brent_minimize) over a Python objective."""
+    import ctypes
+    from spark_ensemble_b200 import _native as N
+    lib = N.load()
+    cb = N.FN1(lambda x, _u: float(fn(x)))
+    x, f, ne = ctypes.c_double(), ctypes.c_double(), ctypes.c_int()
+    rc = lib.se_brent_minimize(cb, None, 0.0, 100.0, 1.0, rel, abs_tol, max_eval, ctypes.byref(x), ctypes.byref(f),
+                               ctypes.byref(ne))
+    return rc, x.value, f.value, ne.value
+
+
+@pytest.mark.parametrize("n", [1, 5, 1023, 4096, 100003, 1200007])
+@pytest.mark.parametrize("weighted", [False, True])
+def test_fused_squared_round(ctx, oracle, rng, n, weighted):
+    """se_gbm_round as ONE cooperative launch (statistics -> Brent on the device -> update + residual + loss):
+    statistics, F, r and the loss against the fp64 oracle (1e-5), and the in-kernel Brent against the host Brent
+    (same template) on the kernel's own statistics: alpha and the evaluation count bit for bit."""
+    from spark_ensemble_b200 import _native as N
+    dim, par, y, F, h, w = setup_gbm(ctx, rng, "squared", n, weighted)
+    h = f32((y - F[0]) * 0.6 + 0.2 * rng.standard_normal(n)).reshape(1, n)
+    ctx.upload(N.SLOT_H, h)
+    ws = float(np.sum(w.astype(np.float64))) if weighted else float(n)
+    ws_dev = ctx.gbm_linesearch_stats()[3]
+    assert ws_dev == pytest.approx(ws, rel=1e-12)
+    ctx.set_option("fused_round", 1)
+    try:
+        Fo = F.astype(np.float64).copy()
+        hh = h[0].astype(np.float64)
+        for rnd in range(3):  # round 0 reads (y, F, h); later rounds read the residual slot (8 B/row)
+            a, ls, ne = ctx.gbm_round(0.7, True, 1e-6, 100, residual=True)
+            assert ctx.get_option("last_round_fused") == 1
+            s = [ctx.get_option(f"last_round_stat{i}") for i in range(3)]
+            d = y.astype(np.float64) - Fo[0]
+            close(s, [np.sum(d * d), np.sum(hh * d), np.sum(hh * hh)], scale=1e-30)
+            rc, xh, fh, neh = _host_brent(lambda x: (s[0] - 2.0 * x * s[1] + x * x * s[2]) / (2.0 * ws_dev))
+            assert rc == 0 and (a, ne) == (xh, neh), (rnd, a, xh, ne, neh)
+            oracle.update(Fo, h, [0.7 * a])
+            close(ctx.download(N.SLOT_F), Fo[0])
+            ro, _, _ = oracle.pseudo_residuals(O.SQUARED, 0.0, 1, y, None, Fo, False)
+            close(ctx.download(N.SLOT_R), ro[0], scale=1.0)
+            assert ls / n == pytest.approx(oracle.mean_loss(O.SQUARED, 0.0, 1, y, Fo), rel=RTOL)
+        # the two-launch path on the same state agrees to rounding of the fp64 sums
+        Fnow = ctx.download(N.SLOT_F).copy()
+        a1, l1, ne1 = ctx.gbm_round(0.7, True, 1e-6, 100, residual=True)
+        F1 = ctx.download(N.SLOT_F).copy()
+        ctx.upload(N.SLOT_F, Fnow)
+        ctx.set_option("fused_round", 0)
+        a2, l2, ne2 = ctx.gbm_round(0.7, True, 1e-6, 100, residual=True)
+        assert ctx.get_option("last_round_fused") == 0
+        assert a1 == pytest.approx(a2, rel=1e-9, abs=1e-12) and l1 == pytest.approx(l2, rel=1e-9)
+        close(F1, ctx.download(N.SLOT_F), rtol=1e-6)
+        # MaxEval exceeded: SE_ERR_OPT (TooManyEvaluationsException in the reference) and F is left untouched
+        ctx.set_option("fused_round", 1)
+        Fbefore = ctx.download(N.SLOT_F).copy()
+        if n > 5:
+            with pytest.raises(N.ConvergenceError):
+                ctx.gbm_round(0.7, True, 1e-12, 2, residual=True)
+            np.testing.assert_array_equal(Fbefore, ctx.download(N.SLOT_F))
+    finally:
+        ctx.set_option("fused_round", -1)
+
+
+def test_fused_squared_round_with_bag(ctx, oracle, rng):
+    from spark_ensemble_b200 import _native as N
+    n = 50007
+    dim, par, y, F, h, w = setup_gbm(ctx, rng, "squared", n, True)
+    bag = rng.poisson(1.0, n).astype(np.float32)
+    ctx.gbm_set_bag(bag)
+    ctx.set_option("fused_round", 1)
+    try:
+        a, ls, ne = ctx.gbm_round(0.5, True, 1e-6, 100, residual=True)
+    finally:
+        ctx.set_option("fused_round", -1)
+    c = bag.astype(np.float64); d = y.astype(np.float64) - F[0]; hh = h[0].astype(np.float64)
+    star = float(np.clip(np.sum(c * hh * d) / np.sum(c * hh * hh), 0, 100))  # the line search runs on the bag (quirk 4)
+    assert a == pytest.approx(star, rel=1e-5, abs=2e-6)
+    Fo = F.astype(np.float64).copy(); oracle.update(Fo, h, [0.5 * a])
+    close(ctx.download(N.SLOT_F), Fo[0])                                      # the update on all rows
+    assert ls / n == pytest.approx(oracle.mean_loss(O.SQUARED, 0.0, 1, y, Fo), rel=RTOL)
+    ctx.gbm_configure(4, 0, 1, "squared", 0.0, False)  # drops the bag for the tests that follow
+
+
+LS_LOSSES = ["absolute", "huber", "quantile", "logcosh", "scaledlogcosh", "bernoulli", "exponential"]
+
+
+@pytest.mark.parametrize("name", LS_LOSSES)
+@pytest.mark.parametrize("n,ctas,resident", [(3, 4, 1), (2049, 4, 1), (40013, 4, 1), (700001, 1, 0), (700001, 1, 1),
+                                             (2000003, 2, 1)])
+def test_device_line_search_matches_host_brent(ctx, oracle, rng, name, n, ctas, resident):
+    """Brent's whole line search in ONE persistent launch (workers + coordinator warp, tiles resident in shared
+    memory, the first evaluation builds the signed view of the binary losses).  ls_mode 2 runs the HOST Brent over
+    single-evaluation launches of the same kernel: alpha, the objective and the evaluation count must be identical
+    bit for bit.  Against the oracle: the objective value at the minimiser within 1e-5."""
+    from spark_ensemble_b200 import _native as N
+    dim, par, y, F, h, w = setup_gbm(ctx, rng, name, n, weighted=(n % 2 == 0))
+    lid = O.LOSS_IDS[name]
+    r, _, _ = oracle.pseudo_residuals(lid, par, 1, y, None, F, False)
+    h = f32(0.6 * r + 0.2 * rng.standard_normal((1, n)))
+    ctx.upload(N.SLOT_H, h)
+    ctx.set_option("ls_ctas_per_sm", ctas)
+    ctx.set_option("ls_resident", resident)
+    try:
+        ctx.set_option("ls_mode", 1)
+        dev = ctx.gbm_linesearch_brent()
+        passes = ctx.get_option("last_ls_passes")
+        assert passes == dev[2] and ctx.get_option("last_ls_workers") >= 1
+        dev_again = ctx.gbm_linesearch_brent()
+        assert dev_again == dev  # deterministic: fixed tile ownership, fixed reduction order
+        ctx.set_option("ls_mode", 2)
+        host = ctx.gbm_linesearch_brent()
+        assert dev == host, (dev, host)
+        ctx.set_option("ls_mode", 0)
+        old = ctx.gbm_linesearch_brent()
+        assert old[1] == pytest.approx(dev[1], rel=1e-6)
+        if n <= 700001:
+            f = lambda x: oracle.linesearch_eval(lid, par, y, w, F, h, [x])[0]
+            ao, neo, st = oracle.brent(f)
+            assert st == 0
+            assert dev[1] == pytest.approx(f(ao), rel=RTOL)
+            assert f(dev[0]) <= f(ao) * (1 + 1e-5)
+        ctx.set_option("ls_mode", 1)
+        if n > 3:
+            with pytest.raises(N.ConvergenceError):
+                ctx.gbm_linesearch_brent(0.0, 100.0, 1.0, 1e-12, 1e-12, 3)
+            assert ctx.gbm_linesearch_brent() == dev  # the failed search left the rendezvous state clean
+        # the update that follows must see untouched (y, F, h)
+        ls, _ = ctx.gbm_update([0.5 * dev[0]], residual=True, loss=True)
+        Fo = F.astype(np.float64).copy(); oracle.update(Fo, h, [0.5 * dev[0]])
+        assert ls / n == pytest.approx(oracle.mean_loss(lid, par, 1, y, Fo), rel=RTOL)
+    finally:
+        ctx.set_option("ls_mode", 1)
+        ctx.set_option("ls_ctas_per_sm", 4)
+        ctx.set_option("ls_resident", 1)
+
+
+def test_options_roundtrip(ctx):
+    from spark_ensemble_b200 import _native as N
+    for key, val in (("fused_round", 1), ("ls_mode", 2), ("peer_timeout_ms", 2500.0), ("l2_persist_frac", 0.5)):
+        old = ctx.get_option(key)
+        ctx.set_option(key, val)
+        assert ctx.get_option(key) == val
+        ctx.set_option(key, old)
+    with pytest.raises(ValueError):
+        ctx.set_option("no_such_option", 1)
+    with pytest.raises(ValueError):
+        ctx.set_option("last_round_fused", 1)  # read-only
+    assert ctx.get_option("l2_persist_max_bytes") >= 0
