@@ -128,7 +128,7 @@ def _pinned_array(n: int):
 
 
 # ------------------------------------------------------------------ CPU arm (oracle port)
-def cpu_reference_round(orc, y, F, h, r_buf, lr=0.5, tol=1e-6, max_iter=100):
+def cpu_reference_round(orc, y, F, h, r_buf, lr=0.1, tol=1e-6, max_iter=100):
     """One reference round on the CPU: Brent with a full pass per evaluation (GBMLoss.scala:50-74 via
     RDDLossFunction), F update, next pseudo-residuals, mean loss."""
     from oracle import oracle as O
@@ -271,7 +271,8 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     workload = (f"GBMRegressor boosting iteration (Brent line search + fused F update / next pseudo-residuals / "
-                f"loss), squared loss, {args.rows} rows x {args.features} features fp32 per GPU, synthetic")
+                f"loss), squared loss, {args.rows} rows x {args.features} features fp32 per GPU, synthetic; "
+                f"direction h = 0.5*y + 0.5*N(0,1) (a base learner correlated with the label), learningRate 0.1")
 
     if args.impl == "reference":
         if rank != 0:
@@ -315,15 +316,24 @@ def main():
     eng = GBMEngine(ctx, n, 0, 1, "squared", 0.0, has_weights=False)
     seed = 1000 * (rank + 1)
     ctx.fill_synthetic(N.SLOT_Y, "normal", seed + 1, 0.0, 1.0)
-    ctx.fill(N.SLOT_F, 0.0)
-    ctx.fill_synthetic(N.SLOT_H, "normal", seed + 2, 0.0, 1.0)
+
+    def make_direction():
+        """h = 0.5*y + 0.5*N(0,1) built on the device with ABI calls only (same law as the CPU arm's direction):
+        F <- N(0, 0.5); H <- y; F <- F + 0.5*H; H <- F; F <- 0."""
+        ctx.fill_synthetic(N.SLOT_F, "normal", seed + 2, 0.0, 0.5)
+        ctx.copy_slot(N.SLOT_H, N.SLOT_Y)
+        ctx.gbm_update([0.5], residual=False, loss=False)
+        ctx.copy_slot(N.SLOT_H, N.SLOT_F)
+        ctx.fill(N.SLOT_F, 0.0)
+
+    make_direction()
     have_x = not args.no_features
     if have_x:
         ctx.alloc(N.SLOT_X, d, n)
         ctx.fill_synthetic(N.SLOT_X, "normal", seed + 3, 0.0, 1.0)
     ctx.gbm_pseudo_residuals(False)
     ctx.sync()
-    lr, tol, max_iter = 0.5, 1e-6, 100
+    lr, tol, max_iter = 0.1, 1e-6, 100
 
     def barrier():
         ctx.sync()
@@ -443,8 +453,15 @@ def main():
     def timed_rounds(n_rows, steps, loss="squared"):
         ctx.gbm_configure(n_rows, 0, 1, loss, 0.0, False)   # re-uses the resident slots (no reallocation)
         if loss != "squared":
+            # labels ~ Bernoulli(0.4); direction h = y + N(0, 0.5): correlated with the label like a fitted base learner
             ctx.fill_synthetic(N.SLOT_Y, "bernoulli", seed + 7, 0.4, 1.0)
-            ctx.fill(N.SLOT_F, 0.0)
+            ctx.fill_synthetic(N.SLOT_F, "normal", seed + 8, 0.0, 0.5)
+            ctx.copy_slot(N.SLOT_H, N.SLOT_Y)
+            ctx.set_option("fused_round", 0)
+            ctx.gbm_update([1.0], residual=False, loss=False)
+            ctx.set_option("fused_round", -1)
+            ctx.copy_slot(N.SLOT_H, N.SLOT_F)
+        ctx.fill(N.SLOT_F, 0.0)
         ctx.gbm_pseudo_residuals(False)
         for _ in range(3):
             ctx.gbm_round(lr if loss == "squared" else 0.1, True, tol, max_iter, residual=True)
@@ -490,7 +507,7 @@ def main():
         # the weak-scaling configuration itself (full shard per GPU, the round `value` was timed on)
         ctx.gbm_configure(n, 0, 1, "squared", 0.0, False)
         ctx.fill_synthetic(N.SLOT_Y, "normal", seed + 1, 0.0, 1.0)
-        ctx.fill(N.SLOT_F, 0.0)
+        make_direction()
         ctx.gbm_pseudo_residuals(False)
         ctx.gbm_round(lr, True, tol, max_iter, residual=True)
         parity.append(parity_check(ctx, n, lr, tol, max_iter, world, rank, dist, "weak shard (the timed configuration)"))

@@ -114,7 +114,7 @@ SE_API int se_ctx_kernel_timing(se_ctx* ctx, int on);
 SE_API int se_ctx_kernel_time(se_ctx* ctx, int family, double* total_ms, int64_t* launches);
 SE_API int se_ctx_kernel_time_reset(se_ctx* ctx);
 /* Tunables and diagnostics by name (doubles).  Settable: "fused_round" (-1 auto by shard size / 0 / 1: squared-loss
- * round in ONE cooperative launch), "fused_round_max_rows", "fused_ctas_per_sm", "ls_mode" (non-squared Brent line
+ * round in ONE cooperative launch), "fused_round_max_rows", "fused_ctas_per_sm", "fused_prefetch_mb", "ls_mode" (non-squared Brent line
  * search: 0 = one launch per evaluation, 1 = one persistent launch with Brent on the device [default], 2 = host Brent
  * over single-evaluation launches of the persistent kernel — bit-identical to 1, for tests), "ls_resident",
  * "ls_ctas_per_sm", "l2_persist", "l2_persist_frac", "peer_timeout_ms" (spin bound of the fused peer exchange,

@@ -178,12 +178,18 @@ struct se_ctx {
   int fused_round = -1;               // squared-loss round in one launch: -1 by shard size, 0 off, 1 on
   int64_t fused_round_max_rows = 40000000;
   int fused_ctas_per_sm = 3;
+  double fused_prefetch_mb = 0.0;     // (measured: no gain at 6-12 M rows, -2 % at 25-50 M rows: off)
+  int fused_timing = 0;               // diagnostic: in-kernel %globaltimer stamps of the fused round
+  double last_fused_us[3] = {0, 0, 0};  // statistics phase, fold+exchange+Brent, update phase    // L2 budget of the update-phase prefetch issued while the grid waits for the step
   int ls_mode = 1;                    // non-squared line search: 0 one launch per evaluation (round-1 kernels), 1 one
                                       // persistent launch (device Brent), 2 host Brent over single-evaluation launches of
                                       // the persistent kernel (bit-identity check of mode 1)
   int ls_resident = 1;                // workers keep their first tiles in shared memory
   int ls_ctas_per_sm = 4;
-  int l2_persist = 1;                 // mark the packed line-search view as L2-persisting
+  int l2_persist = 0;                 // mark the packed line-search view as L2-persisting.  OFF by default: measured on
+                                      // B200 the 83 MB carve-out buys the search nothing (2.86 vs 2.75 ms of evaluations per
+                                      // round at 50 M rows) and, while it is configured, every STREAMING kernel runs 2x slower
+                                      // (K1 0.36 vs 0.17 ms at 50 M rows) — profiles/r02_ls_sweep.json
   size_t l2_persist_max = 0;          // cudaDevAttrMaxPersistingL2CacheSize
   size_t l2_window_max = 0;           // cudaDevAttrMaxAccessPolicyWindowSize
   size_t l2_persist_set = 0;          // current cudaLimitPersistingL2CacheSize
@@ -466,6 +472,9 @@ int release_l2_persist(se_ctx* ctx) {
   if (!ctx->l2_persist_dirty) return SE_OK;
   ctx->l2_persist_dirty = false;
   cudaCtxResetPersistingL2Cache();
+  // the carve-out itself (not only the lines in it) slows streaming kernels down: give the L2 back
+  cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 0);
+  ctx->l2_persist_set = 0;
   cudaGetLastError();
   return SE_OK;
 }
@@ -746,13 +755,14 @@ int se_ctx_kernel_time_reset(se_ctx* ctx) {
 
 namespace {
 struct OptKey { const char* name; int id; };
-enum { OPT_FUSED_ROUND, OPT_FUSED_MAX_ROWS, OPT_FUSED_CTAS, OPT_LS_MODE, OPT_LS_RESIDENT, OPT_LS_CTAS, OPT_L2_PERSIST,
+enum { OPT_FUSED_TIMING, OPT_LAST_FUSED_US0, OPT_LAST_FUSED_US1, OPT_LAST_FUSED_US2, OPT_FUSED_PREFETCH_MB, OPT_FUSED_ROUND, OPT_FUSED_MAX_ROWS, OPT_FUSED_CTAS, OPT_LS_MODE, OPT_LS_RESIDENT, OPT_LS_CTAS, OPT_L2_PERSIST,
        OPT_L2_PERSIST_FRAC, OPT_PEER_TIMEOUT_MS, OPT_ALTERNATE, OPT_L2_HINTS, OPT_CTAS_PER_SM, OPT_HOST_MIRROR,
        // read-only diagnostics
        OPT_LAST_ROUND_FUSED, OPT_LAST_LS_WORKERS, OPT_LAST_LS_PASSES, OPT_LAST_LS_HIT_RATIO, OPT_LAST_FUSED_GRID,
        OPT_L2_PERSIST_MAX, OPT_L2_WINDOW_MAX, OPT_LAST_STAT0, OPT_LAST_STAT1, OPT_LAST_STAT2 };
 const OptKey kOpts[] = {
-  {"fused_round", OPT_FUSED_ROUND}, {"fused_round_max_rows", OPT_FUSED_MAX_ROWS}, {"fused_ctas_per_sm", OPT_FUSED_CTAS},
+  {"fused_timing", OPT_FUSED_TIMING}, {"last_fused_stats_us", OPT_LAST_FUSED_US0}, {"last_fused_brent_us", OPT_LAST_FUSED_US1},
+  {"last_fused_update_us", OPT_LAST_FUSED_US2}, {"fused_prefetch_mb", OPT_FUSED_PREFETCH_MB}, {"fused_round", OPT_FUSED_ROUND}, {"fused_round_max_rows", OPT_FUSED_MAX_ROWS}, {"fused_ctas_per_sm", OPT_FUSED_CTAS},
   {"ls_mode", OPT_LS_MODE}, {"ls_resident", OPT_LS_RESIDENT}, {"ls_ctas_per_sm", OPT_LS_CTAS}, {"l2_persist", OPT_L2_PERSIST},
   {"l2_persist_frac", OPT_L2_PERSIST_FRAC}, {"peer_timeout_ms", OPT_PEER_TIMEOUT_MS}, {"alternate_passes", OPT_ALTERNATE},
   {"l2_hints", OPT_L2_HINTS}, {"ctas_per_sm", OPT_CTAS_PER_SM}, {"host_mirror", OPT_HOST_MIRROR},
@@ -775,6 +785,8 @@ int se_ctx_set_option(se_ctx* ctx, const char* key, double value) {
   switch (opt_id(key)) {
     case OPT_FUSED_ROUND: ctx->fused_round = value < 0 ? -1 : (iv != 0); break;
     case OPT_FUSED_MAX_ROWS: ctx->fused_round_max_rows = (int64_t)value; break;
+    case OPT_FUSED_TIMING: ctx->fused_timing = iv != 0; break;
+    case OPT_FUSED_PREFETCH_MB: SE_REQUIRE(ctx, value >= 0.0 && value <= 512.0, SE_ERR_ARG, "fused_prefetch_mb in [0,512]"); ctx->fused_prefetch_mb = value; break;
     case OPT_FUSED_CTAS: SE_REQUIRE(ctx, iv >= 1 && iv <= 8, SE_ERR_ARG, "fused_ctas_per_sm in [1,8]"); ctx->fused_ctas_per_sm = iv; break;
     case OPT_LS_MODE: SE_REQUIRE(ctx, iv >= 0 && iv <= 2, SE_ERR_ARG, "ls_mode in {0,1,2}"); ctx->ls_mode = iv; break;
     case OPT_LS_RESIDENT: ctx->ls_resident = iv != 0; break;
@@ -796,6 +808,11 @@ int se_ctx_get_option(const se_ctx* ctx, const char* key, double* value) {
   switch (opt_id(key)) {
     case OPT_FUSED_ROUND: *value = ctx->fused_round; break;
     case OPT_FUSED_MAX_ROWS: *value = (double)ctx->fused_round_max_rows; break;
+    case OPT_FUSED_PREFETCH_MB: *value = ctx->fused_prefetch_mb; break;
+    case OPT_FUSED_TIMING: *value = ctx->fused_timing; break;
+    case OPT_LAST_FUSED_US0: *value = ctx->last_fused_us[0]; break;
+    case OPT_LAST_FUSED_US1: *value = ctx->last_fused_us[1]; break;
+    case OPT_LAST_FUSED_US2: *value = ctx->last_fused_us[2]; break;
     case OPT_FUSED_CTAS: *value = ctx->fused_ctas_per_sm; break;
     case OPT_LS_MODE: *value = ctx->ls_mode; break;
     case OPT_LS_RESIDENT: *value = ctx->ls_resident; break;
@@ -1532,6 +1549,7 @@ int linesearch_persist(se_ctx* ctx, double lo, double hi, double start, double r
   const int passes = (int)res[3];
   if (ctx->p2p && ctx->nranks > 1 && passes > 1) ctx->red_seq = seq0 + (unsigned long long)(passes - 1);
   ctx->last_ls_passes = passes;
+  release_l2_persist(ctx);
   if (rc != SE_OK) return rc;
   if (alpha) *alpha = res[0];
   if (loss) *loss = res[1];
@@ -1678,6 +1696,12 @@ int round_squared_fused(se_ctx* ctx, double learning_rate, double tol, int max_i
   a.host_res = mirror ? ctx->d_mirror + kMirrorRound : nullptr;
   a.sync = ctx->d_fsync;
   a.epoch = ++ctx->fused_epoch;
+  {
+    // tiles of 16 KB per array; y and F are prefetched: 32 KB per tile, over at most fused_ctas_per_sm * sms CTAs
+    const double per_cta = ctx->fused_prefetch_mb * 1e6 / (32768.0 * (double)(ctx->fused_ctas_per_sm * ctx->sms));
+    a.prefetch_tiles = per_cta < 0.0 ? 0 : (per_cta > 64.0 ? 64 : (int)(per_cta + 0.5));
+  }
+  a.timing = ctx->fused_timing;
   const int write_r = (flags & SE_UPD_RESIDUAL) ? 1 : 0;
   int grid = 0;
   SE_LAUNCH_T(ctx, SE_KF_UPDATE, launch_gbm_round_sq_fused(a, write_r, ctx->sms, ctx->fused_ctas_per_sm, ctx->stream, &grid));
@@ -1694,6 +1718,13 @@ int round_squared_fused(se_ctx* ctx, double learning_rate, double tol, int max_i
     for (int i = 0; i < 7; ++i) res[i] = ctx->h_scal[kScalRound + i];
   }
   for (int i = 0; i < 3; ++i) ctx->last_round_stats[i] = res[i];
+  if (ctx->fused_timing) {
+    double t[4];
+    SE_CUDA(ctx, cudaMemcpyAsync(ctx->h_scal + kScalRound + 10, ctx->d_scal + kScalRound + 10, sizeof(double) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    SE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < 4; ++i) t[i] = ctx->h_scal[kScalRound + 10 + i];
+    ctx->last_fused_us[0] = t[1] - t[0]; ctx->last_fused_us[1] = t[2] - t[1]; ctx->last_fused_us[2] = t[3] - t[2];
+  }
   if (alpha) *alpha = res[4];
   if (n_eval) *n_eval = (int)fabs(res[6]);
   if (loss_sum) *loss_sum = ls;

@@ -47,6 +47,16 @@ __device__ __forceinline__ void red_release_gpu_add_u32(unsigned int* p, unsigne
   asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+// bulk L2 prefetch of a contiguous global range (bytes: multiple of 16, address 16 B aligned)
+__device__ __forceinline__ double global_timer_us() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return (double)t * 1e-3;
+}
+__device__ __forceinline__ void prefetch_l2_bulk(const void* p, unsigned int bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
 // =================================================================================== squared-loss round, one launch
 constexpr int U_SQ = 4;  // float4 groups per thread per tile (as the two-launch kernels)
 
@@ -62,6 +72,7 @@ __global__ void __launch_bounds__(kBlock, 3) gbm_round_sq_fused_kernel(const SqR
   const bool has_bag = (a.bag != nullptr);
   const uint64_t pol_keep = l2_policy(false), pol_stream = l2_policy(a.l2_hints != 0);
 
+  if (a.timing && blockIdx.x == 0 && threadIdx.x == 0) a.out[10] = global_timer_us();
   // ---- phase A: Σ(y-F)², Σh(y-F), Σh² (from the current residual slot when it is valid: 8 B/row)
   double acc[3] = {0.0, 0.0, 0.0};
   for (int64_t i = 0; i < cnt; ++i) {
@@ -112,6 +123,7 @@ __global__ void __launch_bounds__(kBlock, 3) gbm_round_sq_fused_kernel(const SqR
   if (last) {
     __syncthreads();  // a.out[0..2] were written by other threads of this CTA
     if (threadIdx.x == 0) {
+      if (a.timing) a.out[11] = global_timer_us();  // statistics folded (and summed across GPUs)
       const double s0 = a.out[0], s1 = a.out[1], s2 = a.out[2];
       const BrentParabola f{s0, s1, s2, a.wsum};
       double x = 1.0, fx = 0.0;
@@ -127,6 +139,7 @@ __global__ void __launch_bounds__(kBlock, 3) gbm_round_sq_fused_kernel(const SqR
       // MaxEval exceeded: the host reports SE_ERR_OPT and F must stay untouched (F + 0*h == F, r is recomputed)
       a.sync->x = (rc == kBrentOk) ? a.lr * x : 0.0;
       st_release_gpu_u64(&a.sync->flag, a.epoch);
+      if (a.timing) a.out[12] = global_timer_us();  // step published
     }
   }
 
@@ -149,7 +162,24 @@ __global__ void __launch_bounds__(kBlock, 3) gbm_round_sq_fused_kernel(const SqR
   int64_t i = cnt - 1;
   if (i >= 0) load_tile(i);  // in flight while the last CTA reduces, exchanges and runs Brent
   if (threadIdx.x == 0) {
-    while (ld_acquire_gpu_u64(&a.sync->flag) != a.epoch) {}
+    // The wait (partials fold + cross-GPU exchange + ~30 dependent fp64 Brent iterations: 10-20 us) is turned into
+    // useful HBM time: every CTA pulls the y and F ranges of its next update tiles into the L2 with bulk prefetches
+    // (one instruction per 16 KB), bounded so that the whole grid stays within a.prefetch_tiles tiles per CTA.
+    int64_t pf = i - 1;
+    int budget = a.prefetch_tiles;
+    while (ld_acquire_gpu_u64(&a.sync->flag) != a.epoch) {
+      if (budget > 0 && pf >= 0) {
+        const int64_t g0 = (blockIdx.x + pf * G) * tile;           // first float4 group of the tile
+        int64_t groups = n4 - g0;
+        if (groups > tile) groups = tile;
+        if (groups > 0) {
+          prefetch_l2_bulk(a.y + 4 * g0, (unsigned int)(groups * 16));
+          prefetch_l2_bulk(a.F + 4 * g0, (unsigned int)(groups * 16));
+        }
+        --pf;
+        --budget;
+      }
+    }
     s_coef = (float)a.sync->x;  // same rounding as the host path: (float)(lr * alpha)
   }
   __syncthreads();
@@ -186,7 +216,8 @@ __global__ void __launch_bounds__(kBlock, 3) gbm_round_sq_fused_kernel(const SqR
     if (WRITE_R) a.r[j] = d;
     accb[0] += (double)(0.5f * d * d);
   }
-  block_reduce_publish<1>(accb, a.ws_b);  // Σloss -> a.ws_b.out (+ cross-GPU sum, host mirror + ticket)
+  const bool last_b = block_reduce_publish<1>(accb, a.ws_b);  // Σloss -> a.ws_b.out (+ cross-GPU sum, host mirror + ticket)
+  if (a.timing && last_b && threadIdx.x == 0) a.out[13] = global_timer_us();
 }
 
 // =================================================================================== persistent line search
@@ -198,6 +229,25 @@ struct LsTraits {
   static constexpr int kU = 2;
   static constexpr int kTileBytes = kNarr * kU * kBlock * 16;
 };
+
+// Binary losses as functions of their argument z, with the label encoding and constant factors folded into the
+// packed view (multiplications by +-1 / +-2 are exact, so z equals the argument the plain evaluators form bit for bit):
+//   bernoulli   (GBMLoss.scala:297-301): loss = log1pExp(-2 y~ p),  z = 2 y~ p  -> scale 2 y~
+//   exponential (:272-276):               loss = exp(-y~ p),         z = y~ p    -> scale y~
+template <int LOSS>
+__device__ __forceinline__ float signed_scale(float y) {
+  const float ye = 2.0f * y - 1.0f;
+  return (LOSS == SE_LOSS_BERNOULLI) ? 2.0f * ye : ye;
+}
+template <int LOSS>
+__device__ __forceinline__ float binary_loss_of_z(float z) {
+  if constexpr (LOSS == SE_LOSS_BERNOULLI) {
+    const float t = exp_neg_fast(-fabsf(z));
+    return fmaxf(-z, 0.f) + log1p_unit(t);
+  } else {
+    return exp_fast(-z);
+  }
+}
 
 template <int LOSS>
 __global__ void __launch_bounds__(kBlock, 4) gbm_linesearch_persist_kernel(const LsArgs a) {
@@ -277,8 +327,8 @@ __global__ void __launch_bounds__(kBlock, 4) gbm_linesearch_persist_kernel(const
   const uint64_t pol_keep = l2_policy(false);
 
   auto row_loss = [&](float c0, float c1, float c2, float coef) -> float {
-    // PACKED: (u, v): label 1 => (2y-1) == 1;  otherwise (y, F, h)
-    if constexpr (PACKED) return eval_loss<LOSS>(1.0f, fmaf(coef, c1, c0), param).l;
+    // PACKED: (u, v) hold the loss ARGUMENT directly (signed_scale folded in, exact): z = u + coef*v
+    if constexpr (PACKED) return binary_loss_of_z<LOSS>(fmaf(coef, c1, c0));
     else return eval_loss<LOSS>(c0, fmaf(coef, c2, c1), param).l;
   };
 
@@ -306,7 +356,7 @@ __global__ void __launch_bounds__(kBlock, 4) gbm_linesearch_persist_kernel(const
           if constexpr (PACKED) {
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-              const float ye = 2.0f * f4at(y4, q) - 1.0f;  // GBMLoss.scala:272,297
+              const float ye = signed_scale<LOSS>(f4at(y4, q));
               f4at(reg[0][u], q) = ye * f4at(F4, q);
               f4at(reg[1][u], q) = ye * f4at(h4, q);
             }
@@ -386,7 +436,7 @@ __global__ void __launch_bounds__(kBlock, 4) gbm_linesearch_persist_kernel(const
     if (blockIdx.x == 0 && tid < (a.n & 3)) {  // scalar tail (n % 4 rows), always from the source arrays
       const int64_t j = (n4 << 2) + tid;
       if constexpr (PACKED) {
-        const float ye = 2.0f * a.y[j] - 1.0f;
+        const float ye = signed_scale<LOSS>(a.y[j]);
         acc += (double)row_loss(ye * a.F[j], ye * a.h[j], 0.f, coef);
       } else {
         acc += (double)row_loss(a.y[j], a.F[j], a.h[j], coef);
@@ -418,9 +468,14 @@ cudaError_t launch_ls(const LsArgs& a0, int sms, const LsLaunch& cfg, cudaStream
     int dev = 0, optin = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
+    cudaFuncAttributes fa;
+    cudaError_t e = cudaFuncGetAttributes(&fa, kern);
     if (e != cudaSuccess) return e;
-    max_smem = optin;
+    // static + dynamic shared memory together must stay within the opt-in limit
+    const int dyn_max = optin - (int)fa.sharedSizeBytes;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_max);
+    if (e != cudaSuccess) return e;
+    max_smem = dyn_max;
     // co-resident CTAs per SM are bounded by registers / threads (4 by __launch_bounds__): share the SM's shared
     // memory between them
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_full, kern, kBlock, 0);

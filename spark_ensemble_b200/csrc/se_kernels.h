@@ -91,6 +91,8 @@ struct SqRoundArgs {
   int64_t n = 0;
   int stats_from_r = 0;
   int l2_hints = 0;
+  int timing = 0;          // write %globaltimer stamps (us) to out[10..13]: start, statistics folded, step published, end
+  int prefetch_tiles = 0;  // y/F tiles of the update phase each CTA prefetches into L2 while it waits for the step
   double lr = 1.0, wsum = 1.0;                                   // learning rate, Σw (objective scale)
   double lo = 0.0, hi = 100.0, start = 1.0, rel = 1e-6, abs_tol = 1e-6;
   int max_eval = 100;

@@ -951,7 +951,8 @@ def test_fused_squared_round(ctx, oracle, rng, n, weighted):
             s = [ctx.get_option(f"last_round_stat{i}") for i in range(3)]
             d = y.astype(np.float64) - Fo[0]
             close(s, [np.sum(d * d), np.sum(hh * d), np.sum(hh * hh)], scale=1e-30)
-            rc, xh, fh, neh = _host_brent(lambda x: (s[0] - 2.0 * x * s[1] + x * x * s[2]) / (2.0 * ws_dev))
+            inv = 1.0 / (2.0 * ws_dev)  # se_brent.h BrentParabola: one reciprocal, then multiplications
+            rc, xh, fh, neh = _host_brent(lambda x: (s[0] - 2.0 * x * s[1] + x * x * s[2]) * inv)
             assert rc == 0 and (a, ne) == (xh, neh), (rnd, a, xh, ne, neh)
             oracle.update(Fo, h, [0.7 * a])
             close(ctx.download(N.SLOT_F), Fo[0])
@@ -1036,7 +1037,7 @@ def test_device_line_search_matches_host_brent(ctx, oracle, rng, name, n, ctas, 
             ao, neo, st = oracle.brent(f)
             assert st == 0
             assert dev[1] == pytest.approx(f(ao), rel=RTOL)
-            assert f(dev[0]) <= f(ao) * (1 + 1e-5)
+            assert f(dev[0]) <= f(ao) * (1 + 1e-5) + 1e-12
         ctx.set_option("ls_mode", 1)
         if n > 3:
             with pytest.raises(N.ConvergenceError):
