@@ -112,6 +112,7 @@ struct FinArgs {
   float* raw;
   float* prob;
   float* label;
+  int* bad_label;  // raised when a vote is not a class index in [0, K)
 };
 
 // raw value from the stage-1 sum.  Real: the mean is a shift common to all classes (soft-max invariant), so fp32 is
@@ -170,6 +171,7 @@ __global__ void __launch_bounds__(kBlock) agg_votes_kernel(const float* __restri
   extern __shared__ __align__(8) unsigned char hist_raw[];
   HT* hist = reinterpret_cast<HT*>(hist_raw);  // [K][kBlock]
   const int K = f.K;
+  bool bad_vote = false;
   for (int64_t i0 = (int64_t)blockIdx.x * kBlock; i0 < f.n; i0 += (int64_t)gridDim.x * kBlock) {
     const int64_t i = i0 + threadIdx.x;
     for (int c = 0; c < K; ++c) hist[c * kBlock + threadIdx.x] = (HT)0;
@@ -182,8 +184,10 @@ __global__ void __launch_bounds__(kBlock) agg_votes_kernel(const float* __restri
 #pragma unroll
         for (int u = 0; u < MU; ++u)
           if (m0 + u < M) {
-            const int c = (int)v[u];
-            if (c >= 0 && c < K) hist[c * kBlock + threadIdx.x] += (HT)(a ? a[m0 + u] : 1.0f);
+            bool bad = false;
+            const int c = checked_label(v[u], K, bad);  // a vote is a predicted class index
+            if (!bad) hist[c * kBlock + threadIdx.x] += (HT)(a ? a[m0 + u] : 1.0f);
+            bad_vote = bad_vote || bad;
           }
       }
       // epilogue out of the thread's own histogram column, which doubles as fp32 scratch (ncu on the generic
@@ -220,6 +224,7 @@ __global__ void __launch_bounds__(kBlock) agg_votes_kernel(const float* __restri
       f.label[i] = (float)am;
     }
   }
+  if (bad_vote && f.bad_label != nullptr) *reinterpret_cast<volatile int*>(f.bad_label) = 1;
 }
 
 // ------------------------------------------------------------------ class-wide sums through TMA tiles
@@ -653,6 +658,7 @@ cudaError_t launch_agg(const AggArgs& a, int ctas_per_sm, int sms, cudaStream_t 
   FinArgs f{};
   f.kind = a.kind; f.K = a.K; f.dim = a.dim; f.loss = a.loss; f.M = a.M;
   f.n = a.n; f.ld = a.ld_out; f.raw = a.raw; f.prob = a.prob; f.label = a.label;
+  f.bad_label = a.bad_label;
   f.sum_a = 0.0;
   {
     bool launched = false;

@@ -156,6 +156,8 @@ struct se_ctx {
   double** d_mbox_table = nullptr;    // device copy of the pointer table
   int* d_p2p_err = nullptr;           // device alias of h_p2p_err (mapped pinned host memory: no copy to poll it)
   int* h_p2p_err = nullptr;
+  int* h_bad_label = nullptr;         // raised by kernels that met a label / vote outside [0, K) (mapped pinned memory)
+  int* d_bad_label = nullptr;
   unsigned long long red_seq = 0;
   bool last_reduce_global = false;    // the kernel just launched already produced cross-GPU sums
   // host mirror of the scalar block (mapped pinned memory written by the reducing kernel's last CTA)
@@ -320,6 +322,7 @@ RedWs red_ws(se_ctx* ctx, int out_offset = 0, bool exchange = true) {
   ws.partials = ctx->d_partials;
   ws.counter = ctx->d_counter;
   ws.out = ctx->d_scal + out_offset;
+  ws.bad_label = ctx->d_bad_label;
   ctx->last_reduce_global = false;
   ctx->mirror_valid = false;
   // results can be mirrored to the host by the kernel itself when they are final on this GPU: single GPU, or
@@ -354,6 +357,17 @@ int allreduce_dev(se_ctx* ctx, int off, int count, int op = kNcclSum) {
   int rc = api.AllReduce(ctx->d_scal + off, ctx->d_scal + off, (size_t)count, kNcclFloat64, op,
                          ctx->comm, ctx->stream);
   if (rc != 0) return fail(ctx, SE_ERR_NCCL, "ncclAllReduce: %s", api.GetErrorString(rc));
+  return SE_OK;
+}
+
+// Labels are class indices for LogLoss / SAMME(.R) / vote aggregation.  The reference throws on the JVM for a label
+// outside [0, numClasses) or a fractional one (GBMLoss.scala:200-204 `res(label.toInt) = 1.0`, Classifier.validateLabel);
+// here the kernels raise a flag instead of indexing out of bounds and the call that observes it fails with SE_ERR_ARG.
+int check_labels(se_ctx* ctx) {
+  if (ctx->h_bad_label && *reinterpret_cast<volatile int*>(ctx->h_bad_label)) {
+    *reinterpret_cast<volatile int*>(ctx->h_bad_label) = 0;
+    return fail(ctx, SE_ERR_ARG, "a label (or vote) is not an integer class index in [0, numClasses): results of this call are invalid");
+  }
   return SE_OK;
 }
 
@@ -400,6 +414,7 @@ int fetch_scalars(se_ctx* ctx, int off, int count, double* out, int op = kNcclSu
     SE_TRY(end(ctx));
     SE_TRY(wait_mirror(ctx));
     for (int i = 0; i < count; ++i) out[i] = ctx->h_mirror[i];
+    SE_TRY(check_labels(ctx));
     return check_p2p(ctx);
   }
   SE_TRY(allreduce_dev(ctx, off, count, op));
@@ -408,6 +423,7 @@ int fetch_scalars(se_ctx* ctx, int off, int count, double* out, int op = kNcclSu
   SE_TRY(end(ctx));
   SE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   for (int i = 0; i < count; ++i) out[i] = ctx->h_scal[off + i];
+  SE_TRY(check_labels(ctx));
   return check_p2p(ctx);
 }
 
@@ -608,6 +624,9 @@ int se_ctx_create(int device, se_ctx** out) {
   SE_CREATE_CUDA(cudaMalloc(&ctx->d_partials, sizeof(double) * (size_t)kMaxGridPartials * kMaxRed));
   SE_CREATE_CUDA(cudaMalloc(&ctx->d_counter, sizeof(unsigned int)));
   SE_CREATE_CUDA(cudaMemset(ctx->d_counter, 0, sizeof(unsigned int)));
+  SE_CREATE_CUDA(cudaHostAlloc(&ctx->h_bad_label, sizeof(int), cudaHostAllocMapped));
+  *ctx->h_bad_label = 0;
+  SE_CREATE_CUDA(cudaHostGetDevicePointer(&ctx->d_bad_label, ctx->h_bad_label, 0));
   SE_CREATE_CUDA(cudaMalloc(&ctx->d_fsync, sizeof(FusedSync)));
   SE_CREATE_CUDA(cudaMemset(ctx->d_fsync, 0, sizeof(FusedSync)));
   ctx->clock_khz = prop.clockRate > 0 ? prop.clockRate : 1965000;
@@ -653,6 +672,7 @@ int se_ctx_destroy(se_ctx* ctx) {
   if (ctx->d_partials) cudaFree(ctx->d_partials);
   if (ctx->d_counter) cudaFree(ctx->d_counter);
   if (ctx->d_fsync) cudaFree(ctx->d_fsync);
+  if (ctx->h_bad_label) cudaFreeHost(ctx->h_bad_label);
   if (ctx->d_small) cudaFree(ctx->d_small);
   if (ctx->h_mirror) cudaFreeHost(ctx->h_mirror);
   if (ctx->d_ls_u) cudaFree(ctx->d_ls_u);  // (u, v) share one allocation
@@ -672,7 +692,7 @@ int se_ctx_sync(se_ctx* ctx) {
   if (!ctx) return fail(nullptr, SE_ERR_ARG, "null context");
   SE_CUDA(ctx, cudaSetDevice(ctx->device));
   SE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  return SE_OK;
+  return check_labels(ctx);
 }
 
 int se_ctx_device(const se_ctx* ctx, int* device) {
@@ -1183,7 +1203,7 @@ int se_download(se_ctx* ctx, int slot, float* host, int64_t count, int64_t offse
     return SE_OK;
   }));
   SE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  return SE_OK;
+  return check_labels(ctx);  // e.g. the probabilities of an aggregation that met a vote outside [0, K)
 }
 
 int se_download_scaled(se_ctx* ctx, int slot, double scale, float* host, int64_t count, int64_t offset) {
@@ -2031,6 +2051,7 @@ int se_agg_run(se_ctx* ctx, const double* weights, const double* init) {
   a.ld_out = ctx->slot[SE_SLOT_RAW].rows > 1 ? ctx->slot[SE_SLOT_RAW].ld : ctx->slot[SE_SLOT_RAW].cols;
   a.prob = ctx->slot[SE_SLOT_PROB].d;
   a.label = ctx->slot[SE_SLOT_LABEL].d;
+  a.bad_label = ctx->d_bad_label;
   // small operands: narrowed to fp32 and staged through pinned memory into d_small
   float* hs = reinterpret_cast<float*>(ctx->h_small);
   size_t used = 0;

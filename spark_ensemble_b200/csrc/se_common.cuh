@@ -163,6 +163,9 @@ struct RedWs {
   unsigned long long seq = 0;      // reduction sequence number (same on every rank), >= 1
   int* err = nullptr;              // set to 1 if a peer never showed up (bounded spin) or poisoned the reduction
   long long timeout_clocks = 0;    // spin bound of the peer exchange in SM clocks (0 = wait forever)
+  // ---- label validation (Classifier.validateLabel / GBMLoss.scala:200-204 `res(label.toInt) = 1.0` throws on the JVM):
+  // kernels that use a label as a class index set this flag (mapped host memory) instead of indexing out of bounds
+  int* bad_label = nullptr;
   // ---- host mirror: the final sums are also stored into mapped pinned host memory, followed by a ticket, so
   // the host can pick them up by polling one cache line instead of a D2H copy + stream synchronisation
   double* host_out = nullptr;
@@ -318,6 +321,18 @@ __device__ __forceinline__ bool block_reduce_publish(double (&acc)[NRED], const 
   __syncthreads();
   peer_exchange(tot, NRED, ws);  // per-GPU totals -> ws.out (summed across GPUs when a peer communicator is attached)
   return true;
+}
+
+// Class index of a label, validated: integer-valued and inside [0, K).  Anything else (negative, >= K, fractional,
+// NaN) raises `bad` and maps to class 0, so no kernel ever forms an out-of-range shared/global address from a label.
+__device__ __forceinline__ int checked_label(float y, int K, bool& bad) {
+  const int yi = (int)y;
+  const bool ok = (y >= 0.f) && (yi < K) && ((float)yi == y);
+  bad = bad || !ok;
+  return ok ? yi : 0;
+}
+__device__ __forceinline__ void report_bad_label(bool bad, const RedWs& ws) {
+  if (bad && ws.bad_label != nullptr) *reinterpret_cast<volatile int*>(ws.bad_label) = 1;
 }
 
 // ---- counter-based synthetic generator (bench / tests): identical integer stream on host -----

@@ -228,6 +228,7 @@ __global__ void __launch_bounds__(kBlock) gbm_logloss_kernel(const GbmArgs a) {
   const bool has_w = (a.w != nullptr);
   constexpr int NRED = KMAX + 1;
   double acc[NRED];
+  bool bad_label = false;
 #pragma unroll
   for (int k = 0; k < NRED; ++k) acc[k] = 0.0;
 
@@ -299,6 +300,7 @@ __global__ void __launch_bounds__(kBlock) gbm_logloss_kernel(const GbmArgs a) {
     for (int e = 0; e < VEC; ++e) {
       const bool in = (i0 + e < a.n);
       const float yf = yv[e];  // labels are compared as floats (exact small integers): no float->int conversion
+      if (in) (void)checked_label(yf, K, bad_label);
       float m = -INFINITY;
       int am = 0;
 #pragma unroll
@@ -374,6 +376,7 @@ __global__ void __launch_bounds__(kBlock) gbm_logloss_kernel(const GbmArgs a) {
       }
     }
   }
+  report_bad_label(bad_label, a.ws);
   if (T::kReduce) block_reduce_publish<NRED>(acc, a.ws);
 }
 

@@ -188,6 +188,7 @@ struct AggArgs {
   int64_t n = 0, ld = 0, ld_out = 0;
   double sum_weights = 0.0;  // Σ a_m of the fp32-narrowed weights (boosting discrete epilogue, boosting-regressor mean)
   const double* weights64 = nullptr;  // device [M] fp64 (weighted median cumulative sums)
+  int* bad_label = nullptr;           // raised (mapped host memory) when a vote is not a class index in [0, K)
 };
 cudaError_t launch_agg(const AggArgs& a, int ctas_per_sm, int sms, cudaStream_t s);
 

@@ -1065,3 +1065,57 @@ def test_options_roundtrip(ctx):
     with pytest.raises(ValueError):
         ctx.set_option("last_round_fused", 1)  # read-only
     assert ctx.get_option("l2_persist_max_bytes") >= 0
+
+
+@pytest.mark.parametrize("bad", [-1.0, "K", 2.5, float("nan")])
+@pytest.mark.parametrize("K", [3, 9, 40])
+def test_bad_labels_fail_loudly(ctx, rng, K, bad):
+    """A label that is not an integer class index in [0, K) makes the reference throw on the JVM
+    (GBMLoss.scala:200-204 `res(label.toInt) = 1.0`; Classifier.validateLabel).  Here: SE_ERR_ARG from the call that
+    observes it, never an out-of-bounds access (run under compute-sanitizer in profiles/r02_sanitizer.md), and the
+    context stays usable."""
+    from spark_ensemble_b200 import _native as N
+    n = 5003
+    badv = float(K) if bad == "K" else bad
+    y = f32(rng.integers(0, K, n))
+    F = f32(rng.standard_normal((K, n)))
+    h = f32(rng.standard_normal((K, n)))
+    yb = y.copy(); yb[n // 2] = badv; yb[n - 1] = badv
+    # LogLoss: line-search evaluation, fused update (register kernel K <= 4, TMA-tiled kernel K >= 5)
+    ctx.gbm_configure(n, 0, K, "logloss", 0.0, False)
+    ctx.upload(N.SLOT_F, F); ctx.upload(N.SLOT_H, h)
+    ctx.upload(N.SLOT_Y, yb)
+    with pytest.raises(ValueError, match="class index"):
+        ctx.gbm_linesearch_eval(np.ones(K))
+    with pytest.raises(ValueError, match="class index"):
+        ctx.gbm_update(np.full(K, 0.1), residual=True, loss=True)
+    with pytest.raises(ValueError, match="class index"):
+        ctx.gbm_pseudo_residuals(False)
+        ctx.sync()
+    ctx.upload(N.SLOT_Y, y); ctx.upload(N.SLOT_F, F)
+    l, g = ctx.gbm_linesearch_eval(np.ones(K))
+    assert np.isfinite(l) and np.all(np.isfinite(g))
+    # SAMME.R (register kernel K < 5, TMA-tiled K >= 5)
+    P = rng.random((K, n)); P = f32(P / P.sum(0))
+    ctx.boost_configure(n, K, True)
+    ctx.upload(N.SLOT_PROBA, P); ctx.fill(N.SLOT_BW, 1.0)
+    ctx.upload(N.SLOT_Y, yb)
+    with pytest.raises(ValueError, match="class index"):
+        ctx.boost_real_update(float(n))
+    ctx.upload(N.SLOT_Y, y); ctx.fill(N.SLOT_BW, 1.0)
+    e, s = ctx.boost_real_update(float(n))
+    assert 0.0 <= e <= 1.0 and s > 0
+    # hard votes
+    M = 7
+    votes = f32(rng.integers(0, K, (M, n)))
+    vb = votes.copy(); vb[3, 17] = badv
+    ctx.agg_configure(N.AGG_BAGGING_HARD, M, K, 1, 0, n)
+    ctx.upload(N.SLOT_P, vb)
+    ctx.agg_run()
+    with pytest.raises(ValueError, match="class index"):
+        ctx.sync()
+    ctx.upload(N.SLOT_P, votes)
+    ctx.agg_run()
+    ctx.sync()
+    raw = ctx.download(N.SLOT_RAW)
+    assert np.all(raw.reshape(K, n).sum(0) == M)
