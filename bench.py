@@ -43,16 +43,18 @@ sys.path.insert(0, ROOT)
 METRIC = "boosting-iter rows/sec (grad+update)"
 BYTES_K1 = 20  # y,F,h read + F',r written, fp32
 BYTES_K2 = 8   # squared-loss statistics read the current residual r = y - F and h (12 when r is stale: y,F,h)
+BYTES_ROUND = BYTES_K1 + BYTES_K2  # the one-launch round runs both passes inside one kernel
 
 
-def _ncu_traffic(rows: int):
-    """DRAM bytes per K1 launch from the committed `ncu --set full` capture (profiles/), if it was taken at
-    this row count."""
+def _ncu_traffic(rows: int, bytes_per_row: int):
+    """DRAM bytes per launch of the roofline kernel from the committed `ncu --set full` capture (profiles/), if it
+    was taken at this row count for this kernel."""
     p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     try:
         d = json.load(open(p))
-        if int(d["rows"]) == int(rows):
-            return float(d["k1_dram_bytes_per_launch"])
+        key = "fused_round" if bytes_per_row == BYTES_ROUND else "k1"
+        if int(d[key]["rows"]) == int(rows):
+            return float(d[key]["dram_bytes_per_launch"])
     except Exception:
         pass
     return None
@@ -461,6 +463,8 @@ def main():
             ctx.gbm_update([1.0], residual=False, loss=False)
             ctx.set_option("fused_round", -1)
             ctx.copy_slot(N.SLOT_H, N.SLOT_F)
+        else:
+            make_direction()   # the tree extras overwrote H
         ctx.fill(N.SLOT_F, 0.0)
         ctx.gbm_pseudo_residuals(False)
         for _ in range(3):
@@ -521,13 +525,22 @@ def main():
 
     peak, peak_src = _peaks()
     k1 = ktimes.get("update", {"ms": float("nan"), "launches": 1})
-    k2 = ktimes.get("sq_stats", {"ms": float("nan"), "launches": 1})
+    k2 = ktimes.get("sq_stats", None)
     k1_ms = k1["ms"] / max(k1["launches"], 1)
-    k2_ms = k2["ms"] / max(k2["launches"], 1)
-    achieved = BYTES_K1 * n / (k1_ms * 1e-3) / 1e9
-    extras["k2_stats_kernel"] = {"ms": k2_ms, "achieved_gbs": BYTES_K2 * n / (k2_ms * 1e-3) / 1e9,
-                                 "frac": BYTES_K2 * n / (k2_ms * 1e-3) / 1e9 / peak}
-    extras["kernel_ms_share_of_step"] = (k1["ms"] + k2["ms"]) / ms_dev if ms_dev > 0 else None
+    if k2 is None:
+        # one cooperative launch per round: statistics pass (8 B/row) + update pass (20 B/row) inside ONE kernel
+        roof_kernel = ("gbm_round_sq_fused_kernel (whole round in one launch: statistics r,h -> Brent -> "
+                       "F update + residual; 8 + 20 B/row)")
+        roof_bytes = BYTES_ROUND
+        extras["kernel_ms_share_of_step"] = k1["ms"] / ms_dev if ms_dev > 0 else None
+    else:
+        roof_kernel = "gbm_scalar_kernel<squared, UPDATE_RESID> (K1: F update + residual + loss)"
+        roof_bytes = BYTES_K1
+        k2_ms = k2["ms"] / max(k2["launches"], 1)
+        extras["k2_stats_kernel"] = {"ms": k2_ms, "achieved_gbs": BYTES_K2 * n / (k2_ms * 1e-3) / 1e9,
+                                     "frac": BYTES_K2 * n / (k2_ms * 1e-3) / 1e9 / peak}
+        extras["kernel_ms_share_of_step"] = (k1["ms"] + k2["ms"]) / ms_dev if ms_dev > 0 else None
+    achieved = roof_bytes * n / (k1_ms * 1e-3) / 1e9
     extras["device_ms_per_step"] = ms_dev / args.steps
     extras["wall_ms_per_step"] = ms_wall / args.steps
     extras["strong_scaling"] = strong
@@ -558,9 +571,9 @@ def main():
                 "note": "direction h host->device and pseudo-residuals device->host (pinned) every round"},
         "gpu_launches": int(launches),
         "parity_ok": (all(p["ok"] for p in parity) if parity else None), "parity": parity, "p2p_active": p2p_active,
-        "roofline": {"kernel": "gbm_scalar_kernel<squared, UPDATE_RESID> (K1: F update + residual + loss)",
+        "roofline": {"kernel": roof_kernel,
                      "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": _ncu_traffic(n), "peak_source": peak_src, "bytes_per_row": BYTES_K1, "ms_per_launch": k1_ms,
+                     "traffic": _ncu_traffic(n, roof_bytes), "peak_source": peak_src, "bytes_per_row": roof_bytes, "ms_per_launch": k1_ms,
                      "launches_timed": k1["launches"]},
         "cpu_baseline": cpu,
         "extras": extras,

@@ -21,6 +21,25 @@ if what in ("squared", "bernoulli", "exponential", "logcosh", "absolute"):
     for _ in range(3):
         ctx.gbm_linesearch_eval([0.7])
         ctx.gbm_update([1e-3], residual=True, loss=True)
+elif what in ("fused_round", "two_launch_round"):
+    ctx.gbm_configure(n, 0, 1, "squared", 0.0, False)
+    ctx.fill_synthetic(N.SLOT_Y, "normal", 1, 0, 1)
+    ctx.fill_synthetic(N.SLOT_F, "normal", 2, 0, 0.5)
+    ctx.copy_slot(N.SLOT_H, N.SLOT_Y)
+    ctx.gbm_update([0.5], residual=False, loss=False)
+    ctx.copy_slot(N.SLOT_H, N.SLOT_F)   # h = 0.5 y + N(0, 0.5)
+    ctx.fill(N.SLOT_F, 0.0)
+    ctx.gbm_pseudo_residuals(False)
+    ctx.set_option("fused_round", 1 if what == "fused_round" else 0)
+    for _ in range(8):
+        ctx.gbm_round(0.1, True, 1e-6, 100, residual=True)
+elif what == "ls_persist":
+    ctx.gbm_configure(n, 0, 1, "bernoulli", 0.0, False)
+    ctx.fill_synthetic(N.SLOT_Y, "bernoulli", 1, 0.4, 1)
+    ctx.fill_synthetic(N.SLOT_F, "normal", 2, 0, 0.5)
+    ctx.fill_synthetic(N.SLOT_H, "normal", 3, 0, 1)
+    for _ in range(3):
+        ctx.gbm_linesearch_brent()
 elif what.startswith("logloss"):
     K = int(what[7:])
     ctx.gbm_configure(n, 0, K, "logloss", 0.0, False)

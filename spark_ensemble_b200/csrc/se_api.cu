@@ -178,9 +178,11 @@ struct se_ctx {
   FusedSync* d_fsync = nullptr;
   unsigned long long fused_epoch = 0;
   int fused_round = -1;               // squared-loss round in one launch: -1 by shard size, 0 off, 1 on
-  int64_t fused_round_max_rows = 40000000;
+  int64_t fused_round_max_rows = (int64_t)1 << 40;  // measured faster than two launches from 6 M to 100 M rows
   int fused_ctas_per_sm = 3;
   double fused_prefetch_mb = 0.0;     // (measured: no gain at 6-12 M rows, -2 % at 25-50 M rows: off)
+  int fused_loss_reduce = 0;          // 1: reduce the train loss over the rows even when the closed form applies
+  int fused_l2_mode = 0;              // experiment: 1 = evict_last on r/h, 2 = persisting window over r
   int fused_timing = 0;               // diagnostic: in-kernel %globaltimer stamps of the fused round
   double last_fused_us[3] = {0, 0, 0};  // statistics phase, fold+exchange+Brent, update phase    // L2 budget of the update-phase prefetch issued while the grid waits for the step
   int ls_mode = 1;                    // non-squared line search: 0 one launch per evaluation (round-1 kernels), 1 one
@@ -775,13 +777,13 @@ int se_ctx_kernel_time_reset(se_ctx* ctx) {
 
 namespace {
 struct OptKey { const char* name; int id; };
-enum { OPT_FUSED_TIMING, OPT_LAST_FUSED_US0, OPT_LAST_FUSED_US1, OPT_LAST_FUSED_US2, OPT_FUSED_PREFETCH_MB, OPT_FUSED_ROUND, OPT_FUSED_MAX_ROWS, OPT_FUSED_CTAS, OPT_LS_MODE, OPT_LS_RESIDENT, OPT_LS_CTAS, OPT_L2_PERSIST,
+enum { OPT_FUSED_LOSS_REDUCE, OPT_FUSED_L2_MODE, OPT_FUSED_TIMING, OPT_LAST_FUSED_US0, OPT_LAST_FUSED_US1, OPT_LAST_FUSED_US2, OPT_FUSED_PREFETCH_MB, OPT_FUSED_ROUND, OPT_FUSED_MAX_ROWS, OPT_FUSED_CTAS, OPT_LS_MODE, OPT_LS_RESIDENT, OPT_LS_CTAS, OPT_L2_PERSIST,
        OPT_L2_PERSIST_FRAC, OPT_PEER_TIMEOUT_MS, OPT_ALTERNATE, OPT_L2_HINTS, OPT_CTAS_PER_SM, OPT_HOST_MIRROR,
        // read-only diagnostics
        OPT_LAST_ROUND_FUSED, OPT_LAST_LS_WORKERS, OPT_LAST_LS_PASSES, OPT_LAST_LS_HIT_RATIO, OPT_LAST_FUSED_GRID,
        OPT_L2_PERSIST_MAX, OPT_L2_WINDOW_MAX, OPT_LAST_STAT0, OPT_LAST_STAT1, OPT_LAST_STAT2 };
 const OptKey kOpts[] = {
-  {"fused_timing", OPT_FUSED_TIMING}, {"last_fused_stats_us", OPT_LAST_FUSED_US0}, {"last_fused_brent_us", OPT_LAST_FUSED_US1},
+  {"fused_loss_reduce", OPT_FUSED_LOSS_REDUCE}, {"fused_l2_mode", OPT_FUSED_L2_MODE}, {"fused_timing", OPT_FUSED_TIMING}, {"last_fused_stats_us", OPT_LAST_FUSED_US0}, {"last_fused_brent_us", OPT_LAST_FUSED_US1},
   {"last_fused_update_us", OPT_LAST_FUSED_US2}, {"fused_prefetch_mb", OPT_FUSED_PREFETCH_MB}, {"fused_round", OPT_FUSED_ROUND}, {"fused_round_max_rows", OPT_FUSED_MAX_ROWS}, {"fused_ctas_per_sm", OPT_FUSED_CTAS},
   {"ls_mode", OPT_LS_MODE}, {"ls_resident", OPT_LS_RESIDENT}, {"ls_ctas_per_sm", OPT_LS_CTAS}, {"l2_persist", OPT_L2_PERSIST},
   {"l2_persist_frac", OPT_L2_PERSIST_FRAC}, {"peer_timeout_ms", OPT_PEER_TIMEOUT_MS}, {"alternate_passes", OPT_ALTERNATE},
@@ -806,6 +808,8 @@ int se_ctx_set_option(se_ctx* ctx, const char* key, double value) {
     case OPT_FUSED_ROUND: ctx->fused_round = value < 0 ? -1 : (iv != 0); break;
     case OPT_FUSED_MAX_ROWS: ctx->fused_round_max_rows = (int64_t)value; break;
     case OPT_FUSED_TIMING: ctx->fused_timing = iv != 0; break;
+    case OPT_FUSED_LOSS_REDUCE: ctx->fused_loss_reduce = iv != 0; break;
+    case OPT_FUSED_L2_MODE: SE_REQUIRE(ctx, iv >= 0 && iv <= 2, SE_ERR_ARG, "fused_l2_mode in {0,1,2}"); ctx->fused_l2_mode = iv; if (iv != 2) release_l2_persist(ctx); break;
     case OPT_FUSED_PREFETCH_MB: SE_REQUIRE(ctx, value >= 0.0 && value <= 512.0, SE_ERR_ARG, "fused_prefetch_mb in [0,512]"); ctx->fused_prefetch_mb = value; break;
     case OPT_FUSED_CTAS: SE_REQUIRE(ctx, iv >= 1 && iv <= 8, SE_ERR_ARG, "fused_ctas_per_sm in [1,8]"); ctx->fused_ctas_per_sm = iv; break;
     case OPT_LS_MODE: SE_REQUIRE(ctx, iv >= 0 && iv <= 2, SE_ERR_ARG, "ls_mode in {0,1,2}"); ctx->ls_mode = iv; break;
@@ -830,6 +834,8 @@ int se_ctx_get_option(const se_ctx* ctx, const char* key, double* value) {
     case OPT_FUSED_MAX_ROWS: *value = (double)ctx->fused_round_max_rows; break;
     case OPT_FUSED_PREFETCH_MB: *value = ctx->fused_prefetch_mb; break;
     case OPT_FUSED_TIMING: *value = ctx->fused_timing; break;
+    case OPT_FUSED_LOSS_REDUCE: *value = ctx->fused_loss_reduce; break;
+    case OPT_FUSED_L2_MODE: *value = ctx->fused_l2_mode; break;
     case OPT_LAST_FUSED_US0: *value = ctx->last_fused_us[0]; break;
     case OPT_LAST_FUSED_US1: *value = ctx->last_fused_us[1]; break;
     case OPT_LAST_FUSED_US2: *value = ctx->last_fused_us[2]; break;
@@ -1704,15 +1710,33 @@ int round_squared_fused(se_ctx* ctx, double learning_rate, double tol, int max_i
   a.wsum = g.wsum;
   a.lo = 0.0; a.hi = 100.0; a.start = 1.0; a.rel = tol; a.abs_tol = tol; a.max_eval = max_iter;
   a.out = ctx->d_scal + kScalRound;
+  // The train loss after the update follows from the (global) statistics in closed form — no second reduction, no
+  // second cross-GPU exchange, and the host is served before the update phase ends.  With a bag the statistics run
+  // over the bag while the loss runs over all rows: then the loss is reduced over the rows as in the two-launch path.
+  const bool loss_reduce = g.use_bag || ctx->fused_loss_reduce;
   a.ws_a = red_ws(ctx, kScalRound);            // sequence number s (statistics)
-  a.ws_a.host_out = nullptr;                   // the mirror ticket belongs to the SECOND reduction
+  a.ws_a.host_out = nullptr;                   // the mirror ticket is written after Brent / the second reduction
   a.ws_a.host_flag = nullptr;
-  if (ctx->mirror_valid) --ctx->mirror_ticket; // red_ws armed the mirror for ws_a: hand the ticket to ws_b instead
-  a.ws_b = red_ws(ctx, kScalRound + 8);        // sequence number s + 1 (loss), host mirror + ticket
-  a.ws_b.partials = ctx->d_partials + (size_t)(kMaxGridPartials / 2) * 4;
-  a.ws_b.counter = &ctx->d_fsync->counter_b;
-  const bool mirror = ctx->mirror_valid;
+  if (ctx->mirror_valid) --ctx->mirror_ticket; // red_ws armed the mirror for ws_a: re-armed below
   constexpr int kMirrorRound = 32;             // mirror slots [32..38]: above what a reducing kernel writes before its ticket
+  bool mirror = false;
+  if (loss_reduce) {
+    a.ws_b = red_ws(ctx, kScalRound + 8);      // sequence number s + 1 (loss), host mirror + ticket
+    a.ws_b.partials = ctx->d_partials + (size_t)(kMaxGridPartials / 2) * 4;
+    a.ws_b.counter = &ctx->d_fsync->counter_b;
+    mirror = ctx->mirror_valid;
+  } else {
+    const bool global = ctx->last_reduce_global;  // keep what red_ws decided for the statistics
+    mirror = ctx->use_mirror && ctx->h_mirror && (ctx->nranks <= 1 || ctx->p2p);
+    if (mirror) {
+      a.host_final = ctx->d_mirror;
+      a.host_flag = reinterpret_cast<volatile unsigned long long*>(ctx->d_mirror + kMboxPayload);
+      a.host_ticket = ++ctx->mirror_ticket;
+      ctx->mirror_valid = true;
+      ctx->mirror_off = kScalRound + 8;
+    }
+    ctx->last_reduce_global = global;
+  }
   a.host_res = mirror ? ctx->d_mirror + kMirrorRound : nullptr;
   a.sync = ctx->d_fsync;
   a.epoch = ++ctx->fused_epoch;
@@ -1722,9 +1746,24 @@ int round_squared_fused(se_ctx* ctx, double learning_rate, double tol, int max_i
     a.prefetch_tiles = per_cta < 0.0 ? 0 : (per_cta > 64.0 ? 64 : (int)(per_cta + 0.5));
   }
   a.timing = ctx->fused_timing;
+  a.l2_mode = ctx->fused_l2_mode == 1 ? 1 : 0;
   const int write_r = (flags & SE_UPD_RESIDUAL) ? 1 : 0;
   int grid = 0;
-  SE_LAUNCH_T(ctx, SE_KF_UPDATE, launch_gbm_round_sq_fused(a, write_r, ctx->sms, ctx->fused_ctas_per_sm, ctx->stream, &grid));
+  void* wbase = nullptr;
+  size_t wbytes = 0;
+  if (ctx->fused_l2_mode == 2 && ctx->l2_persist_max > 0 && ctx->l2_window_max > 0) {
+    wbytes = sizeof(float) * (size_t)g.n;
+    if (wbytes > ctx->l2_window_max) wbytes = ctx->l2_window_max;
+    if (wbytes > ctx->l2_persist_max) wbytes = ctx->l2_persist_max;
+    if (ctx->l2_persist_set != wbytes) {
+      if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, wbytes) == cudaSuccess) ctx->l2_persist_set = wbytes;
+      cudaGetLastError();
+    }
+    wbase = a.r;
+    ctx->l2_persist_dirty = true;
+  }
+  SE_LAUNCH_T(ctx, SE_KF_UPDATE, launch_gbm_round_sq_fused(a, write_r, loss_reduce ? 1 : 0, ctx->sms, ctx->fused_ctas_per_sm, ctx->stream,
+                                                           &grid, wbase, wbytes));
   ctx->last_fused_grid = grid;
   ctx->gbm.r_current = write_r != 0;
   double ls = 0.0;
@@ -1762,8 +1801,8 @@ int se_gbm_round(se_ctx* ctx, double learning_rate, int optimized, double tol, i
   if (sq_search) {
     // commons-math3 BrentOptimizer constructor checks (the host path performs them in brent_impl's caller)
     SE_REQUIRE(ctx, tol >= 2.0 * 2.220446049250313e-16 && tol > 0.0, SE_ERR_ARG, "tolerance %g too small for Brent", tol);
-    // One cooperative launch per round on shards where the fixed costs matter (default: <= 40 M rows).  With a
-    // communicator it additionally needs the fused peer exchange (an NCCL all-reduce cannot run inside the kernel).
+    // One cooperative launch per round (measured on B200: 52 vs 74 us at 12.5 M rows, 440 vs 454 us at 100 M rows).
+    // With a communicator it needs the fused peer exchange (an NCCL all-reduce cannot run inside the kernel).
     const bool can = (ctx->nranks <= 1 || ctx->p2p);
     const bool want = ctx->fused_round > 0 || (ctx->fused_round < 0 && ctx->gbm.n <= ctx->fused_round_max_rows);
     if (can && want && getenv("SE_DEVICE_BRENT") == nullptr) {

@@ -60,7 +60,47 @@ __device__ __forceinline__ void prefetch_l2_bulk(const void* p, unsigned int byt
 // =================================================================================== squared-loss round, one launch
 constexpr int U_SQ = 4;  // float4 groups per thread per tile (as the two-launch kernels)
 
-template <bool WRITE_R>
+// The line search of the fused round, executed by ONE thread of the last CTA once the statistics are folded (and
+// summed across GPUs) while every other CTA waits for the step with its first update tile's loads in flight.
+template <bool LOSS_REDUCE>
+__device__ __forceinline__ void fused_round_brent(const SqRoundArgs& a) {
+  if (a.timing) a.out[11] = global_timer_us();  // statistics folded (and summed across GPUs)
+  const double s0 = a.out[0], s1 = a.out[1], s2 = a.out[2];
+  const BrentParabola f{s0, s1, s2, a.wsum};
+  double x = 1.0, fx = 0.0;
+  int evals = 0;
+  const int rc = brent_core(f, a.lo, a.hi, a.start, a.rel, a.abs_tol, a.max_eval, &x, &fx, &evals);
+  const double ne = (rc == kBrentOk) ? (double)evals : -(double)evals;  // negative: MaxEval exceeded
+  a.out[4] = x, a.out[5] = fx, a.out[6] = ne;
+  // MaxEval exceeded: the host reports SE_ERR_OPT and F must stay untouched (F + 0*h == F, r is recomputed)
+  const double step = (rc == kBrentOk) ? a.lr * x : 0.0;
+  a.sync->x = step;
+  st_release_gpu_u64(&a.sync->flag, a.epoch);  // the grid starts the update NOW; the host is served next
+  if (a.timing) a.out[12] = global_timer_us();  // step published
+  if (a.host_res) {  // mapped host memory, above what a reducing kernel writes before its ticket
+    a.host_res[0] = s0, a.host_res[1] = s1, a.host_res[2] = s2;
+    a.host_res[4] = x, a.host_res[5] = fx, a.host_res[6] = ne;
+  }
+  if constexpr (!LOSS_REDUCE) {
+    // Train loss after the update WITHOUT a second pass-wide reduction (and, across GPUs, without a second
+    // exchange): Σ (y - F - c h)²/2 = (s0 - 2 c s1 + c² s2)/2 exactly, from the GLOBAL statistics every GPU already
+    // holds; c is the fp32 step the update applies.  (Differs from summing the fp32 rows by their rounding only,
+    // ~1e-7 relative.)  The host gets alpha, the loss and its ticket here — while the update phase is still
+    // running — so the next round's launch overlaps this round's tail.
+    const double c = (double)(float)step;
+    const double loss = 0.5 * (s0 - 2.0 * c * s1 + c * c * s2);
+    a.out[8] = loss;
+    if (a.host_final) {
+      a.host_final[0] = loss;
+      __threadfence_system();
+      *a.host_flag = a.host_ticket;
+    }
+  } else if (a.host_res) {
+    __threadfence_system();
+  }
+}
+
+template <bool WRITE_R, bool LOSS_REDUCE>
 __global__ void __launch_bounds__(kBlock, 3) gbm_round_sq_fused_kernel(const SqRoundArgs a) {
   constexpr int U = U_SQ;
   __shared__ float s_coef;
@@ -70,7 +110,12 @@ __global__ void __launch_bounds__(kBlock, 3) gbm_round_sq_fused_kernel(const SqR
   const int64_t G = gridDim.x;
   const int64_t cnt = (ntiles > (int64_t)blockIdx.x) ? (ntiles - 1 - blockIdx.x) / G + 1 : 0;  // tiles b, b+G, ...
   const bool has_bag = (a.bag != nullptr);
-  const uint64_t pol_keep = l2_policy(false), pol_stream = l2_policy(a.l2_hints != 0);
+  // l2_mode 1: r and h are the arrays worth keeping between phases / rounds (r: written by the update, read by the
+  // next statistics pass; h: read by both phases) -> evict_last; y and F stream through -> evict_first
+  const uint64_t pol_stream = l2_policy(a.l2_hints != 0);
+  const uint64_t pol_keep = (a.l2_mode == 1) ? l2_policy_evict_last() : l2_policy(false);
+  const uint64_t pol_r_in = (a.l2_mode == 1) ? pol_keep : pol_stream;
+  const uint64_t pol_h_b = (a.l2_mode == 1) ? pol_keep : pol_stream;
 
   if (a.timing && blockIdx.x == 0 && threadIdx.x == 0) a.out[10] = global_timer_us();
   // ---- phase A: Σ(y-F)², Σh(y-F), Σh² (from the current residual slot when it is valid: 8 B/row)
@@ -85,7 +130,7 @@ __global__ void __launch_bounds__(kBlock, 3) gbm_round_sq_fused_kernel(const SqR
       ok[u] = g < n4;
       if (ok[u]) {
         if (a.stats_from_r) {
-          vy[u] = ld_rw4_p(a.r + 4 * g, pol_stream);  // r is rewritten by phase B without being read again
+          vy[u] = ld_rw4_p(a.r + 4 * g, pol_r_in);  // r is rewritten by phase B without being read again
         } else {
           vy[u] = ld_stream4_p(a.y + 4 * g, pol_keep);
           vF[u] = ld_rw4_p(a.F + 4 * g, pol_keep);
@@ -122,25 +167,7 @@ __global__ void __launch_bounds__(kBlock, 3) gbm_round_sq_fused_kernel(const SqR
   const bool last = block_reduce_publish<3>(acc, a.ws_a);  // the last CTA also sums across GPUs (peer_exchange)
   if (last) {
     __syncthreads();  // a.out[0..2] were written by other threads of this CTA
-    if (threadIdx.x == 0) {
-      if (a.timing) a.out[11] = global_timer_us();  // statistics folded (and summed across GPUs)
-      const double s0 = a.out[0], s1 = a.out[1], s2 = a.out[2];
-      const BrentParabola f{s0, s1, s2, a.wsum};
-      double x = 1.0, fx = 0.0;
-      int evals = 0;
-      const int rc = brent_core(f, a.lo, a.hi, a.start, a.rel, a.abs_tol, a.max_eval, &x, &fx, &evals);
-      const double ne = (rc == kBrentOk) ? (double)evals : -(double)evals;  // negative: MaxEval exceeded
-      a.out[4] = x, a.out[5] = fx, a.out[6] = ne;
-      if (a.host_res) {  // mapped host memory, above what a reducing kernel writes before its ticket
-        a.host_res[0] = s0, a.host_res[1] = s1, a.host_res[2] = s2;
-        a.host_res[4] = x, a.host_res[5] = fx, a.host_res[6] = ne;
-        __threadfence_system();
-      }
-      // MaxEval exceeded: the host reports SE_ERR_OPT and F must stay untouched (F + 0*h == F, r is recomputed)
-      a.sync->x = (rc == kBrentOk) ? a.lr * x : 0.0;
-      st_release_gpu_u64(&a.sync->flag, a.epoch);
-      if (a.timing) a.out[12] = global_timer_us();  // step published
-    }
+    if (threadIdx.x == 0) fused_round_brent<LOSS_REDUCE>(a);
   }
 
   // ---- phase B: F' = F + step*h, r = y - F', Σ (y-F')²/2 — tiles in the opposite direction
@@ -155,7 +182,7 @@ __global__ void __launch_bounds__(kBlock, 3) gbm_round_sq_fused_kernel(const SqR
       if (ok[u]) {
         vy[u] = ld_stream4_p(a.y + 4 * g, pol_stream);
         vF[u] = ld_rw4_p(a.F + 4 * g, pol_stream);
-        vh[u] = ld_stream4_p(a.h + 4 * g, pol_stream);  // the update is h's last reader
+        vh[u] = ld_stream4_p(a.h + 4 * g, pol_h_b);  // the update is h's last reader
       }
     }
   };
@@ -199,11 +226,11 @@ __global__ void __launch_bounds__(kBlock, 3) gbm_round_sq_fused_kernel(const SqR
         const float d = f4at(vy[u], e) - p;
         f4at(oF, e) = p;
         f4at(oR, e) = d;                                             // -g(y, F') (:383)
-        l_acc = fmaf(0.5f * d, d, l_acc);                            // GBMLoss.scala:129-137
+        if (LOSS_REDUCE) l_acc = fmaf(0.5f * d, d, l_acc);           // GBMLoss.scala:129-137
       }
       st_stream4_p(a.F + 4 * g, oF, pol_stream);
       if (WRITE_R) st_stream4_p(a.r + 4 * g, oR, pol_keep);  // the next statistics pass starts where this one ends
-      accb[0] += (double)l_acc;
+      if (LOSS_REDUCE) accb[0] += (double)l_acc;
     }
     --i;
     if (i >= 0) load_tile(i);
@@ -216,8 +243,14 @@ __global__ void __launch_bounds__(kBlock, 3) gbm_round_sq_fused_kernel(const SqR
     if (WRITE_R) a.r[j] = d;
     accb[0] += (double)(0.5f * d * d);
   }
-  const bool last_b = block_reduce_publish<1>(accb, a.ws_b);  // Σloss -> a.ws_b.out (+ cross-GPU sum, host mirror + ticket)
-  if (a.timing && last_b && threadIdx.x == 0) a.out[13] = global_timer_us();
+  if constexpr (LOSS_REDUCE) {
+    const bool last_b = block_reduce_publish<1>(accb, a.ws_b);  // Σloss -> a.ws_b.out (+ cross-GPU sum, host mirror + ticket)
+    if (a.timing && last_b && threadIdx.x == 0) a.out[13] = global_timer_us();
+  } else if (a.timing) {
+    // no reduction (the loss came from the statistics): the latest stamp of any CTA marks the end of the update
+    __syncthreads();
+    if (threadIdx.x == 0) atomicMax(reinterpret_cast<unsigned long long*>(&a.out[13]), (unsigned long long)__double_as_longlong(global_timer_us()));
+  }
 }
 
 // =================================================================================== persistent line search
@@ -534,16 +567,17 @@ cudaError_t launch_ls(const LsArgs& a0, int sms, const LsLaunch& cfg, cudaStream
 
 }  // namespace
 
-cudaError_t launch_gbm_round_sq_fused(const SqRoundArgs& a, int write_r, int sms, int max_ctas_per_sm, cudaStream_t st,
-                                      int* grid_out) {
-  static int blocks_r = -1, blocks_n = -1;
-  if (blocks_r < 0) {
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_r, gbm_round_sq_fused_kernel<true>, kBlock, 0);
-    if (e != cudaSuccess) return e;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_n, gbm_round_sq_fused_kernel<false>, kBlock, 0);
+cudaError_t launch_gbm_round_sq_fused(const SqRoundArgs& a, int write_r, int loss_reduce, int sms, int max_ctas_per_sm,
+                                      cudaStream_t st, int* grid_out, void* window_base, size_t window_bytes) {
+  static int blocks[4] = {-1, -1, -1, -1};
+  void (*kerns[4])(const SqRoundArgs) = {gbm_round_sq_fused_kernel<false, false>, gbm_round_sq_fused_kernel<false, true>,
+                                         gbm_round_sq_fused_kernel<true, false>, gbm_round_sq_fused_kernel<true, true>};
+  const int which = (write_r ? 2 : 0) + (loss_reduce ? 1 : 0);
+  if (blocks[which] < 0) {
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks[which], kerns[which], kBlock, 0);
     if (e != cudaSuccess) return e;
   }
-  int per_sm = write_r ? blocks_r : blocks_n;
+  int per_sm = blocks[which];
   if (per_sm > max_ctas_per_sm) per_sm = max_ctas_per_sm;
   if (per_sm < 1) return cudaErrorLaunchOutOfResources;
   const int64_t ntiles = ((a.n >> 2) + (int64_t)kBlock * U_SQ - 1) / ((int64_t)kBlock * U_SQ);
@@ -556,14 +590,23 @@ cudaError_t launch_gbm_round_sq_fused(const SqRoundArgs& a, int write_r, int sms
   lc.blockDim = dim3(kBlock);
   lc.dynamicSmemBytes = 0;
   lc.stream = st;
-  cudaLaunchAttribute attr;
-  attr.id = cudaLaunchAttributeCooperative;
-  attr.val.cooperative = 1;  // co-residency of all CTAs is what makes the in-kernel flag wait deadlock-free
-  lc.attrs = &attr;
-  lc.numAttrs = 1;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeCooperative;
+  attr[0].val.cooperative = 1;  // co-residency of all CTAs is what makes the in-kernel flag wait deadlock-free
+  int na = 1;
+  if (window_base != nullptr && window_bytes > 0) {
+    attr[na].id = cudaLaunchAttributeAccessPolicyWindow;
+    attr[na].val.accessPolicyWindow.base_ptr = window_base;
+    attr[na].val.accessPolicyWindow.num_bytes = window_bytes;
+    attr[na].val.accessPolicyWindow.hitRatio = 1.0f;
+    attr[na].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    attr[na].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    ++na;
+  }
+  lc.attrs = attr;
+  lc.numAttrs = na;
   if (grid_out) *grid_out = (int)grid;
-  if (write_r) return cudaLaunchKernelEx(&lc, gbm_round_sq_fused_kernel<true>, a);
-  return cudaLaunchKernelEx(&lc, gbm_round_sq_fused_kernel<false>, a);
+  return cudaLaunchKernelEx(&lc, kerns[which], a);
 }
 
 bool gbm_linesearch_persist_supported(int loss) {

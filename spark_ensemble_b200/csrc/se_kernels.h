@@ -91,20 +91,25 @@ struct SqRoundArgs {
   int64_t n = 0;
   int stats_from_r = 0;
   int l2_hints = 0;
+  int l2_mode = 0;         // 0: evict_normal / evict_first hints; 1: evict_last on r and h (experiment)
   int timing = 0;          // write %globaltimer stamps (us) to out[10..13]: start, statistics folded, step published, end
   int prefetch_tiles = 0;  // y/F tiles of the update phase each CTA prefetches into L2 while it waits for the step
   double lr = 1.0, wsum = 1.0;                                   // learning rate, Σw (objective scale)
   double lo = 0.0, hi = 100.0, start = 1.0, rel = 1e-6, abs_tol = 1e-6;
   int max_eval = 100;
   RedWs ws_a{};  // statistics: out = `out`, no host mirror
-  RedWs ws_b{};  // loss: out = out + 8, host mirror + ticket
+  RedWs ws_b{};  // loss (only when it is reduced over the rows: bags): out = out + 8, host mirror + ticket
   double* out = nullptr;       // [0..2] statistics, [4] alpha, [5] objective, [6] +-evaluations, [8] Σloss
   double* host_res = nullptr;  // mapped host copy of out[0..6] (nullable)
+  // loss-from-statistics mode: the Brent thread also serves the host (final value + ticket) before the update phase ends
+  double* host_final = nullptr;
+  volatile unsigned long long* host_flag = nullptr;
+  unsigned long long host_ticket = 0;
   FusedSync* sync = nullptr;
   unsigned long long epoch = 0;
 };
-cudaError_t launch_gbm_round_sq_fused(const SqRoundArgs& a, int write_r, int sms, int max_ctas_per_sm, cudaStream_t stream,
-                                      int* grid_out);
+cudaError_t launch_gbm_round_sq_fused(const SqRoundArgs& a, int write_r, int loss_reduce, int sms, int max_ctas_per_sm,
+                                      cudaStream_t stream, int* grid_out, void* window_base = nullptr, size_t window_bytes = 0);
 
 // Brent's whole line search for a dim-1 scalar loss in one launch (persistent workers + coordinator warp).
 struct LsArgs {

@@ -967,8 +967,17 @@ def test_fused_squared_round(ctx, oracle, rng, n, weighted):
         ctx.set_option("fused_round", 0)
         a2, l2, ne2 = ctx.gbm_round(0.7, True, 1e-6, 100, residual=True)
         assert ctx.get_option("last_round_fused") == 0
-        assert a1 == pytest.approx(a2, rel=1e-9, abs=1e-12) and l1 == pytest.approx(l2, rel=1e-9)
+        assert a1 == pytest.approx(a2, rel=1e-9, abs=1e-12)
+        assert l1 == pytest.approx(l2, rel=RTOL)  # closed form over the fp64 statistics vs the sum of the fp32 rows
         close(F1, ctx.download(N.SLOT_F), rtol=1e-6)
+        # the in-kernel row reduction of the loss (the path bags use) agrees with the closed form
+        ctx.upload(N.SLOT_F, Fnow)
+        ctx.set_option("fused_round", 1)
+        ctx.set_option("fused_loss_reduce", 1)
+        a3, l3, ne3 = ctx.gbm_round(0.7, True, 1e-6, 100, residual=True)
+        ctx.set_option("fused_loss_reduce", 0)
+        assert (a3, ne3) == (a1, ne1) and l3 == pytest.approx(l1, rel=RTOL)
+        np.testing.assert_array_equal(F1, ctx.download(N.SLOT_F))
         # MaxEval exceeded: SE_ERR_OPT (TooManyEvaluationsException in the reference) and F is left untouched
         ctx.set_option("fused_round", 1)
         Fbefore = ctx.download(N.SLOT_F).copy()
