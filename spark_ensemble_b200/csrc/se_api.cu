@@ -1337,11 +1337,11 @@ int se_gbm_configure(se_ctx* ctx, int64_t n_train, int64_t n_valid, int dim, int
   SE_TRY(slot_alloc2d(ctx, SE_SLOT_H, dim, n_train));
   SE_TRY(slot_alloc2d(ctx, SE_SLOT_R, dim, n_train));
   if (g.has_w) SE_TRY(slot_alloc2d(ctx, SE_SLOT_W, 1, n_train));
-  if (n_valid > 0) {
-    SE_TRY(slot_alloc2d(ctx, SE_SLOT_VY, 1, n_valid));
-    SE_TRY(slot_alloc2d(ctx, SE_SLOT_VF, dim, n_valid));
-    SE_TRY(slot_alloc2d(ctx, SE_SLOT_VH, dim, n_valid));
-  }
+  // validation slots exist even for an EMPTY local validation shard (trailing row shards may be empty,
+  // ensemble.row_partition): the rank must still launch every validation reduction so that its peers' collectives complete
+  SE_TRY(slot_alloc2d(ctx, SE_SLOT_VY, 1, n_valid));
+  SE_TRY(slot_alloc2d(ctx, SE_SLOT_VF, dim, n_valid));
+  SE_TRY(slot_alloc2d(ctx, SE_SLOT_VH, dim, n_valid));
   return SE_OK;
 }
 
@@ -1461,8 +1461,12 @@ int se_gbm_update(se_ctx* ctx, const double* step, int flags, double* loss_sum, 
 int se_gbm_mean_loss(se_ctx* ctx, int which, double* out) {
   if (!ctx || !out) return fail(ctx, SE_ERR_ARG, "null argument");
   SE_REQUIRE(ctx, ctx->gbm.on, SE_ERR_STATE, "se_gbm_configure first");
-  SE_REQUIRE(ctx, which == 0 || (which == 1 && ctx->gbm.nv > 0), SE_ERR_ARG, "no validation shard");
+  SE_REQUIRE(ctx, which == 0 || which == 1, SE_ERR_ARG, "which must be 0 (train) or 1 (validation)");
   SE_TRY(ensure_counts(ctx));
+  // the GLOBAL count decides: a rank whose local shard is empty still launches the reduction (n = 0) so that the
+  // collective of its peers completes
+  SE_REQUIRE(ctx, (which == 1 ? ctx->gbm.nv_global : ctx->gbm.n_global) > 0.0, SE_ERR_ARG,
+             which == 1 ? "no validation rows on any rank" : "no training rows on any rank");
   SE_TRY(begin(ctx));
   GbmArgs a = gbm_args(ctx, which == 1);
   a.ws = red_ws(ctx);
@@ -1475,8 +1479,9 @@ int se_gbm_mean_loss(se_ctx* ctx, int which, double* out) {
 
 int se_gbm_update_validation(se_ctx* ctx, const double* step, double* mean_loss) {
   if (!ctx || !step) return fail(ctx, SE_ERR_ARG, "null argument");
-  SE_REQUIRE(ctx, ctx->gbm.on && ctx->gbm.nv > 0, SE_ERR_STATE, "no validation shard configured");
+  SE_REQUIRE(ctx, ctx->gbm.on, SE_ERR_STATE, "se_gbm_configure first");
   SE_TRY(ensure_counts(ctx));
+  SE_REQUIRE(ctx, ctx->gbm.nv_global > 0.0, SE_ERR_STATE, "no validation rows configured on any rank");
   SE_TRY(begin(ctx));
   GbmArgs a = gbm_args(ctx, true);
   for (int j = 0; j < ctx->gbm.dim; ++j) a.coef[j] = (float)step[j];

@@ -112,6 +112,19 @@ def main():
     assert abs(mx - orc.r2_max_error(v, pr)) <= 1e-6 * mx
     e2 = ctx.boostreg_error(sw, "exponential", mx)
     assert abs(e2 - orc.r2_estimator_error("exponential", v, pr, wb, sw, mx)) <= RT * e2
+    # ---- an EMPTY local validation shard still joins the validation collectives
+    nv_tiny = world - 1  # one validation row on every rank but the last
+    yv = rng.standard_normal(max(nv_tiny, 1)).astype(np.float32)
+    Fv = rng.standard_normal(max(nv_tiny, 1)).astype(np.float32)
+    mine = 1 if rank < world - 1 else 0
+    ctx.gbm_configure(1000, mine, 1, "squared", 0.0, False)
+    ctx.fill(N.SLOT_Y, 1.0); ctx.fill(N.SLOT_F, 0.0); ctx.fill(N.SLOT_H, 1.0)
+    if mine:
+        ctx.upload(N.SLOT_VY, yv[rank:rank + 1]); ctx.upload(N.SLOT_VF, Fv[rank:rank + 1]); ctx.fill(N.SLOT_VH, 0.0)
+    ml = ctx.gbm_mean_loss(True)
+    ref = float(np.mean(0.5 * (yv[:nv_tiny].astype(np.float64) - Fv[:nv_tiny]) ** 2))
+    assert abs(ml - ref) <= RT * ref, (ml, ref)
+    assert abs(ctx.gbm_update_validation([0.0]) - ref) <= RT * ref
     # ---- cooperative kernels across shards: the cross-GPU sums happen INSIDE the running kernel (peer mailboxes)
     import time
     if p2p:
