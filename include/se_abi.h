@@ -288,7 +288,13 @@ SE_API int se_agg_run(se_ctx* ctx, const double* weights, const double* init);
 /* Decision tree in array form (node i: feature[i] < 0 => leaf with value[i]; else go left when
  * x[feature[i]] <= threshold[i], as Spark's ContinuousSplit.shouldGoLeft).  Writes out_slot row
  * `out_row` ([.][n]) from X (which = 0: SE_SLOT_X, 1: SE_SLOT_VX). `subspace` maps model feature index
- * -> column of X (HasSubBag.slice, ensemble/HasSubBag.scala:81-84) or NULL for identity. */
+ * -> column of X (HasSubBag.slice, ensemble/HasSubBag.scala:81-84) or NULL for identity.
+ * The arrays must describe a TREE rooted at node 0: a node reached twice (cycle / shared child) fails with
+ * SE_ERR_ARG before anything is launched.  Thresholds: the device compares the fp32 feature with the fp32 threshold;
+ * pass the LARGEST float <= the fp64 threshold (round toward -inf: learners.py / FlatTree do) — then `x <= thr`
+ * decides exactly like the JVM for every feature value that is itself a float (which is what HBM holds).  A fp64
+ * feature value strictly between that float and the fp64 threshold can still change sides: the resident feature
+ * matrix is fp32 by contract (north_star), so transform with the model on the same fp32 features. */
 SE_API int se_tree_predict(se_ctx* ctx, int which, int n_nodes, const int32_t* feature,
                     const float* threshold, const int32_t* left, const int32_t* right,
                     const float* value, const int32_t* subspace, int n_subspace, int out_slot,

@@ -11,6 +11,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <unistd.h>
 
 #include <mutex>
 #include <string>
@@ -153,6 +154,7 @@ struct se_ctx {
   bool p2p = false;
   double* mbox_local = nullptr;
   std::vector<void*> mbox_peers;      // opened IPC mappings (index = rank; own entry = mbox_local)
+  std::vector<char> mbox_ipc;         // 1: mbox_peers[p] came from cudaIpcOpenMemHandle (close it); 0: same-process peer pointer
   double** d_mbox_table = nullptr;    // device copy of the pointer table
   int* d_p2p_err = nullptr;           // device alias of h_p2p_err (mapped pinned host memory: no copy to poll it)
   int* h_p2p_err = nullptr;
@@ -661,7 +663,7 @@ int se_ctx_destroy(se_ctx* ctx) {
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   if (ctx->comm && nccl().ok) {
     for (int p = 0; p < (int)ctx->mbox_peers.size(); ++p)
-      if (p != ctx->rank && ctx->mbox_peers[p]) cudaIpcCloseMemHandle(ctx->mbox_peers[p]);
+      if (p != ctx->rank && ctx->mbox_peers[p] && ctx->mbox_ipc[p]) cudaIpcCloseMemHandle(ctx->mbox_peers[p]);
     if (ctx->mbox_local) cudaFree(ctx->mbox_local);
     if (ctx->d_mbox_table) cudaFree(ctx->d_mbox_table);
     if (ctx->h_p2p_err) cudaFreeHost(ctx->h_p2p_err);
@@ -926,11 +928,19 @@ int se_comm_init(se_ctx* ctx, int nranks, int rank, const void* id, int bytes) {
          cudaIpcGetMemHandle(&mine, ctx->mbox_local) == cudaSuccess;
     cudaGetLastError();
   }
-  // exchange the handles (and everyone's readiness) through NCCL
-  const size_t hb = sizeof(cudaIpcMemHandle_t) + 8;
+  // exchange the handles (and everyone's readiness) through NCCL.  Ranks that live in the SAME process (one JVM /
+  // one Python process driving several GPUs: sharded.ShardedContext) cannot open each other's IPC handles — they
+  // exchange the raw device pointer instead and enable peer access between the two devices.
+  struct PeerBlob { cudaIpcMemHandle_t handle; unsigned char ok; unsigned char pad[3]; int32_t pid; int32_t device; int32_t pad2; uint64_t ptr; };
+  const size_t hb = sizeof(PeerBlob);
   std::vector<unsigned char> send(hb, 0), recv(hb * nranks, 0);
-  memcpy(send.data(), &mine, sizeof(mine));
-  send[sizeof(mine)] = (unsigned char)ok;
+  {
+    PeerBlob b;
+    memset(&b, 0, sizeof(b));
+    b.handle = mine; b.ok = (unsigned char)ok; b.pid = (int32_t)getpid(); b.device = ctx->device;
+    b.ptr = (uint64_t)(uintptr_t)ctx->mbox_local;
+    memcpy(send.data(), &b, sizeof(b));
+  }
   unsigned char *d_send = nullptr, *d_recv = nullptr;
   SE_CUDA(ctx, cudaMalloc(&d_send, hb));
   SE_CUDA(ctx, cudaMalloc(&d_recv, hb * nranks));
@@ -944,15 +954,28 @@ int se_comm_init(se_ctx* ctx, int nranks, int rank, const void* id, int bytes) {
   SE_CUDA(ctx, cudaMemcpyAsync(recv.data(), d_recv, hb * nranks, cudaMemcpyDeviceToHost, ctx->stream));
   SE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   int all_ok = 1;
-  for (int p = 0; p < nranks; ++p) all_ok &= recv[p * hb + sizeof(mine)];
+  for (int p = 0; p < nranks; ++p) all_ok &= reinterpret_cast<const PeerBlob*>(recv.data() + p * hb)->ok;
   ctx->mbox_peers.assign(nranks, nullptr);
+  ctx->mbox_ipc.assign(nranks, 0);
   if (all_ok) {
     for (int p = 0; p < nranks && all_ok; ++p) {
       if (p == rank) { ctx->mbox_peers[p] = ctx->mbox_local; continue; }
-      cudaIpcMemHandle_t h;
-      memcpy(&h, recv.data() + p * hb, sizeof(h));
+      PeerBlob b;
+      memcpy(&b, recv.data() + p * hb, sizeof(b));
       void* ptr = nullptr;
-      if (cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { all_ok = 0; cudaGetLastError(); }
+      if (b.pid == (int32_t)getpid()) {
+        int can = 0;
+        if (b.device == ctx->device) can = 1;
+        else if (cudaDeviceCanAccessPeer(&can, ctx->device, b.device) == cudaSuccess && can) {
+          const cudaError_t pe = cudaDeviceEnablePeerAccess(b.device, 0);
+          if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) can = 0;
+        }
+        cudaGetLastError();
+        if (can) ptr = (void*)(uintptr_t)b.ptr; else all_ok = 0;
+      } else {
+        if (cudaIpcOpenMemHandle(&ptr, b.handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { all_ok = 0; cudaGetLastError(); }
+        else ctx->mbox_ipc[p] = 1;
+      }
       ctx->mbox_peers[p] = ptr;
     }
   }
@@ -994,8 +1017,9 @@ int se_comm_clear_error(se_ctx* ctx) {
 
 static void release_p2p(se_ctx* ctx) {
   for (int p = 0; p < (int)ctx->mbox_peers.size(); ++p)
-    if (p != ctx->rank && ctx->mbox_peers[p]) cudaIpcCloseMemHandle(ctx->mbox_peers[p]);
+    if (p != ctx->rank && ctx->mbox_peers[p] && ctx->mbox_ipc[p]) cudaIpcCloseMemHandle(ctx->mbox_peers[p]);
   ctx->mbox_peers.clear();
+  ctx->mbox_ipc.clear();
   if (ctx->mbox_local) cudaFree(ctx->mbox_local);
   if (ctx->d_mbox_table) cudaFree(ctx->d_mbox_table);
   if (ctx->h_p2p_err) cudaFreeHost(ctx->h_p2p_err);
@@ -2167,6 +2191,24 @@ static int tree_predict_impl(se_ctx* ctx, int which, int n_nodes, const int32_t*
       SE_REQUIRE(ctx, left[i] >= 0 && left[i] < n_nodes && right[i] >= 0 && right[i] < n_nodes, SE_ERR_ARG, "node %d: bad child", i);
     }
     hf[i] = f; ht[i] = threshold[i]; hl[i] = left[i]; hr[i] = right[i];
+  }
+  // The device walk follows child links until it meets a leaf: reject anything that is not a tree rooted at node 0
+  // (a node reached twice means a cycle or a DAG: the kernel could spin forever on it)
+  {
+    std::vector<char> seen((size_t)n_nodes, 0);
+    std::vector<int32_t> stack;
+    stack.push_back(0);
+    seen[0] = 1;
+    while (!stack.empty()) {
+      const int32_t i = stack.back();
+      stack.pop_back();
+      if (hf[i] < 0) continue;  // leaf
+      for (const int32_t c : {hl[i], hr[i]}) {
+        SE_REQUIRE(ctx, !seen[c], SE_ERR_ARG, "node %d is reached twice (child of node %d): not a tree", c, i);
+        seen[c] = 1;
+        stack.push_back(c);
+      }
+    }
   }
   memcpy(hv, value, sizeof(float) * (size_t)n_nodes * n_out);
   SE_CUDA(ctx, cudaMemcpyAsync(ctx->d_small, ctx->h_small, bytes, cudaMemcpyHostToDevice, ctx->stream));

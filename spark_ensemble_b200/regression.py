@@ -95,7 +95,10 @@ class GBMRegressor(Params):
         param = exact_quantile(y, self("alpha")) if loss == "huber" else self("alpha")
         newton = updates == "newton" and loss == "squared"  # HasScalarHessian among selectable losses :369
 
-        ctx = Context(self.device)
+        # Param `devices` with two or more GPUs: rows are sharded over one context per GPU (sharded.ShardedContext),
+        # the per-round scalars are summed across GPUs inside the kernels; everything below is unchanged
+        from .sharded import make_context
+        ctx = make_context(self.device, self("devices"))
         try:
             eng = GBMEngine(ctx, n, nv, 1, loss, param, has_weights=w is not None)
             const_init = hasattr(init, "prediction")  # Dummy model: broadcast the constant on device
@@ -177,8 +180,12 @@ _preg = [
     # expert Param: "brent" = the reference's optimiser (default); "newton" = curvature-based line search on
     # the same objective (dim 1, losses with a hessian): same minimiser within tol, ~6x fewer data passes
     Param("lineSearch", "line-search optimiser for dim 1: brent (reference) or newton", lambda v: v in ("brent", "newton"), str),
+    # expert Param: GPUs to shard the rows of a fit over (one context per GPU, contiguous row blocks); [] = `device`
+    Param("devices", "CUDA device ordinals to shard the training rows over", lambda v: all(int(d) >= 0 for d in v),
+          lambda v: [int(d) for d in v]),
 ]
 _GBM_REG_DEFAULTS = {**_d, **_ds, **_db, **_dg, "loss": "squared", "alpha": 0.9, "initStrategy": "constant", "residentFeatures": False, "lineSearch": "brent",
+                     "devices": [],
                      "seed": java_string_hash("org.apache.spark.ml.regression.GBMRegressor")}
 GBMRegressor._declare(_p + _ps + _pb + _pg + _preg, _GBM_REG_DEFAULTS)
 

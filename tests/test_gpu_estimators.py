@@ -315,3 +315,57 @@ def test_boosting_classifier_resident_features(algorithm):
     for a, b in zip(host.trainingHistory, dev.trainingHistory):
         assert a["estimatorError"] == pytest.approx(b["estimatorError"], rel=1e-6, abs=1e-9)
         assert a["sumWeights"] == pytest.approx(b["sumWeights"], rel=1e-6)
+
+
+def test_gbm_regressor_fit_sharded_over_two_gpus():
+    """Param `devices`: the SAME fit with the rows sharded over two contexts in one process (sharded.ShardedContext;
+    cross-GPU sums inside the kernels) reproduces the single-GPU fit: same number of learners, weights within the
+    optimiser tolerance, predictions within 1e-5."""
+    import numpy as np
+    from spark_ensemble_b200 import DataFrame, _native as N
+    from spark_ensemble_b200.learners import DecisionTreeRegressor
+    from spark_ensemble_b200.regression import GBMRegressor
+    if N.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    rng = np.random.default_rng(3)
+    n, d = 20011, 9
+    X = rng.standard_normal((n, d)).astype(np.float32)
+    y = (X[:, 0] * 2 - X[:, 1] + 0.3 * X[:, 2] * X[:, 3] + 0.1 * rng.standard_normal(n)).astype(np.float64)
+    val = rng.random(n) < 0.2
+    df = DataFrame(features=X, label=y, validation=val)
+    fits = []
+    for devices in ([], [0, 1]):
+        for resident in (False, True):
+            g = (GBMRegressor().setBaseLearner(DecisionTreeRegressor(maxDepth=4)).setNumBaseLearners(8)
+                 .setValidationIndicatorCol("validation").setLearningRate(0.5))
+            g.set("devices", devices)
+            g.set("residentFeatures", resident)
+            m = g.fit(df)
+            fits.append((devices, resident, m))
+    base = fits[0][2]
+    pb = base.transform(df)["prediction"]
+    for devices, resident, m in fits[1:]:
+        assert m.numModels == base.numModels
+        np.testing.assert_allclose(m.weights, base.weights, rtol=1e-5, atol=4e-6)
+        np.testing.assert_allclose(m.transform(df)["prediction"], pb, rtol=1e-5, atol=1e-5 * float(np.abs(pb).max()))
+
+
+def test_tree_arrays_must_form_a_tree(monkeypatch):
+    """A child reached twice (cycle / shared node) would make the device walk spin: rejected with SE_ERR_ARG
+    before anything is launched."""
+    import numpy as np
+    from spark_ensemble_b200 import _native as N
+    from spark_ensemble_b200.context import Context
+    with Context(0) as ctx:
+        n, d = 64, 3
+        ctx.alloc(N.SLOT_X, d, n)
+        ctx.fill(N.SLOT_X, 0.5)
+        ctx.alloc(N.SLOT_H, 1, n)
+        good = {"feature": [0, -1, -1], "threshold": [0.0, 0, 0], "left": [1, 0, 0], "right": [2, 0, 0], "value": [0, 1.0, 2.0]}
+        ctx.tree_predict(good, N.SLOT_H, 0)
+        assert np.all(ctx.download(N.SLOT_H) == 2.0)
+        for bad in ({**good, "left": [0, 0, 0]},                      # node 0 is its own child
+                    {**good, "left": [1, 0, 0], "right": [1, 0, 0]},  # shared child
+                    {"feature": [0, 1, -1], "threshold": [0.0, 0, 0], "left": [1, 0, 0], "right": [2, 2, 0], "value": [0, 0, 1.0]}):
+            with pytest.raises(ValueError, match="not a tree"):
+                ctx.tree_predict(bad, N.SLOT_H, 0)
