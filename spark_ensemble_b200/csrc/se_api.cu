@@ -13,6 +13,7 @@
 #include <string.h>
 #include <unistd.h>
 
+#include <algorithm>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -98,6 +99,22 @@ struct SlotBuf {
   float* d = nullptr;
   int64_t rows = 0, cols = 0, ld = 0;
   size_t bytes = 0;
+};
+
+// uint8 rank matrix of a feature-matrix slot for the tree walk (se_models.cu): per column the sorted thresholds seen
+// so far (<= 255), X8[col][i] = #{thresholds of col strictly below X[col][i]}
+struct BinState {
+  uint8_t* d8 = nullptr;
+  int64_t ld8 = 0, n = 0;
+  int d = 0;
+  bool valid = false;                      // X8 reflects the current contents of the slot for every column with edges
+  std::vector<std::vector<float>> edges;   // per column
+  std::vector<char> dirty;
+  float* d_edges = nullptr;                // [d][256]
+  int32_t* d_nedges = nullptr;             // [d]
+  int32_t* d_cols = nullptr;               // [d]
+  uint4* d_nodes = nullptr;
+  size_t nodes_cap = 0;
 };
 
 }  // namespace
@@ -207,6 +224,10 @@ struct se_ctx {
   int last_round_fused = 0, last_ls_workers = 0, last_ls_resident = 0, last_ls_passes = 0, last_fused_grid = 0;
   double last_ls_hit_ratio = 0.0;
   double last_round_stats[3] = {0.0, 0.0, 0.0};
+  // binned (uint8) copies of X / VX for the tree walk
+  BinState bins[2];
+  int tree_bins = 1;                  // 0: always walk the fp32 matrix
+  int last_tree_binned = 0, last_tree_rebinned_cols = 0;
   std::string err;
   // stopwatch + per-kernel-family timing
   cudaEvent_t tm0 = nullptr, tm1 = nullptr;
@@ -431,8 +452,24 @@ int fetch_scalars(se_ctx* ctx, int off, int count, double* out, int op = kNcclSu
   return check_p2p(ctx);
 }
 
+// any write to a feature-matrix slot makes its rank matrix stale
+void touch_slot(se_ctx* ctx, int slot) {
+  if (slot == SE_SLOT_X) ctx->bins[0].valid = false;
+  if (slot == SE_SLOT_VX) ctx->bins[1].valid = false;
+}
+
+void free_bins(BinState& B) {
+  if (B.d8) cudaFree(B.d8);
+  if (B.d_edges) cudaFree(B.d_edges);
+  if (B.d_nedges) cudaFree(B.d_nedges);
+  if (B.d_cols) cudaFree(B.d_cols);
+  if (B.d_nodes) cudaFree(B.d_nodes);
+  B = BinState();
+}
+
 int slot_alloc2d(se_ctx* ctx, int slot, int64_t rows, int64_t cols) {
   SE_REQUIRE(ctx, slot >= 0 && slot < SE_NUM_SLOTS, SE_ERR_ARG, "bad slot %d", slot);
+  touch_slot(ctx, slot);
   SE_REQUIRE(ctx, rows >= 1 && cols >= 0, SE_ERR_ARG, "bad slot shape %lld x %lld", (long long)rows,
              (long long)cols);
   SlotBuf& s = ctx->slot[slot];
@@ -676,6 +713,8 @@ int se_ctx_destroy(se_ctx* ctx) {
   if (ctx->d_partials) cudaFree(ctx->d_partials);
   if (ctx->d_counter) cudaFree(ctx->d_counter);
   if (ctx->d_fsync) cudaFree(ctx->d_fsync);
+  free_bins(ctx->bins[0]);
+  free_bins(ctx->bins[1]);
   if (ctx->h_bad_label) cudaFreeHost(ctx->h_bad_label);
   if (ctx->d_small) cudaFree(ctx->d_small);
   if (ctx->h_mirror) cudaFreeHost(ctx->h_mirror);
@@ -779,12 +818,13 @@ int se_ctx_kernel_time_reset(se_ctx* ctx) {
 
 namespace {
 struct OptKey { const char* name; int id; };
-enum { OPT_FUSED_LOSS_REDUCE, OPT_FUSED_L2_MODE, OPT_FUSED_TIMING, OPT_LAST_FUSED_US0, OPT_LAST_FUSED_US1, OPT_LAST_FUSED_US2, OPT_FUSED_PREFETCH_MB, OPT_FUSED_ROUND, OPT_FUSED_MAX_ROWS, OPT_FUSED_CTAS, OPT_LS_MODE, OPT_LS_RESIDENT, OPT_LS_CTAS, OPT_L2_PERSIST,
+enum { OPT_TREE_BINS, OPT_LAST_TREE_BINNED, OPT_LAST_TREE_REBINNED, OPT_FUSED_LOSS_REDUCE, OPT_FUSED_L2_MODE, OPT_FUSED_TIMING, OPT_LAST_FUSED_US0, OPT_LAST_FUSED_US1, OPT_LAST_FUSED_US2, OPT_FUSED_PREFETCH_MB, OPT_FUSED_ROUND, OPT_FUSED_MAX_ROWS, OPT_FUSED_CTAS, OPT_LS_MODE, OPT_LS_RESIDENT, OPT_LS_CTAS, OPT_L2_PERSIST,
        OPT_L2_PERSIST_FRAC, OPT_PEER_TIMEOUT_MS, OPT_ALTERNATE, OPT_L2_HINTS, OPT_CTAS_PER_SM, OPT_HOST_MIRROR,
        // read-only diagnostics
        OPT_LAST_ROUND_FUSED, OPT_LAST_LS_WORKERS, OPT_LAST_LS_PASSES, OPT_LAST_LS_HIT_RATIO, OPT_LAST_FUSED_GRID,
        OPT_L2_PERSIST_MAX, OPT_L2_WINDOW_MAX, OPT_LAST_STAT0, OPT_LAST_STAT1, OPT_LAST_STAT2 };
 const OptKey kOpts[] = {
+  {"tree_bins", OPT_TREE_BINS}, {"last_tree_binned", OPT_LAST_TREE_BINNED}, {"last_tree_rebinned_cols", OPT_LAST_TREE_REBINNED},
   {"fused_loss_reduce", OPT_FUSED_LOSS_REDUCE}, {"fused_l2_mode", OPT_FUSED_L2_MODE}, {"fused_timing", OPT_FUSED_TIMING}, {"last_fused_stats_us", OPT_LAST_FUSED_US0}, {"last_fused_brent_us", OPT_LAST_FUSED_US1},
   {"last_fused_update_us", OPT_LAST_FUSED_US2}, {"fused_prefetch_mb", OPT_FUSED_PREFETCH_MB}, {"fused_round", OPT_FUSED_ROUND}, {"fused_round_max_rows", OPT_FUSED_MAX_ROWS}, {"fused_ctas_per_sm", OPT_FUSED_CTAS},
   {"ls_mode", OPT_LS_MODE}, {"ls_resident", OPT_LS_RESIDENT}, {"ls_ctas_per_sm", OPT_LS_CTAS}, {"l2_persist", OPT_L2_PERSIST},
@@ -811,6 +851,7 @@ int se_ctx_set_option(se_ctx* ctx, const char* key, double value) {
     case OPT_FUSED_MAX_ROWS: ctx->fused_round_max_rows = (int64_t)value; break;
     case OPT_FUSED_TIMING: ctx->fused_timing = iv != 0; break;
     case OPT_FUSED_LOSS_REDUCE: ctx->fused_loss_reduce = iv != 0; break;
+    case OPT_TREE_BINS: ctx->tree_bins = iv != 0; break;
     case OPT_FUSED_L2_MODE: SE_REQUIRE(ctx, iv >= 0 && iv <= 2, SE_ERR_ARG, "fused_l2_mode in {0,1,2}"); ctx->fused_l2_mode = iv; if (iv != 2) release_l2_persist(ctx); break;
     case OPT_FUSED_PREFETCH_MB: SE_REQUIRE(ctx, value >= 0.0 && value <= 512.0, SE_ERR_ARG, "fused_prefetch_mb in [0,512]"); ctx->fused_prefetch_mb = value; break;
     case OPT_FUSED_CTAS: SE_REQUIRE(ctx, iv >= 1 && iv <= 8, SE_ERR_ARG, "fused_ctas_per_sm in [1,8]"); ctx->fused_ctas_per_sm = iv; break;
@@ -837,6 +878,9 @@ int se_ctx_get_option(const se_ctx* ctx, const char* key, double* value) {
     case OPT_FUSED_PREFETCH_MB: *value = ctx->fused_prefetch_mb; break;
     case OPT_FUSED_TIMING: *value = ctx->fused_timing; break;
     case OPT_FUSED_LOSS_REDUCE: *value = ctx->fused_loss_reduce; break;
+    case OPT_TREE_BINS: *value = ctx->tree_bins; break;
+    case OPT_LAST_TREE_BINNED: *value = ctx->last_tree_binned; break;
+    case OPT_LAST_TREE_REBINNED: *value = ctx->last_tree_rebinned_cols; break;
     case OPT_FUSED_L2_MODE: *value = ctx->fused_l2_mode; break;
     case OPT_LAST_FUSED_US0: *value = ctx->last_fused_us[0]; break;
     case OPT_LAST_FUSED_US1: *value = ctx->last_fused_us[1]; break;
@@ -1086,6 +1130,8 @@ int se_slot_free(se_ctx* ctx, int slot) {
   SE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   if (ctx->slot[slot].d) SE_CUDA(ctx, cudaFree(ctx->slot[slot].d));
   ctx->slot[slot] = SlotBuf();
+  if (slot == SE_SLOT_X) free_bins(ctx->bins[0]);
+  if (slot == SE_SLOT_VX) free_bins(ctx->bins[1]);
   return SE_OK;
 }
 
@@ -1094,6 +1140,7 @@ int se_slot_info(const se_ctx* ctx, int slot, void** device_ptr, int64_t* count)
   if (slot < 0 || slot >= SE_NUM_SLOTS) return fail(nullptr, SE_ERR_ARG, "bad slot %d", slot);
   if (device_ptr) {
     *device_ptr = ctx->slot[slot].d;
+    touch_slot(const_cast<se_ctx*>(ctx), slot);
     // the caller may write through the raw pointer: drop everything cached about the slot's contents
     se_ctx* mctx = const_cast<se_ctx*>(ctx);
     if (slot == SE_SLOT_Y || slot == SE_SLOT_F || slot == SE_SLOT_R) mctx->gbm.r_current = false;
@@ -1115,6 +1162,7 @@ int se_slot_layout(const se_ctx* ctx, int slot, int64_t* rows, int64_t* cols, in
 int se_upload(se_ctx* ctx, int slot, const float* host, int64_t count, int64_t offset) {
   if (!ctx || !host) return fail(ctx, SE_ERR_ARG, "null argument");
   SE_REQUIRE(ctx, slot >= 0 && slot < SE_NUM_SLOTS, SE_ERR_ARG, "bad slot %d", slot);
+  touch_slot(ctx, slot);
   SE_CUDA(ctx, cudaSetDevice(ctx->device));
   if (slot == SE_SLOT_W || slot == SE_SLOT_BAG) ctx->gbm.wsum_valid = false;
   if (slot == SE_SLOT_Y || slot == SE_SLOT_F || slot == SE_SLOT_R) ctx->gbm.r_current = false;
@@ -1130,6 +1178,7 @@ int se_upload(se_ctx* ctx, int slot, const float* host, int64_t count, int64_t o
 int se_upload_f64(se_ctx* ctx, int slot, const double* host, int64_t count, int64_t offset) {
   if (!ctx || !host) return fail(ctx, SE_ERR_ARG, "null argument");
   SE_REQUIRE(ctx, slot >= 0 && slot < SE_NUM_SLOTS, SE_ERR_ARG, "bad slot %d", slot);
+  touch_slot(ctx, slot);
   SE_CUDA(ctx, cudaSetDevice(ctx->device));
   if (slot == SE_SLOT_W || slot == SE_SLOT_BAG) ctx->gbm.wsum_valid = false;
   if (slot == SE_SLOT_Y || slot == SE_SLOT_F || slot == SE_SLOT_R) ctx->gbm.r_current = false;
@@ -1151,6 +1200,7 @@ int se_upload_f64(se_ctx* ctx, int slot, const double* host, int64_t count, int6
 int se_upload_rowmajor(se_ctx* ctx, int slot, const float* host, int64_t n_rows, int d, int64_t row_offset) {
   if (!ctx || (!host && n_rows > 0)) return fail(ctx, SE_ERR_ARG, "null argument");
   SE_REQUIRE(ctx, slot >= 0 && slot < SE_NUM_SLOTS, SE_ERR_ARG, "bad slot %d", slot);
+  touch_slot(ctx, slot);
   const SlotBuf& X = ctx->slot[slot];
   SE_REQUIRE(ctx, X.d && X.rows == d, SE_ERR_STATE, "slot %d must be allocated as [%d][n] (has [%lld][%lld])", slot, d,
              (long long)X.rows, (long long)X.cols);
@@ -1247,6 +1297,7 @@ int se_download_scaled(se_ctx* ctx, int slot, double scale, float* host, int64_t
 int se_fill(se_ctx* ctx, int slot, float value, int64_t count, int64_t offset) {
   if (!ctx) return fail(nullptr, SE_ERR_ARG, "null context");
   SE_REQUIRE(ctx, slot >= 0 && slot < SE_NUM_SLOTS, SE_ERR_ARG, "bad slot %d", slot);
+  touch_slot(ctx, slot);
   SE_CUDA(ctx, cudaSetDevice(ctx->device));
   if (slot == SE_SLOT_W || slot == SE_SLOT_BAG) ctx->gbm.wsum_valid = false;
   if (slot == SE_SLOT_Y || slot == SE_SLOT_F || slot == SE_SLOT_R) ctx->gbm.r_current = false;
@@ -1262,6 +1313,7 @@ int se_copy_slot(se_ctx* ctx, int dst_slot, int src_slot) {
              SE_ERR_ARG, "bad slot");
   const SlotBuf &d = ctx->slot[dst_slot], &s = ctx->slot[src_slot];
   SE_REQUIRE(ctx, d.d && s.d && d.rows == s.rows && d.cols == s.cols, SE_ERR_STATE, "slot shapes differ");
+  touch_slot(ctx, dst_slot);
   if (dst_slot == SE_SLOT_Y || dst_slot == SE_SLOT_F || dst_slot == SE_SLOT_R) ctx->gbm.r_current = false;
   SE_CUDA(ctx, cudaSetDevice(ctx->device));
   SE_CUDA(ctx, cudaMemcpyAsync(d.d, s.d, sizeof(float) * (size_t)(s.rows * s.ld), cudaMemcpyDeviceToDevice, ctx->stream));
@@ -1272,6 +1324,7 @@ int se_fill_synthetic(se_ctx* ctx, int slot, int kind, uint64_t seed, double a, 
                       int64_t offset) {
   if (!ctx) return fail(nullptr, SE_ERR_ARG, "null context");
   SE_REQUIRE(ctx, slot >= 0 && slot < SE_NUM_SLOTS, SE_ERR_ARG, "bad slot %d", slot);
+  touch_slot(ctx, slot);
   SE_REQUIRE(ctx, kind >= 0 && kind <= 3, SE_ERR_ARG, "bad synthetic kind %d", kind);
   SE_CUDA(ctx, cudaSetDevice(ctx->device));
   if (slot == SE_SLOT_W || slot == SE_SLOT_BAG) ctx->gbm.wsum_valid = false;
@@ -2159,6 +2212,87 @@ int se_agg_run(se_ctx* ctx, const double* weights, const double* init) {
 }
 
 // ---- on-device base models ---------------------------------------------------------------------
+namespace {
+// Walk the uint8 rank matrix instead of the fp32 features when every threshold of the tree fits the per-column edge
+// lists (<= 255 per column; Spark's trees draw theirs from the <= maxBins - 1 candidates of findSplits, the same on
+// every round).  Returns 1 when the binned kernel was launched, 0 when the caller must take the fp32 walk.
+int tree_predict_binned(se_ctx* ctx, int which, const SlotBuf& X, int n_nodes, const int32_t* col, const float* thr,
+                        const int32_t* left, const int32_t* right, const TreeArgs& t) {
+  ctx->last_tree_binned = 0;
+  ctx->last_tree_rebinned_cols = 0;
+  if (!ctx->tree_bins || n_nodes > 65535 || X.rows > 65535 || X.cols == 0) return 0;
+  BinState& B = ctx->bins[which];
+  const int d = (int)X.rows;
+  if (!B.d8 || B.d != d || B.n != X.cols) {
+    free_bins(B);
+    const int64_t ld8 = ((X.cols + 127) / 128) * 128;
+    bool ok = cudaMalloc(&B.d8, (size_t)d * (size_t)ld8) == cudaSuccess && cudaMalloc(&B.d_edges, sizeof(float) * 256 * (size_t)d) == cudaSuccess &&
+              cudaMalloc(&B.d_nedges, sizeof(int32_t) * (size_t)d) == cudaSuccess && cudaMalloc(&B.d_cols, sizeof(int32_t) * (size_t)d) == cudaSuccess;
+    if (!ok) {  // e.g. no room for another d x n bytes: keep walking the fp32 matrix
+      cudaGetLastError();
+      free_bins(B);
+      ctx->tree_bins = 0;
+      return 0;
+    }
+    B.ld8 = ld8; B.n = X.cols; B.d = d;
+    B.edges.assign((size_t)d, std::vector<float>());
+    B.dirty.assign((size_t)d, 0);
+    B.valid = true;
+  }
+  if (!B.valid) {  // the slot was rewritten: every column that has edges must be re-ranked
+    for (int c = 0; c < d; ++c) B.dirty[c] = B.edges[c].empty() ? 0 : 1;
+    B.valid = true;
+  }
+  for (int i = 0; i < n_nodes; ++i) {
+    if (col[i] < 0) continue;
+    if (!(thr[i] == thr[i])) return 0;  // NaN threshold: leave it to the fp32 walk
+    std::vector<float>& E = B.edges[col[i]];
+    auto it = std::lower_bound(E.begin(), E.end(), thr[i]);
+    if (it != E.end() && *it == thr[i]) continue;
+    if (E.size() >= 255) return 0;      // this column needs more ranks than a byte holds
+    E.insert(it, thr[i]);
+    B.dirty[col[i]] = 1;
+  }
+  std::vector<int32_t> cols;
+  for (int c = 0; c < d; ++c)
+    if (B.dirty[c]) cols.push_back(c);
+  if (!cols.empty()) {
+    std::vector<int32_t> ne((size_t)d);
+    for (int c = 0; c < d; ++c) ne[c] = (int32_t)B.edges[c].size();
+    for (int32_t c : cols)
+      SE_CUDA(ctx, cudaMemcpyAsync(B.d_edges + (size_t)c * 256, B.edges[c].data(), sizeof(float) * B.edges[c].size(), cudaMemcpyHostToDevice, ctx->stream));
+    SE_CUDA(ctx, cudaMemcpyAsync(B.d_nedges, ne.data(), sizeof(int32_t) * (size_t)d, cudaMemcpyHostToDevice, ctx->stream));
+    SE_CUDA(ctx, cudaMemcpyAsync(B.d_cols, cols.data(), sizeof(int32_t) * cols.size(), cudaMemcpyHostToDevice, ctx->stream));
+    SE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // the host vectors above go out of scope
+    BinArgs b;
+    b.X = X.d; b.X8 = B.d8; b.n = X.cols; b.ld = X.rows > 1 ? X.ld : X.cols; b.ld8 = B.ld8;
+    b.cols = B.d_cols; b.edges = B.d_edges; b.n_edges = B.d_nedges;
+    SE_LAUNCH_T(ctx, SE_KF_OTHER, launch_bin_columns(b, (int)cols.size(), ctx->sms, ctx->stream));
+    for (int32_t c : cols) B.dirty[c] = 0;
+    ctx->last_tree_rebinned_cols = (int)cols.size();
+  }
+  if (B.nodes_cap < (size_t)n_nodes) {
+    if (B.d_nodes) cudaFree(B.d_nodes);
+    B.d_nodes = nullptr; B.nodes_cap = 0;
+    SE_CUDA(ctx, cudaMalloc(&B.d_nodes, sizeof(uint4) * (size_t)n_nodes));
+    B.nodes_cap = (size_t)n_nodes;
+  }
+  std::vector<uint4> nodes((size_t)n_nodes);
+  for (int i = 0; i < n_nodes; ++i) {
+    if (col[i] < 0) { nodes[i] = make_uint4(0u, 0u, 0x80000000u, 0u); continue; }
+    const std::vector<float>& E = B.edges[col[i]];
+    const uint32_t j = (uint32_t)(std::lower_bound(E.begin(), E.end(), thr[i]) - E.begin());  // x <= t_j  <=>  rank(x) <= j
+    const uint64_t off = (uint64_t)col[i] * (uint64_t)B.ld8;
+    nodes[i] = make_uint4((uint32_t)off, (uint32_t)(off >> 32), j, (uint32_t)left[i] | ((uint32_t)right[i] << 16));
+  }
+  SE_CUDA(ctx, cudaMemcpyAsync(B.d_nodes, nodes.data(), sizeof(uint4) * (size_t)n_nodes, cudaMemcpyHostToDevice, ctx->stream));
+  SE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  SE_LAUNCH_T(ctx, SE_KF_TREE, launch_tree_predict_binned(t, B.d8, B.d_nodes, ctx->sms, ctx->stream));
+  ctx->last_tree_binned = 1;
+  return 1;
+}
+}  // namespace
+
 static int tree_predict_impl(se_ctx* ctx, int which, int n_nodes, const int32_t* feature, const float* threshold,
                              const int32_t* left, const int32_t* right, const float* value, int n_out,
                              const int32_t* subspace, int n_subspace, int out_slot, int out_row) {
@@ -2223,6 +2357,11 @@ static int tree_predict_impl(se_ctx* ctx, int which, int n_nodes, const int32_t*
   t.n_out = n_out;
   t.ld_out = O.rows > 1 ? O.ld : O.cols;
   t.out = O.d + (int64_t)out_row * t.ld_out;
+  {
+    const int rc = tree_predict_binned(ctx, which, X, n_nodes, hf, ht, hl, hr, t);
+    if (rc < 0) return rc;
+    if (rc == 1) return end(ctx);
+  }
   SE_LAUNCH_T(ctx, SE_KF_TREE, launch_tree_predict(t, ctx->sms, ctx->stream));
   return end(ctx);
 }

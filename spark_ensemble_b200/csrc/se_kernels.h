@@ -212,6 +212,18 @@ struct TreeArgs {
   int64_t ld_out = 0;
 };
 cudaError_t launch_tree_predict(const TreeArgs& a, int sms, cudaStream_t s);
+// uint8 rank matrix of X for the tree walk (se_models.cu): X8[col][i] = #{thresholds of col strictly below X[col][i]}
+struct BinArgs {
+  const float* X = nullptr;      // [d][ld]
+  uint8_t* X8 = nullptr;         // [d][ld8]
+  int64_t n = 0, ld = 0, ld8 = 0;
+  const int32_t* cols = nullptr;     // device: the columns to (re)build, one per blockIdx.y
+  const float* edges = nullptr;      // device [d][256]: sorted thresholds per column
+  const int32_t* n_edges = nullptr;  // device [d]
+};
+cudaError_t launch_bin_columns(const BinArgs& a, int n_cols, int sms, cudaStream_t s);
+// nodes: packed {x,y: byte offset of the column in X8 (64 bit); z: bin threshold | leaf << 31; w: left | right << 16}
+cudaError_t launch_tree_predict_binned(const TreeArgs& a, const uint8_t* X8, const uint4* nodes, int sms, cudaStream_t s);
 cudaError_t launch_linear_predict(const float* X, int64_t n, int64_t ld, int n_coef,
                                   const float* coef, const int32_t* cols, float intercept,
                                   float* out, int sms, cudaStream_t s);

@@ -6,6 +6,8 @@
 // fitted model here means h never crosses PCIe.  Supported: binary decision trees
 // with continuous splits (Spark ContinuousSplit.shouldGoLeft: x <= threshold goes left) and linear
 // models.  HasSubBag.slice (ensemble/HasSubBag.scala:81-84) is folded into the feature->column map.
+#include <stdlib.h>
+
 #include "se_kernels.h"
 
 namespace se {
@@ -13,6 +15,30 @@ namespace se {
 namespace {
 
 constexpr int TV = 4;  // rows per thread (one float4 of outputs)
+
+// Outputs of TV consecutive rows whose leaves are node[0..TV): the leaf value (regression / label) or the leaf's
+// class-probability vector (one coalesced row store per class).
+__device__ __forceinline__ void write_leaf_outputs(const TreeArgs& a, const int (&node)[TV], int64_t i0, const float* s_val) {
+  if (s_val == nullptr) {
+    for (int k = 0; k < a.n_out; ++k) {
+      if (i0 + TV <= a.n) {
+        st_stream4(a.out + (int64_t)k * a.ld_out + i0,
+                   make_float4(__ldg(a.value + node[0] * a.n_out + k), __ldg(a.value + node[1] * a.n_out + k),
+                               __ldg(a.value + node[2] * a.n_out + k), __ldg(a.value + node[3] * a.n_out + k)));
+      } else {
+#pragma unroll
+        for (int e = 0; e < TV; ++e)
+          if (i0 + e < a.n) a.out[(int64_t)k * a.ld_out + i0 + e] = __ldg(a.value + node[e] * a.n_out + k);
+      }
+    }
+  } else if (i0 + TV <= a.n) {
+    st_stream4(a.out + i0, make_float4(s_val[node[0]], s_val[node[1]], s_val[node[2]], s_val[node[3]]));
+  } else {
+#pragma unroll
+    for (int e = 0; e < TV; ++e)
+      if (i0 + e < a.n) a.out[i0 + e] = s_val[node[e]];
+  }
+}
 
 // Tree arrays are staged once per CTA in shared memory; each thread walks TV rows in lockstep so
 // TV independent gathers are in flight.  Rows of a warp are consecutive, so every X access of a
@@ -60,26 +86,120 @@ __global__ void __launch_bounds__(kBlock) tree_predict_kernel(const TreeArgs a) 
           any |= live[e];
         }
     }
-    if (!scalar) {
-      // leaf vectors (class probabilities of a classification tree): one coalesced row store per class
-      for (int k = 0; k < a.n_out; ++k) {
-        if (i0 + TV <= a.n) {
-          st_stream4(a.out + (int64_t)k * a.ld_out + i0,
-                     make_float4(__ldg(a.value + node[0] * a.n_out + k), __ldg(a.value + node[1] * a.n_out + k),
-                                 __ldg(a.value + node[2] * a.n_out + k), __ldg(a.value + node[3] * a.n_out + k)));
+    write_leaf_outputs(a, node, i0, scalar ? s_val : nullptr);
+  }
+}
+
+// ------------------------------------------------------------------ binned feature matrix (uint8) and its tree walk
+// ncu on the fp32 walk above (round 1): 174 B/row of DRAM traffic for a depth-6 tree whose algorithmic need is 24 B/row
+// — once the rows of a warp diverge every 4-byte gather drags a whole 32-byte sector (8 rows) in.  Decision trees only
+// COMPARE features with thresholds, and Spark's trees draw every threshold of a feature from the <= maxBins - 1 split
+// candidates `findSplits` computes once per fit: so X can be replaced, for the walk, by the RANK of each value among the
+// thresholds seen so far — bin(x) = #{t : t < x} in a uint8 — and `x <= t_j` becomes `bin(x) <= j`, EXACTLY (no
+// rounding involved: it is the same comparison, pre-evaluated).  A gather then costs 1 byte and a sector holds 32 rows:
+// 3.5x fewer DRAM bytes for the same walk.  The host side (se_api.cu tree_predict_impl) keeps the per-column threshold
+// lists, re-bins the columns a new tree adds thresholds to, and falls back to the fp32 walk when a column would need
+// more than 255 thresholds.
+
+// One CTA = one (column, row tile): the column's sorted thresholds sit in shared memory; a thread turns 4 fp32 values
+// into 4 ranks (branch-free binary search over <= 255 edges: 8 steps) and stores them as one 32-bit word.
+__global__ void __launch_bounds__(kBlock) bin_columns_kernel(const BinArgs a) {
+  __shared__ float s_edge[256];
+  const int which = blockIdx.y;
+  const int col = a.cols[which];
+  const int ne = a.n_edges[col];
+  for (int i = threadIdx.x; i < 256; i += kBlock) s_edge[i] = (i < ne) ? a.edges[(size_t)col * 256 + i] : INFINITY;
+  __syncthreads();
+  const float* x = a.X + (int64_t)col * a.ld;
+  uint8_t* out = a.X8 + (int64_t)col * a.ld8;
+  const int64_t n4 = (a.n + 3) >> 2;  // the slot is padded: a 128-bit read at a 4-aligned row below n stays inside
+  for (int64_t g = (int64_t)blockIdx.x * kBlock + threadIdx.x; g < n4; g += (int64_t)gridDim.x * kBlock) {
+    const float4 v = ld_stream4(x + 4 * g);
+    uint32_t word = 0;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float xv = f4at(v, e);
+      // rank = number of edges strictly below xv (NaN ranks 0... Spark sends NaN/missing nowhere: not supported)
+      int lo = 0;
+#pragma unroll
+      for (int step = 128; step > 0; step >>= 1)
+        if (lo + step <= 256 && s_edge[lo + step - 1] < xv) lo += step;
+      word |= (uint32_t)(lo > 255 ? 255 : lo) << (8 * e);
+    }
+    *reinterpret_cast<uint32_t*>(out + 4 * g) = word;
+  }
+}
+
+// Packed node (16 bytes, one 128-bit shared-memory read per row and level): x,y = byte offset of the node's column
+// in X8 (column * ld8, 64 bit); z = bin threshold | leaf << 31; w = left | right << 16.
+// ncu on the first version (two 8-byte node reads per row and level, 64-bit multiply for the column offset): 39
+// instructions per row and level, 45 % issue utilisation at 49 % occupancy — the walk was issue-bound, not DRAM-bound
+// (52 % of peak).
+template <int W, int MINB>  // W words of 4 consecutive rows per thread (independent gather chains), MINB CTAs per SM
+__global__ void __launch_bounds__(kBlock, MINB) tree_predict_binned_kernel(const TreeArgs a, const uint8_t* __restrict__ X8,
+                                                                           const uint4* __restrict__ nodes) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint4* s_node = reinterpret_cast<uint4*>(smem_raw);
+  float* s_val = reinterpret_cast<float*>(s_node + a.n_nodes);
+  const bool scalar = (a.n_out == 1);
+  for (int i = threadIdx.x; i < a.n_nodes; i += kBlock) {
+    s_node[i] = nodes[i];
+    if (scalar) s_val[i] = a.value[i];
+  }
+  __syncthreads();
+  const int64_t ngroups = (a.n + TV - 1) / TV;          // groups of 4 rows
+  const int64_t nsuper = (ngroups + W - 1) / W;         // a thread owns W groups, kBlock apart inside a CTA tile
+  for (int64_t sg = blockIdx.x; sg * kBlock < nsuper * kBlock && sg * (int64_t)kBlock * W < ngroups; sg += gridDim.x) {
+    int node[W][TV];
+    int64_t i0[W];
+    bool done[W];
+#pragma unroll
+    for (int w = 0; w < W; ++w) {
+      const int64_t g = (sg * W + w) * kBlock + threadIdx.x;   // coalesced: consecutive threads, consecutive groups
+      i0[w] = g * TV;
+      done[w] = g >= ngroups;
+#pragma unroll
+      for (int e = 0; e < TV; ++e) node[w][e] = 0;
+    }
+    for (;;) {
+      bool any = false;
+#pragma unroll
+      for (int w = 0; w < W; ++w) {
+        if (done[w]) continue;
+        const bool full = (i0[w] + TV <= a.n);
+        const uint8_t* row = X8 + i0[w];
+        uint4 nd[TV];
+        bool live[TV];
+        bool anyw = false;
+#pragma unroll
+        for (int e = 0; e < TV; ++e) {
+          nd[e] = s_node[node[w][e]];
+          live[e] = ((nd[e].z >> 31) == 0) && (full || i0[w] + e < a.n);
+          anyw |= live[e];
+        }
+        if (!anyw) { done[w] = true; continue; }
+        any = true;
+        uint32_t b[TV];
+        // rows of a word that still share a node (always at the root, often below it) are served by ONE 32-bit load
+        if (full && node[w][0] == node[w][1] && node[w][1] == node[w][2] && node[w][2] == node[w][3]) {
+          const uint64_t off = ((uint64_t)nd[0].y << 32) | nd[0].x;
+          const uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(row + off));
+#pragma unroll
+          for (int e = 0; e < TV; ++e) b[e] = (v >> (8 * e)) & 0xFFu;
         } else {
 #pragma unroll
           for (int e = 0; e < TV; ++e)
-            if (i0 + e < a.n) a.out[(int64_t)k * a.ld_out + i0 + e] = __ldg(a.value + node[e] * a.n_out + k);
+            if (live[e]) b[e] = __ldg(row + ((((uint64_t)nd[e].y) << 32) | nd[e].x) + e);
         }
-      }
-    } else if (i0 + TV <= a.n) {
-      st_stream4(a.out + i0, make_float4(s_val[node[0]], s_val[node[1]], s_val[node[2]], s_val[node[3]]));
-    } else {
 #pragma unroll
-      for (int e = 0; e < TV; ++e)
-        if (i0 + e < a.n) a.out[i0 + e] = s_val[node[e]];
+        for (int e = 0; e < TV; ++e)
+          if (live[e]) node[w][e] = (b[e] <= (nd[e].z & 0xFFu)) ? (int)(nd[e].w & 0xFFFFu) : (int)(nd[e].w >> 16);
+      }
+      if (!any) break;
     }
+#pragma unroll
+    for (int w = 0; w < W; ++w)
+      if ((sg * W + w) * kBlock + threadIdx.x < ngroups) write_leaf_outputs(a, node[w], i0[w], scalar ? s_val : nullptr);
   }
 }
 
@@ -141,6 +261,46 @@ cudaError_t launch_tree_predict(const TreeArgs& a, int sms, cudaStream_t st) {
   if (need < 1) need = 1;
   const int64_t cap = (int64_t)sms * 8;
   tree_predict_kernel<<<(int)(need < cap ? need : cap), kBlock, smem, st>>>(a);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_bin_columns(const BinArgs& a, int n_cols, int sms, cudaStream_t st) {
+  if (n_cols <= 0) return cudaSuccess;
+  const int64_t n4 = (a.n + 3) >> 2;
+  int64_t gx = (n4 + kBlock - 1) / kBlock;
+  const int64_t cap = ((int64_t)sms * 16 + n_cols - 1) / n_cols;
+  if (gx > cap) gx = cap;
+  if (gx < 1) gx = 1;
+  bin_columns_kernel<<<dim3((unsigned)gx, (unsigned)n_cols), kBlock, 0, st>>>(a);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_tree_predict_binned(const TreeArgs& a, const uint8_t* X8, const uint4* nodes, int sms, cudaStream_t st) {
+  const size_t smem = (size_t)a.n_nodes * (sizeof(uint4) + sizeof(float));
+  if (smem > 200 * 1024) return cudaErrorInvalidValue;
+  static const int variant = [] { const char* e = getenv("SE_TREE_VARIANT"); return e ? atoi(e) : 0; }();
+  const int64_t ngroups = (a.n + TV - 1) / TV;
+#define SE_TREE_LAUNCH(W, MINB)                                                                                      \
+  do {                                                                                                               \
+    auto kern = tree_predict_binned_kernel<W, MINB>;                                                                 \
+    if (smem > 48 * 1024) {                                                                                          \
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);            \
+      if (e != cudaSuccess) return e;                                                                                \
+    }                                                                                                                \
+    int64_t need = (ngroups + (int64_t)kBlock * W - 1) / ((int64_t)kBlock * W);                                      \
+    if (need < 1) need = 1;                                                                                          \
+    const int64_t cap = (int64_t)sms * 16;                                                                           \
+    kern<<<(int)(need < cap ? need : cap), kBlock, smem, st>>>(a, X8, nodes);                                        \
+  } while (0)
+  switch (variant) {
+    case 1: SE_TREE_LAUNCH(1, 8); break;
+    case 2: SE_TREE_LAUNCH(2, 4); break;
+    case 3: SE_TREE_LAUNCH(2, 3); break;
+    case 4: SE_TREE_LAUNCH(4, 2); break;
+    case 5: SE_TREE_LAUNCH(1, 6); break;
+    default: SE_TREE_LAUNCH(1, 4); break;
+  }
+#undef SE_TREE_LAUNCH
   return cudaGetLastError();
 }
 

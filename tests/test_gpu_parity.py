@@ -1128,3 +1128,100 @@ def test_bad_labels_fail_loudly(ctx, rng, K, bad):
     ctx.sync()
     raw = ctx.download(N.SLOT_RAW)
     assert np.all(raw.reshape(K, n).sum(0) == M)
+
+
+def _random_tree(rng, depth, d, candidates, n_out=1):
+    """Complete binary tree in array form; thresholds drawn from per-feature candidate lists (like Spark's findSplits)."""
+    nn = 2 ** (depth + 1) - 1
+    idx = np.arange(nn)
+    leaf = idx >= 2 ** depth - 1
+    feat = rng.integers(0, d, nn)
+    thr = np.array([candidates[f][rng.integers(0, len(candidates[f]))] for f in feat], dtype=np.float32)
+    t = {"feature": np.where(leaf, -1, feat).astype(np.int32), "threshold": np.where(leaf, 0.0, thr).astype(np.float32),
+         "left": np.where(leaf, 0, 2 * idx + 1).astype(np.int32), "right": np.where(leaf, 0, 2 * idx + 2).astype(np.int32),
+         "value": rng.standard_normal(nn).astype(np.float32)}
+    if n_out > 1:
+        t["values"] = rng.random((nn, n_out)).astype(np.float32)
+    return t
+
+
+def _walk(tree, X):
+    """Plain numpy walk: x <= threshold goes left (Spark ContinuousSplit.shouldGoLeft)."""
+    node = np.zeros(X.shape[0], dtype=np.int64)
+    for _ in range(64):
+        f = tree["feature"][node]
+        live = f >= 0
+        if not live.any():
+            break
+        x = X[np.arange(X.shape[0]), np.maximum(f, 0)]
+        nxt = np.where(x <= tree["threshold"][node], tree["left"][node], tree["right"][node])
+        node = np.where(live, nxt, node)
+    return node
+
+
+@pytest.mark.parametrize("n,d,depth", [(1, 3, 2), (1027, 7, 4), (200_003, 33, 6)])
+def test_tree_walk_over_binned_features_is_exact(ctx, rng, n, d, depth):
+    """The tree walk over the uint8 RANK matrix (bin(x) = #{thresholds < x}; `x <= t_j` <=> `bin <= j`) must pick the
+    same leaf as the fp32 walk for every row — including rows sitting exactly ON a threshold —, keep doing so as new
+    trees add thresholds (columns are re-ranked), after the feature matrix is rewritten, through a subspace map, and
+    for leaf vectors; a column that needs more than 255 thresholds sends the tree to the fp32 walk."""
+    from spark_ensemble_b200 import _native as N
+    X = rng.standard_normal((n, d)).astype(np.float32)
+    cand = [np.unique(np.concatenate([rng.standard_normal(31).astype(np.float32), X[rng.integers(0, n, 4), f]])) for f in range(d)]
+    ctx.alloc(N.SLOT_X, d, n)
+    ctx.upload_rowmajor(N.SLOT_X, X)
+    ctx.alloc(N.SLOT_H, 1, n)
+    ctx.set_option("tree_bins", 1)
+    rebinned = 0
+    for k in range(6):
+        tree = _random_tree(rng, depth, d, cand)
+        leaf = _walk(tree, X)
+        ctx.tree_predict(tree, N.SLOT_H, 0)
+        assert ctx.get_option("last_tree_binned") == 1
+        rebinned += ctx.get_option("last_tree_rebinned_cols")
+        np.testing.assert_array_equal(ctx.download(N.SLOT_H), tree["value"][leaf])
+    assert rebinned >= 1
+    # once every candidate threshold has been seen nothing is re-ranked any more (the steady state of a Spark fit)
+    for f in range(d):
+        for t0 in range(0, len(cand[f]), 3):
+            ts = list(cand[f][t0:t0 + 3]) + [cand[f][0]] * 3
+            stump = {"feature": [f, f, f, -1, -1, -1, -1], "threshold": [ts[0], ts[1], ts[2], 0, 0, 0, 0],
+                     "left": [1, 3, 5, 0, 0, 0, 0], "right": [2, 4, 6, 0, 0, 0, 0], "value": [0, 0, 0, 1.0, 2.0, 3.0, 4.0]}
+            ctx.tree_predict(stump, N.SLOT_H, 0)
+    tree = _random_tree(rng, depth, d, cand)
+    ctx.tree_predict(tree, N.SLOT_H, 0)
+    assert ctx.get_option("last_tree_binned") == 1 and ctx.get_option("last_tree_rebinned_cols") == 0
+    np.testing.assert_array_equal(ctx.download(N.SLOT_H), tree["value"][_walk(tree, X)])
+    # rewriting the feature matrix invalidates the ranks
+    X2 = rng.standard_normal((n, d)).astype(np.float32)
+    ctx.upload_rowmajor(N.SLOT_X, X2)
+    tree = _random_tree(rng, depth, d, cand)
+    ctx.tree_predict(tree, N.SLOT_H, 0)
+    assert ctx.get_option("last_tree_binned") == 1 and ctx.get_option("last_tree_rebinned_cols") >= 1
+    np.testing.assert_array_equal(ctx.download(N.SLOT_H), tree["value"][_walk(tree, X2)])
+    # fp32 walk on the same tree: identical
+    ctx.set_option("tree_bins", 0)
+    ctx.tree_predict(tree, N.SLOT_H, 0)
+    assert ctx.get_option("last_tree_binned") == 0
+    np.testing.assert_array_equal(ctx.download(N.SLOT_H), tree["value"][_walk(tree, X2)])
+    ctx.set_option("tree_bins", 1)
+    # subspace map + leaf vectors
+    if d >= 3:
+        sub = np.sort(rng.choice(d, size=max(2, d // 2), replace=False)).astype(np.int32)
+        tr = _random_tree(rng, depth, len(sub), [cand[c] for c in sub], n_out=3)
+        ctx.alloc(N.SLOT_PROBA, 3, n)
+        ctx.tree_predict_multi(tr, N.SLOT_PROBA, subspace=sub)
+        assert ctx.get_option("last_tree_binned") == 1
+        np.testing.assert_array_equal(ctx.download(N.SLOT_PROBA).reshape(3, n), tr["values"][_walk(tr, X2[:, sub])].T)
+    # a column with more than 255 distinct thresholds cannot be ranked in a byte: fp32 walk, still exact
+    many = [np.sort(rng.standard_normal(400).astype(np.float32))]
+    seen_fallback = False
+    for k in range(200):
+        tr = _random_tree(rng, 6, d, [many[0]] * d)
+        ctx.tree_predict(tr, N.SLOT_H, 0)
+        seen_fallback |= ctx.get_option("last_tree_binned") == 0
+        np.testing.assert_array_equal(ctx.download(N.SLOT_H), tr["value"][_walk(tr, X2)])
+        if seen_fallback:
+            break
+    assert seen_fallback
+    ctx.free(N.SLOT_X)
