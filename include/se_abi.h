@@ -68,7 +68,7 @@ enum se_slot {
   SE_SLOT_F = 2,      /* [dim][n]   running predictions  (GBMRegressor.scala:313, GBMClassifier.scala:294) */
   SE_SLOT_H = 3,      /* [dim][n]   directions = base model outputs this round (:405,:435)     */
   SE_SLOT_R = 4,      /* [dim][n]   pseudo-residuals = base-learner labels (:368-385)          */
-  SE_SLOT_WOUT = 5,   /* [dim][n]   base-learner weights (newton: 1/2 h/S w, :379)             */
+  SE_SLOT_WOUT = 5,   /* [dim][n]   base-learner weights (newton: 1/2 h/S w, :379; the device holds 1/2 h w, se_download applies 1/S_dim) */
   SE_SLOT_VY = 6,     /* [nv]       validation labels                                          */
   SE_SLOT_VF = 7,     /* [dim][nv]  validation predictions (:324,:444-449)                     */
   SE_SLOT_VH = 8,     /* [dim][nv]  validation directions                                      */

@@ -507,6 +507,64 @@ __global__ void __launch_bounds__(T) agg_wmedian_kernel(const float* __restrict_
   }
 }
 
+// Any number of models (M <= 8192): ONE WARP per row.  The row's words live in the warp's slice of shared memory and
+// are sorted by a warp-cooperative bitonic network (lane e handles the pairs (e, e^j), e^j > e, 32 at a time); lane 0
+// then accumulates the weights in sorted order, sequentially in fp64 — the reference's order (ensemble/Utils.scala:
+// 26-40), so the selected element is identical.  The reference has no bound on M (JVM arrays); this is the general
+// path behind the register (M <= 64) and thread-per-row (M <= 256) kernels.
+constexpr int kWmWarps = 2;
+__global__ void __launch_bounds__(32 * kWmWarps) agg_wmedian_warp_kernel(const float* __restrict__ P, int64_t n, int64_t ld,
+                                                                         int M, int Mp, const double* __restrict__ a,
+                                                                         float* __restrict__ out) {
+  extern __shared__ __align__(128) unsigned char wm_raw[];
+  double* s_a = reinterpret_cast<double*>(wm_raw);  // [M]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned long long* words = reinterpret_cast<unsigned long long*>(s_a + M) + (size_t)warp * Mp;  // [Mp], this warp's
+  for (int m = threadIdx.x; m < M; m += 32 * kWmWarps) s_a[m] = a[m];
+  __syncthreads();
+  for (int64_t row = (int64_t)blockIdx.x * kWmWarps + warp; row < n; row += (int64_t)gridDim.x * kWmWarps) {
+    for (int m = lane; m < Mp; m += 32) {
+      unsigned long long w = ~0ull;  // padding sorts last
+      if (m < M) w = ((unsigned long long)wm_key(ld_stream1(P + (int64_t)m * ld + row)) << 32) | (unsigned long long)(unsigned)m;
+      words[m] = w;
+    }
+    __syncwarp();
+    for (int k = 2; k <= Mp; k <<= 1) {
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        for (int e = lane; e < Mp; e += 32) {
+          const int l = e ^ j;
+          if (l > e) {
+            const unsigned long long x = words[e], y = words[l];
+            const bool up = ((e & k) == 0);
+            if ((x > y) == up) {
+              words[e] = y;
+              words[l] = x;
+            }
+          }
+        }
+        __syncwarp();
+      }
+    }
+    if (lane == 0) {
+      double total = 0.0;
+      for (int m = 0; m < M; ++m) total += s_a[(unsigned)words[m]];
+      const double half = 0.5 * total;
+      double cum = 0.0;
+      unsigned long long pick = words[M - 1];
+      for (int m = 0; m < M; ++m) {
+        const unsigned long long w = words[m];
+        cum += s_a[(unsigned)w];
+        if (cum >= half) {
+          pick = w;
+          break;
+        }
+      }
+      out[row] = wm_unkey((uint32_t)(pick >> 32));
+    }
+    __syncwarp();
+  }
+}
+
 // Same algorithm with the row's words in REGISTERS (Mp <= 64): the network is fully unrolled, so every
 // compare-exchange is ~6 ALU instructions and no memory traffic — the shared-memory form above moves 32 B per
 // compare-exchange and thread and is bound by shared-memory bandwidth (measured 8.0 ms for 25 M rows at M = 32).
@@ -705,7 +763,20 @@ cudaError_t launch_agg(const AggArgs& a, int ctas_per_sm, int sms, cudaStream_t 
       }
       const int T = 64;
       const size_t smem = (size_t)a.M * sizeof(double) + (size_t)Mp * T * sizeof(unsigned long long);
-      if (smem > 200 * 1024) return cudaErrorInvalidValue;
+      if (smem > 200 * 1024) {  // M > 256: one warp per row
+        const size_t wsmem = (size_t)a.M * sizeof(double) + (size_t)kWmWarps * Mp * sizeof(unsigned long long);
+        if (wsmem > 200 * 1024) return cudaErrorInvalidValue;  // M > 8192
+        if (wsmem > 48 * 1024) {
+          cudaError_t e = cudaFuncSetAttribute(agg_wmedian_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem);
+          if (e != cudaSuccess) return e;
+        }
+        int per_sm_w = (int)((220 * 1024) / (wsmem + 1024));
+        if (per_sm_w < 1) per_sm_w = 1;
+        if (per_sm_w > 16) per_sm_w = 16;
+        const int gridw = grid_rows(a.n, kWmWarps, per_sm_w, sms);
+        agg_wmedian_warp_kernel<<<gridw, 32 * kWmWarps, wsmem, st>>>(a.P, a.n, a.ld, a.M, Mp, a.weights64, a.raw);
+        return cudaGetLastError();
+      }
       auto kern = agg_wmedian_kernel<64>;
       if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -224,6 +224,19 @@ struct se_ctx {
   int last_round_fused = 0, last_ls_workers = 0, last_ls_resident = 0, last_ls_passes = 0, last_fused_grid = 0;
   double last_ls_hit_ratio = 0.0;
   double last_round_stats[3] = {0.0, 0.0, 0.0};
+  // newton updates: SE_SLOT_WOUT holds 1/2 hc w; the 1/S_j of each dimension is applied on download
+  std::vector<float> wout_scale;
+  bool wout_scaled = false;
+  // LogLoss with more than kMaxDim classes (se_gbm_generic.cu): buffers sized for the configured dim
+  struct {
+    int dim = 0, grid = 0;
+    float* d_coef = nullptr;
+    float* h_coef = nullptr;      // pinned
+    double* d_partials = nullptr; // [grid][dim + 1]
+    double* d_out = nullptr;      // [dim + 1]
+    double* h_out = nullptr;      // pinned
+    bool pending = false;         // the last GBM launch left its sums in d_out
+  } big;
   // binned (uint8) copies of X / VX for the tree walk
   BinState bins[2];
   int tree_bins = 1;                  // 0: always walk the fp32 matrix
@@ -454,6 +467,7 @@ int fetch_scalars(se_ctx* ctx, int off, int count, double* out, int op = kNcclSu
 
 // any write to a feature-matrix slot makes its rank matrix stale
 void touch_slot(se_ctx* ctx, int slot) {
+  if (slot == SE_SLOT_WOUT) ctx->wout_scaled = false;
   if (slot == SE_SLOT_X) ctx->bins[0].valid = false;
   if (slot == SE_SLOT_VX) ctx->bins[1].valid = false;
 }
@@ -715,6 +729,11 @@ int se_ctx_destroy(se_ctx* ctx) {
   if (ctx->d_fsync) cudaFree(ctx->d_fsync);
   free_bins(ctx->bins[0]);
   free_bins(ctx->bins[1]);
+  if (ctx->big.d_coef) cudaFree(ctx->big.d_coef);
+  if (ctx->big.h_coef) cudaFreeHost(ctx->big.h_coef);
+  if (ctx->big.d_partials) cudaFree(ctx->big.d_partials);
+  if (ctx->big.d_out) cudaFree(ctx->big.d_out);
+  if (ctx->big.h_out) cudaFreeHost(ctx->big.h_out);
   if (ctx->h_bad_label) cudaFreeHost(ctx->h_bad_label);
   if (ctx->d_small) cudaFree(ctx->d_small);
   if (ctx->h_mirror) cudaFreeHost(ctx->h_mirror);
@@ -1283,6 +1302,14 @@ int se_download(se_ctx* ctx, int slot, float* host, int64_t count, int64_t offse
     return SE_OK;
   }));
   SE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (slot == SE_SLOT_WOUT && ctx->wout_scaled) {
+    // newton base-learner weights: 1/2 hc w on the device, x 1/S_dim here (GBMRegressor.scala:379)
+    const int64_t cols = ctx->slot[slot].cols;
+    for (int64_t i = 0; i < count; ++i) {
+      const size_t j = (size_t)(cols > 0 ? (offset + i) / cols : 0);
+      if (j < ctx->wout_scale.size()) host[i] *= ctx->wout_scale[j];
+    }
+  }
   return check_labels(ctx);  // e.g. the probabilities of an aggregation that met a vote outside [0, K)
 }
 
@@ -1399,7 +1426,7 @@ int se_gbm_configure(se_ctx* ctx, int64_t n_train, int64_t n_valid, int dim, int
   if (!ctx) return fail(nullptr, SE_ERR_ARG, "null context");
   SE_REQUIRE(ctx, n_train >= 0 && n_valid >= 0, SE_ERR_ARG, "negative row count");
   SE_REQUIRE(ctx, loss >= SE_LOSS_SQUARED && loss <= SE_LOSS_LOGLOSS, SE_ERR_ARG, "unknown loss %d", loss);
-  SE_REQUIRE(ctx, dim >= 1 && dim <= kMaxDim, SE_ERR_ARG, "dim %d outside [1,%d]", dim, kMaxDim);
+  SE_REQUIRE(ctx, dim >= 1 && dim <= kMaxDimGeneric, SE_ERR_ARG, "dim %d outside [1,%d]", dim, kMaxDimGeneric);
   SE_REQUIRE(ctx, (loss == SE_LOSS_LOGLOSS) || dim == 1, SE_ERR_ARG, "scalar losses have dim 1 (got %d)", dim);
   SE_CUDA(ctx, cudaSetDevice(ctx->device));
   auto& g = ctx->gbm;
@@ -1440,20 +1467,92 @@ int se_gbm_set_bag(se_ctx* ctx, int on) {
   return SE_OK;
 }
 
-static int newton_finish(se_ctx* ctx, double* sum_hess) {
-  // S_j (all-reduced) -> WOUT_j *= 1/S_j   (GBMRegressor.scala:373,379; GBMClassifier.scala:344-355,364)
+namespace {
+int ensure_big(se_ctx* ctx, int dim) {
+  auto& b = ctx->big;
+  if (b.dim >= dim && b.d_out) return SE_OK;
+  if (b.d_coef) cudaFree(b.d_coef);
+  if (b.h_coef) cudaFreeHost(b.h_coef);
+  if (b.d_partials) cudaFree(b.d_partials);
+  if (b.d_out) cudaFree(b.d_out);
+  if (b.h_out) cudaFreeHost(b.h_out);
+  b.d_coef = nullptr; b.h_coef = nullptr; b.d_partials = nullptr; b.d_out = nullptr; b.h_out = nullptr; b.dim = 0; b.grid = 0; b.pending = false;
+  int grid = ctx->sms * 8;
+  if (grid > 1024) grid = 1024;
+  SE_CUDA(ctx, cudaMalloc(&b.d_coef, sizeof(float) * (size_t)dim));
+  SE_CUDA(ctx, cudaMallocHost(&b.h_coef, sizeof(float) * (size_t)dim));
+  SE_CUDA(ctx, cudaMalloc(&b.d_partials, sizeof(double) * (size_t)grid * (size_t)(dim + 1)));
+  SE_CUDA(ctx, cudaMalloc(&b.d_out, sizeof(double) * (size_t)(dim + 1)));
+  SE_CUDA(ctx, cudaMallocHost(&b.h_out, sizeof(double) * (size_t)(dim + 1)));
+  b.dim = dim;
+  b.grid = grid;
+  return SE_OK;
+}
+
+// One GBM kernel launch for the configured loss.  `coef` (alpha or step, gbm.dim values, nullable) goes into the kernel
+// arguments for dim <= kMaxDim and into a device buffer for the general LogLoss path beyond it.
+int gbm_launch(se_ctx* ctx, int family, int mode, GbmArgs& a, const double* coef) {
   const int dim = ctx->gbm.dim;
-  double s[1 + kMaxDim];
-  SE_TRY(fetch_scalars(ctx, 0, 1 + dim, s));
-  float* fact = reinterpret_cast<float*>(ctx->h_small);
+  ctx->big.pending = false;
+  if (dim <= kMaxDim) {
+    if (coef)
+      for (int j = 0; j < dim; ++j) a.coef[j] = (float)coef[j];
+    SE_LAUNCH_T(ctx, family, launch_gbm(ctx->gbm.loss, mode, a, ctx->ctas_per_sm, ctx->sms, ctx->stream));
+    return SE_OK;
+  }
+  SE_TRY(ensure_big(ctx, dim));
+  auto& b = ctx->big;
+  if (coef) {
+    SE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // h_coef may still feed the previous launch
+    for (int j = 0; j < dim; ++j) b.h_coef[j] = (float)coef[j];
+    SE_CUDA(ctx, cudaMemcpyAsync(b.d_coef, b.h_coef, sizeof(float) * (size_t)dim, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  GenericArgs ga;
+  ga.coef = b.d_coef;
+  ga.partials = b.d_partials;
+  ga.out = b.d_out;
+  const int64_t groups = (a.n + 31) / 32;
+  int grid = (int)(groups < (int64_t)b.grid ? (groups > 0 ? groups : 1) : b.grid);
+  // the sums of this path are all-reduced by NCCL (fetch below): disarm the in-kernel exchange / host mirror
+  ctx->last_reduce_global = false;
+  ctx->mirror_valid = false;
+  SE_LAUNCH_T(ctx, family, launch_gbm_logloss_generic(mode, a, ga, grid, ctx->stream));
+  b.pending = true;
+  return SE_OK;
+}
+
+// The sums of the last gbm_launch: [0] Σloss, [1 + j] per-dimension sums — global (summed across GPUs).
+int gbm_fetch(se_ctx* ctx, int count, double* out) {
+  if (!ctx->big.pending) return fetch_scalars(ctx, 0, count, out);
+  auto& b = ctx->big;
+  b.pending = false;
+  if (ctx->comm && ctx->nranks > 1) {
+    NcclApi& api = nccl();
+    int rc = api.AllReduce(b.d_out, b.d_out, (size_t)(ctx->gbm.dim + 1), kNcclFloat64, kNcclSum, ctx->comm, ctx->stream);
+    if (rc != 0) return fail(ctx, SE_ERR_NCCL, "ncclAllReduce: %s", api.GetErrorString(rc));
+  }
+  SE_CUDA(ctx, cudaMemcpyAsync(b.h_out, b.d_out, sizeof(double) * (size_t)count, cudaMemcpyDeviceToHost, ctx->stream));
+  SE_TRY(end(ctx));
+  SE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  for (int i = 0; i < count; ++i) out[i] = b.h_out[i];
+  return check_labels(ctx);
+}
+}  // namespace
+
+static int newton_finish(se_ctx* ctx, double* sum_hess) {
+  // S_j (all-reduced) -> the base-learner weights are WOUT_j * 1/S_j  (GBMRegressor.scala:373,379;
+  // GBMClassifier.scala:344-355,364).  The kernel left the unnormalised 1/2 hc w in SE_SLOT_WOUT; the per-dimension
+  // factor 1/S_j is applied where the weights LEAVE the device (se_download / se_download_scaled on SE_SLOT_WOUT) —
+  // round 1 ran a separate 8 B/row pass over WOUT for it (newton K1 0.76-0.87 of the HBM roofline because of that pass).
+  const int dim = ctx->gbm.dim;
+  std::vector<double> s((size_t)dim + 1);
+  SE_TRY(gbm_fetch(ctx, 1 + dim, s.data()));
+  ctx->wout_scale.assign((size_t)dim, 0.f);
   for (int j = 0; j < dim; ++j) {
-    fact[j] = (float)(1.0 / s[1 + j]);
+    ctx->wout_scale[j] = (float)(1.0 / s[1 + j]);
     if (sum_hess) sum_hess[j] = s[1 + j];
   }
-  SE_CUDA(ctx, cudaMemcpyAsync(ctx->d_small, fact, sizeof(float) * dim, cudaMemcpyHostToDevice, ctx->stream));
-  const SlotBuf& wo = ctx->slot[SE_SLOT_WOUT];
-  SE_LAUNCH(ctx, launch_scale_rows(wo.d, ctx->gbm.n, wo.ld, dim, reinterpret_cast<const float*>(ctx->d_small),
-                                   ctx->sms, ctx->stream));
+  ctx->wout_scaled = true;
   ctx->h_scal[0] = s[0];
   return SE_OK;
 }
@@ -1465,9 +1564,9 @@ int se_gbm_pseudo_residuals(se_ctx* ctx, int newton, double* sum_hess) {
   SE_TRY(begin(ctx));
   if (newton) SE_TRY(slot_alloc2d(ctx, SE_SLOT_WOUT, ctx->gbm.dim, ctx->gbm.n));
   GbmArgs a = gbm_args(ctx, false);
+  ctx->wout_scaled = false;
   if (newton) a.ws = red_ws(ctx);  // Σ max(H,1e-2): reducing launch
-  SE_LAUNCH_T(ctx, SE_KF_RESID, launch_gbm(ctx->gbm.loss, newton ? GBM_RESID_NEWTON : GBM_RESID, a, ctx->ctas_per_sm,
-                            ctx->sms, ctx->stream));
+  SE_TRY(gbm_launch(ctx, SE_KF_RESID, newton ? GBM_RESID_NEWTON : GBM_RESID, a, nullptr));
   if (newton) SE_TRY(newton_finish(ctx, sum_hess));
   ctx->gbm.r_current = true;  // squared loss: r = y - F for gradient and newton (h = 1) alike
   return end(ctx);
@@ -1480,7 +1579,6 @@ int se_gbm_linesearch_eval(se_ctx* ctx, const double* alpha, double* loss, doubl
   SE_TRY(begin(ctx));
   const int dim = ctx->gbm.dim;
   GbmArgs a = gbm_args(ctx, false);
-  for (int j = 0; j < dim; ++j) a.coef[j] = (float)alpha[j];
   if (ctx->ls_packed) {  // inside se_gbm_linesearch_brent: bit-identical 8 B/row view
     a.y = nullptr;
     a.F = ctx->d_ls_u;
@@ -1489,9 +1587,9 @@ int se_gbm_linesearch_eval(se_ctx* ctx, const double* alpha, double* loss, doubl
   a.ws = red_ws(ctx);
   // Brent consumes the objective value only: skip the gradient/curvature arithmetic when nobody asked for it
   const int eval_mode = (!grad && ctx->gbm.loss != SE_LOSS_LOGLOSS) ? GBM_EVAL_LOSS : GBM_EVAL;
-  SE_LAUNCH_T(ctx, SE_KF_EVAL, launch_gbm(ctx->gbm.loss, eval_mode, a, ctx->ctas_per_sm, ctx->sms, ctx->stream));
-  double s[1 + kMaxDim];
-  SE_TRY(fetch_scalars(ctx, 0, 1 + dim, s));
+  SE_TRY(gbm_launch(ctx, SE_KF_EVAL, eval_mode, a, alpha));
+  std::vector<double> s((size_t)dim + 1);
+  SE_TRY(gbm_fetch(ctx, 1 + dim, s.data()));
   // lossSum is accumulated `dim` times per row in the reference (GBMLoss.scala:60-64)
   *loss = (double)dim * s[0] / ctx->gbm.wsum;
   if (grad)
@@ -1521,17 +1619,17 @@ int se_gbm_update(se_ctx* ctx, const double* step, int flags, double* loss_sum, 
   SE_TRY(begin(ctx));
   if (newton) SE_TRY(slot_alloc2d(ctx, SE_SLOT_WOUT, ctx->gbm.dim, ctx->gbm.n));
   GbmArgs a = gbm_args(ctx, false);
-  for (int j = 0; j < ctx->gbm.dim; ++j) a.coef[j] = (float)step[j];
   const int mode = newton ? GBM_UPDATE_NEWTON : ((flags & SE_UPD_RESIDUAL) ? GBM_UPDATE_RESID : GBM_UPDATE);
+  if (newton) ctx->wout_scaled = false;
   a.ws = red_ws(ctx);
-  SE_LAUNCH_T(ctx, SE_KF_UPDATE, launch_gbm(ctx->gbm.loss, mode, a, ctx->ctas_per_sm, ctx->sms, ctx->stream));
+  SE_TRY(gbm_launch(ctx, SE_KF_UPDATE, mode, a, step));
   ctx->gbm.r_current = (mode != GBM_UPDATE);  // the fused modes refresh R from the new F
   if (newton) {
     SE_TRY(newton_finish(ctx, sum_hess));
     if (loss_sum) *loss_sum = ctx->h_scal[0];
     return end(ctx);
   }
-  if ((flags & SE_UPD_LOSS) && loss_sum) return fetch_scalars(ctx, 0, 1, loss_sum);
+  if ((flags & SE_UPD_LOSS) && loss_sum) return gbm_fetch(ctx, 1, loss_sum);
   return end(ctx);
 }
 
@@ -1547,9 +1645,9 @@ int se_gbm_mean_loss(se_ctx* ctx, int which, double* out) {
   SE_TRY(begin(ctx));
   GbmArgs a = gbm_args(ctx, which == 1);
   a.ws = red_ws(ctx);
-  SE_LAUNCH_T(ctx, SE_KF_MEAN_LOSS, launch_gbm(ctx->gbm.loss, GBM_MEAN_LOSS, a, ctx->ctas_per_sm, ctx->sms, ctx->stream));
+  SE_TRY(gbm_launch(ctx, SE_KF_MEAN_LOSS, GBM_MEAN_LOSS, a, nullptr));
   double s = 0.0;
-  SE_TRY(fetch_scalars(ctx, 0, 1, &s));
+  SE_TRY(gbm_fetch(ctx, 1, &s));
   *out = s / (which == 1 ? ctx->gbm.nv_global : ctx->gbm.n_global);
   return SE_OK;
 }
@@ -1561,11 +1659,10 @@ int se_gbm_update_validation(se_ctx* ctx, const double* step, double* mean_loss)
   SE_REQUIRE(ctx, ctx->gbm.nv_global > 0.0, SE_ERR_STATE, "no validation rows configured on any rank");
   SE_TRY(begin(ctx));
   GbmArgs a = gbm_args(ctx, true);
-  for (int j = 0; j < ctx->gbm.dim; ++j) a.coef[j] = (float)step[j];
   a.ws = red_ws(ctx);
-  SE_LAUNCH_T(ctx, SE_KF_UPDATE, launch_gbm(ctx->gbm.loss, GBM_UPDATE, a, ctx->ctas_per_sm, ctx->sms, ctx->stream));
+  SE_TRY(gbm_launch(ctx, SE_KF_UPDATE, GBM_UPDATE, a, step));
   double s = 0.0;
-  SE_TRY(fetch_scalars(ctx, 0, 1, &s));
+  SE_TRY(gbm_fetch(ctx, 1, &s));
   if (mean_loss) *mean_loss = s / ctx->gbm.nv_global;
   return SE_OK;
 }
@@ -2135,7 +2232,7 @@ int se_agg_configure(se_ctx* ctx, int kind, int num_models, int num_classes, int
     case SE_AGG_BAGGING_REGRESSOR:
     case SE_AGG_BOOSTING_REG_MEAN: g.width = 1; g.C = 1; break;
     case SE_AGG_BOOSTING_REG_MEDIAN:
-      SE_REQUIRE(ctx, num_models >= 1 && num_models <= 256, SE_ERR_ARG, "weighted median supports 1..256 models (got %d)", num_models);
+      SE_REQUIRE(ctx, num_models >= 1 && num_models <= 8192, SE_ERR_ARG, "weighted median supports 1..8192 models (got %d)", num_models);
       g.width = 1; g.C = 1; break;
     case SE_AGG_GBM_CLASSIFIER:
       SE_REQUIRE(ctx, dim >= 1 && num_classes >= 2, SE_ERR_ARG, "bad dim/numClasses");

@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(kBlock, LossTune<LOSS>::kMinCtas) gbm_scalar_k
     if (T::kNewton) {
       const float hc = fmaxf(o.h, 1e-2f);   // GBMRegressor.scala:371
       ro = -o.g * rcp_approx(hc);                      // :377
-      wo = 0.5f * hc * w;                   // :379 (× 1/S applied by launch_scale_rows)
+      wo = 0.5f * hc * w;                   // :379 (x 1/S applied when the weights leave the device: se_download)
       x_acc = fmaf(c, hc, x_acc);
     } else if (T::kWriteR) {
       ro = -o.g;                            // :383
@@ -404,22 +404,6 @@ __global__ void __launch_bounds__(kBlock) pack_signed_kernel(const float* __rest
   }
 }
 
-__global__ void __launch_bounds__(kBlock) scale_rows_kernel(float* a, int64_t n, int64_t ld, int dim,
-                                                            const float* factors) {
-  for (int j = 0; j < dim; ++j) {
-    const float f = factors[j];
-    float* row = a + j * ld;
-    const int64_t n4 = n >> 2;
-    for (int64_t g = (int64_t)blockIdx.x * kBlock + threadIdx.x; g < n4;
-         g += (int64_t)gridDim.x * kBlock) {
-      float4 v = ld_rw4(row + 4 * g);
-      v.x *= f; v.y *= f; v.z *= f; v.w *= f;
-      st_stream4(row + 4 * g, v);
-    }
-    if (blockIdx.x == 0 && threadIdx.x < (n & 3)) row[(n4 << 2) + threadIdx.x] *= f;
-  }
-}
-
 __global__ void sq_alpha_kernel(const double* stats, double* out) {
   const double s1 = stats[1], s2 = stats[2];
   double al = (s2 > 0.0) ? s1 / s2 : 1.0;
@@ -533,13 +517,6 @@ cudaError_t launch_gbm(int loss, int mode, const GbmArgs& a, int ctas_per_sm, in
 cudaError_t launch_gbm_pack_signed(const float* y, const float* F, const float* h, float* u, float* v, int64_t n,
                                    int sms, cudaStream_t st) {
   pack_signed_kernel<<<grid_for(n >> 2, kBlock, 4, sms), kBlock, 0, st>>>(y, F, h, u, v, n);
-  return cudaGetLastError();
-}
-
-cudaError_t launch_scale_rows(float* a, int64_t n, int64_t ld, int dim, const float* factors,
-                              int sms, cudaStream_t st) {
-  const int grid = grid_for(n >> 2, kBlock, 8, sms);
-  scale_rows_kernel<<<grid, kBlock, 0, st>>>(a, n, ld, dim, factors);
   return cudaGetLastError();
 }
 

@@ -8,7 +8,8 @@
 
 namespace se {
 
-constexpr int kMaxDim = 64;  // LogLoss classes: per-class sums are reduced by one kernel (kMaxRed, mailbox width)
+constexpr int kMaxDim = 64;  // LogLoss classes served by the specialised kernels: per-class sums reduced in one kernel (kMaxRed, mailbox width)
+constexpr int kMaxDimGeneric = 16384;  // beyond kMaxDim: the general kernels of se_gbm_generic.cu (shared-memory accumulators)
 
 // ---- GBM (se_gbm.cu) -------------------------------------------------------------------------
 enum GbmMode {
@@ -58,11 +59,16 @@ cudaError_t launch_gbm(int loss, int mode, const GbmArgs& a, int ctas_per_sm, in
 // Brent evaluation reads two arrays instead of three (launch_gbm GBM_EVAL with y == nullptr, F = u, h = v)
 cudaError_t launch_gbm_pack_signed(const float* y, const float* F, const float* h, float* u, float* v, int64_t n,
                                    int sms, cudaStream_t stream);
+// LogLoss(K) for K > kMaxDim (se_gbm_generic.cu): coefficients, per-CTA partials [grid][K+1] and the K+1 sums live in
+// device buffers sized for K; the cross-GPU sum of `out` is an NCCL all-reduce issued by the caller
+struct GenericArgs {
+  const float* coef = nullptr;  // device [K]
+  double* partials = nullptr;   // device [grid][K+1]
+  double* out = nullptr;        // device [K+1]
+};
+cudaError_t launch_gbm_logloss_generic(int mode, const GbmArgs& a, const GenericArgs& ga, int grid, cudaStream_t stream);
 // LogLoss(K), wide K: 2-D TMA tiles of 256 rows x K classes, four rows per thread (se_gbm_tiled.cu)
 cudaError_t launch_gbm_logloss_tiled(int mode, const GbmArgs& a, int sms, cudaStream_t stream);
-// WOUT[j][i] *= 0.5/S_j was folded: scale rows of a [dim][n] array by per-row factors
-cudaError_t launch_scale_rows(float* a, int64_t n, int64_t ld, int dim, const float* factors,
-                              int sms, cudaStream_t stream);
 // squared-loss line search on the device: Brent over the parabola of stats[0..2]; out[0] = alpha, out[1] = objective,
 // out[2] = evaluations (negative: MaxEval exceeded); out_host (mapped pinned memory) is optional
 cudaError_t launch_brent_parabola(const double* stats, double wsum, double lo, double hi, double start, double rel,

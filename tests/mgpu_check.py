@@ -112,6 +112,19 @@ def main():
     assert abs(mx - orc.r2_max_error(v, pr)) <= 1e-6 * mx
     e2 = ctx.boostreg_error(sw, "exponential", mx)
     assert abs(e2 - orc.r2_estimator_error("exponential", v, pr, wb, sw, mx)) <= RT * e2
+    # ---- LogLoss beyond 64 classes: the general kernels, sums all-reduced by NCCL across the shards
+    Kb, nb = 70, 30_011
+    yb = rng.integers(0, Kb, nb).astype(np.float32)
+    Fb = (0.5 * rng.standard_normal((Kb, nb))).astype(np.float32)
+    hb = rng.standard_normal((Kb, nb)).astype(np.float32)
+    s0, s1 = row_partition(nb, world, rank)
+    ctx.gbm_configure(s1 - s0, 0, Kb, "logloss", 0.0, False)
+    ctx.upload(N.SLOT_Y, yb[s0:s1]); ctx.upload(N.SLOT_F, np.ascontiguousarray(Fb[:, s0:s1])); ctx.upload(N.SLOT_H, np.ascontiguousarray(hb[:, s0:s1]))
+    ab = rng.random(Kb) + 0.5
+    lg, gg = ctx.gbm_linesearch_eval(ab)
+    lo, go = orc.linesearch_eval(O.LOGLOSS, 0.0, yb, None, Fb, hb, ab)
+    assert abs(lg - lo) <= RT * abs(lo), (lg, lo)
+    assert np.all(np.abs(gg - go) <= RT * np.maximum(np.abs(go), np.abs(go).max()))
     # ---- an EMPTY local validation shard still joins the validation collectives
     nv_tiny = world - 1  # one validation row on every rank but the last
     yv = rng.standard_normal(max(nv_tiny, 1)).astype(np.float32)

@@ -476,7 +476,7 @@ def test_multi_gpu_sharded_parity():
         assert f"p2p_allreduce={p2p == '1'}" in out.stdout
 
 
-@pytest.mark.parametrize("K", [9, 26, 32, 33, 64])
+@pytest.mark.parametrize("K", [9, 26, 32, 33, 64, 65, 200, 1000])
 @pytest.mark.parametrize("n", [1, 127, 129, 255, 256, 257, 40961])
 def test_logloss_wide_k_tiled_kernels(ctx, oracle, rng, K, n):
     """LogLoss with K >= 5 runs through the TMA-tiled kernels (se_gbm_tiled.cu, 256-row tiles): every mode,
@@ -595,7 +595,7 @@ def test_adaboost_r2_kernels(ctx, oracle, rng, loss_type, n):
     assert ctx.boostreg_error(sw, loss_type, 0.0) == 0.0
 
 
-@pytest.mark.parametrize("M,n", [(1, 5), (10, 4099), (64, 1001), (200, 300)])
+@pytest.mark.parametrize("M,n", [(1, 5), (10, 4099), (64, 1001), (200, 300), (257, 77), (1000, 131), (3000, 9)])
 def test_agg_boosting_regressor(ctx, oracle, rng, M, n):
     from spark_ensemble_b200 import _native as N
     P = f32(rng.standard_normal((M, n)))
