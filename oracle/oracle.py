@@ -29,8 +29,10 @@ _FN1 = C.CFUNCTYPE(C.c_double, C.c_double, C.c_void_p)
 
 def build(force: bool = False) -> None:
     """Compile liboracle.so / liboracle_omp.so with the committed Makefile."""
-    need = force or not all(
-        os.path.exists(os.path.join(_HERE, f)) for f in ("liboracle.so", "liboracle_omp.so"))
+    libs = [os.path.join(_HERE, f) for f in ("liboracle.so", "liboracle_omp.so")]
+    srcs = [os.path.join(_HERE, f) for f in ("se_oracle.c", "se_oracle.h", "Makefile")]
+    need = force or not all(os.path.exists(l) for l in libs) or \
+        max(os.path.getmtime(s) for s in srcs if os.path.exists(s)) > min(os.path.getmtime(l) for l in libs)
     if need:
         subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
 

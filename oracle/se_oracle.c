@@ -16,7 +16,7 @@
 #include <omp.h>
 #endif
 
-#define ORC_MAX_DIM 256
+#define ORC_MAX_DIM 4096 /* stack arrays per row: LogLoss class counts used by the tests stay well below */
 
 /* Spark ml.impl.Utils.EPSILON: smallest eps with 1 + eps/2 == 1  (= 2^-52). */
 static const double SPARK_EPSILON = 2.220446049250313e-16;

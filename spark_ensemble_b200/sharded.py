@@ -50,9 +50,18 @@ class ShardedContext:
         raise ValueError(f"slot {slot} is not row-sharded by ShardedContext")
 
     def close(self):
-        for c in self.ctxs:
-            c.close()
-        self._pool.shutdown(wait=True)
+        if not self.ctxs:
+            return
+        # every rank leaves the communicator at the same time, each from its own thread (NCCL tears a communicator
+        # down collectively), and only then are the contexts (and the mailboxes their peers map) released
+        try:
+            self._all(lambda r, c: c.sync())
+            self._all(lambda r, c: c.comm_destroy())
+        finally:
+            for c in self.ctxs:
+                c.close()
+            self.ctxs = []
+            self._pool.shutdown(wait=True)
 
     def __enter__(self):
         return self

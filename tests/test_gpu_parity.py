@@ -564,8 +564,9 @@ def test_abi_utilities(ctx, rng):
         ctx.download(N.SLOT_VY, count=1)
     with pytest.raises(ValueError):
         ctx.gbm_configure(10, 0, 3, "squared")  # scalar losses have dim 1
+    ctx.gbm_configure(10, 0, 65, "logloss")  # beyond 64 classes: the general kernels (no cap short of 16384)
     with pytest.raises(ValueError):
-        ctx.gbm_configure(10, 0, 65, "logloss")  # dim > 64
+        ctx.gbm_configure(10, 0, 20000, "logloss")
 
 
 @pytest.mark.parametrize("loss_type", ["exponential", "linear", "squared"])
