@@ -82,11 +82,11 @@ elif what == "agg_real":
     ctx.fill_synthetic(N.SLOT_P, "uniform", 5, 0.01, 1.0)
     for _ in range(3):
         ctx.agg_run()
-elif what == "votes":
+elif what in ("votes", "wvotes"):
     M, K = 64, 26
-    ctx.agg_configure(N.AGG_BAGGING_HARD, M, K, 1, 0, n)
+    ctx.agg_configure(N.AGG_BAGGING_HARD if what == "votes" else N.AGG_BOOSTING_DISCRETE, M, K, 1, 0, n)
     ctx.fill_synthetic(N.SLOT_P, "randint", 5, 0, K)
     for _ in range(3):
-        ctx.agg_run()
+        ctx.agg_run(None if what == "votes" else np.linspace(0.5, 1.5, M))
 ctx.sync()
 ctx.close()
