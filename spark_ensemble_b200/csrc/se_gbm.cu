@@ -300,7 +300,6 @@ __global__ void __launch_bounds__(kBlock) gbm_logloss_kernel(const GbmArgs a) {
     for (int e = 0; e < VEC; ++e) {
       const bool in = (i0 + e < a.n);
       const float yf = yv[e];  // labels are compared as floats (exact small integers): no float->int conversion
-      if (in) (void)checked_label(yf, K, bad_label);
       float m = -INFINITY;
       int am = 0;
 #pragma unroll
@@ -313,15 +312,18 @@ __global__ void __launch_bounds__(kBlock) gbm_logloss_kernel(const GbmArgs a) {
       // log Σ exp(p_k) = m + log1p(Σ_{k != argmax} exp(p_k - m)): the max term is exactly 1 and is kept
       // out of the sum so a well-fitted row (loss -> 0) keeps full relative precision
       float srest = 0.f, py = 0.f;
+      bool hit = false;  // the label equals one of the class indices 0..K-1: valid (no conversion instructions: the
+                         // float->int round trip of checked_label shares the XU pipe with ex2/rcp and cost 10 % here)
       float ex[KMAX];
 #pragma unroll
       for (int k = 0; k < KMAX; ++k) {
         if (k < K) {
           ex[k] = ex2_approx((p[k][e] - m) * kLog2e);
           if (k != am) srest += ex[k];
-          if (yf == (float)k) py = p[k][e];
+          if (yf == (float)k) { py = p[k][e]; hit = true; }
         }
       }
+      if (in && !hit) bad_label = true;  // GBMLoss.scala:200-204 throws for such a label
       const float lse = m + log1p_pos(srest);
       const float inv_s = rcp_approx(1.0f + srest);
       if (T::kSumLoss && in) g_loss += ((MODE == GBM_EVAL) ? cv[e] : 1.0f) * (lse - py);  // -Σ y_k (p_k - lse)  :206-221
