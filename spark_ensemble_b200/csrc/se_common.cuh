@@ -156,8 +156,8 @@ __device__ __forceinline__ void block_max_publish(double v, double* partials, un
 // Reduction workspace owned by the context: partials[kMaxGridPartials][nred], a self-resetting
 // ticket counter, and the output scalar block.  With a peer-memory communicator attached (nranks > 1,
 // mbox != nullptr) the kernel that reduces ALSO performs the cross-GPU sum itself (see peer_exchange).
-constexpr int kMboxPayload = 72;   // doubles per mailbox row (>= kMaxRed)
-constexpr int kMboxStride = 80;    // doubles per row: payload + sequence word + padding (640 B)
+constexpr int kMboxPayload = 72;   // totals per mailbox row (>= kMaxRed); also the width of the host mirror
+constexpr int kMboxStride = 160;   // 64-bit words per row: two flagged packets per total (144) + padding (1280 B)
 struct RedWs {
   double* partials;
   unsigned int* counter;
@@ -196,51 +196,77 @@ __device__ __forceinline__ double ld_relaxed_sys_f64(const double* p) {
 }
 
 // Cross-GPU sum of `nred` per-GPU totals, executed by ONE WARP (all 32 lanes converged) — the collective is part
-// of the reducing kernel, not a separate NCCL launch:
-//   1. every lane p < nranks stores this GPU's totals into rank p's mailbox row [my rank][seq parity] with
-//      plain P2P stores over NVLink, then publishes them with a release store of the sequence number;
-//   2. it then spins (acquire loads, bounded by ws.timeout_clocks; 0 = unbounded) on its OWN mailbox until rank p's
-//      row carries this sequence;
-//   3. the rows are summed in rank order, so every GPU produces bit-identical results; emit(k, sum_k) is called by
-//      lane k % 32 for every k < nred.
+// of the reducing kernel, not a separate NCCL launch.  Mailbox rows are written in 8-BYTE PACKETS that carry their own
+// validity flag (the low-latency protocol NCCL calls LL): every fp64 total travels as two 64-bit words
+// {low 32 bits, flag} and {high 32 bits, flag}, flag = the reduction's sequence number (31 bits).  An aligned 8-byte
+// store is single-copy atomic, so a receiver that sees the flag has the data — NO release/acquire fence pair, no
+// separate "ready" word, one NVLink hop:
+//   1. lane p < nranks stores this GPU's packets into rank p's mailbox row [my rank][seq parity] (plain relaxed
+//      system-scope P2P stores over NVLink);
+//   2. lane k < nred then polls its OWN mailbox, rank by rank, until both packets of total k carry this sequence
+//      (bounded by ws.timeout_clocks; 0 = unbounded), and adds the values in rank order: bit-identical sums on every GPU;
+//      emit(k, sum_k) is called by lane k % 32.
 // Rows are double-buffered by sequence parity: a peer can be at most one reduction ahead.
-// Failure protocol: a rank that gives up (timeout) or sees a poisoned row overwrites the sequence word of ITS row in
-// every peer's mailbox with seq | kPoisonBit, so that a late peer fails the SAME reduction instead of completing it
+// Failure protocol: a rank that gives up (timeout) or meets a poisoned packet overwrites ITS packets in every peer's
+// mailbox with the poison flag (seq | 0x80000000), so that a late peer fails the SAME reduction instead of completing it
 // with a sum its partners never saw; every rank then reports NaN sums + the sticky error flag (-> SE_ERR_NCCL).
-constexpr unsigned long long kPoisonBit = 1ull << 63;
+constexpr unsigned int kPoisonFlag = 0x80000000u;
+__device__ __forceinline__ void st_relaxed_sys_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
 template <class Emit>
 __device__ __forceinline__ bool peer_allreduce_warp(const double* tot, int nred, const RedWs& ws, Emit emit) {
   const int lane = threadIdx.x & 31;
   const int par = (int)(ws.seq & 1ull);
+  const unsigned int flag = (unsigned int)(ws.seq & 0x7fffffffull);
   for (int p = lane; p < ws.nranks; p += 32) {
-    double* row = ws.mbox[p] + (size_t)(ws.rank * 2 + par) * kMboxStride;
-    for (int k = 0; k < nred; ++k) st_relaxed_sys_f64(row + k, tot[k]);
-    st_release_sys_u64(reinterpret_cast<unsigned long long*>(row + kMboxPayload), ws.seq);
+    unsigned long long* row = reinterpret_cast<unsigned long long*>(ws.mbox[p]) + (size_t)(ws.rank * 2 + par) * kMboxStride;
+    for (int k = 0; k < nred; ++k) {
+      const unsigned long long bits = (unsigned long long)__double_as_longlong(tot[k]);
+      st_relaxed_sys_u64(row + 2 * k, ((bits & 0xffffffffull) << 32) | flag);
+      st_relaxed_sys_u64(row + 2 * k + 1, ((bits >> 32) << 32) | flag);
+    }
   }
   bool ok = true;
-  for (int p = lane; p < ws.nranks; p += 32) {
-    const double* row = ws.mbox[ws.rank] + (size_t)(p * 2 + par) * kMboxStride;
+  const unsigned long long* mine = reinterpret_cast<const unsigned long long*>(ws.mbox[ws.rank]);
+  const int rounds = (nred + 31) / 32;
+  double sums[3] = {0.0, 0.0, 0.0};  // nred <= kMboxPayload = 72 -> at most 3 totals per lane
+  for (int q = 0; q < rounds; ++q) {
+    const int k = lane + 32 * q;
+    if (k >= nred) break;
+    double sum = 0.0;
     const long long t0 = clock64();
-    for (;;) {
-      const unsigned long long s = ld_acquire_sys_u64(reinterpret_cast<const unsigned long long*>(row + kMboxPayload));
-      if (s == ws.seq) break;
-      if (s == (ws.seq | kPoisonBit)) { ok = false; break; }                          // the peer gave up on this one
-      if (ws.timeout_clocks > 0 && clock64() - t0 > ws.timeout_clocks) { ok = false; break; }  // it never launched
+    for (int p = 0; p < ws.nranks && ok; ++p) {
+      const unsigned long long* row = mine + (size_t)(p * 2 + par) * kMboxStride;
+      unsigned long long lo, hi;
+      for (;;) {
+        lo = ld_relaxed_sys_u64(row + 2 * k);
+        hi = ld_relaxed_sys_u64(row + 2 * k + 1);
+        const unsigned int fl = (unsigned int)lo, fh = (unsigned int)hi;
+        if (fl == flag && fh == flag) break;
+        if (fl == (flag | kPoisonFlag) || fh == (flag | kPoisonFlag)) { ok = false; break; }   // the peer gave up on this one
+        if (ws.timeout_clocks > 0 && clock64() - t0 > ws.timeout_clocks) { ok = false; break; }  // it never launched
+      }
+      sum += __longlong_as_double((long long)((hi & 0xffffffff00000000ull) | (lo >> 32)));
     }
+    sums[q] = sum;
   }
   ok = __all_sync(0xffffffffu, ok);
   if (!ok) {
     for (int p = lane; p < ws.nranks; p += 32) {
-      double* row = ws.mbox[p] + (size_t)(ws.rank * 2 + par) * kMboxStride;
-      st_release_sys_u64(reinterpret_cast<unsigned long long*>(row + kMboxPayload), ws.seq | kPoisonBit);
+      unsigned long long* row = reinterpret_cast<unsigned long long*>(ws.mbox[p]) + (size_t)(ws.rank * 2 + par) * kMboxStride;
+      for (int k = 0; k < 2 * nred; ++k) st_relaxed_sys_u64(row + k, (unsigned long long)(flag | kPoisonFlag));
     }
     if (lane == 0 && ws.err) *ws.err = 1;
   }
-  for (int k = lane; k < nred; k += 32) {
-    double sum = 0.0;
-    for (int p = 0; p < ws.nranks; ++p)
-      sum += ld_relaxed_sys_f64(ws.mbox[ws.rank] + (size_t)(p * 2 + par) * kMboxStride + k);
-    emit(k, ok ? sum : __longlong_as_double(0x7ff8000000000000ll));
+  for (int q = 0; q < rounds; ++q) {
+    const int k = lane + 32 * q;
+    if (k < nred) emit(k, ok ? sums[q] : __longlong_as_double(0x7ff8000000000000ll));
   }
   return ok;
 }
