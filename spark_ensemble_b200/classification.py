@@ -115,7 +115,8 @@ class GBMClassifier(Params):
             if init_raw.shape[0] != dim:
                 raise ValueError("prior init needs every class present in the training labels")
 
-        ctx = Context(self.device)
+        from .sharded import make_context
+        ctx = make_context(self.device, self("devices"))  # Param `devices`: rows sharded over several GPUs
         try:
             eng = GBMEngine(ctx, n, nv, dim, loss, 0.0, has_weights=w is not None)
             eng.load(y, w, init_raw, yv, init_raw if with_validation else None)
@@ -189,9 +190,11 @@ _pcls = [
     # expert Param: "brent" = the reference's optimiser (default); "newton" = curvature-based line search on
     # the same objective (dim 1, losses with a hessian): same minimiser within tol, ~6x fewer data passes
     Param("lineSearch", "line-search optimiser for dim 1: brent (reference) or newton", lambda v: v in ("brent", "newton"), str),
+    Param("devices", "CUDA device ordinals to shard the training rows over", lambda v: all(int(d) >= 0 for d in v),
+          lambda v: [int(d) for d in v]),
 ]
 _GBM_CLS_DEFAULTS = {**_d, **_dc, **_ds, **_db, **_dg, "loss": "logloss", "initStrategy": "prior",
-                     "residentFeatures": False, "lineSearch": "brent",
+                     "residentFeatures": False, "lineSearch": "brent", "devices": [],
                      "seed": java_string_hash("org.apache.spark.ml.classification.GBMClassifier")}
 GBMClassifier._declare(_p + _pc + _ps + _pb + _pg + _pcls, _GBM_CLS_DEFAULTS)
 

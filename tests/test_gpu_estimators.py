@@ -348,6 +348,19 @@ def test_gbm_regressor_fit_sharded_over_two_gpus():
         assert m.numModels == base.numModels
         np.testing.assert_allclose(m.weights, base.weights, rtol=1e-5, atol=4e-6)
         np.testing.assert_allclose(m.transform(df)["prediction"], pb, rtol=1e-5, atol=1e-5 * float(np.abs(pb).max()))
+    # GBMClassifier (LogLoss over 3 classes: per-class line-search gradients summed across the GPUs)
+    from spark_ensemble_b200.classification import GBMClassifier
+    yc = (np.digitize(y, np.quantile(y, [0.33, 0.66]))).astype(np.float64)
+    dfc = DataFrame(features=X, label=yc)
+    ms = []
+    for devices in ([], [0, 1]):
+        g = GBMClassifier().setBaseLearner(DecisionTreeRegressor(maxDepth=3)).setNumBaseLearners(4).setLoss("logloss")
+        g.set("devices", devices)
+        ms.append(g.fit(dfc))
+    assert len(ms[0].weights) == len(ms[1].weights)
+    for w0, w1 in zip(ms[0].weights, ms[1].weights):
+        np.testing.assert_allclose(w1, w0, rtol=1e-4, atol=1e-5)  # L-BFGS-B iterates see sums that differ in the last bits
+    np.testing.assert_array_equal(ms[0].transform(dfc)["prediction"], ms[1].transform(dfc)["prediction"])
 
 
 def test_tree_arrays_must_form_a_tree(monkeypatch):
