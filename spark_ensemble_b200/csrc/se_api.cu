@@ -1717,6 +1717,7 @@ int linesearch_persist(se_ctx* ctx, double lo, double hi, double start, double r
   a.wsum = ctx->gbm.wsum;
   a.lo = lo; a.hi = hi; a.start = start; a.rel = rel; a.abs_tol = abs_tol; a.max_eval = max_eval;
   a.single = single;
+  a.timing = ctx->fused_timing;
   a.first_parity = parity;
   a.partials = ctx->d_partials;
   a.sync = ctx->d_fsync;
@@ -1757,6 +1758,13 @@ int linesearch_persist(se_ctx* ctx, double lo, double hi, double start, double r
   const int passes = (int)res[3];
   if (ctx->p2p && ctx->nranks > 1 && passes > 1) ctx->red_seq = seq0 + (unsigned long long)(passes - 1);
   ctx->last_ls_passes = passes;
+  if (ctx->fused_timing) {
+    SE_CUDA(ctx, cudaMemcpyAsync(ctx->h_scal + kScalRound + 20, ctx->d_scal + kScalRound + 20, sizeof(double) * 2, cudaMemcpyDeviceToHost, ctx->stream));
+    SE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->last_fused_us[0] = ctx->h_scal[kScalRound + 20];  // worker passes
+    ctx->last_fused_us[1] = ctx->h_scal[kScalRound + 21];  // fold + exchange + Brent step
+    ctx->last_fused_us[2] = 0.0;
+  }
   release_l2_persist(ctx);
   if (rc != SE_OK) return rc;
   if (alpha) *alpha = res[0];

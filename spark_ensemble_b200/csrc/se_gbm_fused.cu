@@ -299,6 +299,7 @@ __global__ void __launch_bounds__(kBlock, 4) gbm_linesearch_persist_kernel(const
     if (warp != 0) return;
     int e = 0;
     bool failed = false;
+    double t_pub = a.timing ? global_timer_us() : 0.0, t_pass = 0.0, t_fold = 0.0;  // diagnostics (lane 0)
     auto f = [&](double x) -> double {
       ++e;
       if (e > 1) {  // the first abscissa (start / the single point) is known to every worker at launch
@@ -309,8 +310,11 @@ __global__ void __launch_bounds__(kBlock, 4) gbm_linesearch_persist_kernel(const
         }
         __syncwarp();
       }
+      if (a.timing && e > 1) t_pub = global_timer_us();
       const unsigned int want = (unsigned int)W * (unsigned int)e;
       while (ld_acquire_gpu_u32(&a.sync->arrive) != want) {}
+      const double t_arr = a.timing ? global_timer_us() : 0.0;
+      if (a.timing) t_pass += t_arr - t_pub;
       double s = 0.0;
       for (int b = lane; b < W; b += 32) s += __ldcg(&a.partials[b]);  // fixed order: deterministic sums
       s = warp_sum(s);
@@ -323,6 +327,7 @@ __global__ void __launch_bounds__(kBlock, 4) gbm_linesearch_persist_kernel(const
         s = __shfl_sync(0xffffffffu, g, 0);
         if (!ok) failed = true;
       }
+      if (a.timing) { const double t1 = global_timer_us(); t_fold += t1 - t_arr; t_pub = t1; }
       return s / a.wsum;  // dim == 1: lossSum / weightSum (GBMLoss.scala:60-65)
     };
     double x = a.start, fx = 0.0;
@@ -341,6 +346,7 @@ __global__ void __launch_bounds__(kBlock, 4) gbm_linesearch_persist_kernel(const
       st_release_gpu_u64(&a.sync->flag, a.epoch0 + (unsigned long long)(e + 1));
       const double ne = (rc == kBrentOk) ? (double)evals : -(double)evals;
       a.out[0] = x, a.out[1] = fx, a.out[2] = ne, a.out[3] = (double)e;
+      if (a.timing) a.out[4] = t_pass, a.out[5] = t_fold;  // us in worker passes (publish -> all arrived) / in fold + exchange
       if (a.ws.host_out) {
         a.ws.host_out[0] = x, a.ws.host_out[1] = fx, a.ws.host_out[2] = ne, a.ws.host_out[3] = (double)e;
         __threadfence_system();

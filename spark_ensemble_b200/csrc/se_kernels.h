@@ -129,6 +129,7 @@ struct LsArgs {
   double wsum = 1.0;
   double lo = 0.0, hi = 100.0, start = 1.0, rel = 1e-6, abs_tol = 1e-6;
   int max_eval = 100;
+  int timing = 0;        // diagnostics: out[4] = us spent in worker passes, out[5] = us in fold + cross-GPU exchange
   int single = 0;        // evaluate the objective at `start` once (host-driven search over the same kernel)
   int first_parity = 0;  // tile direction of evaluation e is (first_parity + e) & 1
   int resident_tiles = 0;
