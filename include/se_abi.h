@@ -284,6 +284,13 @@ SE_API int se_agg_configure(se_ctx* ctx, int kind, int num_models, int num_class
  * (GBM classifier) or NULL; init: [dim] or NULL. Fills RAW (+PROB, LABEL for classifiers). */
 SE_API int se_agg_run(se_ctx* ctx, const double* weights, const double* init);
 
+/* ---- row sub-sampling: Spark's sampler restated for the host side that has no Spark ------------- */
+/* Multiplicities (0/1) of RDD.sample(withReplacement = false, fraction, seed) for `n` rows that sit in Spark partition
+ * `partition` (regression/GBMRegressor.scala:357-359): java.util.Random(seed) -> per-partition seed ->
+ * XORShiftRandom -> BernoulliSampler (gap sampling for fraction <= 0.4).  Host-only, no GPU involved; restated from the
+ * Spark 3.3.1 sources and UNPINNED (no Spark here) — a Spark host uploads the multiplicities Spark drew instead. */
+SE_API int se_spark_bernoulli_sample(int64_t seed, double fraction, int64_t n, int partition, float* counts);
+
 /* ---- on-device base-model evaluation over column-major X ------------------- */
 /* Decision tree in array form (node i: feature[i] < 0 => leaf with value[i]; else go left when
  * x[feature[i]] <= threshold[i], as Spark's ContinuousSplit.shouldGoLeft).  Writes out_slot row

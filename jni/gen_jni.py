@@ -135,6 +135,7 @@ NOT_BOUND = {
     "se_last_error": "consumed inside the shim: its text becomes the exception message",
     "se_brent_minimize": "takes a C callback; the JVM side keeps commons-math3's BrentOptimizer (or calls gbmLinesearchBrent / gbmRound)",
     "se_slot_info": "returns a raw device pointer: not exposed to the JVM",
+    "se_spark_bernoulli_sample": "restates Spark's BernoulliSampler for hosts WITHOUT Spark; the JVM side draws with Spark itself",
 }
 
 HAND_CPP = r'''

@@ -109,6 +109,7 @@ PROTOTYPES = {
     "se_boostreg_update": [_vp, _d, _i32, _d, _d, _dp],
     "se_agg_configure": [_vp, _i32, _i32, _i32, _i32, _i32, _i64],
     "se_agg_run": [_vp, _dp, _dp],
+    "se_spark_bernoulli_sample": [_i64, _d, _i64, _i32, _fp],
     "se_tree_predict": [_vp, _i32, _i32, _ip, _fp, _ip, _ip, _fp, _ip, _i32, _i32, _i32],
     "se_tree_predict_multi": [_vp, _i32, _i32, _ip, _fp, _ip, _ip, _fp, _i32, _ip, _i32, _i32],
     "se_linear_predict": [_vp, _i32, _i32, _fp, _f, _ip, _i32, _i32],

@@ -2107,6 +2107,84 @@ int se_brent_minimize(se_fn1 f, void* user, double lo, double hi, double start, 
   return SE_OK;
 }
 
+// ---- Spark's Bernoulli row sampler, restated (host only) -----------------------------------------
+// RDD.sample(withReplacement = false, fraction, seed) as the reference calls it (regression/GBMRegressor.scala:357-359,
+// classification/GBMClassifier.scala:329-331) for data that sits in ONE partition:
+//   PartitionwiseSampledRDD: partition p gets the seed  new java.util.Random(seed).nextLong()  (p-th call);
+//   BernoulliSampler.setSeed -> XORShiftRandom(seed'): state = hashSeed(seed') (MurmurHash3 of the 8 big-endian bytes);
+//   sample(): fraction <= 0.4 -> GapSampling (skip floor(log(max(u, 5e-11)) / log1p(-fraction)) rows between picks),
+//             else keep the row iff nextDouble() <= fraction.
+// java.util.Random is specified by the Java SE API documentation; MurmurHash3 and XORShift are pinned by published
+// vectors / their definitions (tests/test_thirdparty_golden.py); the sampler logic itself is restated from the Spark
+// 3.3.1 sources (org/apache/spark/util/random/RandomSampler.scala, rdd/PartitionwiseSampledRDD.scala) and is UNPINNED
+// (no Spark in this image).  A Spark host uploads the multiplicities Spark itself drew (GBMRegressorNative.scala).
+namespace {
+struct JavaRandom {
+  uint64_t seed;
+  explicit JavaRandom(int64_t s) : seed(((uint64_t)s ^ 0x5DEECE66DULL) & ((1ULL << 48) - 1)) {}
+  int32_t next(int bits) {
+    seed = (seed * 0x5DEECE66DULL + 0xBULL) & ((1ULL << 48) - 1);
+    return (int32_t)((int64_t)seed >> (48 - bits));
+  }
+  int64_t next_long() { const int64_t hi = next(32); const int64_t lo = next(32); return (int64_t)((uint64_t)hi << 32) + lo; }
+};
+uint32_t murmur3_bytes(const unsigned char* data, int len, uint32_t seed) {
+  auto rotl = [](uint32_t x, int r) { return (x << r) | (x >> (32 - r)); };
+  uint32_t h = seed;
+  int i = 0;
+  for (; len - i >= 4; i += 4) {
+    uint32_t k = (uint32_t)data[i] | ((uint32_t)data[i + 1] << 8) | ((uint32_t)data[i + 2] << 16) | ((uint32_t)data[i + 3] << 24);
+    k *= 0xcc9e2d51u; k = rotl(k, 15); k *= 0x1b873593u;
+    h ^= k; h = rotl(h, 13); h = h * 5u + 0xe6546b64u;
+  }
+  uint32_t k = 0;
+  const int rem = len - i;
+  if (rem == 3) k ^= (uint32_t)data[i + 2] << 16;
+  if (rem >= 2) k ^= (uint32_t)data[i + 1] << 8;
+  if (rem >= 1) { k ^= (uint32_t)data[i]; k *= 0xcc9e2d51u; k = rotl(k, 15); k *= 0x1b873593u; h ^= k; }
+  h ^= (uint32_t)len;
+  h ^= h >> 16; h *= 0x85ebca6bu; h ^= h >> 13; h *= 0xc2b2ae35u; h ^= h >> 16;
+  return h;
+}
+struct XorShift {
+  uint64_t s;
+  explicit XorShift(int64_t init) {
+    unsigned char b[8];
+    for (int i = 0; i < 8; ++i) b[i] = (unsigned char)((uint64_t)init >> (56 - 8 * i));  // ByteBuffer.putLong: big endian
+    const uint32_t low = murmur3_bytes(b, 8, 0x3c074a61u);  // MurmurHash3.arraySeed
+    const uint32_t high = murmur3_bytes(b, 8, low);
+    s = ((uint64_t)high << 32) | (uint64_t)low;
+  }
+  int32_t next(int bits) {
+    s ^= s << 21; s ^= s >> 35; s ^= s << 4;
+    return (int32_t)(s & ((1ULL << bits) - 1));
+  }
+  double next_double() { return (double)(((int64_t)next(26) << 27) + next(27)) * (1.0 / (double)(1LL << 53)); }
+};
+}  // namespace
+
+int se_spark_bernoulli_sample(int64_t seed, double fraction, int64_t n, int partition, float* counts) {
+  if (!counts || n < 0 || partition < 0) return fail(nullptr, SE_ERR_ARG, "bad argument");
+  JavaRandom jr(seed);
+  int64_t pseed = 0;
+  for (int p = 0; p <= partition; ++p) pseed = jr.next_long();
+  XorShift rng(pseed);
+  if (fraction <= 0.0) { for (int64_t i = 0; i < n; ++i) counts[i] = 0.f; return SE_OK; }
+  if (fraction >= 1.0) { for (int64_t i = 0; i < n; ++i) counts[i] = 1.f; return SE_OK; }
+  if (fraction <= 0.4) {  // RandomSampler.defaultMaxGapSamplingFraction
+    const double lnq = log1p(-fraction), eps = 5e-11;  // RandomSampler.rngEpsilon
+    auto advance = [&]() { const double u = fmax(rng.next_double(), eps); return (int64_t)(log(u) / lnq); };
+    int64_t drop = advance();  // the GapSampling constructor advances once
+    for (int64_t i = 0; i < n; ++i) {
+      if (drop > 0) { --drop; counts[i] = 0.f; }
+      else { drop = advance(); counts[i] = 1.f; }
+    }
+  } else {
+    for (int64_t i = 0; i < n; ++i) counts[i] = (rng.next_double() <= fraction) ? 1.f : 0.f;
+  }
+  return SE_OK;
+}
+
 // ---- Boosting ----------------------------------------------------------------------------------
 int se_boost_configure(se_ctx* ctx, int64_t n, int num_classes, int real) {
   if (!ctx) return fail(nullptr, SE_ERR_ARG, "null context");

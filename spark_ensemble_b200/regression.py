@@ -31,14 +31,24 @@ def _extract_instances(est: Params, dataset: DataFrame):
 
 def bag_counts(n: int, subsample_ratio: float, replacement: bool, seed: int):
     """Multiplicity of every train row in `RDD.sample(replacement, ratio, seed)`; None when the bag is the
-    whole set.  Spark's sampler is partition- and RNG-specific; on a Spark host the mask comes from Spark —
-    here numpy draws it (Bernoulli(ratio) without, Poisson(ratio) with replacement), once, because the
-    reference passes the same seed every round (quirk 3)."""
+    whole set.  Drawn once, because the reference passes the same seed every round (quirk 3).
+    Without replacement: Spark's own algorithm for rows in ONE partition (java.util.Random -> per-partition seed ->
+    XORShiftRandom -> BernoulliSampler with gap sampling below 0.4), restated in the native library
+    (se_spark_bernoulli_sample; unpinned: no Spark here).  With replacement Spark uses commons-math3's
+    PoissonDistribution over a Well19937c generator, which is not restated: numpy draws Poisson(ratio).
+    On a Spark host the multiplicities come from Spark itself (GBMRegressorNative.scala)."""
     if subsample_ratio == 1.0 and not replacement:
         return None
+    if not replacement:
+        import ctypes as C
+        lib = N.load()
+        c = np.zeros(n, dtype=np.float32)
+        s64 = int(seed) & 0xFFFFFFFFFFFFFFFF
+        s64 = s64 - (1 << 64) if s64 >= (1 << 63) else s64
+        N.check(lib.se_spark_bernoulli_sample(C.c_int64(s64), float(subsample_ratio), n, 0, N.fptr(c)))
+        return c
     rng = np.random.default_rng(seed & 0xFFFFFFFF)
-    c = rng.poisson(subsample_ratio, n) if replacement else (rng.random(n) < subsample_ratio)
-    return c.astype(np.float32)
+    return rng.poisson(subsample_ratio, n).astype(np.float32)
 
 
 def _split_validation(est: Params, dataset: DataFrame):

@@ -319,7 +319,13 @@ class _FakeCtx:
         self.dim = 1
 
     def close(self):
+        self.closed = True
+
+    def sync(self):
         pass
+
+    def comm_destroy(self):
+        self.left = True
 
     def gbm_configure(self, n, nv, dim, loss, param=0.0, has_weights=False):
         import numpy as np
@@ -378,7 +384,9 @@ def test_sharded_context_splits_and_reassembles_rows():
         np.testing.assert_array_equal(np.asarray(sc.download(N.SLOT_Y)).reshape(-1), y)
         assert sc.gbm_update([0.5] * dim, residual=True)[0] == 1.25
         assert all(c.calls == [("update", tuple([0.5] * dim))] for c in sc.ctxs)
+        ctxs = list(sc.ctxs)
         sc.close()
+        assert all(getattr(c, "left", False) and getattr(c, "closed", False) for c in ctxs)  # communicator left first
 
 
 def test_gbm_regressor_has_devices_param():

@@ -103,3 +103,62 @@ def test_murmur3_published_vectors_and_xorshift_properties():
     counts = np.histogram(draws, bins=10, range=(0, 1))[0]
     chi2 = float(((counts - 10_000) ** 2 / 10_000).sum())
     assert chi2 < 27.88  # 99.9 % quantile of chi-square with 9 degrees of freedom
+
+
+def test_spark_bernoulli_sampler_restatement(lib):
+    """se_spark_bernoulli_sample (host-only) = java.util.Random -> per-partition seed -> XORShiftRandom ->
+    BernoulliSampler.  Pinned pieces: java.util.Random by its specification (new Random(42).nextInt() == -1170105035 is
+    the value the Java documentation's LCG gives; checked through the Python restatement below), XORShift / MurmurHash3
+    by the vectors above; the sampler logic (gap sampling below 0.4, `nextDouble() <= fraction` above) is restated from
+    the Spark 3.3.1 sources and only checked for self-consistency and its statistical contract here."""
+    import ctypes as C
+    from spark_ensemble_b200 import _native as N
+    from spark_ensemble_b200.ensemble import XORShiftRandom
+
+    class JavaRandom:  # java.util.Random as specified in the Java SE API documentation
+        def __init__(self, seed):
+            self.s = (seed ^ 0x5DEECE66D) & ((1 << 48) - 1)
+
+        def next(self, bits):
+            self.s = (self.s * 0x5DEECE66D + 0xB) & ((1 << 48) - 1)
+            v = self.s >> (48 - bits)
+            return v - (1 << bits) if v >= (1 << (bits - 1)) else v
+
+        def next_long(self):
+            return ((self.next(32) << 32) + self.next(32) + (1 << 63)) % (1 << 64) - (1 << 63)
+
+    assert JavaRandom(42).next(32) == -1170105035          # widely published first nextInt() of new Random(42)
+    assert JavaRandom(42).next_long() == -5025562857975149833
+
+    def native(seed, fraction, n, part=0):
+        c = np.zeros(n, dtype=np.float32)
+        assert lib.se_spark_bernoulli_sample(C.c_int64(seed), fraction, n, part, N.fptr(c)) == 0
+        return c
+
+    n = 20000
+    for seed, part in ((42, 0), (-7, 0), (123456789012345, 2)):
+        jr = JavaRandom(seed)
+        for _ in range(part + 1):
+            pseed = jr.next_long()
+        # fraction > 0.4: one draw per row, keep iff nextDouble() <= fraction
+        rng = XORShiftRandom(pseed)
+        want = np.array([1.0 if rng.next_double() <= 0.7 else 0.0 for _ in range(n)], dtype=np.float32)
+        np.testing.assert_array_equal(native(seed, 0.7, n, part), want)
+        # fraction <= 0.4: gap sampling
+        rng = XORShiftRandom(pseed)
+        lnq = math.log1p(-0.25)
+        adv = lambda: int(math.log(max(rng.next_double(), 5e-11)) / lnq)
+        drop, want = adv(), []
+        for _ in range(n):
+            if drop > 0:
+                drop -= 1; want.append(0.0)
+            else:
+                drop = adv(); want.append(1.0)
+        np.testing.assert_array_equal(native(seed, 0.25, n, part), np.array(want, dtype=np.float32))
+    # statistical contract of RDD.sample: E[kept] = fraction * n
+    for f in (0.1, 0.25, 0.5, 0.9):
+        kept = native(2024, f, 200_000).mean()
+        assert abs(kept - f) < 4 * math.sqrt(f * (1 - f) / 200_000)
+    assert native(1, 1.0, 10).sum() == 10 and native(1, 0.0, 10).sum() == 0
+    # the same seed draws the same bag every time (the reference reuses one seed per fit: quirk 3)
+    np.testing.assert_array_equal(native(9, 0.6, 1000), native(9, 0.6, 1000))
