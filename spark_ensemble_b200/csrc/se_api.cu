@@ -177,6 +177,10 @@ struct se_ctx {
   int* h_p2p_err = nullptr;
   int* h_bad_label = nullptr;         // raised by kernels that met a label / vote outside [0, K) (mapped pinned memory)
   int* d_bad_label = nullptr;
+  // labels used as class indices are validated once per upload: 0 unknown, 1 validation launched (result not yet
+  // observed), 2 known good — per label slot (SE_SLOT_Y, SE_SLOT_VY) together with the K they were checked for
+  int y_state[2] = {0, 0};
+  int y_state_k[2] = {0, 0};
   unsigned long long red_seq = 0;
   bool last_reduce_global = false;    // the kernel just launched already produced cross-GPU sums
   // host mirror of the scalar block (mapped pinned memory written by the reducing kernel's last CTA)
@@ -402,7 +406,13 @@ int allreduce_dev(se_ctx* ctx, int off, int count, int op = kNcclSum) {
 // outside [0, numClasses) or a fractional one (GBMLoss.scala:200-204 `res(label.toInt) = 1.0`, Classifier.validateLabel);
 // here the kernels raise a flag instead of indexing out of bounds and the call that observes it fails with SE_ERR_ARG.
 int check_labels(se_ctx* ctx) {
-  if (ctx->h_bad_label && *reinterpret_cast<volatile int*>(ctx->h_bad_label)) {
+  if (!(ctx->h_bad_label && *reinterpret_cast<volatile int*>(ctx->h_bad_label))) {
+    for (int& st : ctx->y_state)
+      if (st == 1) st = 2;  // a validation pass completed before this point (same stream) and raised nothing
+    return SE_OK;
+  }
+  if (ctx->h_bad_label) {
+    ctx->y_state[0] = ctx->y_state[1] = 0;  // unknown again: the next call re-validates (and fails again if unchanged)
     *reinterpret_cast<volatile int*>(ctx->h_bad_label) = 0;
     return fail(ctx, SE_ERR_ARG, "a label (or vote) is not an integer class index in [0, numClasses): results of this call are invalid");
   }
@@ -467,6 +477,8 @@ int fetch_scalars(se_ctx* ctx, int off, int count, double* out, int op = kNcclSu
 
 // any write to a feature-matrix slot makes its rank matrix stale
 void touch_slot(se_ctx* ctx, int slot) {
+  if (slot == SE_SLOT_Y) ctx->y_state[0] = 0;
+  if (slot == SE_SLOT_VY) ctx->y_state[1] = 0;
   if (slot == SE_SLOT_WOUT) ctx->wout_scaled = false;
   if (slot == SE_SLOT_X) ctx->bins[0].valid = false;
   if (slot == SE_SLOT_VX) ctx->bins[1].valid = false;
@@ -1435,6 +1447,7 @@ int se_gbm_configure(se_ctx* ctx, int64_t n_train, int64_t n_valid, int dim, int
   g.use_bag = false;
   g.r_current = false;
   g.wsum_valid = false; g.counts_valid = false;
+  ctx->y_state[0] = ctx->y_state[1] = 0;
   release_l2_persist(ctx);
   SE_TRY(slot_alloc2d(ctx, SE_SLOT_Y, 1, n_train));
   SE_TRY(slot_alloc2d(ctx, SE_SLOT_F, dim, n_train));
@@ -1489,11 +1502,26 @@ int ensure_big(se_ctx* ctx, int dim) {
   return SE_OK;
 }
 
+// Labels as class indices: one validation pass per upload of the label slot (see validate_labels_kernel).
+int ensure_labels_checked(se_ctx* ctx, int which /*0 train, 1 validation*/, int K, int64_t n) {
+  if (ctx->y_state[which] == 2 && ctx->y_state_k[which] == K) return SE_OK;
+  const SlotBuf& y = ctx->slot[which ? SE_SLOT_VY : SE_SLOT_Y];
+  if (!y.d || n <= 0) return SE_OK;
+  SE_LAUNCH(ctx, launch_validate_labels(y.d, n, K, ctx->d_bad_label, ctx->sms, ctx->stream));
+  ctx->y_state[which] = 1;
+  ctx->y_state_k[which] = K;
+  return SE_OK;
+}
+
 // One GBM kernel launch for the configured loss.  `coef` (alpha or step, gbm.dim values, nullable) goes into the kernel
 // arguments for dim <= kMaxDim and into a device buffer for the general LogLoss path beyond it.
 int gbm_launch(se_ctx* ctx, int family, int mode, GbmArgs& a, const double* coef) {
   const int dim = ctx->gbm.dim;
   ctx->big.pending = false;
+  if (ctx->gbm.loss == SE_LOSS_LOGLOSS) {
+    const int which = (a.y == ctx->slot[SE_SLOT_VY].d && a.y != nullptr && a.y != ctx->slot[SE_SLOT_Y].d) ? 1 : 0;
+    SE_TRY(ensure_labels_checked(ctx, which, dim, a.n));
+  }
   if (dim <= kMaxDim) {
     if (coef)
       for (int j = 0; j < dim; ++j) a.coef[j] = (float)coef[j];
@@ -2200,6 +2228,7 @@ int se_boost_configure(se_ctx* ctx, int64_t n, int num_classes, int real) {
 
 static BoostArgs boost_args(se_ctx* ctx, double sum_w) {
   release_l2_persist(ctx);
+  ensure_labels_checked(ctx, 0, ctx->boost.K, ctx->boost.n);  // SAMME / SAMME.R compare (and index with) the label
   BoostArgs a;
   a.y = ctx->slot[SE_SLOT_Y].d;
   a.w = ctx->slot[SE_SLOT_BW].d;

@@ -56,7 +56,6 @@ __global__ void __launch_bounds__(kBlock) boost_real_kernel(const BoostArgs a) {
   const float inv_km1 = 1.0f / (float)(K - 1);
   const float scale = -((float)(K - 1) / (float)K);
   double acc[2] = {0.0, 0.0};
-  bool bad_label = false;  // a label outside [0, K) or fractional (Classifier.validateLabel throws in the reference)
   const int64_t n4 = a.n >> 2;
   for (int64_t g = (int64_t)blockIdx.x * kBlock + threadIdx.x; g < n4;
        g += (int64_t)gridDim.x * kBlock) {
@@ -67,7 +66,7 @@ __global__ void __launch_bounds__(kBlock) boost_real_kernel(const BoostArgs a) {
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       st[e].best = -INFINITY; st[e].sum_log = 0.f; st[e].log_y = 0.f; st[e].am = 0;
-      yi[e] = checked_label(f4at(vy, e), K, bad_label);
+      yi[e] = (int)f4at(vy, e);  // compared only (validity is checked once per label upload)
     }
     for (int k0 = 0; k0 < K; k0 += KU) {
       float4 vp[KU];
@@ -99,7 +98,7 @@ __global__ void __launch_bounds__(kBlock) boost_real_kernel(const BoostArgs a) {
   if (blockIdx.x == 0 && threadIdx.x < (a.n & 3)) {
     const int64_t i = (n4 << 2) + threadIdx.x;
     RowState st{-INFINITY, 0.f, 0.f, 0};
-    const int yi = checked_label(a.y[i], K, bad_label);
+    const int yi = (int)a.y[i];
     for (int k = 0; k < K; ++k) row_step(st, a.proba[(int64_t)k * a.ld + i], k, yi);
     const float wn = a.w[i] * a.inv_sum_w;
     const float loss = (1.0f + inv_km1) * st.log_y - inv_km1 * st.sum_log;
@@ -108,7 +107,6 @@ __global__ void __launch_bounds__(kBlock) boost_real_kernel(const BoostArgs a) {
     acc[0] += (st.am != yi) ? (double)wn : 0.0;
     acc[1] += (double)wo;
   }
-  report_bad_label(bad_label, a.ws);
   block_reduce_publish<2>(acc, a.ws);
 }
 
@@ -136,7 +134,6 @@ __global__ void __launch_bounds__(kRT) boost_real_tiled_kernel(const BoostArgs a
   const float scale = -((float)(K - 1) / (float)K);
   const int64_t ntiles = (a.n + kRR - 1) / kRR;
   double acc[2] = {0.0, 0.0};
-  bool bad_label = false;  // a label outside [0, K) or fractional (Classifier.validateLabel throws in the reference)
   uint32_t it = 0;
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
     if (tid == 0) {  // the other resident CTAs of the SM cover this tile's load latency
@@ -150,7 +147,7 @@ __global__ void __launch_bounds__(kRT) boost_real_tiled_kernel(const BoostArgs a
     const float4 vw = any_in ? ld_rw4(a.w + row0) : make_float4(0.f, 0.f, 0.f, 0.f);
     int yi[4];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) yi[e] = (row0 + e < a.n) ? checked_label(f4at(vy, e), K, bad_label) : 0;
+    for (int e = 0; e < 4; ++e) yi[e] = min(max((int)f4at(vy, e), 0), K - 1);  // clamp = memory safety; validity checked once per upload
     mbar_wait(&bar, it & 1);
     const float* sP = tileP + 4 * tid;
     float best[4], sum_lg[4];
@@ -172,7 +169,7 @@ __global__ void __launch_bounds__(kRT) boost_real_tiled_kernel(const BoostArgs a
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       const bool in = row0 + e < a.n;
-      const float log_y = lg2_approx(fmaxf(sP[yi[e] * kRR + e], kSparkEps)) * kLn2;  // yi is validated: inside [0, K)
+      const float log_y = lg2_approx(fmaxf(sP[yi[e] * kRR + e], kSparkEps)) * kLn2;  // yi is clamped into [0, K)
       const float wn = f4at(vw, e) * a.inv_sum_w;  // :186
       const float loss = (1.0f + inv_km1) * log_y - inv_km1 * (sum_lg[e] * kLn2);  // :218-224
       const float wo = wn * exp_fast(scale * loss);                                // :226
@@ -191,7 +188,6 @@ __global__ void __launch_bounds__(kRT) boost_real_tiled_kernel(const BoostArgs a
     acc[1] += (double)sum4;
     __syncthreads();  // everyone is done with the tile before it is refilled
   }
-  report_bad_label(bad_label, a.ws);
   block_reduce_publish<2, kRT>(acc, a.ws);
 }
 

@@ -228,7 +228,6 @@ __global__ void __launch_bounds__(kBlock) gbm_logloss_kernel(const GbmArgs a) {
   const bool has_w = (a.w != nullptr);
   constexpr int NRED = KMAX + 1;
   double acc[NRED];
-  bool bad_label = false;
 #pragma unroll
   for (int k = 0; k < NRED; ++k) acc[k] = 0.0;
 
@@ -312,18 +311,15 @@ __global__ void __launch_bounds__(kBlock) gbm_logloss_kernel(const GbmArgs a) {
       // log Σ exp(p_k) = m + log1p(Σ_{k != argmax} exp(p_k - m)): the max term is exactly 1 and is kept
       // out of the sum so a well-fitted row (loss -> 0) keeps full relative precision
       float srest = 0.f, py = 0.f;
-      bool hit = false;  // the label equals one of the class indices 0..K-1: valid (no conversion instructions: the
-                         // float->int round trip of checked_label shares the XU pipe with ex2/rcp and cost 10 % here)
       float ex[KMAX];
 #pragma unroll
       for (int k = 0; k < KMAX; ++k) {
         if (k < K) {
           ex[k] = ex2_approx((p[k][e] - m) * kLog2e);
           if (k != am) srest += ex[k];
-          if (yf == (float)k) { py = p[k][e]; hit = true; }
+          if (yf == (float)k) py = p[k][e];
         }
       }
-      if (in && !hit) bad_label = true;  // GBMLoss.scala:200-204 throws for such a label
       const float lse = m + log1p_pos(srest);
       const float inv_s = rcp_approx(1.0f + srest);
       if (T::kSumLoss && in) g_loss += ((MODE == GBM_EVAL) ? cv[e] : 1.0f) * (lse - py);  // -Σ y_k (p_k - lse)  :206-221
@@ -378,7 +374,6 @@ __global__ void __launch_bounds__(kBlock) gbm_logloss_kernel(const GbmArgs a) {
       }
     }
   }
-  report_bad_label(bad_label, a.ws);
   if (T::kReduce) block_reduce_publish<NRED>(acc, a.ws);
 }
 

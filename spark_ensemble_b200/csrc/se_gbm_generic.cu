@@ -36,7 +36,6 @@ __global__ void __launch_bounds__(32) gbm_logloss_generic_kernel(const GbmArgs a
   const bool has_w = (a.w != nullptr);
   constexpr bool kBagMode = (MODE == GBM_EVAL) || T::kNewton;
   const bool has_bag = kBagMode && (a.bag != nullptr);
-  bool bad_label = false;
   double loss_acc = 0.0;
   const int64_t ngroups = (a.n + 31) / 32;
   for (int64_t g = blockIdx.x; g < ngroups; g += gridDim.x) {
@@ -44,7 +43,7 @@ __global__ void __launch_bounds__(32) gbm_logloss_generic_kernel(const GbmArgs a
     const bool in = i < a.n;
     const int64_t ii = in ? i : a.n - 1;  // out-of-range lanes shadow the last row (they never store or count)
     const float yf = a.y[ii];
-    const int yi = in ? checked_label(yf, K, bad_label) : 0;
+    const int yi = min(max((int)yf, 0), K - 1);  // validity is checked once per label upload (se_api.cu)
     const float c = has_bag ? a.bag[ii] : 1.0f;
     const float w = (T::kNewton && has_w) ? a.w[ii] : 1.0f;
     // sweep 1: p_k = F_k + coef_k h_k (GBMLoss.scala:56-59), running max (first maximum), F update
@@ -95,7 +94,6 @@ __global__ void __launch_bounds__(32) gbm_logloss_generic_kernel(const GbmArgs a
       }
     }
   }
-  report_bad_label(bad_label, a.ws);
   if (!T::kReduce) return;
   loss_acc = warp_sum(loss_acc);
   if (lane == 0) s_acc[0] = loss_acc;

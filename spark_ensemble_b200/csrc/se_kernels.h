@@ -246,6 +246,8 @@ cudaError_t launch_transpose_rows(const float* src, int64_t rows, int d, float* 
                                   cudaStream_t s);
 
 // ---- utilities (se_util.cu) ------------------------------------------------------------------
+// raises *bad (mapped host memory) when a label is not an integer class index in [0, K)
+cudaError_t launch_validate_labels(const float* y, int64_t n, int K, int* bad, int sms, cudaStream_t s);
 cudaError_t launch_fill(float* p, float v, int64_t n, int sms, cudaStream_t s);
 cudaError_t launch_fill_synthetic(float* p, int kind, uint64_t seed, double a, double b, int64_t n,
                                   int64_t index_offset, int sms, cudaStream_t s);

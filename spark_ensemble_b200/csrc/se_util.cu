@@ -10,6 +10,20 @@ __global__ void __launch_bounds__(kBlock) fill_kernel(float* p, float v, int64_t
     p[i] = v;
 }
 
+// Labels used as class indices (LogLoss, SAMME / SAMME.R) are validated ONCE per upload of the label slot, by this
+// 4 B/row pass, instead of in every hot kernel (the per-row float->int->float round trip shares the XU pipe with
+// ex2 / rcp: it cost the register LogLoss kernel 10-25 % and the SAMME.R tiles 5 %).  A label that is not an integer in
+// [0, K) raises the flag; the reference throws for it (GBMLoss.scala:200-204, Classifier.validateLabel).
+__global__ void __launch_bounds__(kBlock) validate_labels_kernel(const float* __restrict__ y, int64_t n, int K, int* bad) {
+  bool b = false;
+  for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += (int64_t)gridDim.x * kBlock) {
+    bool bb = false;
+    (void)checked_label(y[i], K, bb);
+    b = b || bb;
+  }
+  if (b && bad != nullptr) *reinterpret_cast<volatile int*>(bad) = 1;
+}
+
 // kind 0 uniform[a,b), 1 normal(mean a, sd b) (Box-Muller), 2 integer uniform in [a,b), 3 bernoulli(a)
 __global__ void __launch_bounds__(kBlock) synth_kernel(float* p, int kind, uint64_t seed, float a, float b,
                                                       int64_t n, int64_t index_offset) {
@@ -109,6 +123,10 @@ cudaError_t launch_transpose_rows(const float* src, int64_t rows, int d, float* 
   if (rows <= 0 || d <= 0) return cudaSuccess;
   dim3 grid((unsigned)((rows + 31) / 32), (unsigned)((d + 31) / 32));
   transpose_rows_kernel<<<grid, 256, 0, s>>>(src, rows, d, X, ld, row0);
+  return cudaGetLastError();
+}
+cudaError_t launch_validate_labels(const float* y, int64_t n, int K, int* bad, int sms, cudaStream_t s) {
+  validate_labels_kernel<<<grid1(n, sms), kBlock, 0, s>>>(y, n, K, bad);
   return cudaGetLastError();
 }
 cudaError_t launch_fill(float* p, float v, int64_t n, int sms, cudaStream_t s) {
