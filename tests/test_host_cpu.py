@@ -308,6 +308,12 @@ def test_rewired_scala_train_uses_only_existing_natives():
     for call in ("gbmPseudoResiduals", "gbmLinesearchEval", "gbmRound", "gbmUpdate", "gbmUpdateValidation", "quantile",
                  "treePredict", "uploadRowmajor"):
         assert call in used
+    # BoostingClassifier.train() (SAMME / SAMME.R), rewired the same way
+    src = open(os.path.join(root, "scala", "org", "apache", "spark", "ml", "classification", "BoostingClassifierNative.scala")).read()
+    used = set(re.findall(r"SeNative\.(\w+)\(", src))
+    assert used and used <= natives, used - natives
+    for call in ("boostConfigure", "boostRealUpdate", "boostDiscreteError", "boostDiscreteUpdate", "slotSum", "downloadScaled"):
+        assert call in used
 
 
 # ------------------------------------------------------------------ row sharding over several contexts (Param `devices`)
