@@ -117,7 +117,7 @@ SE_API int se_ctx_kernel_time_reset(se_ctx* ctx);
  * round in ONE cooperative launch), "fused_round_max_rows", "fused_ctas_per_sm", "fused_prefetch_mb", "ls_mode" (non-squared Brent line
  * search: 0 = one launch per evaluation, 1 = one persistent launch with Brent on the device [default], 2 = host Brent
  * over single-evaluation launches of the persistent kernel — bit-identical to 1, for tests), "ls_resident",
- * "ls_ctas_per_sm", "l2_persist", "l2_persist_frac", "peer_timeout_ms" (spin bound of the fused peer exchange,
+ * "ls_ctas_per_sm", "ls_ring" (cp.async ring stages for the streamed tiles, 0 = register prefetch [default]), "l2_persist", "l2_persist_frac", "peer_timeout_ms" (spin bound of the fused peer exchange,
  * 0 = forever), "alternate_passes", "l2_hints", "ctas_per_sm", "host_mirror".  Read-only: "last_round_fused",
  * "last_ls_workers", "last_ls_passes", "last_ls_hit_ratio", "last_fused_grid", "l2_persist_max_bytes",
  * "l2_window_max_bytes".  Unknown keys fail with SE_ERR_ARG. */

@@ -254,6 +254,21 @@ __global__ void __launch_bounds__(kBlock, 3) gbm_round_sq_fused_kernel(const SqR
 }
 
 // =================================================================================== persistent line search
+// 16-byte asynchronous global -> shared copies (LDGSTS).  Every thread copies, waits for and reads back ONLY its own
+// 16-byte slots, so the ring needs no block barrier: cp.async.wait_group orders the executing thread's own copies.
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_pending(int pending) {  // at most `pending` newest groups still in flight
+  switch (pending) {
+    case 0: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
+    case 1: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
+    case 2: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
+    default: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
+  }
+}
+
 // Tiles hold U float4 groups per thread of NARR arrays: (u, v) for the binary losses, (y, F, h) otherwise.
 template <int LOSS>
 struct LsTraits {
@@ -287,7 +302,7 @@ __global__ void __launch_bounds__(kBlock, 4) gbm_linesearch_persist_kernel(const
   using T = LsTraits<LOSS>;
   constexpr int U = T::kU, NARR = T::kNarr;
   constexpr bool PACKED = T::kPacked;
-  extern __shared__ float4 s_tiles[];  // [resident][NARR][U][kBlock]
+  extern __shared__ float4 s_dyn[];  // [ring stage][NARR][U][kBlock] then [resident][NARR][U][kBlock]
   __shared__ double s_red[kBlock / 32];
   __shared__ double s_x;
   __shared__ int s_cmd;
@@ -364,6 +379,9 @@ __global__ void __launch_bounds__(kBlock, 4) gbm_linesearch_persist_kernel(const
   const int64_t R = cnt < a.resident_tiles ? cnt : a.resident_tiles;                           // kept in shared memory
   const float param = a.param;
   const uint64_t pol_keep = l2_policy(false);
+  const int S = a.ring_stages;
+  float4* const s_ring = s_dyn;
+  float4* const s_tiles = s_dyn + (size_t)S * NARR * U * kBlock;
 
   auto row_loss = [&](float c0, float c1, float c2, float coef) -> float {
     // PACKED: (u, v) hold the loss ARGUMENT directly (signed_scale folded in, exact): z = u + coef*v
@@ -405,7 +423,36 @@ __global__ void __launch_bounds__(kBlock, 4) gbm_linesearch_persist_kernel(const
         }
       }
     };
-    if (nstream > 0) load_tile(stream_index(0), first || !PACKED);
+    // ring: the streamed tiles of this pass travel global -> shared by cp.async, S stages ahead of the arithmetic.
+    // The first S of them are requested BEFORE the wait for the abscissa (they do not depend on it), so the
+    // coordinator's fold + exchange hides their latency.  The first evaluation of a packed loss converts (y, F, h)
+    // on the way and keeps the register path.
+    const bool ring = S > 0 && !(PACKED && first);
+    auto ring_issue = [&](int stage, int64_t i) {
+      const int64_t base = (blockIdx.x + i * (int64_t)W) * tile + tid;
+      float4* st = s_ring + (size_t)stage * NARR * U * kBlock;
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int64_t g = base + (int64_t)u * kBlock;
+        if (g >= n4) continue;
+        if constexpr (PACKED) {
+          cp_async16(&st[(0 * U + u) * kBlock + tid], a.u + 4 * g);
+          cp_async16(&st[(1 * U + u) * kBlock + tid], a.v + 4 * g);
+        } else {
+          cp_async16(&st[(0 * U + u) * kBlock + tid], a.y + 4 * g);
+          cp_async16(&st[(1 * U + u) * kBlock + tid], a.F + 4 * g);
+          cp_async16(&st[(2 * U + u) * kBlock + tid], a.h + 4 * g);
+        }
+      }
+    };
+    if (ring) {
+      for (int s = 0; s < S; ++s) {  // exactly S groups (empty ones past the end keep the wait_group count uniform)
+        if (s < nstream) ring_issue(s, stream_index(s));
+        cp_async_commit();
+      }
+    } else if (nstream > 0) {
+      load_tile(stream_index(0), first || !PACKED);
+    }
     double x;
     if (first) {
       x = a.start;
@@ -421,8 +468,32 @@ __global__ void __launch_bounds__(kBlock, 4) gbm_linesearch_persist_kernel(const
     }
     const float coef = (float)x;  // same narrowing as se_gbm_linesearch_eval
     double acc = 0.0;
-    // streamed tiles (the first one is already in registers)
-    for (int64_t k = 0; k < nstream; ++k) {
+    if (ring) {
+      int stage = 0;
+      for (int64_t k = 0; k < nstream; ++k) {
+        cp_async_wait_pending(S - 1);  // group k (the oldest of the S outstanding) has landed
+        const int64_t base = (blockIdx.x + stream_index(k) * (int64_t)W) * tile + tid;
+        const float4* st = s_ring + (size_t)stage * NARR * U * kBlock;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          if (base + (int64_t)u * kBlock >= n4) continue;
+          float4 c[NARR];
+#pragma unroll
+          for (int q = 0; q < NARR; ++q) c[q] = st[(q * U + u) * kBlock + tid];
+          float l = 0.f;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) l += row_loss(f4at(c[0], q), f4at(c[1], q), f4at(c[NARR - 1], q), coef);
+          acc += (double)l;
+        }
+        // refill this stage only after its values were consumed (the thread's own reads precede its own new copy)
+        if (k + S < nstream) ring_issue(stage, stream_index(k + S));
+        cp_async_commit();
+        stage = (stage + 1 == S) ? 0 : stage + 1;
+      }
+      cp_async_wait_pending(0);
+    }
+    // streamed tiles, register path (the first one is already in registers)
+    for (int64_t k = 0; !ring && k < nstream; ++k) {
       const int64_t i = stream_index(k);
       const int64_t base = (blockIdx.x + i * (int64_t)W) * tile + tid;
 #pragma unroll
@@ -535,12 +606,25 @@ cudaError_t launch_ls(const LsArgs& a0, int sms, const LsLaunch& cfg, cudaStream
   // shared-memory budget per CTA: the SM's capacity split between the co-resident CTAs (1 KB reserved per CTA)
   int64_t budget = (int64_t)smem_cap / per_sm_ctas - 1024 - 256;
   if (budget > max_smem) budget = max_smem;
-  int64_t resident = cfg.resident ? budget / T::kTileBytes : 0;
   const int64_t per_cta = (ntiles + workers - 1) / workers;
+  // ring stages for the tiles that do not stay resident: none when every tile of a worker fits in shared memory,
+  // else cfg.ring as far as the budget allows; what is left of the budget holds resident tiles.  Off by default:
+  // measured (profiles/r02_ls_ring.json) the ring does not beat the register prefetch at 4 CTAs/SM (73.6 vs 75.3 us
+  // per 50 M-row pass) and costs resident tiles on small shards.
+  const int64_t tb = T::kTileBytes;
+  int ring = 0;
+  if (per_cta > (cfg.resident ? budget / tb : 0)) {
+    ring = cfg.ring < 0 ? 0 : (cfg.ring > 4 ? 4 : cfg.ring);
+    if (ring == 1) ring = 2;
+    if ((int64_t)ring * tb > budget) ring = (int)(budget / tb);
+    if (ring < 2) ring = 0;
+  }
+  int64_t resident = cfg.resident ? (budget - (int64_t)ring * tb) / tb : 0;
   if (resident > per_cta) resident = per_cta;
   if (resident < 0) resident = 0;
   a.resident_tiles = (int)resident;
-  const size_t dyn = (size_t)resident * T::kTileBytes;
+  a.ring_stages = ring;
+  const size_t dyn = (size_t)(resident + ring) * T::kTileBytes;
   // the occupancy with this much dynamic shared memory must still cover the grid (cooperative launch would fail)
   int blocks = 0;
   cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, kern, kBlock, dyn);

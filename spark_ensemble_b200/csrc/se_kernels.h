@@ -133,6 +133,7 @@ struct LsArgs {
   int single = 0;        // evaluate the objective at `start` once (host-driven search over the same kernel)
   int first_parity = 0;  // tile direction of evaluation e is (first_parity + e) & 1
   int resident_tiles = 0;
+  int ring_stages = 0;   // > 0: streamed tiles go through a per-thread cp.async ring of this many stages in shared memory
   double* partials = nullptr;
   FusedSync* sync = nullptr;
   unsigned long long epoch0 = 0;
@@ -142,6 +143,7 @@ struct LsArgs {
 struct LsLaunch {
   int max_ctas_per_sm = 4;
   int resident = 1;             // keep each worker's first tiles in shared memory
+  int ring = 0;                 // cp.async ring stages for the streamed tiles: 0 off (register prefetch), 2..4
   void* window_base = nullptr;  // L2 access-policy window (persisting) over the packed view
   size_t window_bytes = 0;
   float hit_ratio = 0.f;

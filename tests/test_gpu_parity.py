@@ -1014,13 +1014,15 @@ LS_LOSSES = ["absolute", "huber", "quantile", "logcosh", "scaledlogcosh", "berno
 
 
 @pytest.mark.parametrize("name", LS_LOSSES)
-@pytest.mark.parametrize("n,ctas,resident", [(3, 4, 1), (2049, 4, 1), (40013, 4, 1), (700001, 1, 0), (700001, 1, 1),
-                                             (2000003, 2, 1)])
-def test_device_line_search_matches_host_brent(ctx, oracle, rng, name, n, ctas, resident):
+@pytest.mark.parametrize("n,ctas,resident,ring", [(3, 4, 1, 0), (2049, 4, 1, 0), (40013, 4, 1, 0), (700001, 1, 0, 3),
+                                                  (700001, 1, 0, 0), (700001, 1, 1, 0), (2000003, 2, 1, 0),
+                                                  (2000003, 4, 0, 2), (2000003, 4, 0, 4), (5000011, 4, 1, 3)])
+def test_device_line_search_matches_host_brent(ctx, oracle, rng, name, n, ctas, resident, ring):
     """Brent's whole line search in ONE persistent launch (workers + coordinator warp, tiles resident in shared
     memory, the first evaluation builds the signed view of the binary losses).  ls_mode 2 runs the HOST Brent over
     single-evaluation launches of the same kernel: alpha, the objective and the evaluation count must be identical
-    bit for bit.  Against the oracle: the objective value at the minimiser within 1e-5."""
+    bit for bit.  Tiles that do not stay resident stream through a per-thread cp.async ring (`ls_ring` stages; 0 = the
+    register prefetch).  Against the oracle: the objective value at the minimiser within 1e-5."""
     from spark_ensemble_b200 import _native as N
     dim, par, y, F, h, w = setup_gbm(ctx, rng, name, n, weighted=(n % 2 == 0))
     lid = O.LOSS_IDS[name]
@@ -1029,6 +1031,7 @@ def test_device_line_search_matches_host_brent(ctx, oracle, rng, name, n, ctas, 
     ctx.upload(N.SLOT_H, h)
     ctx.set_option("ls_ctas_per_sm", ctas)
     ctx.set_option("ls_resident", resident)
+    ctx.set_option("ls_ring", ring)
     try:
         ctx.set_option("ls_mode", 1)
         dev = ctx.gbm_linesearch_brent()
@@ -1061,6 +1064,7 @@ def test_device_line_search_matches_host_brent(ctx, oracle, rng, name, n, ctas, 
         ctx.set_option("ls_mode", 1)
         ctx.set_option("ls_ctas_per_sm", 4)
         ctx.set_option("ls_resident", 1)
+        ctx.set_option("ls_ring", 0)
 
 
 def test_options_roundtrip(ctx):
