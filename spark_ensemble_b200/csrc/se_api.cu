@@ -245,6 +245,8 @@ struct se_ctx {
   // binned (uint8) copies of X / VX for the tree walk
   BinState bins[2];
   int tree_bins = 1;                  // 0: always walk the fp32 matrix
+  int tree_mask = 1;                  // shallow trees (<= 64 internal nodes): all-nodes comparison kernel over the rank matrix
+  int last_tree_mask = 0;
   int last_tree_binned = 0, last_tree_rebinned_cols = 0;
   std::string err;
   // stopwatch + per-kernel-family timing
@@ -851,13 +853,13 @@ int se_ctx_kernel_time_reset(se_ctx* ctx) {
 
 namespace {
 struct OptKey { const char* name; int id; };
-enum { OPT_TREE_BINS, OPT_LAST_TREE_BINNED, OPT_LAST_TREE_REBINNED, OPT_FUSED_LOSS_REDUCE, OPT_FUSED_L2_MODE, OPT_FUSED_TIMING, OPT_LAST_FUSED_US0, OPT_LAST_FUSED_US1, OPT_LAST_FUSED_US2, OPT_FUSED_PREFETCH_MB, OPT_FUSED_ROUND, OPT_FUSED_MAX_ROWS, OPT_FUSED_CTAS, OPT_LS_MODE, OPT_LS_RESIDENT, OPT_LS_CTAS, OPT_LS_RING, OPT_L2_PERSIST,
+enum { OPT_TREE_MASK, OPT_LAST_TREE_MASK, OPT_TREE_BINS, OPT_LAST_TREE_BINNED, OPT_LAST_TREE_REBINNED, OPT_FUSED_LOSS_REDUCE, OPT_FUSED_L2_MODE, OPT_FUSED_TIMING, OPT_LAST_FUSED_US0, OPT_LAST_FUSED_US1, OPT_LAST_FUSED_US2, OPT_FUSED_PREFETCH_MB, OPT_FUSED_ROUND, OPT_FUSED_MAX_ROWS, OPT_FUSED_CTAS, OPT_LS_MODE, OPT_LS_RESIDENT, OPT_LS_CTAS, OPT_LS_RING, OPT_L2_PERSIST,
        OPT_L2_PERSIST_FRAC, OPT_PEER_TIMEOUT_MS, OPT_ALTERNATE, OPT_L2_HINTS, OPT_CTAS_PER_SM, OPT_HOST_MIRROR,
        // read-only diagnostics
        OPT_LAST_ROUND_FUSED, OPT_LAST_LS_WORKERS, OPT_LAST_LS_PASSES, OPT_LAST_LS_HIT_RATIO, OPT_LAST_FUSED_GRID,
        OPT_L2_PERSIST_MAX, OPT_L2_WINDOW_MAX, OPT_LAST_STAT0, OPT_LAST_STAT1, OPT_LAST_STAT2 };
 const OptKey kOpts[] = {
-  {"tree_bins", OPT_TREE_BINS}, {"last_tree_binned", OPT_LAST_TREE_BINNED}, {"last_tree_rebinned_cols", OPT_LAST_TREE_REBINNED},
+  {"tree_bins", OPT_TREE_BINS}, {"tree_mask", OPT_TREE_MASK}, {"last_tree_mask", OPT_LAST_TREE_MASK}, {"last_tree_binned", OPT_LAST_TREE_BINNED}, {"last_tree_rebinned_cols", OPT_LAST_TREE_REBINNED},
   {"fused_loss_reduce", OPT_FUSED_LOSS_REDUCE}, {"fused_l2_mode", OPT_FUSED_L2_MODE}, {"fused_timing", OPT_FUSED_TIMING}, {"last_fused_stats_us", OPT_LAST_FUSED_US0}, {"last_fused_brent_us", OPT_LAST_FUSED_US1},
   {"last_fused_update_us", OPT_LAST_FUSED_US2}, {"fused_prefetch_mb", OPT_FUSED_PREFETCH_MB}, {"fused_round", OPT_FUSED_ROUND}, {"fused_round_max_rows", OPT_FUSED_MAX_ROWS}, {"fused_ctas_per_sm", OPT_FUSED_CTAS},
   {"ls_mode", OPT_LS_MODE}, {"ls_resident", OPT_LS_RESIDENT}, {"ls_ctas_per_sm", OPT_LS_CTAS}, {"ls_ring", OPT_LS_RING}, {"l2_persist", OPT_L2_PERSIST},
@@ -885,6 +887,7 @@ int se_ctx_set_option(se_ctx* ctx, const char* key, double value) {
     case OPT_FUSED_TIMING: ctx->fused_timing = iv != 0; break;
     case OPT_FUSED_LOSS_REDUCE: ctx->fused_loss_reduce = iv != 0; break;
     case OPT_TREE_BINS: ctx->tree_bins = iv != 0; break;
+    case OPT_TREE_MASK: ctx->tree_mask = iv != 0; break;
     case OPT_FUSED_L2_MODE: SE_REQUIRE(ctx, iv >= 0 && iv <= 2, SE_ERR_ARG, "fused_l2_mode in {0,1,2}"); ctx->fused_l2_mode = iv; if (iv != 2) release_l2_persist(ctx); break;
     case OPT_FUSED_PREFETCH_MB: SE_REQUIRE(ctx, value >= 0.0 && value <= 512.0, SE_ERR_ARG, "fused_prefetch_mb in [0,512]"); ctx->fused_prefetch_mb = value; break;
     case OPT_FUSED_CTAS: SE_REQUIRE(ctx, iv >= 1 && iv <= 8, SE_ERR_ARG, "fused_ctas_per_sm in [1,8]"); ctx->fused_ctas_per_sm = iv; break;
@@ -913,6 +916,8 @@ int se_ctx_get_option(const se_ctx* ctx, const char* key, double* value) {
     case OPT_FUSED_TIMING: *value = ctx->fused_timing; break;
     case OPT_FUSED_LOSS_REDUCE: *value = ctx->fused_loss_reduce; break;
     case OPT_TREE_BINS: *value = ctx->tree_bins; break;
+    case OPT_TREE_MASK: *value = ctx->tree_mask; break;
+    case OPT_LAST_TREE_MASK: *value = ctx->last_tree_mask; break;
     case OPT_LAST_TREE_BINNED: *value = ctx->last_tree_binned; break;
     case OPT_LAST_TREE_REBINNED: *value = ctx->last_tree_rebinned_cols; break;
     case OPT_FUSED_L2_MODE: *value = ctx->fused_l2_mode; break;
@@ -2439,6 +2444,7 @@ namespace {
 int tree_predict_binned(se_ctx* ctx, int which, const SlotBuf& X, int n_nodes, const int32_t* col, const float* thr,
                         const int32_t* left, const int32_t* right, const TreeArgs& t) {
   ctx->last_tree_binned = 0;
+  ctx->last_tree_mask = 0;
   ctx->last_tree_rebinned_cols = 0;
   if (!ctx->tree_bins || n_nodes > 65535 || X.rows > 65535 || X.cols == 0) return 0;
   BinState& B = ctx->bins[which];
@@ -2498,8 +2504,10 @@ int tree_predict_binned(se_ctx* ctx, int which, const SlotBuf& X, int n_nodes, c
     B.nodes_cap = (size_t)n_nodes;
   }
   std::vector<uint4> nodes((size_t)n_nodes);
+  int n_internal = 0;
   for (int i = 0; i < n_nodes; ++i) {
     if (col[i] < 0) { nodes[i] = make_uint4(0u, 0u, 0x80000000u, 0u); continue; }
+    ++n_internal;
     const std::vector<float>& E = B.edges[col[i]];
     const uint32_t j = (uint32_t)(std::lower_bound(E.begin(), E.end(), thr[i]) - E.begin());  // x <= t_j  <=>  rank(x) <= j
     const uint64_t off = (uint64_t)col[i] * (uint64_t)B.ld8;
@@ -2507,8 +2515,9 @@ int tree_predict_binned(se_ctx* ctx, int which, const SlotBuf& X, int n_nodes, c
   }
   SE_CUDA(ctx, cudaMemcpyAsync(B.d_nodes, nodes.data(), sizeof(uint4) * (size_t)n_nodes, cudaMemcpyHostToDevice, ctx->stream));
   SE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  SE_LAUNCH_T(ctx, SE_KF_TREE, launch_tree_predict_binned(t, B.d8, B.d_nodes, ctx->sms, ctx->stream));
+  SE_LAUNCH_T(ctx, SE_KF_TREE, launch_tree_predict_binned(t, B.d8, B.d_nodes, n_internal, ctx->tree_mask, ctx->sms, ctx->stream));
   ctx->last_tree_binned = 1;
+  ctx->last_tree_mask = (ctx->tree_mask && n_internal <= 64 && n_nodes <= 256) ? 1 : 0;
   return 1;
 }
 }  // namespace

@@ -232,7 +232,9 @@ struct BinArgs {
 };
 cudaError_t launch_bin_columns(const BinArgs& a, int n_cols, int sms, cudaStream_t s);
 // nodes: packed {x,y: byte offset of the column in X8 (64 bit); z: bin threshold | leaf << 31; w: left | right << 16}
-cudaError_t launch_tree_predict_binned(const TreeArgs& a, const uint8_t* X8, const uint4* nodes, int sms, cudaStream_t s);
+// n_internal: number of internal nodes; mask_mode != 0 allows the all-nodes kernel for trees of <= 64 internal nodes
+cudaError_t launch_tree_predict_binned(const TreeArgs& a, const uint8_t* X8, const uint4* nodes, int n_internal, int mask_mode,
+                                       int sms, cudaStream_t s);
 cudaError_t launch_linear_predict(const float* X, int64_t n, int64_t ld, int n_coef,
                                   const float* coef, const int32_t* cols, float intercept,
                                   float* out, int sms, cudaStream_t s);

@@ -203,6 +203,121 @@ __global__ void __launch_bounds__(kBlock, MINB) tree_predict_binned_kernel(const
   }
 }
 
+
+// ---- shallow trees (<= 64 internal nodes, e.g. depth <= 6): evaluate EVERY node's comparison, then walk in registers.
+// The walk above fetches, per 32 consecutive rows, one 32-byte sector per DISTINCT node its rows sit on at each level:
+// 1 + 2 + 4 + ... sectors, i.e. about one byte per row and internal node — exactly what reading the node's column for
+// every row costs (ncu: 62 B/row for 63 internal nodes).  Same bytes, but here they arrive as fully coalesced,
+// INDEPENDENT vector loads (no level-to-level dependency, one wavefront per 128 rows instead of one per sector), four
+// byte-compares at a time in SWAR form, and the per-row walk reads its decision bits from shared memory.
+//   bit j of a row = rank(x[col_j]) <= t_j; internal node ordinals j are assigned in node order by warp 0.
+constexpr int kTreeMaskWords = 4;  // measured at 100 M x 128, depth 6: 1.51 / 1.22 / 1.15 ms for 1 / 2 / 4 words (walk: 1.47)
+template <int RW> struct MaskVec;
+template <> struct MaskVec<1> { using type = uint32_t; };
+template <> struct MaskVec<2> { using type = uint2; };
+template <> struct MaskVec<4> { using type = uint4; };
+
+__device__ __forceinline__ uint32_t bytes_le(uint32_t x, uint32_t t, uint32_t t_hi) {
+  // bit 7 of every byte lane: x_byte <= t_byte.  Low 7 bits: (t_lo + 128) - x_lo keeps bit 7 iff t_lo >= x_lo (no
+  // borrow crosses a lane: every lane of the minuend is >= 128, of the subtrahend <= 127); top bits decide first.
+  const uint32_t d = t_hi - (x & 0x7f7f7f7fu);
+  return (~x & t) | (~(x ^ t) & d);
+}
+
+template <int RW>  // RW words of 4 consecutive rows per thread, fetched as ONE 4*RW-byte load per node
+__global__ void __launch_bounds__(kBlock, 4) tree_predict_mask_kernel(const TreeArgs a, const uint8_t* __restrict__ X8,
+                                                                      const uint4* __restrict__ nodes) {
+  using V = typename MaskVec<RW>::type;
+  __shared__ unsigned long long s_off[64];
+  __shared__ uint32_t s_thr[64];
+  __shared__ uint32_t s_walk[256];  // ordinal | left << 8 | right << 16 | leaf << 31
+  __shared__ float s_val[256];
+  __shared__ __align__(16) uint32_t s_acc[8][kBlock * RW];  // [8 nodes per byte][thread][word]: byte e = row e of the word
+  __shared__ int s_i8;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const bool scalar = (a.n_out == 1);
+  if (tid < 32) {
+    int base = 0;
+    for (int c = 0; c < a.n_nodes; c += 32) {
+      const int i = c + lane;
+      const uint4 nd = (i < a.n_nodes) ? nodes[i] : make_uint4(0u, 0u, 0x80000000u, 0u);
+      const bool internal = (nd.z >> 31) == 0;
+      const unsigned m = __ballot_sync(0xffffffffu, internal);
+      const int ord = base + __popc(m & ((1u << lane) - 1u));
+      if (i < a.n_nodes) {
+        s_walk[i] = internal ? ((uint32_t)ord | ((nd.w & 0xFFu) << 8) | (((nd.w >> 16) & 0xFFu) << 16)) : 0x80000000u;
+        if (internal) {
+          s_off[ord] = ((unsigned long long)nd.y << 32) | nd.x;
+          s_thr[ord] = (nd.z & 0xFFu) * 0x01010101u;
+        }
+      }
+      base += __popc(m);
+    }
+    __syncwarp();
+    const int i8 = (base + 7) & ~7;  // padded with repeats of node 0's column (their bits are never read)
+    for (int j = base + lane; j < i8; j += 32) {
+      s_off[j] = s_off[0];
+      s_thr[j] = 0u;
+    }
+    if (lane == 0) s_i8 = i8;
+  }
+  if (scalar)
+    for (int i = tid; i < a.n_nodes; i += kBlock) s_val[i] = a.value[i];
+  __syncthreads();
+  const int i8 = s_i8;
+  constexpr int RPT = 4 * RW;
+  const int64_t ngroups = (a.n + RPT - 1) / RPT;
+  const unsigned char* my = reinterpret_cast<const unsigned char*>(&s_acc[0][tid * RW]);
+  constexpr int kPlane = kBlock * RW * 4;  // bytes between the planes of s_acc
+  for (int64_t g = (int64_t)blockIdx.x * kBlock + tid; g < ngroups; g += (int64_t)gridDim.x * kBlock) {
+    const int64_t r0 = g * RPT;  // X8 columns are padded to 128 rows: the vector load stays inside the column
+    const uint8_t* row = X8 + r0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      if (8 * k >= i8) break;
+      uint32_t acc[RW];
+#pragma unroll
+      for (int w = 0; w < RW; ++w) acc[w] = 0u;
+#pragma unroll
+      for (int s = 0; s < 8; ++s) {
+        const int j = 8 * k + s;
+        const uint32_t t = s_thr[j];
+        const V v = __ldg(reinterpret_cast<const V*>(row + s_off[j]));
+        const uint32_t* xs = reinterpret_cast<const uint32_t*>(&v);
+#pragma unroll
+        for (int w = 0; w < RW; ++w) {
+          const uint32_t le = bytes_le(xs[w], t, t | 0x80808080u);
+          acc[w] |= (s == 7 ? le : (le >> (7 - s))) & (0x01010101u << s);
+        }
+      }
+      *reinterpret_cast<V*>(&s_acc[k][tid * RW]) = *reinterpret_cast<const V*>(acc);
+    }
+    // the thread reads back only what it stored itself: no barrier
+#pragma unroll
+    for (int w = 0; w < RW; ++w) {
+      if (r0 + 4 * w >= a.n) break;
+      int node[TV];
+      uint32_t wk[TV];
+#pragma unroll
+      for (int e = 0; e < TV; ++e) node[e] = 0, wk[e] = s_walk[0];
+      for (;;) {
+        bool any = false;
+#pragma unroll
+        for (int e = 0; e < TV; ++e) {
+          if (wk[e] >> 31) continue;
+          any = true;
+          const uint32_t ord = wk[e] & 0xFFu;
+          const uint32_t bits = my[(ord >> 3) * kPlane + 4 * w + e];
+          node[e] = (int)(((bits >> (ord & 7u)) & 1u) ? (wk[e] >> 8) & 0xFFu : (wk[e] >> 16) & 0xFFu);
+          wk[e] = s_walk[node[e]];
+        }
+        if (!any) break;
+      }
+      write_leaf_outputs(a, node, r0 + 4 * w, scalar ? s_val : nullptr);
+    }
+  }
+}
+
 constexpr int LU = 8;
 
 __global__ void __launch_bounds__(kBlock) linear_predict_kernel(const float* __restrict__ X, int64_t n,
@@ -275,11 +390,26 @@ cudaError_t launch_bin_columns(const BinArgs& a, int n_cols, int sms, cudaStream
   return cudaGetLastError();
 }
 
-cudaError_t launch_tree_predict_binned(const TreeArgs& a, const uint8_t* X8, const uint4* nodes, int sms, cudaStream_t st) {
+cudaError_t launch_tree_predict_binned(const TreeArgs& a, const uint8_t* X8, const uint4* nodes, int n_internal, int mask_mode,
+                                       int sms, cudaStream_t st) {
   const size_t smem = (size_t)a.n_nodes * (sizeof(uint4) + sizeof(float));
   if (smem > 200 * 1024) return cudaErrorInvalidValue;
   static const int variant = [] { const char* e = getenv("SE_TREE_VARIANT"); return e ? atoi(e) : 0; }();
   const int64_t ngroups = (a.n + TV - 1) / TV;
+  // shallow trees: all node comparisons from coalesced column reads, then a walk over bits (tree_predict_mask_kernel)
+  // SE_TREE_VARIANT: 0 default, 1-5 and 9 walk variants, 10/11/12 all-nodes kernel with 1/2/4 words per thread
+  if (mask_mode && n_internal <= 64 && a.n_nodes <= 256 && (variant == 0 || variant >= 10)) {
+    const int rw = variant == 10 ? 1 : variant == 11 ? 2 : variant == 12 ? 4 : kTreeMaskWords;
+    const int64_t need0 = (a.n + 4 * rw - 1) / (4 * rw);
+    int64_t need = (need0 + kBlock - 1) / kBlock;
+    if (need < 1) need = 1;
+    const int64_t cap = (int64_t)sms * 16;
+    const int grid = (int)(need < cap ? need : cap);
+    if (rw == 1) tree_predict_mask_kernel<1><<<grid, kBlock, 0, st>>>(a, X8, nodes);
+    else if (rw == 2) tree_predict_mask_kernel<2><<<grid, kBlock, 0, st>>>(a, X8, nodes);
+    else tree_predict_mask_kernel<4><<<grid, kBlock, 0, st>>>(a, X8, nodes);
+    return cudaGetLastError();
+  }
 #define SE_TREE_LAUNCH(W, MINB)                                                                                      \
   do {                                                                                                               \
     auto kern = tree_predict_binned_kernel<W, MINB>;                                                                 \

@@ -1153,7 +1153,7 @@ def _random_tree(rng, depth, d, candidates, n_out=1):
 def _walk(tree, X):
     """Plain numpy walk: x <= threshold goes left (Spark ContinuousSplit.shouldGoLeft)."""
     node = np.zeros(X.shape[0], dtype=np.int64)
-    for _ in range(64):
+    for _ in range(256):
         f = tree["feature"][node]
         live = f >= 0
         if not live.any():
@@ -1164,7 +1164,51 @@ def _walk(tree, X):
     return node
 
 
-@pytest.mark.parametrize("n,d,depth", [(1, 3, 2), (1027, 7, 4), (200_003, 33, 6)])
+def _random_unbalanced_tree(rng, n_internal, d, candidates):
+    """Random binary tree grown by splitting a random leaf n_internal times; node ids in creation order (not a heap)."""
+    feat, thr, left, right = [-1], [0.0], [0], [0]
+    leaves = [0]
+    for _ in range(n_internal):
+        i = leaves.pop(int(rng.integers(0, len(leaves))))
+        f = int(rng.integers(0, d))
+        feat[i], thr[i] = f, float(candidates[f][rng.integers(0, len(candidates[f]))])
+        left[i], right[i] = len(feat), len(feat) + 1
+        for _c in range(2):
+            feat.append(-1); thr.append(0.0); left.append(0); right.append(0)
+        leaves += [left[i], right[i]]
+    return {"feature": np.array(feat, np.int32), "threshold": np.array(thr, np.float32), "left": np.array(left, np.int32),
+            "right": np.array(right, np.int32), "value": rng.standard_normal(len(feat)).astype(np.float32)}
+
+
+@pytest.mark.parametrize("n,d,n_internal", [(5, 3, 1), (4099, 11, 17), (100_003, 40, 64), (100_003, 40, 65), (33_333, 5, 120)])
+def test_shallow_tree_all_nodes_kernel(ctx, rng, n, d, n_internal):
+    """Trees of <= 64 internal nodes go through the all-nodes kernel (every node's comparison from coalesced column
+    reads of the rank matrix, then a walk over bits); larger ones walk.  Arbitrary shapes / node orders, rows ON
+    thresholds, every row count modulo the vector width: the leaf must be the fp32 walk's."""
+    from spark_ensemble_b200 import _native as N
+    X = rng.standard_normal((n, d)).astype(np.float32)
+    cand = [np.unique(np.concatenate([rng.standard_normal(15).astype(np.float32), X[rng.integers(0, n, 4), f]])) for f in range(d)]
+    ctx.alloc(N.SLOT_X, d, n)
+    ctx.upload_rowmajor(N.SLOT_X, X)
+    ctx.alloc(N.SLOT_H, 1, n)
+    ctx.set_option("tree_bins", 1)
+    try:
+        for mask in (1, 0, 1):
+            ctx.set_option("tree_mask", mask)
+            tree = _random_unbalanced_tree(rng, n_internal, d, cand)
+            ctx.tree_predict(tree, N.SLOT_H, 0)
+            assert ctx.get_option("last_tree_binned") == 1
+            assert ctx.get_option("last_tree_mask") == (1 if mask and n_internal <= 64 else 0)
+            np.testing.assert_array_equal(ctx.download(N.SLOT_H), tree["value"][_walk(tree, X)])
+        single = {"feature": [-1], "threshold": [0.0], "left": [0], "right": [0], "value": [2.5]}   # a root-only tree
+        ctx.tree_predict(single, N.SLOT_H, 0)
+        np.testing.assert_array_equal(ctx.download(N.SLOT_H), np.full(n, 2.5, np.float32))
+    finally:
+        ctx.set_option("tree_mask", 1)
+        ctx.free(N.SLOT_X)
+
+
+@pytest.mark.parametrize("n,d,depth", [(1, 3, 2), (1027, 7, 4), (200_003, 33, 6), (50_001, 9, 8)])
 def test_tree_walk_over_binned_features_is_exact(ctx, rng, n, d, depth):
     """The tree walk over the uint8 RANK matrix (bin(x) = #{thresholds < x}; `x <= t_j` <=> `bin <= j`) must pick the
     same leaf as the fp32 walk for every row — including rows sitting exactly ON a threshold —, keep doing so as new
