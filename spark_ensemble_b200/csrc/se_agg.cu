@@ -16,6 +16,7 @@
 #include "se_kernels.h"
 #include "se_loss.cuh"
 #include "se_tma.cuh"
+#include "se_sortnet.h"
 #include "../../include/se_abi.h"
 
 namespace se {
@@ -659,6 +660,35 @@ __global__ void __launch_bounds__(32 * kWmWarps) agg_wmedian_warp_kernel(const f
   }
 }
 
+// sort of the (key, model) words + the reference's sorted-order cumulative sums (ensemble/Utils.scala:31-38)
+template <int MP>
+__device__ __forceinline__ unsigned long long wm_exact_pick(unsigned long long (&w)[MP], int M, const double* s_a) {
+  sortnet_oddeven<MP>(w, [](unsigned long long& x, unsigned long long& y) {
+    const bool swap = x > y;
+    const unsigned long long lo = swap ? y : x, hi = swap ? x : y;
+    x = lo;
+    y = hi;
+  });
+  double total = 0.0;
+#pragma unroll
+  for (int m = 0; m < MP; ++m)
+    if (m < M) total += s_a[(unsigned)w[m]];
+  const double half = 0.5 * total;
+  double cum = 0.0;
+  bool found = false;
+  unsigned long long pick = 0ull;
+#pragma unroll
+  for (int m = 0; m < MP; ++m) {
+    if (m < M) {
+      cum += s_a[(unsigned)w[m]];
+      const bool hit = !found && (cum >= half);
+      pick = (hit || (!found && m == M - 1)) ? w[m] : pick;  // last element when nothing reaches half (NaN weights)
+      found = found || hit;
+    }
+  }
+  return pick;
+}
+
 // Same algorithm with the row's words in REGISTERS (Mp <= 64): the network is fully unrolled, so every
 // compare-exchange is ~6 ALU instructions and no memory traffic — the shared-memory form above moves 32 B per
 // compare-exchange and thread and is bound by shared-memory bandwidth (measured 8.0 ms for 25 M rows at M = 32).
@@ -702,40 +732,147 @@ __global__ void __launch_bounds__(128) agg_wmedian_reg_kernel(const __grid_const
       if (m < M) w[m] = ((unsigned long long)wm_key(src[m * 128]) << 32) | (unsigned long long)(unsigned)m;
     }
     __syncthreads();  // the tile is in registers: its stage may be refilled
+    const unsigned long long pick = wm_exact_pick<MP>(w, M, s_a);
+    if (in) out[row] = wm_unkey((uint32_t)(pick >> 32));
+  }
+}
+
+// ---- weighted median, fast path (M <= 64, all weights finite and >= 0) -------------------------------------------
+// The exact kernels above carry (key, model) words through the sort because the reference accumulates the weights in
+// SORTED order (ensemble/Utils.scala:31-38) — 6 ALU-pipe instructions per compare-exchange, and the ALU pipe issues at
+// half rate: 4.07 ms for 25 M rows x 32 models.  With weights >= 0 the answer is `the smallest value v whose group-end
+// cumulative weight C(v) reaches h = total / 2` (cumulative sums are monotone in fp64 too).  C(v) and h are recursive
+// fp64 sums of the same addends as Ĉ(v) = Σ_{x_j <= v} a_j and ĥ = T̂ / 2 taken in MODEL order, so
+//     |(C(v) - h) - (Ĉ(v) - ĥ)| <= 3 (M - 1) 2^-53 T (1 + eps)
+// and whenever both neighbours of the crossing clear the margin tau = 8 M 2^-53 T̂ the model-order decision IS the
+// reference's decision.  So: sort the 32-bit keys alone (min/max, 2 instructions per compare-exchange, Batcher's
+// 191-element network), bisect the sorted keys on Ĉ (5 x 32 predicated DADDs with the weights as constant-bank
+// operands), and send the rows that do not clear the margin — none for generic weights, the exact ties for
+// small-integer weights — to the exact kernel through a compacted list (mode 2: all weights equal, where both orders
+// produce the same sums and no margin is needed).
+struct WmWeights {
+  double w[64];
+};
+
+template <int MP, int L>
+__device__ __forceinline__ uint32_t wm_candidate(const uint32_t (&s)[MP], uint32_t t) {
+  // level-L bisection probe: position step - 1 + t * 2 * step, t in [0, 2^L) — a select tree over static indices
+  constexpr int step = MP >> (L + 1);
+  uint32_t v = s[step - 1];
 #pragma unroll
-    for (int k = 2; k <= MP; k <<= 1) {
-#pragma unroll
-      for (int j = k >> 1; j > 0; j >>= 1) {
-#pragma unroll
-        for (int e = 0; e < MP; ++e) {
-          const int l = e ^ j;
-          if (l > e) {
-            const unsigned long long x = w[e], y = w[l];
-            const bool swap = (x > y) == ((e & k) == 0);
-            w[e] = swap ? y : x;
-            w[l] = swap ? x : y;
-          }
-        }
-      }
-    }
-    double total = 0.0;
-#pragma unroll
-    for (int m = 0; m < MP; ++m)
-      if (m < M) total += s_a[(unsigned)w[m]];
-    const double half = 0.5 * total;
-    double cum = 0.0;
-    bool found = false;
-    unsigned long long pick = 0ull;
+  for (int q = 1; q < (1 << L); ++q) v = (t == (uint32_t)q) ? s[step - 1 + q * 2 * step] : v;
+  return v;
+}
+
+template <int MP>
+__global__ void __launch_bounds__(128) agg_wmedian_fast_kernel(const __grid_constant__ CUtensorMap mapP, int64_t n, int M,
+                                                               const __grid_constant__ WmWeights wts, double total,
+                                                               double tau, int32_t* __restrict__ list,
+                                                               unsigned int* __restrict__ count, unsigned int cap,
+                                                               float* __restrict__ out) {
+  extern __shared__ __align__(128) unsigned char wm_raw[];
+  float* stage0 = reinterpret_cast<float*>(wm_raw + ((128u - (smem_u32(wm_raw) & 127u)) & 127u));
+  const int stage_floats = M * 128;
+  __shared__ __align__(8) uint64_t full[2];
+  if (threadIdx.x == 0) {
+    mbar_init(&full[0], 1);
+    mbar_init(&full[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const int64_t ntiles = (n + 127) / 128;
+  auto issue = [&](int64_t tile, int st) {
+    mbar_expect_tx(&full[st], (uint32_t)(stage_floats * sizeof(float)));
+    tma_load_tile(stage0 + (size_t)st * stage_floats, &mapP, (int)(tile * 128), &full[st]);
+  };
+  if (threadIdx.x == 0 && blockIdx.x < ntiles) issue(blockIdx.x, 0);
+  const double half = 0.5 * total;
+  constexpr int LOG = (MP == 1) ? 0 : (MP == 2) ? 1 : (MP == 4) ? 2 : (MP == 8) ? 3 : (MP == 16) ? 4 : (MP == 32) ? 5 : 6;
+  uint32_t it = 0;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+    const int st = it & 1;
+    if (threadIdx.x == 0 && tile + gridDim.x < ntiles) issue(tile + gridDim.x, st ^ 1);  // freed by the barrier below
+    const int64_t row = tile * 128 + threadIdx.x;
+    const bool in = row < n;
+    mbar_wait(&full[st], (it >> 1) & 1);
+    const float* src = stage0 + (size_t)st * stage_floats + threadIdx.x;
+    uint32_t key[MP], s[MP];
 #pragma unroll
     for (int m = 0; m < MP; ++m) {
-      if (m < M) {
-        cum += s_a[(unsigned)w[m]];
-        const bool hit = !found && (cum >= half);
-        pick = (hit || (!found && m == M - 1)) ? w[m] : pick;  // last element when nothing reaches half (NaN weights)
-        found = found || hit;
-      }
+      key[m] = 0xFFFFFFFFu;  // padding sorts last and carries weight 0
+      if (m < M) key[m] = wm_key(src[m * 128]);
+      s[m] = key[m];
     }
-    if (in) out[row] = wm_unkey((uint32_t)(pick >> 32));
+    __syncthreads();  // the tile is in registers: its stage may be refilled
+    sortnet_oddeven<MP>(s, [](uint32_t& x, uint32_t& y) {
+      const uint32_t lo = min(x, y), hi = max(x, y);
+      x = lo;
+      y = hi;
+    });
+    // invariant: P(lo) false, P(hi) true with P(k) := Ĉ(s[k]) >= ĥ; lo = t - 1, hi = t after LOG probes
+    uint32_t t = 0, v_hi = s[MP - 1];
+    double c_lo = 0.0, c_hi = total;
+    auto probe = [&](uint32_t v) {
+      double c = 0.0;
+#pragma unroll
+      for (int m = 0; m < MP; ++m) {
+        // model order; padding (and m >= M) weights are 0.  fma(w, 1.0 or 0.0, c) is c + w rounded once, or c: one
+        // select of the high word of the 0/1 factor instead of the two selects `if (...) c += w` compiles to
+        const double b = __hiloint2double((key[m] <= v) ? 0x3ff00000 : 0, 0);
+        c = fma(wts.w[m], b, c);
+      }
+      const bool right = !(c >= half);
+      c_lo = right ? c : c_lo;
+      c_hi = right ? c_hi : c;
+      v_hi = right ? v_hi : v;
+      t = 2u * t + (right ? 1u : 0u);
+    };
+    if constexpr (LOG > 0) probe(wm_candidate<MP, 0>(s, t));
+    if constexpr (LOG > 1) probe(wm_candidate<MP, 1>(s, t));
+    if constexpr (LOG > 2) probe(wm_candidate<MP, 2>(s, t));
+    if constexpr (LOG > 3) probe(wm_candidate<MP, 3>(s, t));
+    if constexpr (LOG > 4) probe(wm_candidate<MP, 4>(s, t));
+    if constexpr (LOG > 5) probe(wm_candidate<MP, 5>(s, t));
+    const bool safe = (c_hi - half > tau) && (half - c_lo > tau);
+    if (in) out[row] = wm_unkey(v_hi);
+    // rows whose decision could depend on the order of summation go to the exact kernel (warp-aggregated append)
+    const bool defer = in && list != nullptr && !safe;
+    const unsigned mask = __ballot_sync(0xffffffffu, defer);
+    if (mask) {
+      const int lane = threadIdx.x & 31, leader = __ffs(mask) - 1;
+      unsigned base = 0;
+      if (lane == leader) base = atomicAdd(count, (unsigned)__popc(mask));
+      base = __shfl_sync(0xffffffffu, base, leader);
+      const unsigned idx = base + (unsigned)__popc(mask & ((1u << lane) - 1u));
+      if (defer && idx < cap) list[idx] = (int32_t)row;
+    }
+  }
+}
+
+// exact pass over the deferred rows (or over ALL rows when the list overflowed): gathers, (key, model) words, the
+// reference's sorted-order sums
+template <int MP>
+__global__ void __launch_bounds__(128) agg_wmedian_list_kernel(const float* __restrict__ P, int64_t n, int64_t ld, int M,
+                                                               const double* __restrict__ a,
+                                                               const int32_t* __restrict__ list,
+                                                               const unsigned int* __restrict__ count, unsigned int cap,
+                                                               float* __restrict__ out) {
+  __shared__ double s_a[64];
+  for (int m = threadIdx.x; m < 64; m += 128) s_a[m] = (m < M) ? a[m] : 0.0;
+  __syncthreads();
+  const unsigned int c = *count;
+  if (c == 0) return;
+  const bool all = c > cap;
+  const int64_t items = all ? n : (int64_t)c;
+  for (int64_t i = (int64_t)blockIdx.x * 128 + threadIdx.x; i < items; i += (int64_t)gridDim.x * 128) {
+    const int64_t row = all ? i : (int64_t)list[i];
+    unsigned long long w[MP];
+#pragma unroll
+    for (int m = 0; m < MP; ++m) {
+      w[m] = ~0ull;
+      if (m < M) w[m] = ((unsigned long long)wm_key(__ldg(P + (int64_t)m * ld + row)) << 32) | (unsigned long long)(unsigned)m;
+    }
+    out[row] = wm_unkey((uint32_t)(wm_exact_pick<MP>(w, M, s_a) >> 32));
   }
 }
 
@@ -841,6 +978,39 @@ cudaError_t launch_agg(const AggArgs& a, int ctas_per_sm, int sms, cudaStream_t 
         if (e != cudaSuccess) return e;
         const size_t smem = 2 * (size_t)a.M * 128 * sizeof(float) + (size_t)a.M * sizeof(double) + 128;
         const int grid = grid_rows(a.n, 128, 8, sms);
+        if (a.wm_mode != 0 && a.weights64_host != nullptr && (a.wm_mode == 2 || (a.wm_list != nullptr && a.wm_count != nullptr))) {
+          // fast path: keys-only sort + model-order sums; rows inside the rounding margin go to the exact list kernel
+          WmWeights wts;
+          double total = 0.0;
+          for (int m = 0; m < 64; ++m) {
+            wts.w[m] = (m < a.M) ? a.weights64_host[m] : 0.0;
+            total += wts.w[m];  // model order, like the kernel's own sums
+          }
+          const bool margin = (a.wm_mode == 1);
+          const double tau = margin ? 8.0 * (double)a.M * 1.1102230246251565e-16 * total : -1.0;  // mode 2: every row is safe
+          const size_t fsmem = 2 * (size_t)a.M * 128 * sizeof(float) + 128;
+          if (margin) {
+            e = cudaMemsetAsync(a.wm_count, 0, sizeof(unsigned int), st);
+            if (e != cudaSuccess) return e;
+          }
+          switch (Mp) {
+#define SE_WMF(MPV)                                                                                             \
+  case MPV: {                                                                                                   \
+    auto kern = agg_wmedian_fast_kernel<MPV>;                                                                   \
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem);                   \
+    if (e != cudaSuccess) return e;                                                                             \
+    kern<<<grid, 128, fsmem, st>>>(mapP, a.n, a.M, wts, total, tau, margin ? a.wm_list : nullptr, a.wm_count,   \
+                                   a.wm_cap, a.raw);                                                            \
+    if (margin) agg_wmedian_list_kernel<MPV><<<sms * 4, 128, 0, st>>>(a.P, a.n, a.ld, a.M, a.weights64, a.wm_list, \
+                                                                     a.wm_count, a.wm_cap, a.raw);              \
+    break;                                                                                                      \
+  }
+            SE_WMF(1) SE_WMF(2) SE_WMF(4) SE_WMF(8) SE_WMF(16) SE_WMF(32) SE_WMF(64)
+#undef SE_WMF
+            default: return cudaErrorInvalidValue;
+          }
+          return cudaGetLastError();
+        }
         switch (Mp) {
 #define SE_WM(MPV)                                                                                              \
   case MPV: {                                                                                                   \

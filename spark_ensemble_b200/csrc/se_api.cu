@@ -245,6 +245,11 @@ struct se_ctx {
   // binned (uint8) copies of X / VX for the tree walk
   BinState bins[2];
   int tree_bins = 1;                  // 0: always walk the fp32 matrix
+  int wm_fast = 1;                    // weighted median (M <= 64, weights >= 0): keys-only sort + margin check, exact kernel for the rest
+  int64_t wm_list_cap = 0;            // deferred-row list capacity (0: n / 4)
+  unsigned int* d_wm = nullptr;       // [0] deferred count, [1..] row list
+  size_t wm_alloc = 0;                // entries allocated in d_wm (count included)
+  int last_wm_mode = 0;
   int tree_mask = 1;                  // shallow trees (<= 64 internal nodes): all-nodes comparison kernel over the rank matrix
   int last_tree_mask = 0;
   int last_tree_binned = 0, last_tree_rebinned_cols = 0;
@@ -745,6 +750,7 @@ int se_ctx_destroy(se_ctx* ctx) {
   if (ctx->d_fsync) cudaFree(ctx->d_fsync);
   free_bins(ctx->bins[0]);
   free_bins(ctx->bins[1]);
+  if (ctx->d_wm) cudaFree(ctx->d_wm);
   if (ctx->big.d_coef) cudaFree(ctx->big.d_coef);
   if (ctx->big.h_coef) cudaFreeHost(ctx->big.h_coef);
   if (ctx->big.d_partials) cudaFree(ctx->big.d_partials);
@@ -853,12 +859,13 @@ int se_ctx_kernel_time_reset(se_ctx* ctx) {
 
 namespace {
 struct OptKey { const char* name; int id; };
-enum { OPT_TREE_MASK, OPT_LAST_TREE_MASK, OPT_TREE_BINS, OPT_LAST_TREE_BINNED, OPT_LAST_TREE_REBINNED, OPT_FUSED_LOSS_REDUCE, OPT_FUSED_L2_MODE, OPT_FUSED_TIMING, OPT_LAST_FUSED_US0, OPT_LAST_FUSED_US1, OPT_LAST_FUSED_US2, OPT_FUSED_PREFETCH_MB, OPT_FUSED_ROUND, OPT_FUSED_MAX_ROWS, OPT_FUSED_CTAS, OPT_LS_MODE, OPT_LS_RESIDENT, OPT_LS_CTAS, OPT_LS_RING, OPT_L2_PERSIST,
+enum { OPT_WM_FAST, OPT_WM_LIST_CAP, OPT_LAST_WM_MODE, OPT_LAST_WM_DEFERRED, OPT_TREE_MASK, OPT_LAST_TREE_MASK, OPT_TREE_BINS, OPT_LAST_TREE_BINNED, OPT_LAST_TREE_REBINNED, OPT_FUSED_LOSS_REDUCE, OPT_FUSED_L2_MODE, OPT_FUSED_TIMING, OPT_LAST_FUSED_US0, OPT_LAST_FUSED_US1, OPT_LAST_FUSED_US2, OPT_FUSED_PREFETCH_MB, OPT_FUSED_ROUND, OPT_FUSED_MAX_ROWS, OPT_FUSED_CTAS, OPT_LS_MODE, OPT_LS_RESIDENT, OPT_LS_CTAS, OPT_LS_RING, OPT_L2_PERSIST,
        OPT_L2_PERSIST_FRAC, OPT_PEER_TIMEOUT_MS, OPT_ALTERNATE, OPT_L2_HINTS, OPT_CTAS_PER_SM, OPT_HOST_MIRROR,
        // read-only diagnostics
        OPT_LAST_ROUND_FUSED, OPT_LAST_LS_WORKERS, OPT_LAST_LS_PASSES, OPT_LAST_LS_HIT_RATIO, OPT_LAST_FUSED_GRID,
        OPT_L2_PERSIST_MAX, OPT_L2_WINDOW_MAX, OPT_LAST_STAT0, OPT_LAST_STAT1, OPT_LAST_STAT2 };
 const OptKey kOpts[] = {
+  {"wm_fast", OPT_WM_FAST}, {"wm_list_cap", OPT_WM_LIST_CAP}, {"last_wm_mode", OPT_LAST_WM_MODE}, {"last_wm_deferred", OPT_LAST_WM_DEFERRED},
   {"tree_bins", OPT_TREE_BINS}, {"tree_mask", OPT_TREE_MASK}, {"last_tree_mask", OPT_LAST_TREE_MASK}, {"last_tree_binned", OPT_LAST_TREE_BINNED}, {"last_tree_rebinned_cols", OPT_LAST_TREE_REBINNED},
   {"fused_loss_reduce", OPT_FUSED_LOSS_REDUCE}, {"fused_l2_mode", OPT_FUSED_L2_MODE}, {"fused_timing", OPT_FUSED_TIMING}, {"last_fused_stats_us", OPT_LAST_FUSED_US0}, {"last_fused_brent_us", OPT_LAST_FUSED_US1},
   {"last_fused_update_us", OPT_LAST_FUSED_US2}, {"fused_prefetch_mb", OPT_FUSED_PREFETCH_MB}, {"fused_round", OPT_FUSED_ROUND}, {"fused_round_max_rows", OPT_FUSED_MAX_ROWS}, {"fused_ctas_per_sm", OPT_FUSED_CTAS},
@@ -888,6 +895,8 @@ int se_ctx_set_option(se_ctx* ctx, const char* key, double value) {
     case OPT_FUSED_LOSS_REDUCE: ctx->fused_loss_reduce = iv != 0; break;
     case OPT_TREE_BINS: ctx->tree_bins = iv != 0; break;
     case OPT_TREE_MASK: ctx->tree_mask = iv != 0; break;
+    case OPT_WM_FAST: ctx->wm_fast = iv != 0; break;
+    case OPT_WM_LIST_CAP: SE_REQUIRE(ctx, value >= 0 && value < 2147483000.0, SE_ERR_ARG, "wm_list_cap in [0, 2^31)"); ctx->wm_list_cap = (int64_t)value; break;
     case OPT_FUSED_L2_MODE: SE_REQUIRE(ctx, iv >= 0 && iv <= 2, SE_ERR_ARG, "fused_l2_mode in {0,1,2}"); ctx->fused_l2_mode = iv; if (iv != 2) release_l2_persist(ctx); break;
     case OPT_FUSED_PREFETCH_MB: SE_REQUIRE(ctx, value >= 0.0 && value <= 512.0, SE_ERR_ARG, "fused_prefetch_mb in [0,512]"); ctx->fused_prefetch_mb = value; break;
     case OPT_FUSED_CTAS: SE_REQUIRE(ctx, iv >= 1 && iv <= 8, SE_ERR_ARG, "fused_ctas_per_sm in [1,8]"); ctx->fused_ctas_per_sm = iv; break;
@@ -917,6 +926,21 @@ int se_ctx_get_option(const se_ctx* ctx, const char* key, double* value) {
     case OPT_FUSED_LOSS_REDUCE: *value = ctx->fused_loss_reduce; break;
     case OPT_TREE_BINS: *value = ctx->tree_bins; break;
     case OPT_TREE_MASK: *value = ctx->tree_mask; break;
+    case OPT_WM_FAST: *value = ctx->wm_fast; break;
+    case OPT_WM_LIST_CAP: *value = (double)ctx->wm_list_cap; break;
+    case OPT_LAST_WM_MODE: *value = ctx->last_wm_mode; break;
+    case OPT_LAST_WM_DEFERRED: {  // rows the last weighted median sent to the exact kernel (synchronises the stream)
+      unsigned int c = 0;
+      if (ctx->d_wm && ctx->last_wm_mode == 1) {
+        cudaSetDevice(ctx->device);
+        if (cudaStreamSynchronize(ctx->stream) != cudaSuccess || cudaMemcpy(&c, ctx->d_wm, sizeof(c), cudaMemcpyDeviceToHost) != cudaSuccess) {
+          cudaGetLastError();
+          return SE_ERR_CUDA;
+        }
+      }
+      *value = (double)c;
+      break;
+    }
     case OPT_LAST_TREE_MASK: *value = ctx->last_tree_mask; break;
     case OPT_LAST_TREE_BINNED: *value = ctx->last_tree_binned; break;
     case OPT_LAST_TREE_REBINNED: *value = ctx->last_tree_rebinned_cols; break;
@@ -2428,6 +2452,38 @@ int se_agg_run(se_ctx* ctx, const double* weights, const double* init) {
     for (int i = 0; i < g.M; ++i) hd[i] = weights[i];
     a.weights64 = reinterpret_cast<const double*>(reinterpret_cast<const float*>(ctx->d_small) + off);
     used = off + 2 * (size_t)g.M;
+    // fast path (launch_agg): every weight finite and >= 0; all equal -> no rounding margin needed
+    ctx->last_wm_mode = 0;
+    if (ctx->wm_fast && g.M >= 1 && g.M <= 64 && g.n > 0) {
+      bool ok = true, equal = true;
+      for (int i = 0; i < g.M; ++i) {
+        ok = ok && (weights[i] >= 0.0) && (weights[i] <= 1.7976931348623157e308);
+        equal = equal && (weights[i] == weights[0]);
+      }
+      if (ok) {
+        a.wm_mode = equal ? 2 : 1;
+        a.weights64_host = weights;
+        if (a.wm_mode == 1) {
+          int64_t cap = ctx->wm_list_cap > 0 ? ctx->wm_list_cap : g.n / 4;
+          if (cap < 1024 && ctx->wm_list_cap == 0) cap = 1024;
+          if (cap > 2147483000LL) cap = 2147483000LL;
+          if (ctx->wm_alloc < (size_t)cap + 1) {
+            if (ctx->d_wm) cudaFree(ctx->d_wm);
+            ctx->d_wm = nullptr; ctx->wm_alloc = 0;
+            if (cudaMalloc(&ctx->d_wm, sizeof(unsigned int) * ((size_t)cap + 1)) == cudaSuccess) ctx->wm_alloc = (size_t)cap + 1;
+            else cudaGetLastError();
+          }
+          if (ctx->d_wm) {
+            a.wm_count = ctx->d_wm;
+            a.wm_list = reinterpret_cast<int32_t*>(ctx->d_wm + 1);
+            a.wm_cap = (unsigned int)cap;
+          } else {
+            a.wm_mode = 0;  // no room for the list: exact kernel
+          }
+        }
+        ctx->last_wm_mode = a.wm_mode;
+      }
+    }
   }
   if (used) SE_CUDA(ctx, cudaMemcpyAsync(ctx->d_small, hs, used * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
   SE_LAUNCH_T(ctx, SE_KF_AGG, launch_agg(a, 8, ctx->sms, ctx->stream));

@@ -203,6 +203,13 @@ struct AggArgs {
   double sum_weights = 0.0;  // Σ a_m of the fp32-narrowed weights (boosting discrete epilogue, boosting-regressor mean)
   const double* weights64 = nullptr;  // device [M] fp64 (weighted median cumulative sums)
   int* bad_label = nullptr;           // raised (mapped host memory) when a vote is not a class index in [0, K)
+  // weighted median fast path (M <= 64): 0 exact kernel only; 1 keys-only sort + model-order sums, rows within the
+  // rounding margin of the half-weight deferred to the exact kernel through wm_list; 2 all weights equal (no margin)
+  int wm_mode = 0;
+  const double* weights64_host = nullptr;  // [M], the same values as weights64
+  int32_t* wm_list = nullptr;              // [wm_cap] deferred rows
+  unsigned int* wm_count = nullptr;        // number of deferred rows (may exceed wm_cap: the exact pass then covers all rows)
+  unsigned int wm_cap = 0;
 };
 cudaError_t launch_agg(const AggArgs& a, int ctas_per_sm, int sms, cudaStream_t s);
 

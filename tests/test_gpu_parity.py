@@ -612,6 +612,58 @@ def test_agg_boosting_regressor(ctx, oracle, rng, M, n):
     close(ctx.download(N.SLOT_RAW), oracle.agg_weighted_mean(P, a.astype(np.float32).astype(np.float64)), scale=0.1)
 
 
+@pytest.mark.parametrize("M", [1, 2, 3, 5, 8, 13, 16, 20, 32, 33, 50, 64])
+@pytest.mark.parametrize("weights", ["random", "equal", "integers", "one_heavy", "zeros", "negative", "tiny_list"])
+def test_weighted_median_fast_path_is_exact(ctx, oracle, rng, M, weights):
+    """M <= 64 and weights >= 0: 32-bit keys sorted alone, the half-weight crossing found by bisection on sums taken
+    in MODEL order, and every row whose crossing lies within the rounding margin of the two summation orders redone by
+    the exact kernel ((key, model) words, sorted-order fp64 sums, ensemble/Utils.scala:31-38).  Bit-exact against
+    the oracle for generic weights (no deferred rows), equal weights (no margin needed), small integers (exact
+    half-weight ties: many deferred rows), a list too small for the deferred rows (exact pass over all rows),
+    all-zero and negative weights (exact kernel only), values with ties / +-0 / huge magnitudes."""
+    from spark_ensemble_b200 import _native as N
+    n = 20_011
+    P = f32(rng.standard_normal((M, n)))
+    P[:, : n // 3] = np.round(P[:, : n // 3], 1)          # ties between members, zeros of both signs
+    P[:, n // 3: n // 3 + 50] *= 1e30
+    P[:, n // 3 + 50: n // 3 + 100] = 0.0
+    if M > 1:
+        P[1, n // 3 + 50: n // 3 + 100] = -0.0
+    ints = rng.integers(1, 4, M).astype(np.float64)
+    if ints.sum() % 2:
+        ints[0] += 1.0                                    # even total: sorted prefixes DO hit the half-weight exactly
+    a = {"random": rng.random(M) + 0.05, "equal": np.full(M, 0.3), "integers": ints,
+         "one_heavy": np.where(np.arange(M) == M // 2, 1e6, 1e-3), "zeros": np.zeros(M),
+         "negative": np.where(np.arange(M) == 0, -0.5, 1.0) * (rng.random(M) + 0.05), "tiny_list": ints}[weights]
+    ctx.agg_configure(N.AGG_BOOSTING_REG_MEDIAN, M, 0, 1, 0, n)
+    ctx.upload(N.SLOT_P, P)
+    ref = oracle.agg_weighted_median(P, a).astype(np.float32)
+    try:
+        ctx.set_option("wm_list_cap", 7 if weights == "tiny_list" else n if weights == "integers" else 0)
+        ctx.agg_run(a)
+        got = ctx.download(N.SLOT_RAW)
+        np.testing.assert_array_equal(got, ref)
+        mode = ctx.get_option("last_wm_mode")
+        deferred = ctx.get_option("last_wm_deferred")
+        if weights == "negative":
+            assert mode == 0
+        elif weights in ("equal", "zeros") or M == 1 or len(set(a.tolist())) == 1:
+            assert mode == 2 and deferred == 0
+        else:
+            assert mode == 1
+            if weights == "random":
+                assert deferred == 0                      # generic weights: nothing lands within 8 M 2^-53 of the half-weight
+            if weights in ("integers", "tiny_list") and M >= 5:
+                assert deferred > (7 if weights == "tiny_list" else 0)   # exact half-weight ties do occur; tiny list overflows
+        ctx.set_option("wm_fast", 0)
+        ctx.agg_run(a)
+        assert ctx.get_option("last_wm_mode") == 0
+        np.testing.assert_array_equal(ctx.download(N.SLOT_RAW), ref)
+    finally:
+        ctx.set_option("wm_fast", 1)
+        ctx.set_option("wm_list_cap", 0)
+
+
 @pytest.mark.parametrize("n", [1, 2, 1000, 100003])
 def test_exact_quantile_radix_select(ctx, rng, n):
     """se_quantile == the ceil(q·N)-th smallest value, bit-exact."""

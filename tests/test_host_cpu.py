@@ -400,3 +400,48 @@ def test_gbm_regressor_has_devices_param():
     g = GBMRegressor()
     assert g("devices") == []
     g.set("devices", [0, 1]) if hasattr(g, "set") else None
+
+
+def test_sort_network_sorts(tmp_path):
+    """csrc/se_sortnet.h (Batcher's odd-even merge sort, the weighted-median kernels' network) compiled for the host:
+    random, many-duplicate and 0/1 inputs (zero-one principle) for every size the kernels instantiate."""
+    import shutil
+    import subprocess
+    if shutil.which("g++") is None:
+        pytest.skip("no g++")
+    src = tmp_path / "sn.cpp"
+    src.write_text(r"""
+#include <cstdio>
+#include <cstdint>
+#include <cstdlib>
+#include <algorithm>
+#include "se_sortnet.h"
+template <int N> int run(int expect) {
+  int ces = 0, bad = 0;
+  for (int it = 0; it < 20000; ++it) {
+    uint64_t v[N], r[N];
+    for (int i = 0; i < N; ++i) v[i] = (it & 1) ? (uint64_t)(rand() & 1) : (rand() % (it % 7 + 2) == 0 ? (uint64_t)(rand() % 5) : ((uint64_t)rand() << 20) ^ (uint64_t)rand());
+    for (int i = 0; i < N; ++i) r[i] = v[i];
+    std::sort(r, r + N);
+    ces = 0;
+    se::sortnet_oddeven<N>(v, [&](uint64_t& a, uint64_t& b) { ++ces; const uint64_t lo = std::min(a, b), hi = std::max(a, b); a = lo; b = hi; });
+    for (int i = 0; i < N; ++i) bad += v[i] != r[i];
+  }
+  if (N == 16) {  // exhaustive 0/1
+    for (uint32_t m = 0; m < (1u << 16); ++m) {
+      uint64_t v[N];
+      for (int i = 0; i < N; ++i) v[i] = (m >> i) & 1;
+      se::sortnet_oddeven<N>(v, [&](uint64_t& a, uint64_t& b) { const uint64_t lo = std::min(a, b), hi = std::max(a, b); a = lo; b = hi; });
+      for (int i = 0; i + 1 < N; ++i) bad += v[i] > v[i + 1];
+    }
+  }
+  std::printf("N=%d ces=%d bad=%d\n", N, ces, bad);
+  return bad + (ces != expect);
+}
+int main() { return run<1>(0) + run<2>(1) + run<4>(5) + run<8>(19) + run<16>(63) + run<32>(191) + run<64>(543); }
+""")
+    exe = tmp_path / "sn"
+    inc = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "spark_ensemble_b200", "csrc")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-I", inc, "-o", str(exe), str(src)], check=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
