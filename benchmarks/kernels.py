@@ -128,6 +128,8 @@ def main():
             else:
                 ctx.fill_synthetic(N.SLOT_P, "uniform", 5, 0.01, 1.0)
             w = np.full(M, 1.0 / M)
+            if kind == N.AGG_BOOSTING_REG_MEDIAN:
+                w = np.linspace(0.5, 1.5, M)   # distinct estimator weights (log 1/beta): the margin-checked fast path
             width = K if kind in (N.AGG_BOOSTING_REAL, N.AGG_BAGGING_SOFT) else 1
             C = K if K else 1
             regr = kind in (N.AGG_GBM_REGRESSOR, N.AGG_BAGGING_REGRESSOR, N.AGG_BOOSTING_REG_MEDIAN)

@@ -118,7 +118,11 @@ SE_API int se_ctx_kernel_time_reset(se_ctx* ctx);
  * search: 0 = one launch per evaluation, 1 = one persistent launch with Brent on the device [default], 2 = host Brent
  * over single-evaluation launches of the persistent kernel — bit-identical to 1, for tests), "ls_resident",
  * "ls_ctas_per_sm", "ls_ring" (cp.async ring stages for the streamed tiles, 0 = register prefetch [default]), "l2_persist", "l2_persist_frac", "peer_timeout_ms" (spin bound of the fused peer exchange,
- * 0 = forever), "alternate_passes", "l2_hints", "ctas_per_sm", "host_mirror".  Read-only: "last_round_fused",
+ * 0 = forever), "alternate_passes", "l2_hints", "ctas_per_sm", "host_mirror", "tree_bins" (uint8 rank matrix for tree
+ * walks), "tree_mask" (all-nodes kernel for trees of <= 64 internal nodes), "wm_fast" (weighted median, M <= 64 and
+ * weights >= 0: keys-only sort + margin-checked model-order sums, exact kernel for the deferred rows), "wm_list_cap"
+ * (deferred-row list capacity, 0 = rows / 4).  Read-only: "last_tree_binned", "last_tree_mask", "last_wm_mode" (0 exact,
+ * 1 fast with margin, 2 equal weights), "last_wm_deferred" (synchronises), "last_round_fused",
  * "last_ls_workers", "last_ls_passes", "last_ls_hit_ratio", "last_fused_grid", "l2_persist_max_bytes",
  * "l2_window_max_bytes".  Unknown keys fail with SE_ERR_ARG. */
 SE_API int se_ctx_set_option(se_ctx* ctx, const char* key, double value);

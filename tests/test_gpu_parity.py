@@ -1011,7 +1011,11 @@ def test_fused_squared_round(ctx, oracle, rng, n, weighted):
             close(ctx.download(N.SLOT_F), Fo[0])
             ro, _, _ = oracle.pseudo_residuals(O.SQUARED, 0.0, 1, y, None, Fo, False)
             close(ctx.download(N.SLOT_R), ro[0], scale=1.0)
-            assert ls / n == pytest.approx(oracle.mean_loss(O.SQUARED, 0.0, 1, y, Fo), rel=RTOL)
+            # F lives in fp32: a residual d = y - F carries |F| 2^-24 of rounding, the loss d^2 / 2 therefore
+            # |d| |F| 2^-24 — invisible next to 1e-5 except when a row's residual has shrunk far below |F| (n = 1)
+            dd = y.astype(np.float64) - Fo[0]
+            atol = 5e-7 * float(np.mean(np.abs(dd) * (np.abs(Fo[0]) + np.abs(y))))
+            assert ls / n == pytest.approx(oracle.mean_loss(O.SQUARED, 0.0, 1, y, Fo), rel=RTOL, abs=atol)
         # the two-launch path on the same state agrees to rounding of the fp64 sums
         Fnow = ctx.download(N.SLOT_F).copy()
         a1, l1, ne1 = ctx.gbm_round(0.7, True, 1e-6, 100, residual=True)
@@ -1021,7 +1025,7 @@ def test_fused_squared_round(ctx, oracle, rng, n, weighted):
         a2, l2, ne2 = ctx.gbm_round(0.7, True, 1e-6, 100, residual=True)
         assert ctx.get_option("last_round_fused") == 0
         assert a1 == pytest.approx(a2, rel=1e-9, abs=1e-12)
-        assert l1 == pytest.approx(l2, rel=RTOL)  # closed form over the fp64 statistics vs the sum of the fp32 rows
+        assert l1 == pytest.approx(l2, rel=RTOL, abs=atol * n)  # closed form over the fp64 statistics vs the sum of the fp32 rows
         close(F1, ctx.download(N.SLOT_F), rtol=1e-6)
         # the in-kernel row reduction of the loss (the path bags use) agrees with the closed form
         ctx.upload(N.SLOT_F, Fnow)
@@ -1029,7 +1033,7 @@ def test_fused_squared_round(ctx, oracle, rng, n, weighted):
         ctx.set_option("fused_loss_reduce", 1)
         a3, l3, ne3 = ctx.gbm_round(0.7, True, 1e-6, 100, residual=True)
         ctx.set_option("fused_loss_reduce", 0)
-        assert (a3, ne3) == (a1, ne1) and l3 == pytest.approx(l1, rel=RTOL)
+        assert (a3, ne3) == (a1, ne1) and l3 == pytest.approx(l1, rel=RTOL, abs=atol * n)
         np.testing.assert_array_equal(F1, ctx.download(N.SLOT_F))
         # MaxEval exceeded: SE_ERR_OPT (TooManyEvaluationsException in the reference) and F is left untouched
         ctx.set_option("fused_round", 1)
