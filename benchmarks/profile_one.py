@@ -75,7 +75,7 @@ elif what == "wmedian":
     ctx.agg_configure(N.AGG_BOOSTING_REG_MEDIAN, M, 2, 1, 0, n)
     ctx.fill_synthetic(N.SLOT_P, "uniform", 5, 0.01, 1.0)
     for _ in range(3):
-        ctx.agg_run(np.full(M, 1.0 / M))
+        ctx.agg_run(np.linspace(0.5, 1.5, M))   # distinct weights: the margin-checked fast path
 elif what == "agg_real":
     M, K = 10, 26
     ctx.agg_configure(N.AGG_BOOSTING_REAL, M, K, 1, 0, n)
