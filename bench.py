@@ -86,7 +86,7 @@ class ClockSampler:
             os.close(fd)
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+                 "-lms", "200"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
@@ -314,6 +314,13 @@ def main():
         dist.broadcast(uid, 0)
         ctx.comm_init(world, rank, bytes(uid.cpu().numpy().tobytes()))
 
+    # clocks are sampled from here (before the inputs are generated: nvidia-smi's own start-up — NVML attaching to every
+    # GPU of the box — is over long before the first timed step, so only its periodic light queries overlap the timed
+    # region) to the end of the e2e loop: the device-resident timed region alone lasts only ~K x 0.5 ms, shorter than
+    # one sampling period
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     n, d = args.rows, args.features
     eng = GBMEngine(ctx, n, 0, 1, "squared", 0.0, has_weights=False)
     seed = 1000 * (rank + 1)
@@ -348,11 +355,6 @@ def main():
         alpha, loss_sum, _ = ctx.gbm_round(lr, True, tol, max_iter, residual=True)
         return alpha, loss_sum
 
-    # clocks are sampled from the first warm-up step to the end of the e2e loop: the device-resident timed
-    # region alone lasts only ~K x 0.6 ms, shorter than one nvidia-smi sampling period
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     for _ in range(args.warmup):
         step()
     barrier()
