@@ -187,3 +187,74 @@ def test_c5_aggregation_m512(ctx, orc):
         assert max_rel(got_mean[a:a + C2], orc.agg_mean(P), scale=1e-3) <= RTOL
         assert max_rel(got_gbm[a:a + C2], orc.agg_weighted_sum(P, w32, 0.7), scale=1e-3) <= RTOL
     ctx.free(N.SLOT_P)
+
+
+def test_tree_kernels_agree_beyond_2g_byte_offsets(ctx):
+    """70 M rows x 40 columns: the uint8 rank matrix is 2.8 GB (column offsets beyond 2^31 bytes), the fp32 matrix 11.2
+    GB.  The all-nodes kernel, the rank-matrix walk and the fp32 walk must pick the same leaf for every row (sums and
+    three 1 M-row windows bit for bit), and a window must equal a plain numpy walk over the downloaded features."""
+    from spark_ensemble_b200 import _native as N
+    n, d, depth = 70_000_000, 40, 6
+    ctx.alloc(N.SLOT_X, d, n)
+    ctx.fill_synthetic(N.SLOT_X, "normal", 51, 0.0, 1.0)
+    ctx.alloc(N.SLOT_H, 1, n)
+    nn = 2 ** (depth + 1) - 1
+    idx = np.arange(nn)
+    leaf = idx >= 2 ** depth - 1
+    feat = np.where(leaf, -1, (d - 1 - (idx * 7) % d))          # node 0 reads the LAST column
+    thr = np.where(leaf, 0.0, ((idx * 13) % 9 - 4) * 0.25).astype(np.float32)
+    tree = {"feature": feat.astype(np.int32), "threshold": thr, "left": np.where(leaf, 0, 2 * idx + 1).astype(np.int32),
+            "right": np.where(leaf, 0, 2 * idx + 2).astype(np.int32), "value": np.linspace(-1, 1, nn).astype(np.float32)}
+    W = 1_000_000
+    wins = (0, (n // 2 // 4) * 4, n - W)
+    got = {}
+    try:
+        for name, bins, mask in (("mask", 1, 1), ("walk", 1, 0), ("fp32", 0, 0)):
+            ctx.set_option("tree_bins", bins)
+            ctx.set_option("tree_mask", mask)
+            ctx.tree_predict(tree, N.SLOT_H, 0)
+            assert ctx.get_option("last_tree_binned") == bins and ctx.get_option("last_tree_mask") == (bins and mask)
+            got[name] = (ctx.slot_sum(N.SLOT_H), [rows(ctx, N.SLOT_H, a, a + W)[0] for a in wins])
+    finally:
+        ctx.set_option("tree_bins", 1)
+        ctx.set_option("tree_mask", 1)
+    for name in ("walk", "fp32"):
+        assert got[name][0] == got["mask"][0], name
+        for u, v in zip(got[name][1], got["mask"][1]):
+            np.testing.assert_array_equal(u, v)
+    a, C2 = wins[1], 100_000
+    X = rows(ctx, N.SLOT_X, a, a + C2, d).astype(np.float32)      # [d][C2]
+    node = np.zeros(C2, dtype=np.int64)
+    for _ in range(depth):
+        f = np.maximum(feat[node], 0)
+        node = np.where(X[f, np.arange(C2)] <= thr[node], tree["left"][node], tree["right"][node])
+    np.testing.assert_array_equal(got["mask"][1][1][:C2], tree["value"][node].astype(np.float64))
+    ctx.free(N.SLOT_X)
+
+
+def test_weighted_median_fast_equals_exact_25m(ctx, orc):
+    """BoostingRegressor.predict shard: 32 models x 25 M rows.  The margin-checked fast path and the exact kernel must
+    return the same values (sum and windows bit for bit); a window against the oracle."""
+    from spark_ensemble_b200 import _native as N
+    M, n = 32, 25_000_000
+    ctx.agg_configure(N.AGG_BOOSTING_REG_MEDIAN, M, 0, 1, 0, n)
+    ctx.fill_synthetic(N.SLOT_P, "normal", 61, 0.0, 1.0)
+    a = np.random.default_rng(9).random(M) + 0.05
+    W = 1_000_000
+    wins = (0, (n // 2 // 4) * 4, n - W)
+    got = {}
+    try:
+        for fast in (1, 0):
+            ctx.set_option("wm_fast", fast)
+            ctx.agg_run(a)
+            assert ctx.get_option("last_wm_mode") == fast
+            got[fast] = (ctx.slot_sum(N.SLOT_RAW), [rows(ctx, N.SLOT_RAW, s, s + W)[0] for s in wins])
+    finally:
+        ctx.set_option("wm_fast", 1)
+    assert got[1][0] == got[0][0]
+    for u, v in zip(got[1][1], got[0][1]):
+        np.testing.assert_array_equal(u, v)
+    s, C2 = wins[1], 200_000
+    P = rows(ctx, N.SLOT_P, s, s + C2, M)
+    np.testing.assert_array_equal(got[1][1][1][:C2], orc.agg_weighted_median(P, a))
+    ctx.free(N.SLOT_P)
