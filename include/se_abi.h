@@ -317,6 +317,19 @@ SE_API int se_tree_predict_multi(se_ctx* ctx, int which, int n_nodes, const int3
                                  const float* threshold, const int32_t* left, const int32_t* right,
                                  const float* values, int n_out, const int32_t* subspace, int n_subspace,
                                  int out_slot);
+/* A whole ensemble of regression trees in ONE pass: out[row] = init + Σ_t weights[t] · tree_t(x_row), accumulated in
+ * fp64 in model order — GBMRegressionModel.predict (regression/GBMRegressor.scala:531-539); with weights 1/M and
+ * init 0, BaggingRegressionModel.predict (regression/BaggingRegressor.scala:221-228).  The trees are concatenated: tree t
+ * owns nodes [offsets[t], offsets[t+1]) of the five node arrays, child indices are TREE-LOCAL, `feature` holds GLOBAL
+ * columns of X (map each member's subspace, ensemble/HasSubBag.scala:81-84, before the call), weights NULL = all 1.
+ * Runs over the uint8 rank matrix (see se_tree_predict; fails with SE_ERR_STATE when a column needs more than 255
+ * thresholds: evaluate the members with se_tree_predict + se_agg_run then): the ranks of every column the forest uses
+ * are staged once per 256-row tile in shared memory and every tree is walked out of shared memory — no [M][n]
+ * intermediate.  Forests larger than the shared-memory budget run in chunks of trees (out accumulates in fp32
+ * between chunks).  Same tree / threshold contract as se_tree_predict. */
+SE_API int se_forest_predict(se_ctx* ctx, int which, int n_trees, const int32_t* offsets, const int32_t* feature,
+                             const float* threshold, const int32_t* left, const int32_t* right, const float* value,
+                             const double* weights, double init, int out_slot, int out_row);
 /* linear model: out = intercept + Σ_j coef[j]·X[subspace[j]] */
 SE_API int se_linear_predict(se_ctx* ctx, int which, int n_coef, const float* coef, float intercept,
                       const int32_t* subspace, int out_slot, int out_row);

@@ -374,6 +374,34 @@ class Context:
                                                  None if sub is None else N.iptr(sub), 0 if sub is None else sub.size,
                                                  out_slot))
 
+    def forest_predict(self, trees, out_slot: int, weights=None, init: float = 0.0, out_row: int = 0,
+                       validation: bool = False, subspaces=None):
+        """out = init + sum_t weights[t] * tree_t(x) for a list of regression trees (dicts as in tree_predict) in one
+        pass over the resident feature matrix (se_forest_predict: GBMRegressionModel.predict,
+        regression/GBMRegressor.scala:531-539).  `subspaces[t]` maps tree t's feature indices to columns of X."""
+        offs = np.zeros(len(trees) + 1, dtype=np.int32)
+        f, t, l, r, v = [], [], [], [], []
+        for i, tr in enumerate(trees):
+            fi = np.asarray(tr["feature"], dtype=np.int32)
+            if subspaces is not None and subspaces[i] is not None:
+                sub = np.asarray(subspaces[i], dtype=np.int32)
+                if np.any(fi >= sub.size):
+                    raise ValueError(f"tree {i}: feature index outside its subspace")
+                fi = np.where(fi >= 0, sub[np.maximum(fi, 0)], fi).astype(np.int32)
+            f.append(fi)
+            t.append(np.asarray(tr["threshold"], dtype=np.float32))
+            l.append(np.asarray(tr["left"], dtype=np.int32))
+            r.append(np.asarray(tr["right"], dtype=np.int32))
+            v.append(np.asarray(tr["value"], dtype=np.float32))
+            offs[i + 1] = offs[i] + fi.size
+        f, t, l, r, v = (np.ascontiguousarray(np.concatenate(a)) for a in (f, t, l, r, v))
+        w = None if weights is None else np.ascontiguousarray(weights, dtype=np.float64)
+        if w is not None and w.size != len(trees):
+            raise ValueError("one weight per tree")
+        self._ck(self._lib.se_forest_predict(self._h, int(validation), len(trees), N.iptr(offs), N.iptr(f), N.fptr(t),
+                                             N.iptr(l), N.iptr(r), N.fptr(v), None if w is None else N.dptr(w),
+                                             float(init), out_slot, out_row))
+
     def linear_predict(self, coef, intercept: float, out_slot: int, out_row: int = 0,
                        validation: bool = False, subspace=None):
         c = np.ascontiguousarray(coef, dtype=np.float32)

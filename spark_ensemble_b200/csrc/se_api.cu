@@ -245,6 +245,9 @@ struct se_ctx {
   // binned (uint8) copies of X / VX for the tree walk
   BinState bins[2];
   int tree_bins = 1;                  // 0: always walk the fp32 matrix
+  unsigned char* d_forest = nullptr;  // packed chunk of trees for se_forest_predict
+  size_t forest_cap = 0;
+  int last_forest_chunks = 0;
   int wm_fast = 1;                    // weighted median (M <= 64, weights >= 0): keys-only sort + margin check, exact kernel for the rest
   int64_t wm_list_cap = 0;            // deferred-row list capacity (0: n / 4)
   unsigned int* d_wm = nullptr;       // [0] deferred count, [1..] row list
@@ -751,6 +754,7 @@ int se_ctx_destroy(se_ctx* ctx) {
   free_bins(ctx->bins[0]);
   free_bins(ctx->bins[1]);
   if (ctx->d_wm) cudaFree(ctx->d_wm);
+  if (ctx->d_forest) cudaFree(ctx->d_forest);
   if (ctx->big.d_coef) cudaFree(ctx->big.d_coef);
   if (ctx->big.h_coef) cudaFreeHost(ctx->big.h_coef);
   if (ctx->big.d_partials) cudaFree(ctx->big.d_partials);
@@ -859,13 +863,13 @@ int se_ctx_kernel_time_reset(se_ctx* ctx) {
 
 namespace {
 struct OptKey { const char* name; int id; };
-enum { OPT_WM_FAST, OPT_WM_LIST_CAP, OPT_LAST_WM_MODE, OPT_LAST_WM_DEFERRED, OPT_TREE_MASK, OPT_LAST_TREE_MASK, OPT_TREE_BINS, OPT_LAST_TREE_BINNED, OPT_LAST_TREE_REBINNED, OPT_FUSED_LOSS_REDUCE, OPT_FUSED_L2_MODE, OPT_FUSED_TIMING, OPT_LAST_FUSED_US0, OPT_LAST_FUSED_US1, OPT_LAST_FUSED_US2, OPT_FUSED_PREFETCH_MB, OPT_FUSED_ROUND, OPT_FUSED_MAX_ROWS, OPT_FUSED_CTAS, OPT_LS_MODE, OPT_LS_RESIDENT, OPT_LS_CTAS, OPT_LS_RING, OPT_L2_PERSIST,
+enum { OPT_LAST_FOREST_CHUNKS, OPT_WM_FAST, OPT_WM_LIST_CAP, OPT_LAST_WM_MODE, OPT_LAST_WM_DEFERRED, OPT_TREE_MASK, OPT_LAST_TREE_MASK, OPT_TREE_BINS, OPT_LAST_TREE_BINNED, OPT_LAST_TREE_REBINNED, OPT_FUSED_LOSS_REDUCE, OPT_FUSED_L2_MODE, OPT_FUSED_TIMING, OPT_LAST_FUSED_US0, OPT_LAST_FUSED_US1, OPT_LAST_FUSED_US2, OPT_FUSED_PREFETCH_MB, OPT_FUSED_ROUND, OPT_FUSED_MAX_ROWS, OPT_FUSED_CTAS, OPT_LS_MODE, OPT_LS_RESIDENT, OPT_LS_CTAS, OPT_LS_RING, OPT_L2_PERSIST,
        OPT_L2_PERSIST_FRAC, OPT_PEER_TIMEOUT_MS, OPT_ALTERNATE, OPT_L2_HINTS, OPT_CTAS_PER_SM, OPT_HOST_MIRROR,
        // read-only diagnostics
        OPT_LAST_ROUND_FUSED, OPT_LAST_LS_WORKERS, OPT_LAST_LS_PASSES, OPT_LAST_LS_HIT_RATIO, OPT_LAST_FUSED_GRID,
        OPT_L2_PERSIST_MAX, OPT_L2_WINDOW_MAX, OPT_LAST_STAT0, OPT_LAST_STAT1, OPT_LAST_STAT2 };
 const OptKey kOpts[] = {
-  {"wm_fast", OPT_WM_FAST}, {"wm_list_cap", OPT_WM_LIST_CAP}, {"last_wm_mode", OPT_LAST_WM_MODE}, {"last_wm_deferred", OPT_LAST_WM_DEFERRED},
+  {"last_forest_chunks", OPT_LAST_FOREST_CHUNKS}, {"wm_fast", OPT_WM_FAST}, {"wm_list_cap", OPT_WM_LIST_CAP}, {"last_wm_mode", OPT_LAST_WM_MODE}, {"last_wm_deferred", OPT_LAST_WM_DEFERRED},
   {"tree_bins", OPT_TREE_BINS}, {"tree_mask", OPT_TREE_MASK}, {"last_tree_mask", OPT_LAST_TREE_MASK}, {"last_tree_binned", OPT_LAST_TREE_BINNED}, {"last_tree_rebinned_cols", OPT_LAST_TREE_REBINNED},
   {"fused_loss_reduce", OPT_FUSED_LOSS_REDUCE}, {"fused_l2_mode", OPT_FUSED_L2_MODE}, {"fused_timing", OPT_FUSED_TIMING}, {"last_fused_stats_us", OPT_LAST_FUSED_US0}, {"last_fused_brent_us", OPT_LAST_FUSED_US1},
   {"last_fused_update_us", OPT_LAST_FUSED_US2}, {"fused_prefetch_mb", OPT_FUSED_PREFETCH_MB}, {"fused_round", OPT_FUSED_ROUND}, {"fused_round_max_rows", OPT_FUSED_MAX_ROWS}, {"fused_ctas_per_sm", OPT_FUSED_CTAS},
@@ -927,6 +931,7 @@ int se_ctx_get_option(const se_ctx* ctx, const char* key, double* value) {
     case OPT_TREE_BINS: *value = ctx->tree_bins; break;
     case OPT_TREE_MASK: *value = ctx->tree_mask; break;
     case OPT_WM_FAST: *value = ctx->wm_fast; break;
+    case OPT_LAST_FOREST_CHUNKS: *value = ctx->last_forest_chunks; break;
     case OPT_WM_LIST_CAP: *value = (double)ctx->wm_list_cap; break;
     case OPT_LAST_WM_MODE: *value = ctx->last_wm_mode; break;
     case OPT_LAST_WM_DEFERRED: {  // rows the last weighted median sent to the exact kernel (synchronises the stream)
@@ -2497,12 +2502,12 @@ namespace {
 // Walk the uint8 rank matrix instead of the fp32 features when every threshold of the tree fits the per-column edge
 // lists (<= 255 per column; Spark's trees draw theirs from the <= maxBins - 1 candidates of findSplits, the same on
 // every round).  Returns 1 when the binned kernel was launched, 0 when the caller must take the fp32 walk.
-int tree_predict_binned(se_ctx* ctx, int which, const SlotBuf& X, int n_nodes, const int32_t* col, const float* thr,
-                        const int32_t* left, const int32_t* right, const TreeArgs& t) {
-  ctx->last_tree_binned = 0;
-  ctx->last_tree_mask = 0;
+// Makes the rank matrix of slot X cover every threshold of the given nodes (col[i] < 0: leaf): allocates it on first
+// use, inserts new thresholds into the per-column edge lists and re-ranks the columns that changed.  Returns 1 when the
+// matrix is ready, 0 when it cannot be used (disabled, no memory, NaN threshold, a column with more than 255 edges).
+int bins_prepare(se_ctx* ctx, int which, const SlotBuf& X, int n_nodes, const int32_t* col, const float* thr) {
   ctx->last_tree_rebinned_cols = 0;
-  if (!ctx->tree_bins || n_nodes > 65535 || X.rows > 65535 || X.cols == 0) return 0;
+  if (!ctx->tree_bins || X.rows > 65535 || X.cols == 0) return 0;
   BinState& B = ctx->bins[which];
   const int d = (int)X.rows;
   if (!B.d8 || B.d != d || B.n != X.cols) {
@@ -2553,6 +2558,19 @@ int tree_predict_binned(se_ctx* ctx, int which, const SlotBuf& X, int n_nodes, c
     for (int32_t c : cols) B.dirty[c] = 0;
     ctx->last_tree_rebinned_cols = (int)cols.size();
   }
+  return 1;
+}
+
+int tree_predict_binned(se_ctx* ctx, int which, const SlotBuf& X, int n_nodes, const int32_t* col, const float* thr,
+                        const int32_t* left, const int32_t* right, const TreeArgs& t) {
+  ctx->last_tree_binned = 0;
+  ctx->last_tree_mask = 0;
+  if (n_nodes > 65535) return 0;
+  {
+    const int rc = bins_prepare(ctx, which, X, n_nodes, col, thr);
+    if (rc <= 0) return rc;
+  }
+  BinState& B = ctx->bins[which];
   if (B.nodes_cap < (size_t)n_nodes) {
     if (B.d_nodes) cudaFree(B.d_nodes);
     B.d_nodes = nullptr; B.nodes_cap = 0;
@@ -2663,6 +2681,155 @@ int se_tree_predict_multi(se_ctx* ctx, int which, int n_nodes, const int32_t* fe
                           const int32_t* subspace, int n_subspace, int out_slot) {
   return tree_predict_impl(ctx, which, n_nodes, feature, threshold, left, right, values, n_out, subspace, n_subspace,
                            out_slot, 0);
+}
+
+// Σ_t weights[t] · tree_t(x) + init for every row in one pass over the rank matrix per chunk of trees
+// (GBMRegressionModel.predict, regression/GBMRegressor.scala:531-539; BaggingRegressionModel.predict,
+// regression/BaggingRegressor.scala:221-228 with weights 1 / M).
+int se_forest_predict(se_ctx* ctx, int which, int n_trees, const int32_t* offsets, const int32_t* feature,
+                      const float* threshold, const int32_t* left, const int32_t* right, const float* value,
+                      const double* weights, double init, int out_slot, int out_row) {
+  if (!ctx || !offsets || !feature || !threshold || !left || !right || !value) return fail(ctx, SE_ERR_ARG, "null argument");
+  SE_REQUIRE(ctx, n_trees >= 1 && n_trees <= (1 << 20), SE_ERR_ARG, "bad tree count %d", n_trees);
+  SE_REQUIRE(ctx, out_slot >= 0 && out_slot < SE_NUM_SLOTS, SE_ERR_ARG, "bad out slot");
+  const SlotBuf& X = ctx->slot[which ? SE_SLOT_VX : SE_SLOT_X];
+  const SlotBuf& O = ctx->slot[out_slot];
+  SE_REQUIRE(ctx, X.d, SE_ERR_STATE, "feature matrix slot not allocated");
+  SE_REQUIRE(ctx, O.d && O.cols == X.cols && out_row >= 0 && out_row < O.rows, SE_ERR_STATE, "output slot shape mismatch");
+  SE_REQUIRE(ctx, offsets[0] == 0, SE_ERR_ARG, "offsets[0] must be 0");
+  const int64_t total = offsets[n_trees];
+  SE_REQUIRE(ctx, total >= n_trees && total <= (1 << 26), SE_ERR_ARG, "bad node count %lld", (long long)total);
+  // every member must be a tree rooted at its first node, with tree-local child indices and GLOBAL column indices
+  {
+    std::vector<char> seen;
+    std::vector<int32_t> stack;
+    for (int t = 0; t < n_trees; ++t) {
+      const int32_t b = offsets[t], nn = offsets[t + 1] - offsets[t];
+      SE_REQUIRE(ctx, nn >= 1 && nn <= 65535, SE_ERR_ARG, "tree %d: %d nodes (1..65535 supported)", t, nn);
+      for (int i = 0; i < nn; ++i) {
+        if (feature[b + i] < 0) continue;
+        SE_REQUIRE(ctx, feature[b + i] < X.rows, SE_ERR_ARG, "tree %d node %d: column %d outside X with %lld columns", t, i,
+                   feature[b + i], (long long)X.rows);
+        SE_REQUIRE(ctx, left[b + i] >= 0 && left[b + i] < nn && right[b + i] >= 0 && right[b + i] < nn, SE_ERR_ARG,
+                   "tree %d node %d: bad child", t, i);
+      }
+      seen.assign((size_t)nn, 0);
+      stack.clear();
+      stack.push_back(0);
+      seen[0] = 1;
+      while (!stack.empty()) {
+        const int32_t i = stack.back();
+        stack.pop_back();
+        if (feature[b + i] < 0) continue;
+        for (const int32_t c : {left[b + i], right[b + i]}) {
+          SE_REQUIRE(ctx, !seen[c], SE_ERR_ARG, "tree %d: node %d is reached twice: not a tree", t, c);
+          seen[c] = 1;
+          stack.push_back(c);
+        }
+      }
+    }
+  }
+  SE_TRY(begin(ctx));
+  release_l2_persist(ctx);
+  SE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  {
+    const int rc = bins_prepare(ctx, which, X, (int)total, feature, threshold);
+    if (rc < 0) return rc;
+    SE_REQUIRE(ctx, rc == 1, SE_ERR_STATE,
+               "the forest kernel needs the uint8 rank matrix (tree_bins on, <= 255 distinct thresholds per column, no NaN "
+               "threshold): evaluate the members with se_tree_predict + se_agg_run instead");
+  }
+  BinState& B = ctx->bins[which];
+  if (out_slot == SE_SLOT_F || out_slot == SE_SLOT_R || out_slot == SE_SLOT_Y) ctx->gbm.r_current = false;
+  ForestArgs a;
+  a.X8 = B.d8; a.n = X.cols; a.ld8 = B.ld8;
+  a.out = O.d + (int64_t)out_row * (O.rows > 1 ? O.ld : O.cols);
+  a.init = init;
+  auto pad = [](size_t v, size_t to) { return (v + to - 1) / to * to; };
+  std::vector<int32_t> local((size_t)X.rows, -1);  // global column -> local column of the current chunk
+  std::vector<int32_t> used;
+  std::vector<unsigned char> blob;
+  int chunks = 0;
+  int t0 = 0;
+  while (t0 < n_trees) {
+    // grow the chunk tree by tree while columns x 256 ranks + packed trees fit the shared-memory budget
+    size_t nodes = 0;
+    int t1 = t0;
+    // a member that does not fit the four-CTAs-per-SM budget alone gets two, then one CTA per SM
+    for (const size_t budget : {(size_t)kForestSmemBudget, (size_t)(100 * 1024), (size_t)(216 * 1024)}) {
+    for (int32_t c : used) local[c] = -1;
+    used.clear();
+    nodes = 0;
+    for (t1 = t0; t1 < n_trees; ++t1) {
+      const int32_t b = offsets[t1], nn = offsets[t1 + 1] - offsets[t1];
+      std::vector<int32_t> added;
+      for (int i = 0; i < nn; ++i) {
+        const int32_t c = feature[b + i];
+        if (c >= 0 && local[c] < 0) { local[c] = (int32_t)(used.size() + added.size()); added.push_back(c); }
+      }
+      const size_t T = (size_t)(t1 - t0 + 1), C = used.size() + added.size(), Nn = nodes + (size_t)nn;
+      const size_t bytes = pad(8 * T + 8 * C + 8 * Nn + pad(4 * (T + 1), 8) + pad(4 * Nn, 16), 16) + C * kForestTile;
+      if (bytes > budget || C > 65535) {
+        for (int32_t c : added) local[c] = -1;
+        break;
+      }
+      used.insert(used.end(), added.begin(), added.end());
+      nodes = Nn;
+    }
+    if (t1 > t0) break;
+    }
+    SE_REQUIRE(ctx, t1 > t0, SE_ERR_ARG, "tree %d alone (%d nodes) does not fit the forest kernel's shared memory", t0,
+               offsets[t0 + 1] - offsets[t0]);
+    const size_t T = (size_t)(t1 - t0), C = used.size(), Nn = nodes;
+    a.T = (int)T; a.C = (int)C;
+    a.off_coloff = (int)(8 * T);
+    a.off_nodes = a.off_coloff + (int)(8 * C);
+    a.off_treeoff = a.off_nodes + (int)(8 * Nn);
+    a.off_values = a.off_treeoff + (int)pad(4 * (T + 1), 8);
+    a.blob_bytes = (int)pad((size_t)a.off_values + 4 * Nn, 16);
+    a.off_ranks = a.blob_bytes;
+    blob.assign((size_t)a.blob_bytes, 0);
+    double* bw = reinterpret_cast<double*>(blob.data());
+    unsigned long long* bco = reinterpret_cast<unsigned long long*>(blob.data() + a.off_coloff);
+    uint2* bn = reinterpret_cast<uint2*>(blob.data() + a.off_nodes);
+    int32_t* bto = reinterpret_cast<int32_t*>(blob.data() + a.off_treeoff);
+    float* bv = reinterpret_cast<float*>(blob.data() + a.off_values);
+    for (size_t c = 0; c < C; ++c) bco[c] = (unsigned long long)used[c] * (unsigned long long)B.ld8;
+    size_t at = 0;
+    for (int t = t0; t < t1; ++t) {
+      const int32_t b = offsets[t], nn = offsets[t + 1] - offsets[t];
+      bw[t - t0] = weights ? weights[t] : 1.0;
+      bto[t - t0] = (int32_t)at;
+      for (int i = 0; i < nn; ++i) {
+        const int32_t c = feature[b + i];
+        bv[at + i] = value[b + i];
+        if (c < 0) { bn[at + i] = make_uint2(0x80000000u, 0u); continue; }
+        const std::vector<float>& E = B.edges[c];
+        const uint32_t j = (uint32_t)(std::lower_bound(E.begin(), E.end(), threshold[b + i]) - E.begin());  // x <= t_j <=> rank <= j
+        bn[at + i] = make_uint2((uint32_t)local[c] | (j << 16), (uint32_t)left[b + i] | ((uint32_t)right[b + i] << 16));
+      }
+      at += (size_t)nn;
+    }
+    bto[T] = (int32_t)at;
+    if (ctx->forest_cap < (size_t)a.blob_bytes) {
+      if (ctx->d_forest) cudaFree(ctx->d_forest);
+      ctx->d_forest = nullptr; ctx->forest_cap = 0;
+      SE_CUDA(ctx, cudaMalloc(&ctx->d_forest, (size_t)a.blob_bytes));
+      ctx->forest_cap = (size_t)a.blob_bytes;
+    }
+    // the previous chunk's kernel may still be reading d_forest
+    SE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    SE_CUDA(ctx, cudaMemcpyAsync(ctx->d_forest, blob.data(), (size_t)a.blob_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    SE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // blob is pageable host memory reused by the next chunk
+    a.blob = ctx->d_forest;
+    a.accumulate = chunks > 0 ? 1 : 0;
+    SE_LAUNCH_T(ctx, SE_KF_TREE, launch_forest_predict(a, ctx->sms, ctx->stream));
+    ++chunks;
+    t0 = t1;
+  }
+  ctx->last_forest_chunks = chunks;
+  ctx->last_tree_binned = 1;
+  return end(ctx);
 }
 
 int se_linear_predict(se_ctx* ctx, int which, int n_coef, const float* coef, float intercept,

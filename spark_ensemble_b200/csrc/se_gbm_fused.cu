@@ -572,11 +572,21 @@ template <int LOSS>
 cudaError_t launch_ls(const LsArgs& a0, int sms, const LsLaunch& cfg, cudaStream_t st, int* workers_out) {
   using T = LsTraits<LOSS>;
   auto kern = gbm_linesearch_persist_kernel<LOSS>;
-  static int max_smem = -1, blocks_full = -1;
-  static size_t smem_cap = 0;
-  if (max_smem < 0) {
-    int dev = 0, optin = 0;
-    cudaGetDevice(&dev);
+  // function attributes are per DEVICE: a process that drives several GPUs (sharded.ShardedContext, a JVM executor with
+  // `devices`) must opt in to the large dynamic shared memory on each of them
+  constexpr int kMaxDev = 64;
+  static int max_smem_dev[kMaxDev];
+  static int blocks_full_dev[kMaxDev];
+  static size_t smem_cap_dev[kMaxDev];
+  static bool ready_dev[kMaxDev] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= kMaxDev) return cudaErrorInvalidDevice;
+  int& max_smem = max_smem_dev[dev];
+  int& blocks_full = blocks_full_dev[dev];
+  size_t& smem_cap = smem_cap_dev[dev];
+  if (!ready_dev[dev]) {
+    int optin = 0;
     cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     cudaFuncAttributes fa;
     cudaError_t e = cudaFuncGetAttributes(&fa, kern);
@@ -594,6 +604,7 @@ cudaError_t launch_ls(const LsArgs& a0, int sms, const LsLaunch& cfg, cudaStream
     int per_sm = 0;
     cudaDeviceGetAttribute(&per_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
     smem_cap = (size_t)per_sm;
+    ready_dev[dev] = true;
   }
   LsArgs a = a0;
   int per_sm_ctas = blocks_full > cfg.max_ctas_per_sm ? cfg.max_ctas_per_sm : blocks_full;

@@ -242,6 +242,29 @@ cudaError_t launch_bin_columns(const BinArgs& a, int n_cols, int sms, cudaStream
 // n_internal: number of internal nodes; mask_mode != 0 allows the all-nodes kernel for trees of <= 64 internal nodes
 cudaError_t launch_tree_predict_binned(const TreeArgs& a, const uint8_t* X8, const uint4* nodes, int n_internal, int mask_mode,
                                        int sms, cudaStream_t s);
+// A whole forest in ONE pass over the uint8 rank matrix: out = (accumulate ? out : init) + Σ_t w_t · tree_t(row)
+// (GBMRegressionModel.predict, regression/GBMRegressor.scala:531-539; BaggingRegressionModel.predict,
+// regression/BaggingRegressor.scala:221-228).  `blob` is the packed chunk of trees, copied verbatim into shared memory:
+//   [0)            double   w[T]
+//   [off_coloff)   uint64   byte offset of local column c in X8 (column * ld8), c < C
+//   [off_nodes)    uint2    nodes: x = local column | rank threshold << 16 | leaf << 31, y = left | right << 16 (tree-local)
+//   [off_treeoff)  int32    first node of tree t (T + 1 entries)
+//   [off_values)   float    leaf value per node
+//   [off_ranks)    uint8    (shared memory only) the tile's ranks, [C][256]
+struct ForestArgs {
+  const uint8_t* X8 = nullptr;
+  int64_t n = 0, ld8 = 0;
+  const unsigned char* blob = nullptr;
+  int blob_bytes = 0;  // multiple of 16
+  int T = 0, C = 0;
+  int off_coloff = 0, off_nodes = 0, off_treeoff = 0, off_values = 0, off_ranks = 0;
+  double init = 0.0;
+  int accumulate = 0;
+  float* out = nullptr;
+};
+constexpr int kForestTile = 256;              // rows per CTA tile (one row per thread)
+constexpr int kForestSmemBudget = 54 * 1024;  // per CTA: four CTAs per SM (the walk is latency-bound: warps matter more than chunk size)
+cudaError_t launch_forest_predict(const ForestArgs& a, int sms, cudaStream_t s);
 cudaError_t launch_linear_predict(const float* X, int64_t n, int64_t ld, int n_coef,
                                   const float* coef, const int32_t* cols, float intercept,
                                   float* out, int sms, cudaStream_t s);

@@ -318,6 +318,75 @@ __global__ void __launch_bounds__(kBlock, 4) tree_predict_mask_kernel(const Tree
   }
 }
 
+
+// ---- a forest in one pass -----------------------------------------------------------------------------------------
+// transform() of a tree ensemble evaluated tree by tree reads each tree's columns of the rank matrix again (one byte per
+// row and internal node, 0.73 ms per depth-5 tree and 100 M rows) and needs an [M][n] prediction array for the
+// aggregation kernel.  Here a CTA stages a 256-row tile of the ranks of every column the forest uses in shared memory
+// (C x 256 bytes), keeps the packed trees next to it, and every thread walks ALL trees for its row out of shared
+// memory, two trees interleaved, accumulating w_t · leaf in fp64 in model order like the reference's loop: the rank
+// matrix is read once per chunk of trees and no intermediate is written.
+__device__ __forceinline__ void forest_step(const uint2* __restrict__ nodes, const unsigned char* __restrict__ myr, int& nd,
+                                            bool& live) {
+  const uint2 w = nodes[nd];
+  live = (w.x >> 31) == 0;
+  if (live) {
+    const uint32_t rank = myr[(w.x & 0xFFFFu) * kForestTile];
+    nd = (int)((rank <= ((w.x >> 16) & 0xFFu)) ? (w.y & 0xFFFFu) : (w.y >> 16));
+  }
+}
+
+__global__ void __launch_bounds__(kForestTile) forest_predict_kernel(const ForestArgs a) {
+  extern __shared__ __align__(16) unsigned char fsm[];
+  for (int i = threadIdx.x; i < a.blob_bytes / 16; i += kForestTile)
+    reinterpret_cast<uint4*>(fsm)[i] = __ldg(reinterpret_cast<const uint4*>(a.blob) + i);
+  const double* s_w = reinterpret_cast<const double*>(fsm);
+  const unsigned long long* s_coloff = reinterpret_cast<const unsigned long long*>(fsm + a.off_coloff);
+  const uint2* s_nodes = reinterpret_cast<const uint2*>(fsm + a.off_nodes);
+  const int* s_toff = reinterpret_cast<const int*>(fsm + a.off_treeoff);
+  const float* s_val = reinterpret_cast<const float*>(fsm + a.off_values);
+  unsigned char* s_rank = fsm + a.off_ranks;
+  const int64_t ntiles = (a.n + kForestTile - 1) / kForestTile;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    __syncthreads();  // the packed trees are staged (first tile) / the previous tile's walks are over
+    const int64_t row0 = tile * kForestTile;
+    for (int i = threadIdx.x; i < a.C * (kForestTile / 4); i += kForestTile) {
+      const int c = i / (kForestTile / 4), q = i % (kForestTile / 4);
+      const int64_t r = row0 + 4 * q;  // columns are padded to 128 rows: a word at r < ld8 stays inside its column
+      uint32_t v = 0;
+      if (r < a.ld8) v = __ldg(reinterpret_cast<const uint32_t*>(a.X8 + s_coloff[c] + r));
+      *reinterpret_cast<uint32_t*>(s_rank + c * kForestTile + 4 * q) = v;
+    }
+    __syncthreads();
+    const int64_t row = row0 + threadIdx.x;
+    if (row < a.n) {
+      double acc = a.accumulate ? (double)a.out[row] : a.init;
+      const unsigned char* myr = s_rank + threadIdx.x;
+      int t = 0;
+      for (; t + 1 < a.T; t += 2) {  // two independent walks in flight
+        const uint2* n0 = s_nodes + s_toff[t];
+        const uint2* n1 = s_nodes + s_toff[t + 1];
+        int d0 = 0, d1 = 0;
+        bool l0 = true, l1 = true;
+        while (l0 || l1) {
+          if (l0) forest_step(n0, myr, d0, l0);
+          if (l1) forest_step(n1, myr, d1, l1);
+        }
+        acc += s_w[t] * (double)s_val[s_toff[t] + d0];  // model order (GBMRegressor.scala:534-537)
+        acc += s_w[t + 1] * (double)s_val[s_toff[t + 1] + d1];
+      }
+      if (t < a.T) {
+        const uint2* n0 = s_nodes + s_toff[t];
+        int d0 = 0;
+        bool l0 = true;
+        while (l0) forest_step(n0, myr, d0, l0);
+        acc += s_w[t] * (double)s_val[s_toff[t] + d0];
+      }
+      a.out[row] = (float)acc;
+    }
+  }
+}
+
 constexpr int LU = 8;
 
 __global__ void __launch_bounds__(kBlock) linear_predict_kernel(const float* __restrict__ X, int64_t n,
@@ -431,6 +500,23 @@ cudaError_t launch_tree_predict_binned(const TreeArgs& a, const uint8_t* X8, con
     default: SE_TREE_LAUNCH(1, 4); break;
   }
 #undef SE_TREE_LAUNCH
+  return cudaGetLastError();
+}
+
+cudaError_t launch_forest_predict(const ForestArgs& a, int sms, cudaStream_t st) {
+  const size_t smem = (size_t)a.off_ranks + (size_t)a.C * kForestTile;
+  if (a.T < 1 || a.C < 0 || smem > 220 * 1024 || (a.blob_bytes & 15) != 0) return cudaErrorInvalidValue;
+  if (smem > 48 * 1024) {  // per device and per launch (a handful of launches per transform)
+    cudaError_t e = cudaFuncSetAttribute(forest_predict_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  int per_sm = (int)((220 * 1024) / (smem + 1024));
+  if (per_sm < 1) per_sm = 1;
+  if (per_sm > 8) per_sm = 8;
+  int64_t need = (a.n + kForestTile - 1) / kForestTile;
+  if (need < 1) need = 1;
+  const int64_t cap = (int64_t)sms * per_sm;
+  forest_predict_kernel<<<(int)(need < cap ? need : cap), kForestTile, smem, st>>>(a);
   return cudaGetLastError();
 }
 

@@ -1268,6 +1268,73 @@ def test_shallow_tree_all_nodes_kernel(ctx, rng, n, d, n_internal):
         ctx.free(N.SLOT_X)
 
 
+@pytest.mark.parametrize("n,d,T,max_internal", [(1, 3, 1, 2), (777, 5, 2, 6), (30_011, 20, 7, 40), (30_011, 20, 41, 63),
+                                                (9_001, 150, 300, 60)])
+def test_forest_predict_matches_member_sum(ctx, n, d, T, max_internal):
+    """se_forest_predict: init + sum_t w_t * tree_t(x) (GBMRegressionModel.predict, GBMRegressor.scala:531-539) in one
+    pass over the rank matrix per chunk of trees, fp64 accumulation in model order.  Against a plain numpy walk of every
+    member (leaf choice exact; the sum within one fp32 rounding per chunk), with per-tree subspaces, on the validation
+    slot, for forests that need several chunks, and the failure modes (not a tree, bad column, > 255 thresholds)."""
+    from spark_ensemble_b200 import _native as N
+    rng = np.random.default_rng(1000 + n + T)
+    X = rng.standard_normal((n, d)).astype(np.float32)
+    cand = [np.unique(np.concatenate([rng.standard_normal(12).astype(np.float32), X[rng.integers(0, n, 3), f]])) for f in range(d)]
+    trees, subs = [], []
+    for t in range(T):
+        if t % 3 == 0 and d >= 3:
+            sub = np.sort(rng.choice(d, size=max(2, d // 2), replace=False)).astype(np.int32)
+        else:
+            sub = None
+        dd = d if sub is None else sub.size
+        cc = cand if sub is None else [cand[c] for c in sub]
+        trees.append(_random_unbalanced_tree(rng, int(rng.integers(0, max_internal + 1)), dd, cc))
+        subs.append(sub)
+    w = rng.random(T) + 0.1
+    init = 0.37
+    want = np.full(n, init)
+    for tr, sub, wt in zip(trees, subs, w):
+        Xs = X if sub is None else X[:, sub]
+        want = want + wt * tr["value"][_walk(tr, Xs)].astype(np.float64)
+    for validation, slot in ((False, N.SLOT_X), (True, N.SLOT_VX)):
+        ctx.alloc(slot, d, n)
+        ctx.upload_rowmajor(slot, X)
+        out = N.SLOT_VH if validation else N.SLOT_H
+        ctx.alloc(out, 1, n)
+        ctx.forest_predict(trees, out, weights=w, init=init, validation=validation, subspaces=subs)
+        chunks = ctx.get_option("last_forest_chunks")
+        assert chunks >= 1 and (T < 300 or chunks > 1)
+        got = ctx.download(out).astype(np.float64)
+        scale = float(np.max(np.abs(want))) + 1.0
+        assert np.max(np.abs(got - want)) <= 1.5e-7 * scale * chunks, (np.max(np.abs(got - want)), chunks)
+        if not validation:   # the per-tree path agrees row by row on the leaf of every member
+            ctx.tree_predict(trees[0], out, 0, subspace=subs[0])
+            Xs = X if subs[0] is None else X[:, subs[0]]
+            np.testing.assert_array_equal(ctx.download(out), trees[0]["value"][_walk(trees[0], Xs)])
+    # weights None == all ones, init 0
+    ctx.forest_predict(trees, N.SLOT_H, subspaces=subs)
+    ones = np.zeros(n)
+    for tr, sub in zip(trees, subs):
+        ones = ones + tr["value"][_walk(tr, X if sub is None else X[:, sub])].astype(np.float64)
+    assert np.max(np.abs(ctx.download(N.SLOT_H).astype(np.float64) - ones)) <= 1.5e-7 * (np.max(np.abs(ones)) + 1.0) * chunks
+    if T >= 2 and n > 1:
+        bad = dict(trees[0]); bad_trees = [bad] + trees[1:]
+        if np.any(np.asarray(bad["feature"]) >= 0):
+            i = int(np.argmax(np.asarray(bad["feature"]) >= 0))
+            bad["left"] = np.array(bad["left"]).copy(); bad["left"][i] = i        # a node that is its own child
+            with pytest.raises(ValueError):
+                ctx.forest_predict(bad_trees, N.SLOT_H, subspaces=subs)
+            bad2 = dict(trees[0]); bad2["feature"] = np.array(bad2["feature"]).copy(); bad2["feature"][i] = d + 5
+            with pytest.raises(ValueError):
+                ctx.forest_predict([bad2] + trees[1:], N.SLOT_H, subspaces=[None] + subs[1:])
+        # a column with more than 255 distinct thresholds cannot be ranked in a byte: SE_ERR_STATE, fall back per tree
+        many = np.sort(rng.standard_normal(400).astype(np.float32))
+        wide = [_random_unbalanced_tree(rng, 60, 1, [many]) for _ in range(8)]
+        with pytest.raises(N.NativeError):
+            ctx.forest_predict(wide, N.SLOT_H, subspaces=[np.array([0], np.int32)] * 8)
+    ctx.free(N.SLOT_X)
+    ctx.free(N.SLOT_VX)
+
+
 @pytest.mark.parametrize("n,d,depth", [(1, 3, 2), (1027, 7, 4), (200_003, 33, 6), (50_001, 9, 8)])
 def test_tree_walk_over_binned_features_is_exact(ctx, rng, n, d, depth):
     """The tree walk over the uint8 RANK matrix (bin(x) = #{thresholds < x}; `x <= t_j` <=> `bin <= j`) must pick the
