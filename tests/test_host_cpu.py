@@ -308,6 +308,12 @@ def test_rewired_scala_train_uses_only_existing_natives():
     for call in ("gbmPseudoResiduals", "gbmLinesearchEval", "gbmRound", "gbmUpdate", "gbmUpdateValidation", "quantile",
                  "treePredict", "uploadRowmajor"):
         assert call in used
+    # GBMRegressionModel.transform per partition: the forest route and the member-by-member route
+    src = open(os.path.join(root, "scala", "org", "apache", "spark", "ml", "regression", "GBMRegressionModelNative.scala")).read()
+    used = set(re.findall(r"SeNative\.(\w+)\(", src))
+    assert used and used <= natives, used - natives
+    for call in ("forestPredict", "uploadRowmajor", "aggConfigure", "aggRun", "download", "ctxDestroy"):
+        assert call in used
     # BoostingClassifier.train() (SAMME / SAMME.R), rewired the same way
     src = open(os.path.join(root, "scala", "org", "apache", "spark", "ml", "classification", "BoostingClassifierNative.scala")).read()
     used = set(re.findall(r"SeNative\.(\w+)\(", src))
