@@ -211,6 +211,10 @@ class ShardedContext:
     def tree_predict_multi(self, tree, out_slot, validation=False, subspace=None):
         self._all(lambda r, c: c.tree_predict_multi(tree, out_slot, validation=validation, subspace=subspace))
 
+    def forest_predict(self, trees, out_slot, weights=None, init=0.0, out_row=0, validation=False, subspaces=None):
+        self._all(lambda r, c: c.forest_predict(trees, out_slot, weights=weights, init=init, out_row=out_row,
+                                                validation=validation, subspaces=subspaces))
+
     def linear_predict(self, coef, intercept, out_slot, out_row=0, validation=False, subspace=None):
         self._all(lambda r, c: c.linear_predict(coef, intercept, out_slot, out_row, validation=validation, subspace=subspace))
 

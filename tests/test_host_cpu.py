@@ -364,6 +364,9 @@ class _FakeCtx:
         a = self.slots[slot]
         return a.copy() if a.shape[0] > 1 else a.reshape(-1).copy()
 
+    def forest_predict(self, trees, out_slot, **kw):
+        self.calls.append(("forest", len(trees), out_slot, kw.get("init", 0.0)))
+
     def gbm_update(self, step, residual=False, newton=False, loss=True):
         self.calls.append(("update", tuple(step)))
         return 1.25, None
@@ -396,6 +399,8 @@ def test_sharded_context_splits_and_reassembles_rows():
         np.testing.assert_array_equal(np.asarray(sc.download(N.SLOT_Y)).reshape(-1), y)
         assert sc.gbm_update([0.5] * dim, residual=True)[0] == 1.25
         assert all(c.calls == [("update", tuple([0.5] * dim))] for c in sc.ctxs)
+        sc.forest_predict([{"feature": [-1]}] * 3, N.SLOT_H, init=0.25)   # every shard evaluates the same forest over its rows
+        assert all(c.calls[-1] == ("forest", 3, N.SLOT_H, 0.25) for c in sc.ctxs)
         ctxs = list(sc.ctxs)
         sc.close()
         assert all(getattr(c, "left", False) and getattr(c, "closed", False) for c in ctxs)  # communicator left first
